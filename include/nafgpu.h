@@ -1,0 +1,168 @@
+/*
+ * nafgpu.h -- C ABI of the B200-native backend for the nafcodec decode hot path.
+ *
+ * This is the boundary a Rust `extern "C"` block (rust_shim/ffi.rs) or any other FFI binds.  It replaces, for
+ * one NAF archive or a batch of archives, the six per-section streaming readers the reference builds in
+ * `setup_block!` (nafcodec/src/decoder/mod.rs:199-242: BufReader<zstd::Decoder<BufReader<IoSlice<R>>>>,
+ * type alias at mod.rs:32) and everything `Decoder::next_record` / `mask_sequence` (mod.rs:356-441) and the
+ * readers of nafcodec/src/decoder/reader.rs compute from them.  Plain pointers and sizes only; no C++ types,
+ * no exceptions cross this boundary.  Every entry point returns 0 or a negative nafgpu_status.
+ *
+ * There is NO CPU fallback: without the CUDA library / a device, nafgpu_ctx_create fails with
+ * NAFGPU_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef NAFGPU_H
+#define NAFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  Mapping onto the reference's `Error` (nafcodec/src/error.rs:4-11) is given per code. */
+typedef enum nafgpu_status {
+    NAFGPU_OK = 0,
+    NAFGPU_ERR_UNEXPECTED_EOF = -1, /* Error::Io(UnexpectedEof): truncated header/section/stream, "failed to get mask unit" (mod.rs:431-434) */
+    NAFGPU_ERR_INVALID_DATA = -2,   /* Error::Io(InvalidData): corrupt zstd data (what zstd-rs reports) */
+    NAFGPU_ERR_PARSE = -3,          /* Error::Nom: bad format descriptor / version / sequence type / separator (parser.rs:50-91) */
+    NAFGPU_ERR_UTF8 = -4,           /* Error::Io(InvalidData) from String::from_utf8 (reader.rs:108-109); ids/comments: reference panics (mod.rs:362,368) */
+    NAFGPU_ERR_CUDA = -5,           /* Error::Io(Other): CUDA runtime failure */
+    NAFGPU_ERR_NOMEM = -6,          /* Error::Io(OutOfMemory) */
+    NAFGPU_ERR_ARGUMENT = -7,       /* caller bug (NULL pointer, bad index) */
+    NAFGPU_ERR_NO_DEVICE = -8,      /* no CUDA device: there is no CPU fallback */
+    NAFGPU_ERR_UNSUPPORTED = -9     /* valid zstd the backend does not handle (dictionaries) */
+} nafgpu_status;
+
+/* Header (nafcodec/src/data.rs:198-205, parsed by decoder/parser.rs:101-123). */
+typedef struct nafgpu_header {
+    int32_t format_version;        /* 1 | 2 (data.rs:46-50) */
+    int32_t sequence_type;         /* 0 dna, 1 rna, 2 protein, 3 text (data.rs:56-62) */
+    uint32_t flags;                /* Flag bits (data.rs:80-97): Quality 1, Sequence 2, Mask 4, Length 8, Comment 0x10, Id 0x20, Title 0x40, Extended 0x80 */
+    int32_t name_separator;
+    uint64_t line_length;
+    uint64_t number_of_sequences;
+} nafgpu_header;
+
+/* Section order is fixed: Id, Comment, Length, Mask, Sequence, Quality (decoder/mod.rs:237-242). */
+enum { NAFGPU_SEC_ID = 0, NAFGPU_SEC_COMMENT = 1, NAFGPU_SEC_LENGTH = 2, NAFGPU_SEC_MASK = 3, NAFGPU_SEC_SEQUENCE = 4, NAFGPU_SEC_QUALITY = 5, NAFGPU_N_SECTIONS = 6 };
+
+/* One compressed section as `setup_block!` finds it: (original_size, compressed_size) varints + byte range. */
+typedef struct nafgpu_section {
+    const uint8_t* data;           /* HOST pointer to the compressed bytes (one magicless zstd frame); borrowed during the call */
+    uint64_t compressed_size;
+    uint64_t original_size;        /* Sequence: residues (encoder/counter.rs:25-34); other sections: bytes */
+    int32_t present;               /* flag set in the header */
+    int32_t _pad;
+} nafgpu_section;
+
+typedef struct nafgpu_archive {
+    nafgpu_header header;
+    nafgpu_section sections[NAFGPU_N_SECTIONS];
+} nafgpu_archive;
+
+/* Field selection == DecoderBuilder::{id,comment,sequence,quality,mask} (decoder/mod.rs:117-148).  Lengths are
+ * always decoded (mod.rs:239). */
+enum { NAFGPU_WANT_ID = 1, NAFGPU_WANT_COMMENT = 2, NAFGPU_WANT_SEQUENCE = 4, NAFGPU_WANT_QUALITY = 8, NAFGPU_WANT_MASK = 16, NAFGPU_WANT_ALL = 31 };
+
+/* Decoded archive, structure-of-arrays.  Pointers are HOST pointers into pinned memory owned by the context,
+ * valid until the next nafgpu_decode* / nafgpu_job_prepare on that context or its destruction.
+ * Record i (0 <= i < n_records) as the reference's iterator would yield it (mod.rs:356-399):
+ *   id       = i < n_ids      ? ids[id_offsets[i] .. id_offsets[i+1]-1)            : None   (NUL stripped)
+ *   comment  = i < n_comments ? comments[comment_offsets[i] .. comment_offsets[i+1]-1) : None
+ *   length   = i < n_lengths  ? lengths[i] : None
+ *   sequence = (i < n_lengths && sequence) ? sequence[record_offsets[i] .. record_offsets[i+1]) : None
+ *   quality  = (i < n_lengths && quality)  ? quality [record_offsets[i] .. record_offsets[i+1]) : None
+ * A NULL blob pointer means the field is absent from the archive or was not requested. */
+typedef struct nafgpu_result {
+    uint64_t n_records;
+    uint64_t n_ids, n_comments, n_lengths;
+    uint64_t total_residues;            /* == record_offsets[n_lengths] */
+    const uint8_t* ids;
+    const uint64_t* id_offsets;         /* n_records + 1 entries */
+    const uint8_t* comments;
+    const uint64_t* comment_offsets;    /* n_records + 1 entries */
+    const uint64_t* lengths;            /* n_records entries */
+    const uint64_t* record_offsets;     /* n_records + 1 entries (exclusive prefix sum of lengths) */
+    const uint8_t* sequence;            /* ASCII, soft-masked; total_residues bytes */
+    const uint8_t* quality;             /* total_residues bytes */
+    uint64_t first_bad_record;          /* UINT64_MAX, or the first record whose text is not UTF-8: records before it are valid,
+                                           the reference yields an error AT that record (reader.rs:108-109) */
+    int32_t record_status;              /* status to raise at first_bad_record (NAFGPU_ERR_UTF8) or 0 */
+    int32_t _pad;
+} nafgpu_result;
+
+/* Sizes of the last prepared job, for throughput arithmetic (B_alg). */
+typedef struct nafgpu_job_stats {
+    uint64_t n_archives, n_frames, n_blocks, n_sequences;
+    uint64_t compressed_bytes;          /* sum of compressed sizes of the decoded sections */
+    uint64_t section_bytes;             /* regenerated bytes of all decoded sections */
+    uint64_t ascii_bytes;               /* sequence ASCII bytes (capacity from the headers) */
+    uint64_t quality_bytes, id_bytes, comment_bytes;
+    uint64_t algorithmic_bytes;         /* compressed in + every output byte once + 8*(n_records+1) offsets */
+    uint64_t h2d_bytes, d2h_bytes;      /* bytes copied per decode */
+    uint32_t kernel_launches;           /* kernels enqueued by one nafgpu_job_run */
+    uint32_t n_stages;                  /* entries nafgpu_job_run_profiled writes */
+} nafgpu_job_stats;
+
+/* ---- host-only helpers -------------------------------------------------------------------------------- */
+
+/* parser::header + title + the setup_block! section table over an in-memory archive (parser.rs:101-139,
+ * mod.rs:169-242).  Section data pointers point into `bytes`.  No GPU needed. */
+int nafgpu_parse_archive(const uint8_t* bytes, uint64_t len, nafgpu_archive* out);
+/* parser::variable_u64 (parser.rs:27-48): returns bytes consumed (>0) or a negative status. */
+int nafgpu_variable_u64(const uint8_t* bytes, uint64_t len, uint64_t* value);
+
+const char* nafgpu_strerror(int status);
+const char* nafgpu_version(void);
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+typedef struct nafgpu_ctx nafgpu_ctx;
+
+/* One context per Decoder (or per worker thread); owns a CUDA stream, device arenas and pinned result buffers.
+ * Not thread-safe; distinct contexts may be used concurrently from distinct threads (cudaSetDevice at every entry). */
+int nafgpu_ctx_create(int device, nafgpu_ctx** out);
+void nafgpu_ctx_destroy(nafgpu_ctx* ctx);
+const char* nafgpu_last_error(const nafgpu_ctx* ctx);
+
+/* Pinned host memory for callers that want zero staging copies (optional). */
+void* nafgpu_host_alloc(size_t bytes);
+void nafgpu_host_free(void* p);
+
+/* ---- decode ------------------------------------------------------------------------------------------------ */
+
+/* Whole path, host buffers in, host buffers out: walk frames, H2D, kernels, D2H, synchronise. */
+int nafgpu_decode(nafgpu_ctx* ctx, const nafgpu_archive* archive, uint32_t want, nafgpu_result* out);
+/* Same for n independent archives in ONE set of kernel launches (the batch / RefSeq-collection shape). */
+int nafgpu_decode_batch(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want, nafgpu_result* out);
+
+/* One magicless zstd frame -> exactly regen_size bytes at dst (host memory).  The pure-zstd boundary: what
+ * zstd::stream::read::Decoder + include_magicbytes(false) (decoder/mod.rs:221-223) yields for one section. */
+int nafgpu_zstd_decompress(nafgpu_ctx* ctx, const uint8_t* frame, uint64_t frame_size, uint64_t regen_size, uint8_t* dst);
+
+/* The same pipeline in three steps, so the device-resident part can be timed on its own:
+ *   prepare: host frame walk + H2D of compressed sections and descriptors (asynchronous on the context's stream)
+ *   run:     enqueue every kernel (asynchronous); may be called repeatedly on a prepared job
+ *   fetch:   D2H of the results + synchronise + validate; fills n results */
+int nafgpu_job_prepare(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want);
+int nafgpu_job_run(nafgpu_ctx* ctx);
+int nafgpu_job_fetch(nafgpu_ctx* ctx, nafgpu_result* out, uint32_t n);
+int nafgpu_job_sync(nafgpu_ctx* ctx);
+int nafgpu_job_get_stats(const nafgpu_ctx* ctx, nafgpu_job_stats* out);
+
+/* Runs the prepared job `iters` times back to back and returns the elapsed device time in milliseconds, measured
+ * with CUDA events on the context's own stream (where the kernels are launched). If flush_l2 != 0 a buffer larger
+ * than L2 is overwritten before every iteration, outside the timed intervals (per-iteration events are summed). */
+int nafgpu_job_time(nafgpu_ctx* ctx, int iters, int flush_l2, float* total_ms);
+/* One run with an event after every stage; stage_ms must hold stats.n_stages floats. Stage names: nafgpu_stage_name. */
+int nafgpu_job_run_profiled(nafgpu_ctx* ctx, float* stage_ms, uint32_t n_stages);
+const char* nafgpu_stage_name(uint32_t stage);
+
+/* Device pointers of the last run's outputs, for callers that keep results in HBM (device-resident variant). */
+int nafgpu_job_device_result(nafgpu_ctx* ctx, uint32_t archive, const uint8_t** sequence_dev, uint64_t* capacity_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAFGPU_H */

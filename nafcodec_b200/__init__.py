@@ -1,0 +1,33 @@
+"""nafcodec_b200 -- B200-native backend for the nafcodec decode hot path (zstd NAF sections -> per-record ASCII).
+
+Surface mirrors `nafcodec` (Rust crate) / `nafcodec` (Python binding) for the decode path:
+Decoder, DecoderBuilder, Record, Header, Flag, Flags, SequenceType, FormatVersion, open.
+The compute runs in hand-written sm_100a kernels behind the C ABI of include/nafgpu.h; there is no CPU fallback.
+"""
+from .data import Flag, Flags, FormatVersion, Header, Record, SequenceType
+from .decoder import ArchiveResult, Context, Decoder, DecoderBuilder, decode_batch, parse_archive, shared_context
+from .errors import NafDeviceError, NafError, NafIoError, NafParseError, NafUnicodeError
+
+__version__ = "0.1.0"
+
+
+class Encoder:
+    """Writing archives is outside the accelerated path: zstd *compression* stays on the CPU in the
+    reference crate.  The name is kept so `open(..., "w")` fails with a clear message instead of an AttributeError."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("nafcodec_b200 accelerates decoding only; use the reference nafcodec.Encoder to write archives")
+
+
+def open(file, mode="r", **options):
+    """nafcodec.open (nafcodec-py/nafcodec/lib.rs:641-653): 'r' -> Decoder, 'w' -> Encoder."""
+    if mode == "r":
+        return Decoder(file, **options)
+    if mode == "w":
+        return Encoder(file, **options)
+    raise ValueError(f"invalid mode: {mode!r}")
+
+
+__all__ = ["Decoder", "DecoderBuilder", "Record", "Header", "Flag", "Flags", "SequenceType", "FormatVersion", "Encoder", "open",
+           "Context", "ArchiveResult", "decode_batch", "parse_archive", "shared_context",
+           "NafError", "NafIoError", "NafParseError", "NafUnicodeError", "NafDeviceError"]

@@ -1,0 +1,21 @@
+// cuda_compat.h -- the one place that decides between the real CUDA toolchain (product build: nvcc, sm_100a)
+// and the CPU SIMT emulator used by the test tier (tests/emul, -DNAFGPU_EMULATE; never shipped).
+#pragma once
+#if defined(NAFGPU_EMULATE)
+#include "cuda_emul.h"
+#define NAF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emul::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define NAF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul::g_dyn_smem)
+#else
+#include <cuda_runtime.h>
+#define NAF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define NAF_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _naf_dyn_smem[]; type* name = reinterpret_cast<type*>(_naf_dyn_smem)
+#endif
+
+// Optional per-stage CUDA events (nafgpu_job_run_profiled): mark() after the kernels of a stage.
+struct StageEvents {
+    cudaEvent_t* ev = nullptr;
+    int n = 0, cap = 0;
+    cudaStream_t st = 0;
+    void mark() { if (ev && n < cap) cudaEventRecord(ev[n++], st); }
+};

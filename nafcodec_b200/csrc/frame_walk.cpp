@@ -1,0 +1,157 @@
+// frame_walk.cpp -- see frame_walk.h.  Format: RFC 8878 3.1.1 (frame header, block header, literals section
+// header, sequences section header).  Only byte-aligned header fields are read here.
+#include "frame_walk.h"
+
+#include <stdio.h>
+
+namespace fw {
+
+static const int ERR_INVALID = -2;   // NAFGPU_ERR_INVALID_DATA
+static const int ERR_EOF = -1;       // NAFGPU_ERR_UNEXPECTED_EOF
+static const int ERR_UNSUPPORTED = -9;
+
+#define FAIL(code, ...) do { char _b[160]; snprintf(_b, sizeof _b, __VA_ARGS__); err = _b; return (code); } while (0)
+
+int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64_t dst_off, uint64_t dst_size,
+               JobPlan& plan, std::string& err) {
+    const uint8_t* s = frame;
+    uint64_t n = src_size, p = 0;
+    if (n < 1) FAIL(ERR_EOF, "zstd frame: empty");
+    uint8_t fhd = s[p++];
+    int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, dict_flag = fhd & 3;
+    if (fhd & 0x08) FAIL(ERR_INVALID, "zstd frame: reserved bit set");
+    uint64_t window = 0;
+    if (!single) {
+        if (p >= n) FAIL(ERR_EOF, "zstd frame: truncated header");
+        uint8_t wd = s[p++];
+        uint64_t base = 1ull << (10 + (wd >> 3));
+        window = base + (base >> 3) * (wd & 7);
+    }
+    static const int dict_sz[4] = {0, 1, 2, 4};
+    uint32_t dict_id = 0;
+    if (p + dict_sz[dict_flag] > n) FAIL(ERR_EOF, "zstd frame: truncated header");
+    for (int i = 0; i < dict_sz[dict_flag]; i++) dict_id |= (uint32_t)s[p++] << (8 * i);
+    if (dict_id != 0) FAIL(ERR_UNSUPPORTED, "zstd frame: dictionaries are not supported");
+    int fcs_sz = fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+    if (p + fcs_sz > n) FAIL(ERR_EOF, "zstd frame: truncated header");
+    uint64_t fcs = 0;
+    for (int i = 0; i < fcs_sz; i++) fcs |= (uint64_t)s[p++] << (8 * i);
+    if (fcs_sz == 2) fcs += 256;
+    if (single) window = fcs;
+    if (fcs_sz && fcs != dst_size) FAIL(ERR_INVALID, "zstd frame: content size %llu differs from the section size %llu",
+                                        (unsigned long long)fcs, (unsigned long long)dst_size);
+
+    zf::FrameDesc fd{};
+    fd.src_off = src_off; fd.src_size = src_size; fd.dst_off = dst_off; fd.dst_size = dst_size;
+    fd.first_block = (uint32_t)plan.blocks.size(); fd.first_seq = (uint32_t)plan.seq_total; fd.window = window;
+    uint32_t frame_idx = (uint32_t)plan.frames.size();
+
+    uint32_t last_huf = zf::NO_BLOCK;
+    uint32_t cur_tbl[3] = {zf::NO_SLOT, zf::NO_SLOT, zf::NO_SLOT};
+    uint64_t known_total = 0;
+    for (;;) {
+        if (p + 3 > n) FAIL(ERR_EOF, "zstd frame: truncated block header");
+        uint32_t bh = s[p] | (s[p + 1] << 8) | (s[p + 2] << 16);
+        p += 3;
+        int last = bh & 1, bt = (bh >> 1) & 3;
+        uint32_t bsize = bh >> 3;
+        if (bt == 3) FAIL(ERR_INVALID, "zstd block: reserved block type");
+        if (bsize > zf::BLOCK_MAX) FAIL(ERR_INVALID, "zstd block: size %u exceeds the block maximum", bsize);
+        zf::BlockDesc b{};
+        b.src_off = src_off + p; b.src_size = bsize; b.frame = frame_idx; b.btype = (uint8_t)bt;
+        b.huf_block = zf::NO_BLOCK; b.tbl[0] = b.tbl[1] = b.tbl[2] = zf::NO_SLOT;
+        uint32_t self = (uint32_t)plan.blocks.size();
+        uint64_t content = (bt == zf::BT_RLE) ? 1 : bsize;
+        if (p + content > n) FAIL(ERR_EOF, "zstd block: truncated content");
+        if (bt != zf::BT_COMPRESSED) {
+            b.known_regen = bsize;
+        } else {
+            const uint8_t* c = s + p;
+            if (bsize < 2) FAIL(ERR_INVALID, "zstd block: compressed block too small");
+            uint8_t b0 = c[0];
+            int lt = b0 & 3, sf = (b0 >> 2) & 3;
+            uint32_t hdr, regen, csize;
+            int streams = 1;
+            if (lt == zf::LT_RAW || lt == zf::LT_RLE) {
+                if (sf == 0 || sf == 2) { hdr = 1; regen = b0 >> 3; }
+                else if (sf == 1) { hdr = 2; if (bsize < 2) FAIL(ERR_INVALID, "zstd literals: truncated"); regen = (b0 >> 4) | ((uint32_t)c[1] << 4); }
+                else { hdr = 3; if (bsize < 3) FAIL(ERR_INVALID, "zstd literals: truncated"); regen = (b0 >> 4) | ((uint32_t)c[1] << 4) | ((uint32_t)c[2] << 12); }
+                csize = (lt == zf::LT_RAW) ? regen : 1;
+            } else {
+                if (sf <= 1) {
+                    hdr = 3; if (bsize < 3) FAIL(ERR_INVALID, "zstd literals: truncated");
+                    uint32_t v = c[0] | (c[1] << 8) | (c[2] << 16);
+                    regen = (v >> 4) & 0x3FF; csize = (v >> 14) & 0x3FF; streams = sf == 0 ? 1 : 4;
+                } else if (sf == 2) {
+                    hdr = 4; if (bsize < 4) FAIL(ERR_INVALID, "zstd literals: truncated");
+                    uint32_t v = c[0] | (c[1] << 8) | (c[2] << 16) | ((uint32_t)c[3] << 24);
+                    regen = (v >> 4) & 0x3FFF; csize = v >> 18; streams = 4;
+                } else {
+                    hdr = 5; if (bsize < 5) FAIL(ERR_INVALID, "zstd literals: truncated");
+                    uint64_t v = c[0] | (c[1] << 8) | (c[2] << 16) | ((uint64_t)c[3] << 24) | ((uint64_t)c[4] << 32);
+                    regen = (uint32_t)((v >> 4) & 0x3FFFF); csize = (uint32_t)((v >> 22) & 0x3FFFF); streams = 4;
+                }
+            }
+            if (regen > zf::BLOCK_MAX) FAIL(ERR_INVALID, "zstd literals: regenerated size %u too large", regen);
+            if ((uint64_t)hdr + csize > bsize) FAIL(ERR_INVALID, "zstd literals: section exceeds the block");
+            b.lit_type = (uint8_t)lt; b.n_streams = (uint8_t)streams; b.lit_regen = regen; b.lit_csize = csize; b.lit_src = hdr;
+            if (lt == zf::LT_HUF) { last_huf = self; b.huf_block = self; }
+            else if (lt == zf::LT_TREELESS) {
+                if (last_huf == zf::NO_BLOCK) FAIL(ERR_INVALID, "zstd literals: treeless block without a previous tree");
+                b.huf_block = last_huf;
+            }
+            if (lt >= zf::LT_HUF) plan.n_huf_blocks++;
+            // sequences section header
+            uint32_t q = hdr + csize;
+            if (q >= bsize) FAIL(ERR_INVALID, "zstd sequences: missing section");
+            uint32_t nseq = c[q++];
+            if (nseq >= 128) {
+                if (nseq == 255) {
+                    if (q + 2 > bsize) FAIL(ERR_INVALID, "zstd sequences: truncated header");
+                    nseq = c[q] + (c[q + 1] << 8) + 0x7F00; q += 2;
+                } else {
+                    if (q + 1 > bsize) FAIL(ERR_INVALID, "zstd sequences: truncated header");
+                    nseq = ((nseq - 128) << 8) + c[q]; q += 1;
+                }
+            }
+            b.n_seq = nseq;
+            if (nseq == 0) {
+                if (q != bsize) FAIL(ERR_INVALID, "zstd sequences: trailing bytes after an empty section");
+                b.known_regen = regen;
+            } else {
+                if (q >= bsize) FAIL(ERR_INVALID, "zstd sequences: truncated header");
+                uint8_t modes = c[q++];
+                if (modes & 3) FAIL(ERR_INVALID, "zstd sequences: reserved mode bits set");
+                b.modes = modes;
+                for (int k = 0; k < 3; k++) {
+                    int m = (modes >> (6 - 2 * k)) & 3;
+                    if (m == zf::SM_PREDEF) { b.tbl[k] = (uint32_t)k; cur_tbl[k] = (uint32_t)k; }
+                    else if (m == zf::SM_REPEAT) {
+                        if (cur_tbl[k] == zf::NO_SLOT) FAIL(ERR_INVALID, "zstd sequences: repeat mode without a previous table");
+                        b.tbl[k] = cur_tbl[k];
+                    } else { b.tbl[k] = plan.n_slots++; b.defines |= (uint8_t)(1 << k); cur_tbl[k] = b.tbl[k]; }
+                }
+                b.seq_base = (uint32_t)plan.seq_total;
+                plan.seq_total += nseq;
+                if (plan.seq_total > 0xFFFFFFF0ull) FAIL(ERR_UNSUPPORTED, "job has too many sequences");
+                plan.n_seq_blocks++;
+                if (lt >= zf::LT_HUF) { b.lit_base = plan.lit_total; plan.lit_total += (regen + 15u) & ~15u; }
+            }
+            b.seq_src = q;
+        }
+        known_total += b.known_regen;
+        plan.blocks.push_back(b);
+        p += content;
+        if (last) break;
+    }
+    if (checksum) { if (p + 4 > n) FAIL(ERR_EOF, "zstd frame: truncated checksum"); p += 4; }
+    fd.n_blocks = (uint32_t)plan.blocks.size() - fd.first_block;
+    fd.n_seq = (uint32_t)plan.seq_total - fd.first_seq;
+    if (fd.n_seq == 0 && known_total != dst_size)
+        FAIL(ERR_INVALID, "zstd frame regenerates %llu bytes but the section header says %llu",
+             (unsigned long long)known_total, (unsigned long long)dst_size);
+    plan.frames.push_back(fd);
+    return 0;
+}
+
+}  // namespace fw

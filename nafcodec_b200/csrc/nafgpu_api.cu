@@ -1,0 +1,545 @@
+// nafgpu_api.cu -- the extern "C" layer of include/nafgpu.h: context, job planning (arena layout + host frame
+// walk), stream orchestration, result marshalling.  The reference-side seam it stands behind is the generic
+// reader parameter of nafcodec/src/decoder/reader.rs instantiated with ZstdDecoder in setup_block!
+// (nafcodec/src/decoder/mod.rs:32,218-226) and consumed by next_record / mask_sequence (mod.rs:356-441).
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nafgpu.h"
+#include "cuda_compat.h"
+#include "frame_walk.h"
+#include "naf_kernels.cuh"
+#include "zstd_kernels.cuh"
+
+namespace {
+
+constexpr uint64_t ALIGN = 128;
+inline uint64_t align_up(uint64_t v, uint64_t a = ALIGN) { return (v + a - 1) / a * a; }
+constexpr int N_STAGES = zk::ZSTD_STAGES + nk::NAF_STAGES;
+constexpr size_t FLUSH_BYTES = 256u << 20;          // > 126 MB L2
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cudaGetLastError(); return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cudaGetLastError(); return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct ArchPlan {
+    uint64_t n_records = 0;
+    bool dec[6] = {false, false, false, false, false, false};
+    uint64_t blob_off[6] = {0, 0, 0, 0, 0, 0};   // arena offset of each regenerated section
+    uint64_t blob_size[6] = {0, 0, 0, 0, 0, 0};
+    bool nucleotide = true;
+};
+
+}  // namespace
+
+struct nafgpu_ctx {
+    int device = 0;
+    cudaStream_t st = 0;
+    std::string err;
+    DevBuf comp, arena, lit, blocks, frames, bstate, tables, table_al, seq32, seq64, misc, nafdev, flush;
+    PinBuf stage, result, misc_host;
+    fw::JobPlan plan;
+    std::vector<nk::NafDev> arch;
+    std::vector<ArchPlan> aplan;
+    zk::JobDev J;
+    uint64_t z1_size = 0, z2_off = 0, z2_size = 0, arena_size = 0, counts_size = 0;
+    uint64_t max_records = 0, max_text = 0;
+    uint32_t max_chunks = 0;
+    bool any_mask = false;
+    size_t misc_words = 0;
+    nafgpu_job_stats stats;
+    bool prepared = false, ran = false;
+    cudaEvent_t ev[N_STAGES + 1];
+    bool ev_ok = false;
+#if !defined(NAFGPU_EMULATE)
+    cudaGraphExec_t graph = nullptr;
+#endif
+};
+
+namespace {
+
+int fail(nafgpu_ctx* c, int code, const std::string& msg) {
+    c->err = msg;
+    return code;
+}
+
+#define CUDA_TRY(c, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    char _b[256]; snprintf(_b, sizeof _b, "%s failed: %s", #expr, cudaGetErrorString(_e)); return fail((c), NAFGPU_ERR_CUDA, _b); } } while (0)
+
+void drop_graph(nafgpu_ctx* c) {
+#if !defined(NAFGPU_EMULATE)
+    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+#else
+    (void)c;
+#endif
+}
+
+// Enqueue one full decode of the prepared job.
+int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
+    cudaStream_t st = c->st;
+    CUDA_TRY(c, cudaMemsetAsync(c->misc.p, 0, c->misc_words * 4, st));
+    if (c->J.n_seq) CUDA_TRY(c, cudaMemsetAsync(c->J.seq_done, 0, c->J.n_seq * 4, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->arena.p, 0, c->counts_size, st));
+    if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
+    int launches = zk::launch_zstd_stage(c->J, st, ev);
+    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)c->nafdev.p, (uint32_t)c->arch.size(), c->max_records,
+                                     c->max_chunks, c->max_text, c->any_mask, c->J.status, st, ev);
+    c->stats.kernel_launches = (uint32_t)launches;
+    CUDA_TRY(c, cudaGetLastError());
+    c->ran = true;
+    return NAFGPU_OK;
+}
+
+int status_to_code(uint32_t s, std::string& msg) {
+    using namespace zc;
+    if (s == 0) return NAFGPU_OK;
+    char b[96];
+    snprintf(b, sizeof b, " (device status 0x%x)", s);
+    if (s & (E_FSE_TABLE | E_HUF_TREE | E_HUF_STREAM | E_SEQ_STREAM | E_LITERALS | E_OFFSET | E_NO_TABLE | E_INTERNAL)) {
+        msg = std::string("corrupt zstd stream") + b; return NAFGPU_ERR_INVALID_DATA;
+    }
+    if (s & E_SIZE) { msg = std::string("section does not regenerate the size its header states") + b; return NAFGPU_ERR_INVALID_DATA; }
+    if (s & E_LENGTHS) { msg = std::string("record lengths exceed the sequence/quality stream") + b; return NAFGPU_ERR_UNEXPECTED_EOF; }
+    if (s & E_MASK) { msg = std::string("failed to get mask unit") + b; return NAFGPU_ERR_UNEXPECTED_EOF; }
+    if (s & E_NUL) { msg = std::string("id/comment stream is not NUL terminated") + b; return NAFGPU_ERR_INVALID_DATA; }
+    if (s & E_UTF8) { msg = std::string("invalid utf-8") + b; return NAFGPU_ERR_UTF8; }
+    msg = std::string("unknown device status") + b;
+    return NAFGPU_ERR_INVALID_DATA;
+}
+
+struct Copy { const uint8_t* src; uint64_t dst, size; };
+
+// Device allocation + H2D of descriptors and compressed frames for the plan in c->plan / c->arch.
+int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp_off, uint32_t n) {
+    const fw::JobPlan& pl = c->plan;
+    const size_t nb = pl.blocks.size(), nf = pl.frames.size();
+    const uint64_t nseq = pl.seq_total;
+
+    // ---- device buffers ----------------------------------------------------------------------------------------------
+    c->misc_words = 1 + (zk::LZ_PASSES + 2) + nf + 8;
+    bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
+              c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) &&
+              c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
+              c->seq32.ensure(nseq * 4 * 7 + 64) && c->seq64.ensure(nseq * 8 + 64) && c->misc.ensure(c->misc_words * 4) &&
+              c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
+    if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
+    size_t stage_bytes = nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev);
+    if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
+        return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+
+    // ---- H2D ---------------------------------------------------------------------------------------------------------
+    uint8_t* sp = (uint8_t*)c->stage.p;
+    if (nb) memcpy(sp, pl.blocks.data(), nb * sizeof(zf::BlockDesc));
+    if (nf) memcpy(sp + nb * sizeof(zf::BlockDesc), pl.frames.data(), nf * sizeof(zf::FrameDesc));
+    if (n) memcpy(sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc), c->arch.data(), (size_t)n * sizeof(nk::NafDev));
+    if (nb) CUDA_TRY(c, cudaMemcpyAsync(c->blocks.p, sp, nb * sizeof(zf::BlockDesc), cudaMemcpyHostToDevice, c->st));
+    if (nf) CUDA_TRY(c, cudaMemcpyAsync(c->frames.p, sp + nb * sizeof(zf::BlockDesc), nf * sizeof(zf::FrameDesc), cudaMemcpyHostToDevice, c->st));
+    if (n) CUDA_TRY(c, cudaMemcpyAsync(c->nafdev.p, sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc), (size_t)n * sizeof(nk::NafDev), cudaMemcpyHostToDevice, c->st));
+    uint64_t h2d = stage_bytes;
+    for (const Copy& cp : copies) {
+        CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->comp.p + cp.dst, cp.src, cp.size, cudaMemcpyHostToDevice, c->st));
+        h2d += cp.size;
+    }
+
+    zk::JobDev& J = c->J;
+    J.comp = (const uint8_t*)c->comp.p; J.out = (uint8_t*)c->arena.p; J.lit = (uint8_t*)c->lit.p;
+    J.frames = (const zf::FrameDesc*)c->frames.p; J.blocks = (const zf::BlockDesc*)c->blocks.p;
+    J.bstate = (zf::BlockState*)c->bstate.p; J.tables = (zc::SeqCell*)c->tables.p; J.table_al = (uint8_t*)c->table_al.p;
+    uint32_t* s32 = (uint32_t*)c->seq32.p;
+    J.seq_ll = s32; J.seq_ml = s32 + nseq; J.seq_off = s32 + 2 * nseq; J.seq_litpos = s32 + 3 * nseq;
+    J.seq_outpos = s32 + 4 * nseq; J.seq_block = s32 + 5 * nseq; J.seq_done = s32 + 6 * nseq;
+    J.match_pos = (uint64_t*)c->seq64.p;
+    uint32_t* misc = (uint32_t*)c->misc.p;
+    J.status = misc; J.remaining = misc + 1; J.frame_bad = misc + 1 + (zk::LZ_PASSES + 2);
+    J.n_frames = (uint32_t)nf; J.n_blocks = (uint32_t)nb; J.n_slots = pl.n_slots; J.n_seq = nseq;
+
+    c->stats.n_archives = n; c->stats.n_frames = nf; c->stats.n_blocks = nb; c->stats.n_sequences = nseq;
+    c->stats.h2d_bytes = h2d; c->stats.d2h_bytes = c->z1_size + c->misc_words * 4;
+    c->stats.n_stages = N_STAGES;
+    c->prepared = true;
+    return NAFGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
+    if (!out) return NAFGPU_ERR_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return NAFGPU_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return NAFGPU_ERR_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return NAFGPU_ERR_CUDA;
+    nafgpu_ctx* c = new nafgpu_ctx();
+    c->device = device;
+    memset(&c->stats, 0, sizeof c->stats);
+    memset(&c->J, 0, sizeof c->J);
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    for (int i = 0; i <= N_STAGES; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    c->ev_ok = true;
+    *out = c;
+    return NAFGPU_OK;
+}
+
+void nafgpu_ctx_destroy(nafgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    drop_graph(c);
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
+    for (DevBuf* b : d) b->release();
+    c->stage.release(); c->result.release(); c->misc_host.release();
+    if (c->ev_ok) for (int i = 0; i <= N_STAGES; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+const char* nafgpu_last_error(const nafgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+void* nafgpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void nafgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n, uint32_t want) {
+    if (!c || (!archives && n)) return NAFGPU_ERR_ARGUMENT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    // the previous job may still be in flight on the stream and owns the staging buffers
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    c->prepared = false; c->ran = false;
+    drop_graph(c);
+    c->plan.clear();
+    c->arch.assign(n, nk::NafDev());
+    c->aplan.assign(n, ArchPlan());
+    memset(&c->stats, 0, sizeof c->stats);
+
+    // ---- arena layout -------------------------------------------------------------------------------------------
+    // Z1 (copied back): counts[n] | per archive: lengths, record offsets, id offsets, comment offsets, ids, comments,
+    //                   quality, sequence ASCII.  Z2 (zeroed every run): mask toggle bitmaps.  Z3: device-only sections.
+    uint64_t off = 0;
+    c->counts_size = align_up((uint64_t)n * sizeof(nk::NafCounts));
+    off = c->counts_size;
+    uint64_t comp_off = 0;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false;
+    for (uint32_t a = 0; a < n; a++) {
+        const nafgpu_archive& A = archives[a];
+        ArchPlan& P = c->aplan[a];
+        nk::NafDev& D = c->arch[a];
+        memset(&D, 0, sizeof D);
+        const uint64_t nrec = A.header.number_of_sequences;
+        P.n_records = nrec;
+        P.nucleotide = A.header.sequence_type <= 1;
+        if (A.header.sequence_type < 0 || A.header.sequence_type > 3) return fail(c, NAFGPU_ERR_ARGUMENT, "bad sequence type");
+        for (int s = 0; s < 6; s++) if (A.sections[s].present && !A.sections[s].data) return fail(c, NAFGPU_ERR_ARGUMENT, "present section without data");
+        const bool has_len = A.sections[NAFGPU_SEC_LENGTH].present;
+        P.dec[NAFGPU_SEC_ID] = A.sections[NAFGPU_SEC_ID].present && (want & NAFGPU_WANT_ID);
+        P.dec[NAFGPU_SEC_COMMENT] = A.sections[NAFGPU_SEC_COMMENT].present && (want & NAFGPU_WANT_COMMENT);
+        P.dec[NAFGPU_SEC_LENGTH] = has_len;                                                  // mod.rs:239: always
+        P.dec[NAFGPU_SEC_SEQUENCE] = has_len && A.sections[NAFGPU_SEC_SEQUENCE].present && (want & NAFGPU_WANT_SEQUENCE);
+        P.dec[NAFGPU_SEC_QUALITY] = has_len && A.sections[NAFGPU_SEC_QUALITY].present && (want & NAFGPU_WANT_QUALITY);
+        P.dec[NAFGPU_SEC_MASK] = P.dec[NAFGPU_SEC_SEQUENCE] && A.sections[NAFGPU_SEC_MASK].present && (want & NAFGPU_WANT_MASK);
+        for (int s = 0; s < 6; s++) {
+            uint64_t o = A.sections[s].original_size;
+            P.blob_size[s] = !P.dec[s] ? 0 : ((s == NAFGPU_SEC_SEQUENCE && P.nucleotide) ? (o + 1) / 2 : o);
+        }
+        const uint64_t residues = P.dec[NAFGPU_SEC_SEQUENCE] ? A.sections[NAFGPU_SEC_SEQUENCE].original_size : 0;
+        D.n_records = nrec;
+        D.seq_type = (uint32_t)A.header.sequence_type;
+        D.has = (P.dec[0] ? nk::HAS_IDS : 0) | (P.dec[1] ? nk::HAS_COMMENTS : 0) | (P.dec[2] ? nk::HAS_LENGTHS : 0) |
+                (P.dec[3] ? nk::HAS_MASK : 0) | (P.dec[4] ? nk::HAS_SEQUENCE : 0) | (P.dec[5] ? nk::HAS_QUALITY : 0);
+        D.seq_residues = residues;
+        D.counts_off = (uint64_t)a * sizeof(nk::NafCounts);
+        D.lengths_off = off; off = align_up(off + 8 * (nrec + 1));
+        D.rec_offsets_off = off; off = align_up(off + 8 * (nrec + 1));
+        D.id_offsets_off = off; if (P.dec[0]) off = align_up(off + 8 * (nrec + 1));
+        D.com_offsets_off = off; if (P.dec[1]) off = align_up(off + 8 * (nrec + 1));
+        auto place = [&](int s) { P.blob_off[s] = off; off = align_up(off + P.blob_size[s] + 32); };
+        if (P.dec[0]) place(0);
+        if (P.dec[1]) place(1);
+        if (P.dec[5]) place(5);
+        if (P.dec[4]) {
+            if (P.nucleotide) { D.ascii_off = off; off = align_up(off + align_up(residues, 32) + 32); }
+            else { place(4); D.ascii_off = P.blob_off[4]; }
+        }
+        c->max_records = std::max(c->max_records, nrec);
+        if (P.dec[4]) {
+            D.n_chunks = (uint32_t)((residues + 1 + nk::CHUNK_RESIDUES - 1) / nk::CHUNK_RESIDUES);
+            c->max_chunks = std::max(c->max_chunks, D.n_chunks);
+            if (P.dec[3]) c->any_mask = true;
+            if (!P.nucleotide) c->max_text = std::max(c->max_text, P.blob_size[4]);
+        }
+        if (P.dec[5]) c->max_text = std::max(c->max_text, P.blob_size[5]);
+        c->stats.ascii_bytes += residues;
+        c->stats.quality_bytes += P.blob_size[5];
+        c->stats.id_bytes += P.blob_size[0];
+        c->stats.comment_bytes += P.blob_size[1];
+        c->stats.algorithmic_bytes += residues + P.blob_size[5] + P.blob_size[0] + P.blob_size[1] + 8 * (nrec + 1);
+    }
+    c->z1_size = off;
+    c->z2_off = off;
+    for (uint32_t a = 0; a < n; a++) {
+        ArchPlan& P = c->aplan[a];
+        nk::NafDev& D = c->arch[a];
+        D.mask_bits_off = off;
+        if (P.dec[3]) off = align_up(off + 4 * ((D.seq_residues + 32) / 32 + 1));
+    }
+    c->z2_size = off - c->z2_off;
+    for (uint32_t a = 0; a < n; a++) {
+        ArchPlan& P = c->aplan[a];
+        nk::NafDev& D = c->arch[a];
+        auto place = [&](int s) { P.blob_off[s] = off; off = align_up(off + P.blob_size[s] + 32); };
+        if (P.dec[2]) place(2);
+        if (P.dec[3]) place(3);
+        if (P.dec[4] && P.nucleotide) place(4);
+        D.mask_bounds_off = off; if (P.dec[3]) off = align_up(off + 8 * (P.blob_size[3] + 2));
+        D.chunk_par_off = off; if (P.dec[3]) off = align_up(off + 4 * ((uint64_t)D.n_chunks + 1));
+        D.ids_off = P.blob_off[0]; D.ids_size = P.blob_size[0];
+        D.com_off = P.blob_off[1]; D.com_size = P.blob_size[1];
+        D.len_off = P.blob_off[2]; D.len_size = P.blob_size[2];
+        D.mask_off = P.blob_off[3]; D.mask_size = P.blob_size[3];
+        D.seq_off = P.blob_off[4]; D.seq_size = P.blob_size[4];
+        D.qual_off = P.blob_off[5]; D.qual_size = P.blob_size[5];
+    }
+    c->arena_size = off + 256;
+
+    // ---- host frame walk (north star: "The host walks the frame and block headers") --------------------------------
+    std::vector<Copy> copies;
+    for (uint32_t a = 0; a < n; a++) {
+        const nafgpu_archive& A = archives[a];
+        ArchPlan& P = c->aplan[a];
+        for (int s = 0; s < 6; s++) {
+            if (!P.dec[s]) continue;
+            const nafgpu_section& S = A.sections[s];
+            std::string e;
+            int rc = fw::walk_frame(S.data, comp_off, S.compressed_size, P.blob_off[s], P.blob_size[s], c->plan, e);
+            if (rc) {
+                static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
+                return fail(c, rc, std::string(names[s]) + " section: " + e);
+            }
+            copies.push_back({S.data, comp_off, S.compressed_size});
+            comp_off = align_up(comp_off + S.compressed_size + zf::COMP_PAD, 16);
+            c->stats.compressed_bytes += S.compressed_size;
+            c->stats.section_bytes += P.blob_size[s];
+        }
+    }
+    c->stats.algorithmic_bytes += c->stats.compressed_bytes;
+    c->stats.algorithmic_bytes += c->stats.compressed_bytes;
+    return finish_prepare(c, copies, comp_off, n);
+}
+
+// One magicless zstd frame -> regen_size bytes at dst (host).  The pure-zstd boundary of the reference
+// (zstd::stream::read::Decoder, decoder/mod.rs:221-223), exposed for parity tests against libzstd.
+int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_size, uint64_t regen_size, uint8_t* dst) {
+    if (!c || !frame || (!dst && regen_size)) return NAFGPU_ERR_ARGUMENT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    c->prepared = false; c->ran = false;
+    drop_graph(c);
+    c->plan.clear(); c->arch.clear(); c->aplan.clear();
+    memset(&c->stats, 0, sizeof c->stats);
+    c->counts_size = ALIGN;
+    c->z1_size = align_up(ALIGN + regen_size + 32);
+    c->z2_off = c->z1_size; c->z2_size = 0;
+    c->arena_size = c->z1_size + 256;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false;
+    std::string e;
+    int rc = fw::walk_frame(frame, 0, frame_size, ALIGN, regen_size, c->plan, e);
+    if (rc) return fail(c, rc, e);
+    std::vector<Copy> copies{{frame, 0, frame_size}};
+    c->stats.compressed_bytes = frame_size; c->stats.section_bytes = regen_size;
+    c->stats.algorithmic_bytes = frame_size + regen_size;
+    rc = finish_prepare(c, copies, align_up(frame_size + zf::COMP_PAD, 16), 0);
+    if (rc) return rc;
+    rc = enqueue_run(c, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    std::string msg;
+    int code = status_to_code(*(const uint32_t*)c->misc_host.p, msg);
+    if (code) return fail(c, code, msg);
+    if (regen_size) memcpy(dst, (const uint8_t*)c->result.p + ALIGN, regen_size);
+    return NAFGPU_OK;
+}
+
+int nafgpu_job_run(nafgpu_ctx* c) {
+    if (!c) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared) return fail(c, NAFGPU_ERR_ARGUMENT, "no prepared job");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return enqueue_run(c, nullptr);
+}
+
+int nafgpu_job_sync(nafgpu_ctx* c) {
+    if (!c) return NAFGPU_ERR_ARGUMENT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    return NAFGPU_OK;
+}
+
+int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
+    if (!c || (!out && n)) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared || !c->ran) return fail(c, NAFGPU_ERR_ARGUMENT, "job has not been run");
+    if (n != c->arch.size()) return fail(c, NAFGPU_ERR_ARGUMENT, "result count differs from the prepared job");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    CUDA_TRY(c, cudaGetLastError());
+    const uint32_t status = *(const uint32_t*)c->misc_host.p;
+    const uint8_t* R = (const uint8_t*)c->result.p;
+    int deferred = NAFGPU_OK;
+    std::string msg;
+    int code = status_to_code(status & ~zc::E_UTF8, msg);
+    if (code) return fail(c, code, msg);
+    for (uint32_t a = 0; a < n; a++) {
+        const nk::NafDev& D = c->arch[a];
+        const ArchPlan& P = c->aplan[a];
+        const nk::NafCounts* C = (const nk::NafCounts*)(R + D.counts_off);
+        nafgpu_result& r = out[a];
+        memset(&r, 0, sizeof r);
+        r.n_records = D.n_records;
+        r.n_ids = std::min<uint64_t>(C->n_ids, D.n_records);
+        r.n_comments = std::min<uint64_t>(C->n_comments, D.n_records);
+        r.n_lengths = C->n_lengths;
+        r.total_residues = C->total_residues;
+        if (P.dec[0]) { r.ids = R + D.ids_off; r.id_offsets = (const uint64_t*)(R + D.id_offsets_off); }
+        if (P.dec[1]) { r.comments = R + D.com_off; r.comment_offsets = (const uint64_t*)(R + D.com_offsets_off); }
+        if (P.dec[2]) { r.lengths = (const uint64_t*)(R + D.lengths_off); r.record_offsets = (const uint64_t*)(R + D.rec_offsets_off); }
+        if (P.dec[4]) r.sequence = R + D.ascii_off;
+        if (P.dec[5]) r.quality = R + D.qual_off;
+        r.first_bad_record = C->first_bad_record;
+        r.record_status = (C->first_bad_record != nk::NO_RECORD) ? NAFGPU_ERR_UTF8 : 0;
+        if (r.record_status) deferred = NAFGPU_ERR_UTF8;
+    }
+    (void)deferred;
+    return NAFGPU_OK;
+}
+
+int nafgpu_decode_batch(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n, uint32_t want, nafgpu_result* out) {
+    int rc = nafgpu_job_prepare(c, archives, n, want);
+    if (rc) return rc;
+    rc = nafgpu_job_run(c);
+    if (rc) return rc;
+    return nafgpu_job_fetch(c, out, n);
+}
+
+int nafgpu_decode(nafgpu_ctx* c, const nafgpu_archive* archive, uint32_t want, nafgpu_result* out) {
+    return nafgpu_decode_batch(c, archive, 1, want, out);
+}
+
+int nafgpu_job_get_stats(const nafgpu_ctx* c, nafgpu_job_stats* out) {
+    if (!c || !out) return NAFGPU_ERR_ARGUMENT;
+    *out = c->stats;
+    return NAFGPU_OK;
+}
+
+int nafgpu_job_time(nafgpu_ctx* c, int iters, int flush_l2, float* total_ms) {
+    if (!c || !total_ms || iters <= 0) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared) return fail(c, NAFGPU_ERR_ARGUMENT, "no prepared job");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (flush_l2 && !c->flush.ensure(FLUSH_BYTES)) return fail(c, NAFGPU_ERR_NOMEM, "flush buffer allocation failed");
+#if !defined(NAFGPU_EMULATE)
+    // Capture one decode into a CUDA graph so that the timed interval holds device work, not launch latency.
+    if (!c->graph) {
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(c, cudaStreamSynchronize(c->st));
+        CUDA_TRY(c, cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_run(c, nullptr);
+        cudaError_t e = cudaStreamEndCapture(c->st, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(c, NAFGPU_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&c->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { c->graph = nullptr; return fail(c, NAFGPU_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e)); }
+    }
+#endif
+    double total = 0;
+    for (int i = 0; i < iters; i++) {
+        if (flush_l2) CUDA_TRY(c, cudaMemsetAsync(c->flush.p, i & 0xFF, FLUSH_BYTES, c->st));
+        CUDA_TRY(c, cudaEventRecord(c->ev[0], c->st));
+#if !defined(NAFGPU_EMULATE)
+        CUDA_TRY(c, cudaGraphLaunch(c->graph, c->st));
+        c->ran = true;
+#else
+        int rc = enqueue_run(c, nullptr);
+        if (rc) return rc;
+#endif
+        CUDA_TRY(c, cudaEventRecord(c->ev[1], c->st));
+        CUDA_TRY(c, cudaEventSynchronize(c->ev[1]));
+        float ms = 0;
+        CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        total += ms;
+    }
+    *total_ms = (float)total;
+    return NAFGPU_OK;
+}
+
+int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
+    if (!c || !stage_ms || n_stages < (uint32_t)N_STAGES) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared) return fail(c, NAFGPU_ERR_ARGUMENT, "no prepared job");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    // memsets first, then the start mark, so that stage 0 is the first kernel only
+    StageEvents se;
+    se.ev = c->ev + 1; se.cap = N_STAGES; se.st = c->st;
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    // enqueue_run issues its memsets before the first kernel; record the start after them by splitting here:
+    CUDA_TRY(c, cudaEventRecord(c->ev[0], c->st));
+    int rc = enqueue_run(c, &se);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    for (int i = 0; i < N_STAGES; i++) {
+        float ms = 0;
+        if (i < se.n) CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        stage_ms[i] = ms;
+    }
+    return NAFGPU_OK;
+}
+
+const char* nafgpu_stage_name(uint32_t s) {
+    static const char* names[N_STAGES] = {"memset+build_tables", "decode_sequences", "frame_scan", "huf_decode", "lz_literals", "lz_passes",
+                                          "lz_sequential", "naf_scan", "mask_fix", "mask_parity", "unpack", "utf8_check"};
+    return s < (uint32_t)N_STAGES ? names[s] : "?";
+}
+
+int nafgpu_job_device_result(nafgpu_ctx* c, uint32_t archive, const uint8_t** sequence_dev, uint64_t* capacity_bytes) {
+    if (!c || !sequence_dev || !capacity_bytes) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared || archive >= c->arch.size()) return fail(c, NAFGPU_ERR_ARGUMENT, "bad archive index");
+    *sequence_dev = (const uint8_t*)c->arena.p + c->arch[archive].ascii_off;
+    *capacity_bytes = c->arch[archive].seq_residues;
+    return NAFGPU_OK;
+}
+
+}  // extern "C"

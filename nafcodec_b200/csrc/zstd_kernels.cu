@@ -1,0 +1,429 @@
+// zstd_kernels.cu -- hand-written sm_100a kernels that replace libzstd's ZSTD_decompressStream on the
+// nafcodec decode path (the reference reaches it through zstd::stream::read::Decoder,
+// nafcodec/src/decoder/mod.rs:32,221-223).  No library decompressor, no CPU fallback.
+//
+// Stage order for one job (any number of frames = NAF sections, possibly of many archives):
+//   k_build_tables      per block: parse FSE table descriptions, build LL/OF/ML decode tables
+//   k_decode_sequences  per block: serial tANS decode of (ll, ml, offset) with a symbolic repeat-offset state
+//   k_frame_scan        per frame: block output offsets (prefix sum) + repeat-offset carry across blocks
+//   k_huf_decode        per block: Huffman literals (1/4 streams), straight into the output when n_seq == 0
+//   k_lz_literals       per block: raw/RLE blocks, literal runs -> output positions
+//   k_lz_pass x N       per match: dependency-resolving passes (a match runs once its source bytes are final)
+//   k_lz_sequential     per frame: ordered fallback for whatever dependency chains remain
+#include "zstd_kernels.cuh"
+
+namespace zk {
+
+using namespace zf;
+using zc::BackBits;
+using zc::SeqCell;
+
+__device__ __forceinline__ void flag_error(const JobDev& J, uint32_t frame, uint32_t bits) {
+    atomicOr(J.status, bits);
+    atomicOr(&J.frame_bad[frame], 1u);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
+__global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
+    __shared__ int16_t norm[3][56];
+    __shared__ uint8_t cell_sym[3][512];
+    __shared__ uint16_t cnt[3][56];
+    __shared__ int al[3];
+    __shared__ int mode[3];
+    __shared__ int rle_sym[3];
+    __shared__ int ok;
+    const int lane = threadIdx.x;
+    const uint32_t bi = blockIdx.x;
+    uint32_t slot[3];
+    uint32_t frame = 0;
+    if (bi == J.n_blocks) {                 // predefined tables
+        if (lane < 3) {
+            int k = lane;
+            for (int s = 0; s <= zc::kind_max_symbol(k); s++) norm[k][s] = zc::predef_norm(k, s);
+            al[k] = zc::predef_al(k);
+            mode[k] = SM_FSE;
+        }
+        if (lane == 0) ok = 1;
+        slot[0] = 0; slot[1] = 1; slot[2] = 2;
+    } else {
+        const BlockDesc& B = J.blocks[bi];
+        if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
+        frame = B.frame;
+        slot[0] = B.tbl[0]; slot[1] = B.tbl[1]; slot[2] = B.tbl[2];
+        if (lane == 0) {
+            ok = 1;
+            const uint8_t* src = J.comp + B.src_off;
+            uint32_t p = B.seq_src;
+            for (int k = 0; k < 3; k++) {
+                int m = (B.modes >> (6 - 2 * k)) & 3;
+                mode[k] = (B.defines >> k) & 1 ? m : -1;
+                if (m == SM_RLE) {
+                    if (p >= B.src_size) { ok = 0; break; }
+                    rle_sym[k] = src[p++];
+                    if (rle_sym[k] > zc::kind_max_symbol(k)) { ok = 0; break; }
+                } else if (m == SM_FSE) {
+                    int a = 0;
+                    uint32_t used = zc::fse_read_ncount(src + p, B.src_size - p, zc::kind_max_symbol(k), zc::kind_max_al(k), norm[k], &a);
+                    if (used == 0 || p + used > B.src_size) { ok = 0; break; }
+                    al[k] = a;
+                    p += used;
+                }
+            }
+            if (p >= B.src_size) ok = 0;      // the bitstream needs at least one byte
+            J.bstate[bi].seq_bits_off = p;
+        }
+    }
+    __syncwarp();
+    if (!ok) {
+        if (lane == 0) flag_error(J, frame, zc::E_FSE_TABLE);
+        return;
+    }
+    if (lane < 3 && mode[lane] >= 0) {
+        int k = lane;
+        SeqCell* T = J.tables + (size_t)slot[k] * FSE_SLOT_CELLS;
+        if (mode[k] == SM_RLE) {
+            T[0] = zc::make_seq_cell(k, rle_sym[k], 0, 0);
+            J.table_al[slot[k]] = 0;
+        } else {
+            bool good = zc::fse_build(norm[k], zc::kind_max_symbol(k), al[k], cell_sym[k], cnt[k],
+                                      [&](int i, int s, int nb, int base) { T[i] = zc::make_seq_cell(k, s, nb, base); });
+            J.table_al[slot[k]] = (uint8_t)al[k];
+            if (!good) flag_error(J, frame, zc::E_FSE_TABLE);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_decode_sequences: the serial FSE stage.  One warp per block, lane 0 walks the three interleaved tANS states.
+// The repeat-offset state is tracked symbolically (each slot = constant, or incoming slot minus a delta) so blocks
+// decode independently; k_frame_scan composes the per-block transfer functions.
+struct RepSym { int32_t src; uint32_t val; };   // src < 0: constant val; else rep_in[src] - val
+
+__device__ __forceinline__ uint32_t encode_off(RepSym r) {
+    return r.src < 0 ? r.val : (OFF_SYMBOLIC | ((uint32_t)r.src << 29) | (r.val & 0x1FFFFFFFu));
+}
+
+__global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
+    const uint32_t bi = blockIdx.x;
+    const BlockDesc& B = J.blocks[bi];
+    if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
+    if (threadIdx.x != 0) return;
+    if (J.frame_bad[B.frame]) return;
+    BlockState& S = J.bstate[bi];
+    const uint8_t* src = J.comp + B.src_off;
+    BackBits bb;
+    if (S.seq_bits_off >= B.src_size || !bb.init(src + S.seq_bits_off, B.src_size - S.seq_bits_off)) {
+        flag_error(J, B.frame, zc::E_SEQ_STREAM);
+        return;
+    }
+    const SeqCell* TLL = J.tables + (size_t)B.tbl[0] * FSE_SLOT_CELLS;
+    const SeqCell* TOF = J.tables + (size_t)B.tbl[1] * FSE_SLOT_CELLS;
+    const SeqCell* TML = J.tables + (size_t)B.tbl[2] * FSE_SLOT_CELLS;
+    uint32_t sLL = bb.read(J.table_al[B.tbl[0]]);
+    uint32_t sOF = bb.read(J.table_al[B.tbl[1]]);
+    uint32_t sML = bb.read(J.table_al[B.tbl[2]]);
+    RepSym rep[3] = {{0, 0}, {1, 0}, {2, 0}};
+    uint32_t litpos = 0, outpos = 0;
+    const uint32_t n = B.n_seq, base = B.seq_base;
+    bool bad = false;
+    for (uint32_t i = 0; i < n; i++) {
+        SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];
+        uint32_t ov = cOF.base_value + bb.read(cOF.add_bits);
+        uint32_t ml = cML.base_value + bb.read(cML.add_bits);
+        uint32_t ll = cLL.base_value + bb.read(cLL.add_bits);
+        RepSym off;
+        if (ov > 3) {
+            off.src = -1; off.val = ov - 3;
+            rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+        } else {
+            uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+            if (idx == 0) {
+                off = rep[0];
+            } else if (idx == 1) {
+                off = rep[1]; rep[1] = rep[0]; rep[0] = off;
+            } else if (idx == 2) {
+                off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+            } else {
+                off = rep[0];
+                if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; }
+                else off.val += 1;
+                rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+            }
+        }
+        if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
+        if (i + 1 < n) {
+            sLL = cLL.next_base + bb.read(cLL.nb);
+            sML = cML.next_base + bb.read(cML.nb);
+            sOF = cOF.next_base + bb.read(cOF.nb);
+        }
+        J.seq_ll[base + i] = ll;
+        J.seq_ml[base + i] = ml;
+        J.seq_off[base + i] = encode_off(off);
+        J.seq_litpos[base + i] = litpos;
+        J.seq_outpos[base + i] = outpos;
+        J.seq_block[base + i] = bi;
+        litpos += ll;
+        outpos += ll + ml;
+        if (bb.P < 0 || outpos > BLOCK_MAX) { bad = true; break; }
+    }
+    if (bad || bb.P != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
+    uint32_t regen = outpos + (B.lit_regen - litpos);
+    if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
+    S.regen = regen;
+    for (int k = 0; k < 3; k++) { S.rep_src[k] = rep[k].src; S.rep_val[k] = rep[k].val; }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_frame_scan: one thread per frame.  Exclusive prefix sum of regenerated block sizes -> out_off; composes the
+// repeat-offset transfer functions -> rep_in per block; checks the total against the size the container states.
+__global__ void k_frame_scan(JobDev J) {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= J.n_frames) return;
+    const FrameDesc& F = J.frames[f];
+    uint64_t off = F.dst_off;
+    uint32_t rep[3] = {1, 4, 8};
+    if (J.frame_bad[f]) return;
+    bool bad = false;
+    for (uint32_t b = F.first_block; b < F.first_block + F.n_blocks && !bad; b++) {
+        const BlockDesc& B = J.blocks[b];
+        BlockState& S = J.bstate[b];
+        uint32_t regen = (B.btype != BT_COMPRESSED || B.n_seq == 0) ? B.known_regen : S.regen;
+        S.regen = regen;
+        S.out_off = off;
+        off += regen;
+        if (off - F.dst_off > F.dst_size) { bad = true; break; }
+        if (B.btype == BT_COMPRESSED && B.n_seq > 0) {
+            uint32_t nr[3];
+            for (int k = 0; k < 3; k++) {
+                S.rep_in[k] = rep[k];
+                if (S.rep_src[k] < 0) nr[k] = S.rep_val[k];
+                else {
+                    uint32_t v = rep[S.rep_src[k]];
+                    if (v <= S.rep_val[k]) { bad = true; nr[k] = 1; }
+                    else nr[k] = v - S.rep_val[k];
+                }
+            }
+            rep[0] = nr[0]; rep[1] = nr[1]; rep[2] = nr[2];
+        }
+    }
+    if (!bad && off - F.dst_off != F.dst_size) bad = true;
+    if (bad) flag_error(J, f, zc::E_SIZE);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_huf_decode (v1): one CTA per block with Huffman-compressed literals; table staged in shared memory; the four
+// streams are decoded by four lanes.  Destination is the output itself when the block has no sequences.
+__global__ void __launch_bounds__(128) k_huf_decode(JobDev J) {
+    __shared__ uint8_t weights[256];
+    __shared__ uint16_t table[1 << zc::HUF_MAX_BITS];
+    __shared__ int s_nsym, s_maxbits;
+    const uint32_t bi = blockIdx.x;
+    const BlockDesc& B = J.blocks[bi];
+    if (B.btype != BT_COMPRESSED || B.lit_type < LT_HUF) return;
+    if (J.frame_bad[B.frame]) return;
+    const BlockDesc& D = J.blocks[B.huf_block];          // block that carries the tree description
+    const uint8_t* tree = J.comp + D.src_off + D.lit_src;
+    if (threadIdx.x == 0) {
+        int mb = 0;
+        s_nsym = zc::huf_read_weights(tree, D.lit_csize, weights, &mb);
+        s_maxbits = mb;
+        if (s_nsym) zc::huf_build_table_serial(weights, s_nsym, mb, table);
+    }
+    __syncthreads();
+    if (s_nsym == 0) {
+        if (threadIdx.x == 0) flag_error(J, B.frame, zc::E_HUF_TREE);
+        return;
+    }
+    const int maxbits = s_maxbits;
+    const uint8_t* pay = J.comp + B.src_off + B.lit_src;
+    uint32_t pay_size = B.lit_csize;
+    if (B.lit_type == LT_HUF) {
+        uint32_t t = pay_size ? zc::huf_tree_desc_size(pay[0]) : 1u;
+        if (t > pay_size) { if (threadIdx.x == 0) flag_error(J, B.frame, zc::E_HUF_TREE); return; }
+        pay += t; pay_size -= t;
+    }
+    uint8_t* dst = (B.n_seq == 0) ? (J.out + J.bstate[bi].out_off) : (J.lit + B.lit_base);
+    const uint32_t regen = B.lit_regen;
+    const int t = threadIdx.x;
+    if (t >= B.n_streams) return;
+    uint32_t s_off, s_size, d_off, d_n;
+    if (B.n_streams == 1) {
+        s_off = 0; s_size = pay_size; d_off = 0; d_n = regen;
+    } else {
+        if (pay_size < 6) { if (t == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+        uint32_t z1 = pay[0] | (pay[1] << 8), z2 = pay[2] | (pay[3] << 8), z3 = pay[4] | (pay[5] << 8);
+        uint32_t seg = (regen + 3) / 4;
+        if (6 + z1 + z2 + z3 >= pay_size + 0u || 3 * seg > regen) { if (t == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+        uint32_t offs[4] = {6, 6 + z1, 6 + z1 + z2, 6 + z1 + z2 + z3};
+        uint32_t sizes[4] = {z1, z2, z3, pay_size - offs[3]};
+        s_off = offs[t]; s_size = sizes[t]; d_off = seg * t; d_n = (t < 3) ? seg : regen - 3 * seg;
+    }
+    BackBits bb;
+    if (!bb.init(pay + s_off, s_size)) { flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+    uint8_t* o = dst + d_off;
+    for (uint32_t i = 0; i < d_n; i++) {
+        uint16_t e = table[bb.peek(maxbits)];
+        bb.P -= (e & 0xFF);
+        o[i] = (uint8_t)(e >> 8);
+    }
+    if (bb.P != 0) flag_error(J, B.frame, zc::E_HUF_STREAM);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_lz_literals: one CTA per block.  Raw / RLE blocks and literal-only blocks are plain copies or fills; for
+// blocks with sequences every literal run goes to its final position and match destinations are published.
+__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, int tid, int nthreads) {
+    for (uint32_t i = tid; i < n; i += nthreads) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
+    const uint32_t bi = blockIdx.x;
+    const BlockDesc& B = J.blocks[bi];
+    if (J.frame_bad[B.frame]) return;
+    const BlockState& S = J.bstate[bi];
+    uint8_t* out = J.out + S.out_off;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (B.btype == BT_RAW) { copy_bytes(out, J.comp + B.src_off, B.src_size, tid, nt); return; }
+    if (B.btype == BT_RLE) {
+        uint8_t v = J.comp[B.src_off];
+        for (uint32_t i = tid; i < B.src_size; i += nt) out[i] = v;
+        return;
+    }
+    const uint8_t* lsrc = nullptr;
+    uint8_t rle = 0;
+    if (B.lit_type == LT_RAW) lsrc = J.comp + B.src_off + B.lit_src;
+    else if (B.lit_type == LT_RLE) rle = J.comp[B.src_off + B.lit_src];
+    else lsrc = J.lit + B.lit_base;
+    if (B.n_seq == 0) {
+        if (B.lit_type == LT_RAW) copy_bytes(out, lsrc, B.lit_regen, tid, nt);
+        else if (B.lit_type == LT_RLE) for (uint32_t i = tid; i < B.lit_regen; i += nt) out[i] = rle;
+        return;                                        // Huffman literals were decoded in place
+    }
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const uint32_t n = B.n_seq, base = B.seq_base;
+    for (uint32_t i = warp; i <= n; i += nw) {
+        uint32_t lp, op, ll;
+        if (i < n) {
+            lp = J.seq_litpos[base + i]; op = J.seq_outpos[base + i]; ll = J.seq_ll[base + i];
+            if (lane == 0) J.match_pos[base + i] = S.out_off + op + ll;
+        } else {                                       // literals after the last sequence
+            uint32_t j = base + n - 1;
+            lp = J.seq_litpos[j] + J.seq_ll[j];
+            op = J.seq_outpos[j] + J.seq_ll[j] + J.seq_ml[j];
+            ll = B.lit_regen - lp;
+        }
+        if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += 32) out[op + k] = rle;
+        else for (uint32_t k = lane; k < ll; k += 32) out[op + k] = lsrc[lp + k];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Match execution.
+__device__ __forceinline__ uint32_t resolve_offset(const JobDev& J, uint32_t v, uint32_t block) {
+    if (!(v & OFF_SYMBOLIC)) return v;
+    uint32_t in = J.bstate[block].rep_in[(v >> 29) & 3];
+    uint32_t d = v & 0x1FFFFFFFu;
+    return in > d ? in - d : 0;
+}
+
+// bytes [d, d+ml) <- periodic extension of [d-off, d): byte k comes from d-off + (k mod off); all sources lie
+// strictly below d, so the copy has no intra-match hazard even when off < ml.
+__device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t off, uint32_t ml, int lane) {
+    const uint8_t* s = out + d - off;
+    if (off >= ml) {
+        for (uint32_t k = lane; k < ml; k += 32) out[d + k] = s[k];
+    } else {
+        for (uint32_t k = lane; k < ml; k += 32) out[d + k] = s[k % off];
+    }
+}
+
+// k_lz_pass: one warp per pending match.  A match may run in pass p if every earlier match whose destination
+// intersects its source range finished in a pass < p (literals are all final before pass 1).
+__global__ void __launch_bounds__(256) k_lz_pass(JobDev J, uint32_t pass) {
+    if (pass > 1 && J.remaining[pass - 1] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= J.n_seq) return;
+    if (J.seq_done[i]) return;
+    const uint32_t bi = J.seq_block[i];
+    const BlockDesc& B = J.blocks[bi];
+    if (J.frame_bad[B.frame]) return;
+    const FrameDesc& F = J.frames[B.frame];
+    const uint32_t ml = J.seq_ml[i];
+    const uint32_t off = resolve_offset(J, J.seq_off[i], bi);
+    const uint64_t d = J.match_pos[i];
+    if (off == 0 || (uint64_t)off > d - F.dst_off) {
+        __syncwarp();                                     // every lane has read seq_done[i] before lane 0 rewrites it
+        if (lane == 0) { flag_error(J, B.frame, zc::E_OFFSET); J.seq_done[i] = pass; }
+        return;
+    }
+    const uint64_t s = d - off;
+    const uint64_t e = (off < ml) ? d : s + ml;           // external source range [s, e)
+    // first earlier match j (same frame) whose destination ends after s
+    uint64_t lo = F.first_seq, hi = i;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (J.match_pos[mid] + J.seq_ml[mid] > s) hi = mid; else lo = mid + 1;
+    }
+    bool ready = true;
+    for (uint64_t j = lo; j < i && J.match_pos[j] < e; j++) {
+        uint32_t dn = J.seq_done[j];
+        if (dn == 0 || dn >= pass) { ready = false; break; }
+    }
+    if (!ready) {
+        if (lane == 0) atomicAdd(&J.remaining[pass], 1u);
+        return;
+    }
+    copy_match(J.out, d, off, ml, lane);
+    __syncwarp();                                         // (also orders the lanes' reads of seq_done[i] before the write)
+    if (lane == 0) J.seq_done[i] = pass;
+}
+
+// k_lz_sequential: ordered fallback, one warp per frame, for dependency chains deeper than LZ_PASSES.
+__global__ void __launch_bounds__(32) k_lz_sequential(JobDev J) {
+    if (J.remaining[LZ_PASSES] == 0) return;
+    const uint32_t f = blockIdx.x;
+    if (J.frame_bad[f]) return;
+    const FrameDesc& F = J.frames[f];
+    const int lane = threadIdx.x;
+    for (uint64_t i = F.first_seq; i < (uint64_t)F.first_seq + F.n_seq; i++) {
+        if (J.seq_done[i]) continue;
+        const uint32_t bi = J.seq_block[i];
+        const uint32_t ml = J.seq_ml[i];
+        const uint32_t off = resolve_offset(J, J.seq_off[i], bi);
+        const uint64_t d = J.match_pos[i];
+        if (off == 0 || (uint64_t)off > d - F.dst_off) {
+            if (lane == 0) flag_error(J, f, zc::E_OFFSET);
+            return;
+        }
+        copy_match(J.out, d, off, ml, lane);
+        __syncwarp();
+        if (lane == 0) J.seq_done[i] = LZ_PASSES + 1;
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
+    StageEvents none;
+    if (!ev) ev = &none;
+    int launches = 0;
+    if (J.n_blocks == 0) { for (int i = 0; i < ZSTD_STAGES; i++) ev->mark(); return 0; }
+    NAF_LAUNCH(k_build_tables, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_frame_scan, (J.n_frames + 63) / 64, 64, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_huf_decode, J.n_blocks, 128, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
+    if (J.n_seq > 0) {
+        const uint32_t warps = 8;
+        uint32_t grid = (uint32_t)((J.n_seq + warps - 1) / warps);
+        for (uint32_t p = 1; p <= (uint32_t)LZ_PASSES; p++) { NAF_LAUNCH(k_lz_pass, grid, warps * 32, 0, st, J, p); launches++; }
+        ev->mark();
+        NAF_LAUNCH(k_lz_sequential, J.n_frames, 32, 0, st, J); launches++; ev->mark();
+    } else { ev->mark(); ev->mark(); }
+    return launches;
+}
+
+}  // namespace zk

@@ -1,0 +1,43 @@
+// zstd_kernels.cuh -- device-side view of a decode job and the launch entry points of the zstd stage.
+#pragma once
+#include "cuda_compat.h"
+#include <stdint.h>
+
+#include "zstd_core.cuh"
+#include "zstd_format.h"
+
+namespace zk {
+
+constexpr int LZ_PASSES = 6;          // dependency-resolving passes before the ordered fallback
+
+// Everything the zstd kernels need, by value.  All pointers are device pointers.
+struct JobDev {
+    const uint8_t* comp;              // compressed sections, each frame 16 B aligned, COMP_PAD slack at the end
+    uint8_t* out;                     // regenerated sections (frame f at frames[f].dst_off)
+    uint8_t* lit;                     // literal staging for blocks with Huffman literals AND sequences
+    const zf::FrameDesc* frames;
+    const zf::BlockDesc* blocks;
+    zf::BlockState* bstate;
+    zc::SeqCell* tables;              // n_slots * FSE_SLOT_CELLS
+    uint8_t* table_al;                // accuracy log per slot
+    uint32_t* seq_ll;
+    uint32_t* seq_ml;
+    uint32_t* seq_off;                // resolved offset, or symbolic (zf::OFF_SYMBOLIC)
+    uint32_t* seq_litpos;             // start of the sequence's literals inside the block's literals
+    uint32_t* seq_outpos;             // start of the sequence's output inside the block
+    uint32_t* seq_block;              // owning block
+    uint64_t* match_pos;              // absolute position of the match destination in `out`
+    uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
+    uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
+    uint32_t* status;                 // OR of zc::E_* bits
+    uint32_t* remaining;              // [LZ_PASSES + 2] matches still pending after pass p
+    uint32_t n_frames, n_blocks, n_slots;
+    uint64_t n_seq;
+};
+
+// Enqueues the whole zstd stage for a job on `stream` (no host synchronisation).
+// Returns the number of kernels launched.  `ev` (optional) gets one mark per stage (7 stages).
+int launch_zstd_stage(const JobDev& job, cudaStream_t stream, StageEvents* ev);
+constexpr int ZSTD_STAGES = 7;
+
+}  // namespace zk

@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference decoder surface over the nafgpu C ABI.
+
+* `DecoderBuilder` / `Decoder` follow nafcodec/src/decoder/mod.rs:53-461 (builder knobs, opt-out fields, iterator that
+  stops after header.number_of_sequences, ExactSizeIterator == __len__).
+* The keyword constructor, properties, `read()` and context-manager protocol follow the Python binding
+  (nafcodec-py/nafcodec/lib.rs:324-461, lib.pyi:36-70).
+
+What differs from the reference by construction: the six per-section streaming zstd readers are replaced by ONE device
+decode of the whole archive (ids, comments, lengths, mask, sequence, quality) on first access; records are then sliced
+out of the structure-of-arrays result.  Errors the reference raises lazily at a record (invalid UTF-8 text) are raised
+at that same record; corrupt compressed data is raised at the first record.
+"""
+import ctypes as C
+import io
+import os
+import threading
+from typing import Iterable, List, Optional
+
+import numpy as np
+
+from . import _ffi
+from .data import Flag, Flags, FormatVersion, Header, Record, SequenceType
+from .errors import NafIoError, raise_for_status
+
+_SEQTYPE_NAMES = {0: "dna", 1: "rna", 2: "protein", 3: "text"}
+
+
+class Context:
+    """One nafgpu context (CUDA stream + arenas).  Not thread-safe: guarded by a lock."""
+
+    def __init__(self, device: int = 0, library: Optional[_ffi.Library] = None):
+        self.lib = library or _ffi.default_library()
+        self.device = device
+        self._ctx = C.c_void_p()
+        self._lock = threading.Lock()
+        raise_for_status(self.lib, self.lib.dll.nafgpu_ctx_create(device, C.byref(self._ctx)), what="nafgpu_ctx_create")
+
+    def close(self):
+        if self._ctx:
+            self.lib.dll.nafgpu_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parsing (host only) ------------------------------------------------------------------------------------
+    def parse(self, buf) -> "_ffi.Archive":
+        return parse_archive(buf, self.lib)
+
+    # -- decode --------------------------------------------------------------------------------------------------
+    def decode(self, archives: List["_ffi.Archive"], want: int = _ffi.WANT_ALL) -> List["ArchiveResult"]:
+        n = len(archives)
+        arr = (_ffi.Archive * n)(*archives)
+        res = (_ffi.Result * n)()
+        with self._lock:
+            rc = self.lib.dll.nafgpu_decode_batch(self._ctx, arr, n, want, res)
+            raise_for_status(self.lib, rc, self._ctx)
+            return [ArchiveResult._copy_from(archives[i].header, res[i]) for i in range(n)]
+
+    def zstd_decompress(self, frame: bytes, regen_size: int) -> bytes:
+        """One magicless zstd frame -> bytes (the pure-zstd boundary; used by the parity tests against libzstd)."""
+        src = (C.c_uint8 * max(len(frame), 1)).from_buffer_copy(frame or b"\0")
+        dst = (C.c_uint8 * max(regen_size, 1))()
+        with self._lock:
+            rc = self.lib.dll.nafgpu_zstd_decompress(self._ctx, src, len(frame), regen_size, dst)
+            raise_for_status(self.lib, rc, self._ctx)
+        return bytes(dst[:regen_size])
+
+    # staged API (bench / profiling)
+    def prepare(self, archives, want=_ffi.WANT_ALL):
+        n = len(archives)
+        self._arr = (_ffi.Archive * n)(*archives)
+        self._n = n
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_prepare(self._ctx, self._arr, n, want), self._ctx)
+
+    def run(self):
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_run(self._ctx), self._ctx)
+
+    def sync(self):
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_sync(self._ctx), self._ctx)
+
+    def fetch_raw(self):
+        res = (_ffi.Result * self._n)()
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_fetch(self._ctx, res, self._n), self._ctx)
+        return res
+
+    def fetch(self):
+        res = self.fetch_raw()
+        return [ArchiveResult._copy_from(self._arr[i].header, res[i]) for i in range(self._n)]
+
+    def stats(self) -> "_ffi.JobStats":
+        s = _ffi.JobStats()
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_get_stats(self._ctx, C.byref(s)), self._ctx)
+        return s
+
+    def time_runs(self, iters: int, flush_l2: bool = True) -> float:
+        """Total device milliseconds of `iters` runs of the prepared job (CUDA events on the launch stream)."""
+        ms = C.c_float()
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_time(self._ctx, iters, int(flush_l2), C.byref(ms)), self._ctx)
+        return ms.value
+
+    def profile_stages(self):
+        n = self.stats().n_stages
+        arr = (C.c_float * n)()
+        raise_for_status(self.lib, self.lib.dll.nafgpu_job_run_profiled(self._ctx, arr, n), self._ctx)
+        return [(self.lib.dll.nafgpu_stage_name(i).decode(), arr[i]) for i in range(n)]
+
+
+def parse_archive(buf, lib: Optional[_ffi.Library] = None) -> "_ffi.Archive":
+    """parser::header + setup_block! section table (parser.rs:101-139, mod.rs:169-242).  `buf` must stay alive while the
+    returned struct is used (its section pointers point into it)."""
+    lib = lib or _ffi.default_library()
+    a = _ffi.Archive()
+    if isinstance(buf, (bytes, bytearray)):
+        keep = (C.c_uint8 * max(len(buf), 1)).from_buffer_copy(bytes(buf) or b"\0")
+        n = len(buf)
+    else:  # numpy uint8 array (e.g. a view of pinned memory)
+        keep = buf
+        n = buf.size
+    ptr = C.cast(keep, C.c_void_p) if not isinstance(keep, np.ndarray) else C.c_void_p(keep.ctypes.data)
+    rc = lib.dll.nafgpu_parse_archive(ptr, n, C.byref(a))
+    raise_for_status(lib, rc, what="header")
+    a._keep = keep
+    return a
+
+
+def _np_copy(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(count, dtype=dtype)
+    nbytes = count * np.dtype(dtype).itemsize
+    return np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype)
+
+
+class ArchiveResult:
+    """Structure-of-arrays result of one archive, copied out of the context's pinned buffers."""
+
+    @classmethod
+    def _copy_from(cls, hdr, r):
+        self = cls()
+        n = r.n_records
+        self.n_records = n
+        self.n_ids, self.n_comments, self.n_lengths = r.n_ids, r.n_comments, r.n_lengths
+        self.total_residues = r.total_residues
+        self.first_bad_record = None if r.first_bad_record == _ffi.NO_RECORD else r.first_bad_record
+        self.record_status = r.record_status
+        self.id_offsets = _np_copy(r.id_offsets, n + 1, np.uint64) if r.ids else None
+        self.ids = C.string_at(r.ids, int(self.id_offsets[self.n_ids])) if r.ids and self.n_ids else (b"" if r.ids else None)
+        self.comment_offsets = _np_copy(r.comment_offsets, n + 1, np.uint64) if r.comments else None
+        self.comments = C.string_at(r.comments, int(self.comment_offsets[self.n_comments])) if r.comments and self.n_comments else (b"" if r.comments else None)
+        self.lengths = _np_copy(r.lengths, n, np.uint64) if r.lengths else None
+        self.record_offsets = _np_copy(r.record_offsets, n + 1, np.uint64) if r.record_offsets else None
+        self.sequence = C.string_at(r.sequence, r.total_residues) if r.sequence else None
+        self.quality = C.string_at(r.quality, r.total_residues) if r.quality else None
+        return self
+
+    # field accessors with the reference's None-ness rules (mod.rs:356-399)
+    def id_bytes(self, i):
+        if self.ids is None or i >= self.n_ids:
+            return None
+        return self.ids[int(self.id_offsets[i]):int(self.id_offsets[i + 1]) - 1]
+
+    def comment_bytes(self, i):
+        if self.comments is None or i >= self.n_comments:
+            return None
+        return self.comments[int(self.comment_offsets[i]):int(self.comment_offsets[i + 1]) - 1]
+
+    def length(self, i):
+        if self.lengths is None or i >= self.n_lengths:
+            return None
+        return int(self.lengths[i])
+
+    def sequence_bytes(self, i):
+        if self.sequence is None or i >= self.n_lengths:
+            return None
+        return self.sequence[int(self.record_offsets[i]):int(self.record_offsets[i + 1])]
+
+    def quality_bytes(self, i):
+        if self.quality is None or i >= self.n_lengths:
+            return None
+        return self.quality[int(self.record_offsets[i]):int(self.record_offsets[i + 1])]
+
+
+_contexts = {}
+_contexts_lock = threading.Lock()
+
+
+def shared_context(device: int = 0, library: Optional[_ffi.Library] = None) -> Context:
+    lib = library or _ffi.default_library()
+    key = (lib.path, device)
+    with _contexts_lock:
+        if key not in _contexts:
+            _contexts[key] = Context(device, lib)
+        return _contexts[key]
+
+
+def _want_bits(id, comment, sequence, quality, mask):
+    return ((_ffi.WANT_ID if id else 0) | (_ffi.WANT_COMMENT if comment else 0) | (_ffi.WANT_SEQUENCE if sequence else 0) |
+            (_ffi.WANT_QUALITY if quality else 0) | (_ffi.WANT_MASK if mask else 0))
+
+
+class Decoder:
+    """A decoder for Nucleotide Archive Format files running on a B200 (surface of nafcodec.Decoder)."""
+
+    def __init__(self, file, *, id: bool = True, comment: bool = True, sequence: bool = True, quality: bool = True,
+                 mask: bool = True, buffer_size: Optional[int] = None, device: int = 0, _library=None):
+        # buffer_size is accepted for surface compatibility (decoder/mod.rs:105-112); whole sections are read at once.
+        self._buffer_size = buffer_size if buffer_size is not None else io.DEFAULT_BUFFER_SIZE
+        self._file = file
+        if hasattr(file, "read"):
+            data = file.read()
+        else:
+            path = os.fspath(file)
+            with open(path, "rb") as f:      # FileNotFoundError / IsADirectoryError as in lib.rs:363-376
+                data = f.read()
+        self._library = _library or _ffi.default_library()
+        if len(data) == 0:
+            # Decoder::new on empty input: Io(UnexpectedEof) "failed to read header" (mod.rs:181-186, test mod.rs:470-476)
+            e = NafIoError("failed to read header")
+            e.status = _ffi.ERR_UNEXPECTED_EOF
+            raise e
+        self._archive = parse_archive(data, self._library)
+        h = self._archive.header
+        self._header = Header(FormatVersion(h.format_version), SequenceType(h.sequence_type), Flags(h.flags),
+                              chr(h.name_separator), h.line_length, h.number_of_sequences)
+        self._want = _want_bits(id, comment, sequence, quality, mask)
+        self._device = device
+        self._n = 0
+        self._result: Optional[ArchiveResult] = None
+
+    # -- Rust-style constructors -----------------------------------------------------------------------------------
+    @classmethod
+    def from_path(cls, path, **kw):          # mod.rs:304-306
+        return cls(path, **kw)
+
+    @classmethod
+    def new(cls, reader, **kw):              # mod.rs:315-317
+        return cls(reader, **kw)
+
+    # -- header ----------------------------------------------------------------------------------------------------
+    def header(self) -> Header:              # mod.rs:326-328
+        return self._header
+
+    @property
+    def sequence_type(self) -> str:          # lib.rs:417-420 (Python surface returns the lowercase name)
+        return _SEQTYPE_NAMES[int(self._header.sequence_type)]
+
+    @property
+    def format_version(self) -> str:
+        return "v1" if self._header.format_version == FormatVersion.V1 else "v2"
+
+    @property
+    def line_length(self) -> int:
+        return self._header.line_length
+
+    @property
+    def name_separator(self) -> str:
+        return self._header.name_separator
+
+    @property
+    def number_of_sequences(self) -> int:
+        return self._header.number_of_sequences
+
+    def into_inner(self):                    # mod.rs:343-350
+        return self._file
+
+    # -- iteration -------------------------------------------------------------------------------------------------
+    def _decoded(self) -> ArchiveResult:
+        if self._result is None:
+            ctx = shared_context(self._device, self._library)
+            self._result = ctx.decode([self._archive], self._want)[0]
+        return self._result
+
+    def __iter__(self):
+        return self
+
+    def __len__(self):                       # ExactSizeIterator (mod.rs:453-459)
+        return self._header.number_of_sequences - self._n
+
+    def __next__(self) -> Record:
+        if self._n >= self._header.number_of_sequences:    # mod.rs:447-449
+            raise StopIteration
+        r = self._decoded()
+        i = self._n
+        if r.first_bad_record is not None and i == r.first_bad_record:
+            self._n += 1
+            raise_for_status(self._library, r.record_status)
+        self._n += 1
+
+        def s(b):
+            return None if b is None else b.decode("utf-8")
+        return _make_record(s(r.id_bytes(i)), s(r.comment_bytes(i)), s(r.sequence_bytes(i)), s(r.quality_bytes(i)), r.length(i))
+
+    def read(self) -> Optional[Record]:      # lib.rs:452-460
+        try:
+            return self.__next__()
+        except StopIteration:
+            return None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        return False
+
+
+def _make_record(id, comment, sequence, quality, length) -> Record:
+    r = Record.__new__(Record)
+    r.id, r.comment, r.sequence, r.quality, r.length = id, comment, sequence, quality, length
+    return r
+
+
+class DecoderBuilder:
+    """Builder with opt-out fields (nafcodec/src/decoder/mod.rs:53-257)."""
+
+    def __init__(self):                      # DecoderBuilder::new (mod.rs:66-75)
+        self._buffer_size = 4096
+        self._id = self._comment = self._sequence = self._quality = self._mask = True
+        self._device = 0
+        self._library = None
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    @classmethod
+    def from_flags(cls, flags):              # mod.rs:93-101 (quirk kept: never clears `id`)
+        flags = int(flags)
+        b = cls()
+        b.quality(bool(flags & Flag.Quality))
+        b.sequence(bool(flags & Flag.Sequence))
+        b.mask(bool(flags & Flag.Mask))
+        b.comment(bool(flags & Flag.Comment))
+        return b
+
+    def buffer_size(self, n):
+        self._buffer_size = n
+        return self
+
+    def id(self, v):
+        self._id = v
+        return self
+
+    def comment(self, v):
+        self._comment = v
+        return self
+
+    def sequence(self, v):
+        self._sequence = v
+        return self
+
+    def quality(self, v):
+        self._quality = v
+        return self
+
+    def mask(self, v):
+        self._mask = v
+        return self
+
+    def device(self, index):                 # extension: which GPU
+        self._device = index
+        return self
+
+    def _kw(self):
+        return dict(id=self._id, comment=self._comment, sequence=self._sequence, quality=self._quality, mask=self._mask,
+                    buffer_size=self._buffer_size, device=self._device, _library=self._library)
+
+    def with_bytes(self, data: bytes) -> Decoder:        # mod.rs:151-156
+        return Decoder(io.BytesIO(data), **self._kw())
+
+    def with_path(self, path) -> Decoder:                # mod.rs:159-166
+        return Decoder(path, **self._kw())
+
+    def with_reader(self, reader) -> Decoder:            # mod.rs:169-257
+        return Decoder(reader, **self._kw())
+
+
+def decode_batch(files: Iterable, *, id=True, comment=True, sequence=True, quality=True, mask=True, device: int = 0,
+                 _library=None) -> List[ArchiveResult]:
+    """Decode many independent archives in one set of kernel launches (the RefSeq-collection shape)."""
+    lib = _library or _ffi.default_library()
+    archives = []
+    for f in files:
+        if isinstance(f, (bytes, bytearray)):
+            data = bytes(f)
+        elif hasattr(f, "read"):
+            data = f.read()
+        else:
+            with open(os.fspath(f), "rb") as fh:
+                data = fh.read()
+        archives.append(parse_archive(data, lib))
+    return shared_context(device, lib).decode(archives, _want_bits(id, comment, sequence, quality, mask))
