@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- measures the nafcodec hot path (zstd NAF sections -> per-record ASCII) on B200.
+
+Contract (one JSON line on stdout, rank 0):
+  metric  : decoded GB/s of ASCII out (BASELINE.json), whole job over all GPUs
+  value   : device-resident throughput: compressed sections + block descriptors already in HBM when the timed region
+            starts; CUDA events on the stream the kernels are launched on; max over ranks
+  e2e     : same metric through the public C-ABI call nafgpu_decode_batch with HOST buffers (pinned), H2D and D2H inside
+            the timed region
+  roofline: dominant kernel's algorithmic bytes / its measured duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the CPU oracle (C restatement of the reference decoder on libzstd; the Rust reference cannot be built in
+            this image) timed on a bounded sample of the same workload, 1 thread (the reference is single-threaded)
+A "step" = one decode of a batch of `--batch` independent cfg2 archives (synthetic 5 Mbp bacterial genome, single
+record, 4-bit sequence + soft-mask runs, zstd level 19) per GPU.  Archives are partitioned across GPUs with no
+collective (nothing reduces): weak scaling.
+`--impl reference` times the reference's CPU path instead (oracle port, all host cores, one archive per core).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "decoded_ascii_GBps"
+UNIT = "GB/s"
+CACHE = os.environ.get("NAFBENCH_CACHE", "/tmp/nafbench_cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# workload: cfg2 archives, generated with the oracle's restatement of the reference encoder (+ mask section)
+def make_archive(seed, n_res, level):
+    import _cases as K
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, f"cfg2_s{seed}_n{n_res}_l{level}.naf")
+    if os.path.exists(path):
+        return open(path, "rb").read()
+    data = K.genome(seed, n_res, level=level, mask=True, records=1)
+    tmp = path + f".{os.getpid()}.tmp"
+    with open(tmp, "wb") as f:
+        f.write(data)
+    os.replace(tmp, path)
+    return data
+
+
+def make_workload(unique, n_res, level, rank):
+    import _oracle as O
+    O.lib()
+    seeds = [1000 + rank * unique + i for i in range(unique)]
+    with ThreadPoolExecutor(max_workers=min(unique, os.cpu_count() or 1)) as ex:     # ctypes releases the GIL
+        return list(ex.map(lambda s: make_archive(s, n_res, level), seeds))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons for one GPU while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+            if self.stop_flag.is_set():
+                break
+        p.kill()
+
+    def summary(self):
+        self.stop_flag.set()
+        time.sleep(0.15)
+        try:
+            self.proc.kill()
+        except Exception:
+            pass
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_decode_all(archives, threads, want_quality=True, want_mask=True):
+    """Reference CPU path (oracle port): one archive per core.  Returns (seconds, ascii bytes)."""
+    import _oracle as O
+
+    def one(a):
+        return O.time_decode(a, quality=want_quality, mask=want_mask, iters=1)[1]
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        nbytes = sum(one(a) for a in archives)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            nbytes = sum(ex.map(one, archives))
+    return time.perf_counter() - t0, nbytes
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import _oracle as O
+    cores = os.cpu_count() or 1
+    uniq = make_workload(args.unique, args.residues, args.level, 0)
+    sample_n = min(args.batch, max(cores, 8))
+    archives = [uniq[i % len(uniq)] for i in range(sample_n)]
+    for _ in range(args.warmup):
+        cpu_decode_all(archives[:cores], cores)
+    total_t, total_b = 0.0, 0
+    for _ in range(args.steps):
+        t, b = cpu_decode_all(archives, cores)
+        total_t += t
+        total_b += b
+    val = total_b / total_t / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(args, sample_n),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample_n} cfg2 archives per step, one archive per core, {cores} threads; oracle/naf_oracle.c on libzstd {O.lib().nafo_zstd_version().decode()} (the Rust reference cannot be built in this image: no cargo/rustc)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"cfg2: synthetic {args.residues / 1e6:g} Mbp bacterial genome, single-record DNA, 4-bit sequence + soft-mask runs, zstd level {args.level}; "
+                        f"decode sequence+mask+ids+comments+lengths",
+            "archives_per_gpu_per_step": batch, "unique_archives_per_gpu": args.unique, "residues_per_archive": args.residues,
+            "zstd_level": args.level, "parallelism": f"archives partitioned over {args.gpus} GPU(s), no collective",
+            "l2": "batch working set (compressed + packed + ASCII) exceeds the 126 MB L2; device-resident timing also overwrites a 256 MB buffer before every timed iteration"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="archives per GPU per step")
+    ap.add_argument("--unique", type=int, default=8, help="distinct generated archives per GPU (cycled to fill the batch)")
+    ap.add_argument("--residues", type=int, default=5_000_000)
+    ap.add_argument("--level", type=int, default=19)
+    ap.add_argument("--single", action="store_true", help="also report single-archive latency")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import nafcodec_b200 as N
+    from nafcodec_b200 import _ffi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nafcodec_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib = _ffi.default_library()
+    ctx = N.Context(local, lib)
+    uniq = make_workload(args.unique, args.residues, args.level, rank)
+    # pinned host copies of the archives: the e2e leg copies from pinned memory
+    pinned = []
+    for a in uniq:
+        p = lib.dll.nafgpu_host_alloc(len(a))
+        C.memmove(p, a, len(a))
+        pinned.append((p, len(a)))
+    archives = []
+    for i in range(args.batch):
+        p, n = pinned[i % len(pinned)]
+        arc = _ffi.Archive()
+        rc = lib.dll.nafgpu_parse_archive(p, n, C.byref(arc))
+        assert rc == 0, rc
+        archives.append(arc)
+    want = _ffi.WANT_ALL
+
+    # ---- parity gate before any timing: device == oracle on the workload's archives ------------------
+    import _oracle as O
+    from _harness import assert_same_as_oracle
+    got = ctx.decode(archives[:len(uniq)], want)
+    for i, a in enumerate(uniq):
+        assert_same_as_oracle(got[i], O.decode(a), f"bench archive {i}")
+    log(f"[rank {rank}] parity gate ok on {len(uniq)} archives")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ---------------------------------------------------------------------------------
+    ctx.prepare(archives, want)
+    ctx.sync()
+    st = ctx.stats()
+    ctx.time_runs(args.warmup, True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms = ctx.time_runs(args.steps, True)
+    barrier()
+    dev_ms = max_over_ranks(dev_ms)
+    ascii_bytes = st.ascii_bytes
+    value = world * ascii_bytes * args.steps / (dev_ms * 1e-3) / 1e9
+
+    # ---- per-stage times (events on the launch stream) for the roofline of the dominant kernel -----------------------
+    stage_acc = None
+    reps = 5
+    for _ in range(reps):
+        s = ctx.profile_stages()
+        stage_acc = [x[1] for x in s] if stage_acc is None else [a + x[1] for a, x in zip(stage_acc, s)]
+    stage_names = [x[0] for x in s]
+    stage_ms = [a / reps for a in stage_acc]
+    dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
+    lits = st.section_bytes                # every regenerated section byte is produced once by the zstd stage
+    kernel_bytes = {                       # algorithmic bytes per launch of each stage (DESIGN.md "Kernels")
+        "huf_decode": st.compressed_bytes + lits,
+        "unpack": lits + st.ascii_bytes,
+        "decode_sequences": st.compressed_bytes,
+        "lz_literals": 2 * lits, "lz_passes": 2 * lits, "lz_sequential": 2 * lits,
+    }
+    dom_name = stage_names[dom]
+    dom_bytes = kernel_bytes.get(dom_name, st.algorithmic_bytes)
+    peak, peak_src = measured_peak()
+    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    path_gbs = st.algorithmic_bytes * args.steps / (dev_ms * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI: pinned host in, pinned host out ------------------------------------------------
+    n = len(archives)
+    arr = (_ffi.Archive * n)(*archives)
+    res = (_ffi.Result * n)()
+
+    def e2e_step():
+        rc = lib.dll.nafgpu_decode_batch(ctx._ctx, arr, n, want, res)
+        if rc:
+            raise RuntimeError(lib.dll.nafgpu_last_error(ctx._ctx).decode())
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    st2 = ctx.stats()
+    e2e_val = world * ascii_bytes * args.steps / e2e_s / 1e9
+    clocks = sampler.summary()
+
+    # ---- single archive latency (cfg2 as one archive) ------------------------------------------------------------------
+    single = None
+    if rank == 0:
+        ctx.prepare(archives[:1], want)
+        ctx.sync()
+        s1 = ctx.stats()
+        ctx.time_runs(3, True)
+        ms1 = ctx.time_runs(20, True) / 20
+        single = {"device_us": ms1 * 1e3, "ascii_GBps": s1.ascii_bytes / (ms1 * 1e-3) / 1e9, "kernel_launches": s1.kernel_launches,
+                  "algorithmic_bytes": s1.algorithmic_bytes, "frac_of_hbm_peak": s1.algorithmic_bytes / (ms1 * 1e-3) / 1e9 / peak}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample, 1 thread ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        k = 0
+        t_cpu, b_cpu = 0.0, 0
+        while t_cpu < 10.0 and k < 400:
+            t, b = O.time_decode(uniq[k % len(uniq)], quality=True, mask=True, iters=1)
+            t_cpu += t
+            b_cpu += b
+            k += 1
+        cpu = {"value": b_cpu / t_cpu / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{k} single-archive decodes (~10 s) of the same cfg2 archives, 1 thread; oracle/naf_oracle.c on libzstd "
+                         f"{O.lib().nafo_zstd_version().decode()} (Rust reference not buildable here: no cargo/rustc)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": workload_config(args, args.batch),
+                "compressed_in_GBps": world * st.compressed_bytes * args.steps / (dev_ms * 1e-3) / 1e9,
+                "path_algorithmic_GBps": path_gbs, "path_frac_of_hbm_peak": path_gbs / peak,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes), "d2h_bytes_per_step": int(st2.d2h_bytes),
+                        "ms_per_step": e2e_s / args.steps * 1e3},
+                "gpu_launches": int(st.kernel_launches) * args.steps,
+                "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "algorithmic_bytes_per_launch": int(dom_bytes),
+                             "stage_ms": {nm: round(ms, 4) for nm, ms in zip(stage_names, stage_ms)}},
+                "cpu_baseline": cpu, "clocks": clocks, "single_archive": single,
+                "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences),
+                        "compressed_bytes": int(st.compressed_bytes), "ascii_bytes": int(st.ascii_bytes), "algorithmic_bytes": int(st.algorithmic_bytes)}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
