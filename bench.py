@@ -245,6 +245,7 @@ def main():
     dev_ms = ctx.time_runs(args.steps, True)
     barrier()
     dev_ms = max_over_ranks(dev_ms)
+    st = ctx.stats()                       # kernel_launches is filled by the runs
     ascii_bytes = st.ascii_bytes
     value = world * ascii_bytes * args.steps / (dev_ms * 1e-3) / 1e9
 
@@ -302,6 +303,7 @@ def main():
         s1 = ctx.stats()
         ctx.time_runs(3, True)
         ms1 = ctx.time_runs(20, True) / 20
+        s1 = ctx.stats()
         single = {"device_us": ms1 * 1e3, "ascii_GBps": s1.ascii_bytes / (ms1 * 1e-3) / 1e9, "kernel_launches": s1.kernel_launches,
                   "algorithmic_bytes": s1.algorithmic_bytes, "frac_of_hbm_peak": s1.algorithmic_bytes / (ms1 * 1e-3) / 1e9 / peak}
 

@@ -6,9 +6,11 @@
 #define NAF_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emul::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define NAF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul::g_dyn_smem)
+#define NAF_SET_MAX_SMEM(kernel, bytes) ((void)0)
 #else
 #include <cuda_runtime.h>
 #define NAF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define NAF_SET_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #define NAF_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _naf_dyn_smem[]; type* name = reinterpret_cast<type*>(_naf_dyn_smem)
 #endif
 

@@ -4,6 +4,8 @@
 
 #include <stdio.h>
 
+#include <algorithm>
+
 namespace fw {
 
 static const int ERR_INVALID = -2;   // NAFGPU_ERR_INVALID_DATA
@@ -100,7 +102,35 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                 if (last_huf == zf::NO_BLOCK) FAIL(ERR_INVALID, "zstd literals: treeless block without a previous tree");
                 b.huf_block = last_huf;
             }
-            if (lt >= zf::LT_HUF) plan.n_huf_blocks++;
+            if (lt >= zf::LT_HUF) {
+                plan.n_huf_blocks++;
+                // locate the bitstreams: [tree description][jump table (4 streams)] streams...
+                uint32_t pay = hdr, pay_size = csize;
+                if (lt == zf::LT_HUF) {
+                    if (pay_size < 1) FAIL(ERR_INVALID, "zstd literals: missing Huffman tree");
+                    uint8_t hb = c[pay];
+                    uint32_t t = hb < 128 ? 1u + hb : 1u + ((uint32_t)(hb - 127) + 1u) / 2u;
+                    if (t > pay_size) FAIL(ERR_INVALID, "zstd literals: Huffman tree exceeds the literals section");
+                    pay += t; pay_size -= t;
+                }
+                if (regen == 0) FAIL(ERR_INVALID, "zstd literals: empty Huffman literals");
+                uint32_t so[4], ss[4], dn[4], dof[4];
+                if (streams == 1) { so[0] = pay; ss[0] = pay_size; dn[0] = regen; dof[0] = 0; }
+                else {
+                    if (pay_size < 6) FAIL(ERR_INVALID, "zstd literals: missing jump table");
+                    uint32_t z1 = c[pay] | (c[pay + 1] << 8), z2 = c[pay + 2] | (c[pay + 3] << 8), z3 = c[pay + 4] | (c[pay + 5] << 8);
+                    uint32_t seg = (regen + 3) / 4;
+                    if (6ull + z1 + z2 + z3 >= pay_size || 3 * seg >= regen) FAIL(ERR_INVALID, "zstd literals: bad jump table");
+                    so[0] = pay + 6; so[1] = so[0] + z1; so[2] = so[1] + z2; so[3] = so[2] + z3;
+                    ss[0] = z1; ss[1] = z2; ss[2] = z3; ss[3] = pay_size - 6 - z1 - z2 - z3;
+                    for (int k = 0; k < 4; k++) { dof[k] = seg * k; dn[k] = k < 3 ? seg : regen - 3 * seg; }
+                }
+                for (int k = 0; k < streams; k++) {
+                    if (ss[k] == 0) FAIL(ERR_INVALID, "zstd literals: empty Huffman stream");
+                    zf::HufItem it{self, so[k], ss[k], dof[k], dn[k], 0};
+                    plan.huf_items.push_back(it);
+                }
+            }
             // sequences section header
             uint32_t q = hdr + csize;
             if (q >= bsize) FAIL(ERR_INVALID, "zstd sequences: missing section");
@@ -152,6 +182,16 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
              (unsigned long long)known_total, (unsigned long long)dst_size);
     plan.frames.push_back(fd);
     return 0;
+}
+
+void JobPlan::finalize(uint32_t small_max_symbols) {
+    auto mid = std::stable_partition(huf_items.begin(), huf_items.end(), [&](const zf::HufItem& it) { return it.n_sym > small_max_symbols; });
+    n_huf_big = (uint32_t)(mid - huf_items.begin());
+    max_huf_stream = max_huf_small = 0;
+    for (size_t i = 0; i < huf_items.size(); i++) {
+        uint32_t& m = i < n_huf_big ? max_huf_stream : max_huf_small;
+        m = std::max(m, huf_items[i].src_size);
+    }
 }
 
 }  // namespace fw

@@ -65,7 +65,7 @@ struct nafgpu_ctx {
     int device = 0;
     cudaStream_t st = 0;
     std::string err;
-    DevBuf comp, arena, lit, blocks, frames, bstate, tables, table_al, seq32, seq64, misc, nafdev, flush;
+    DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, tables, table_al, seq32, seq64, misc, nafdev, flush;
     PinBuf stage, result, misc_host;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -140,6 +140,7 @@ struct Copy { const uint8_t* src; uint64_t dst, size; };
 
 // Device allocation + H2D of descriptors and compressed frames for the plan in c->plan / c->arch.
 int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp_off, uint32_t n) {
+    c->plan.finalize(zk::HUF_SMALL_SYMBOLS);
     const fw::JobPlan& pl = c->plan;
     const size_t nb = pl.blocks.size(), nf = pl.frames.size();
     const uint64_t nseq = pl.seq_total;
@@ -148,12 +149,13 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     c->misc_words = 1 + (zk::LZ_PASSES + 2) + nf + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 4 * 7 + 64) && c->seq64.ensure(nseq * 8 + 64) && c->misc.ensure(c->misc_words * 4) &&
               c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
-    size_t stage_bytes = nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev);
+    const size_t nh = pl.huf_items.size();
+    size_t stage_bytes = nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev) + nh * sizeof(zf::HufItem);
     if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
         return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
 
@@ -165,6 +167,10 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (nb) CUDA_TRY(c, cudaMemcpyAsync(c->blocks.p, sp, nb * sizeof(zf::BlockDesc), cudaMemcpyHostToDevice, c->st));
     if (nf) CUDA_TRY(c, cudaMemcpyAsync(c->frames.p, sp + nb * sizeof(zf::BlockDesc), nf * sizeof(zf::FrameDesc), cudaMemcpyHostToDevice, c->st));
     if (n) CUDA_TRY(c, cudaMemcpyAsync(c->nafdev.p, sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc), (size_t)n * sizeof(nk::NafDev), cudaMemcpyHostToDevice, c->st));
+    {
+        uint8_t* hp = sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev);
+        if (nh) { memcpy(hp, pl.huf_items.data(), nh * sizeof(zf::HufItem)); CUDA_TRY(c, cudaMemcpyAsync(c->hufitems.p, hp, nh * sizeof(zf::HufItem), cudaMemcpyHostToDevice, c->st)); }
+    }
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
         CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->comp.p + cp.dst, cp.src, cp.size, cudaMemcpyHostToDevice, c->st));
@@ -181,6 +187,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.match_pos = (uint64_t*)c->seq64.p;
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.remaining = misc + 1; J.frame_bad = misc + 1 + (zk::LZ_PASSES + 2);
+    J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
     J.n_frames = (uint32_t)nf; J.n_blocks = (uint32_t)nb; J.n_slots = pl.n_slots; J.n_seq = nseq;
 
     c->stats.n_archives = n; c->stats.n_frames = nf; c->stats.n_blocks = nb; c->stats.n_sequences = nseq;
@@ -217,7 +224,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->hufitems, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i <= N_STAGES; i++) cudaEventDestroy(c->ev[i]);
@@ -420,7 +427,6 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
     CUDA_TRY(c, cudaGetLastError());
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
     const uint8_t* R = (const uint8_t*)c->result.p;
-    int deferred = NAFGPU_OK;
     std::string msg;
     int code = status_to_code(status & ~zc::E_UTF8, msg);
     if (code) return fail(c, code, msg);
@@ -442,9 +448,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
         if (P.dec[5]) r.quality = R + D.qual_off;
         r.first_bad_record = C->first_bad_record;
         r.record_status = (C->first_bad_record != nk::NO_RECORD) ? NAFGPU_ERR_UTF8 : 0;
-        if (r.record_status) deferred = NAFGPU_ERR_UTF8;
     }
-    (void)deferred;
     return NAFGPU_OK;
 }
 

@@ -213,62 +213,184 @@ __global__ void k_frame_scan(JobDev J) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// k_huf_decode (v1): one CTA per block with Huffman-compressed literals; table staged in shared memory; the four
-// streams are decoded by four lanes.  Destination is the output itself when the block has no sequences.
-__global__ void __launch_bounds__(128) k_huf_decode(JobDev J) {
-    __shared__ uint8_t weights[256];
-    __shared__ uint16_t table[1 << zc::HUF_MAX_BITS];
-    __shared__ int s_nsym, s_maxbits;
-    const uint32_t bi = blockIdx.x;
-    const BlockDesc& B = J.blocks[bi];
-    if (B.btype != BT_COMPRESSED || B.lit_type < LT_HUF) return;
+// k_huf_decode: one CTA per Huffman bitstream, intra-stream parallel by self-synchronisation.
+//
+// A zstd Huffman stream is one serial bitstream of up to 32 Ki symbols, read backwards.  Decoding it with one thread
+// leaves a 5 Mbp genome with ~80 active lanes.  Instead the stream is cut into HUF_T equal bit ranges; every thread
+// starts decoding at the top of its range as if that were a codeword boundary and runs until it crosses into the next
+// range, publishing where it landed.  Prefix codes resynchronise within a few symbols, so after thread i adopts the
+// landing point of thread i-1 and re-decodes, the landing points stop changing after 2-3 rounds.  The fixpoint is
+// exact, not probabilistic: thread 0 starts on the true first codeword, and start[i+1] == landing(start[i]) for all i
+// implies by induction that every start is a true boundary.  Then: count symbols per thread, block-scan, decode once
+// more writing bytes into a shared-memory image of the output, and flush it with 16-byte stores.
+//
+// Shared memory: decode table (4 KB) | weights | per-thread landing points | compressed stream (16 B-aligned image of
+// global memory, preceded by >= 16 zero bytes so that reads below bit 0 see zeros) | output image (same 16 B phase as
+// the destination so the flush is vector-aligned on both sides).
+constexpr int HUF_T_BIG = 512;                    // threads per stream for 4-stream blocks (up to 32 Ki symbols)
+constexpr int HUF_T_SMALL = 32;                   // one warp for short streams (1-stream blocks, tiny flushed blocks)
+constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;      // streams regenerating at most this many symbols use the warp variant
+__host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : HUF_SMALL_MAX_SYM) + 64u; }
+// table 4096 | weights 256 | wcnt 256 | misc 256 | landing points 4*T | output image | (dynamic) compressed stream image
+__host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 256u + 256u + 256u + 4u * T + huf_sout_bytes(T); }
+
+struct SpanResult { int end; int cnt; };
+
+// Decodes from absolute smem bit position x_start down to the first codeword boundary <= x_bound.
+// sw: stream image as 32-bit words.  out (nullable): destination bytes.
+template <bool WRITE>
+__device__ __forceinline__ SpanResult huf_span(const uint32_t* sw, const uint16_t* table, int maxbits, int x_start, int x_bound, uint8_t* out) {
+    SpanResult r;
+    r.cnt = 0;
+    r.end = x_start;
+    int rem = x_start - x_bound;
+    if (rem <= 0) return r;
+    // window {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q kept in [maxbits, maxbits + 32)
+    int qi = ((x_start - maxbits) >> 5);
+    int rr = x_start - (qi << 5);
+    uint32_t lo = sw[qi], hi = sw[qi + 1];
+    const uint32_t mask = (1u << maxbits) - 1u;
+    int cnt = 0;
+    while (rem > 0) {
+        uint32_t idx = __funnelshift_r(lo, hi, rr - maxbits) & mask;
+        uint32_t e = table[idx];
+        int len = e & 0xFF;
+        if (WRITE) out[cnt] = (uint8_t)(e >> 8);
+        cnt++;
+        rr -= len;
+        rem -= len;
+        if (rr < maxbits) { hi = lo; lo = sw[--qi]; rr += 32; }
+    }
+    r.cnt = cnt;
+    r.end = x_bound + rem;
+    return r;
+}
+
+template <int HUF_T>
+__global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* items) {
+    NAF_DYN_SMEM(unsigned char, smem);
+    constexpr uint32_t HUF_FIXED_SMEM = huf_fixed_smem(HUF_T);
+    uint16_t* table = (uint16_t*)smem;
+    uint8_t* weights = smem + 4096;
+    uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);                    // [8 symbol groups][16 weights]
+    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] scan, [40] nsym, [41] maxbits
+    int* ends = (int*)(smem + 4096 + 768);
+    uint8_t* sout = smem + 4096 + 768 + 4 * HUF_T;
+    uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const HufItem it = items[blockIdx.x];
+    const BlockDesc& B = J.blocks[it.block];
     if (J.frame_bad[B.frame]) return;
-    const BlockDesc& D = J.blocks[B.huf_block];          // block that carries the tree description
-    const uint8_t* tree = J.comp + D.src_off + D.lit_src;
-    if (threadIdx.x == 0) {
+
+    // ---- stage the compressed stream (coalesced 16 B loads of the aligned image) ----------------------------------
+    const uint8_t* g = J.comp + B.src_off + it.src_off;
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    const uint4* gbase = (const uint4*)(g - a);
+    const uint32_t nchunks = (a + it.src_size + 15) >> 4;
+    for (uint32_t c = tid; c < nchunks; c += HUF_T) ((uint4*)scomp)[1 + c] = gbase[c];
+    // ---- Huffman tree: weights (serial, thread 0) ------------------------------------------------------------------
+    if (tid == 0) {
+        const BlockDesc& D = J.blocks[B.huf_block];
         int mb = 0;
-        s_nsym = zc::huf_read_weights(tree, D.lit_csize, weights, &mb);
-        s_maxbits = mb;
-        if (s_nsym) zc::huf_build_table_serial(weights, s_nsym, mb, table);
+        int ns = zc::huf_read_weights(J.comp + D.src_off + D.lit_src, D.lit_csize, weights, &mb);
+        misc[40] = (uint32_t)ns;
+        misc[41] = (uint32_t)mb;
     }
     __syncthreads();
-    if (s_nsym == 0) {
-        if (threadIdx.x == 0) flag_error(J, B.frame, zc::E_HUF_TREE);
-        return;
+    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;                       // bits below the stream start read as zero
+    const int nsym = (int)misc[40], maxbits = (int)misc[41];
+    if (nsym == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_TREE); return; }
+    // ---- decode table, built in parallel: ascending weight, then ascending symbol (RFC 8878 4.2.1) ----------------
+    // symbols are handled in 8 groups of 32 (group g = symbols 32g..32g+31); wcnt[g][w] = symbols of weight w in group g
+    constexpr int GROUPS_PER_PASS = HUF_T >= 256 ? 8 : HUF_T / 32;
+    int wreg[8 / GROUPS_PER_PASS], rankreg[8 / GROUPS_PER_PASS];
+#pragma unroll
+    for (int p = 0; p < 8 / GROUPS_PER_PASS; p++) {
+        wreg[p] = 0; rankreg[p] = 0;
+        if (tid < 32 * GROUPS_PER_PASS) {
+            const int sym = p * 32 * GROUPS_PER_PASS + tid, grp = sym >> 5;
+            const int w = sym < nsym ? weights[sym] : 0;
+            wreg[p] = w;
+            for (int wv = 1; wv <= zc::HUF_MAX_BITS; wv++) {
+                uint32_t bal = __ballot_sync(0xFFFFFFFFu, w == wv);
+                if (lane == 0) wcnt[grp * 16 + wv] = (uint16_t)__popc(bal);
+                if (w == wv) rankreg[p] = __popc(bal & ((1u << lane) - 1u));
+            }
+        }
     }
-    const int maxbits = s_maxbits;
-    const uint8_t* pay = J.comp + B.src_off + B.lit_src;
-    uint32_t pay_size = B.lit_csize;
-    if (B.lit_type == LT_HUF) {
-        uint32_t t = pay_size ? zc::huf_tree_desc_size(pay[0]) : 1u;
-        if (t > pay_size) { if (threadIdx.x == 0) flag_error(J, B.frame, zc::E_HUF_TREE); return; }
-        pay += t; pay_size -= t;
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 8 / GROUPS_PER_PASS; p++) {
+        const int w = wreg[p];
+        if (tid < 32 * GROUPS_PER_PASS && w > 0) {
+            const int sym = p * 32 * GROUPS_PER_PASS + tid, grp = sym >> 5;
+            uint32_t start = 0;
+            for (int wv = 1; wv < w; wv++) {
+                uint32_t c = 0;
+                for (int k = 0; k < 8; k++) c += wcnt[k * 16 + wv];
+                start += c << (wv - 1);
+            }
+            int rank = rankreg[p];
+            for (int k = 0; k < grp; k++) rank += wcnt[k * 16 + w];
+            uint32_t pos = start + ((uint32_t)rank << (w - 1)), n = 1u << (w - 1);
+            uint16_t e = (uint16_t)((sym << 8) | (maxbits + 1 - w));
+            for (uint32_t i = 0; i < n; i++) table[pos + i] = e;
+        }
     }
-    uint8_t* dst = (B.n_seq == 0) ? (J.out + J.bstate[bi].out_off) : (J.lit + B.lit_base);
-    const uint32_t regen = B.lit_regen;
-    const int t = threadIdx.x;
-    if (t >= B.n_streams) return;
-    uint32_t s_off, s_size, d_off, d_n;
-    if (B.n_streams == 1) {
-        s_off = 0; s_size = pay_size; d_off = 0; d_n = regen;
-    } else {
-        if (pay_size < 6) { if (t == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
-        uint32_t z1 = pay[0] | (pay[1] << 8), z2 = pay[2] | (pay[3] << 8), z3 = pay[4] | (pay[5] << 8);
-        uint32_t seg = (regen + 3) / 4;
-        if (6 + z1 + z2 + z3 >= pay_size + 0u || 3 * seg > regen) { if (t == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
-        uint32_t offs[4] = {6, 6 + z1, 6 + z1 + z2, 6 + z1 + z2 + z3};
-        uint32_t sizes[4] = {z1, z2, z3, pay_size - offs[3]};
-        s_off = offs[t]; s_size = sizes[t]; d_off = seg * t; d_n = (t < 3) ? seg : regen - 3 * seg;
+    __syncthreads();
+
+    // ---- self-synchronisation ----------------------------------------------------------------------------------------
+    const int Z = (int)(16 + a) * 8;                                    // smem bit position of stream bit 0
+    const uint8_t last = ((const uint8_t*)scomp)[16 + a + it.src_size - 1];
+    if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+    const int P0 = 8 * (int)(it.src_size - 1) + zc::highbit32(last);
+    int S = (P0 + HUF_T - 1) / HUF_T;
+    if (S < 16) S = 16;
+    int start = Z + P0 - tid * S;
+    if (start < Z) start = Z;
+    if (tid == 0) start = Z + P0;
+    int bound = Z + P0 - (tid + 1) * S;
+    if (bound < Z || tid == HUF_T - 1) bound = Z;
+    bool need = true;
+    SpanResult sr;
+    sr.end = start; sr.cnt = 0;
+    for (int iter = 0; iter <= HUF_T; iter++) {
+        if (need) sr = huf_span<false>(scomp, table, maxbits, start, bound, nullptr);
+        ends[tid] = sr.end;
+        __syncthreads();
+        int ns = tid == 0 ? Z + P0 : ends[tid - 1];
+        need = ns != start;
+        start = ns;
+        if (!__syncthreads_or(need)) break;
     }
-    BackBits bb;
-    if (!bb.init(pay + s_off, s_size)) { flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
-    uint8_t* o = dst + d_off;
-    for (uint32_t i = 0; i < d_n; i++) {
-        uint16_t e = table[bb.peek(maxbits)];
-        bb.P -= (e & 0xFF);
-        o[i] = (uint8_t)(e >> 8);
+    // ---- count, scan, write ------------------------------------------------------------------------------------------
+    uint32_t inc = (uint32_t)sr.cnt;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) misc[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t x = lane < (HUF_T >> 5) ? misc[lane] : 0, o = x;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
+        misc[lane] = x - o;
+        if (lane == 31) misc[32] = x;
     }
-    if (bb.P != 0) flag_error(J, B.frame, zc::E_HUF_STREAM);
+    __syncthreads();
+    const uint32_t off = inc - (uint32_t)sr.cnt + misc[warp];
+    const uint32_t total = misc[32];
+    if (total != it.n_sym || ends[HUF_T - 1] != Z) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+    uint8_t* dst = ((B.n_seq == 0) ? (J.out + J.bstate[it.block].out_off) : (J.lit + B.lit_base)) + it.dst_off;
+    const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
+    huf_span<true>(scomp, table, maxbits, start, bound, sout + a2 + off);
+    __syncthreads();
+    // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends --------------------
+    const uint32_t n = it.n_sym, endb = a2 + n;
+    uint8_t* dal = dst - a2;
+    const uint32_t first_full = a2 ? 1u : 0u, last_full = endb >> 4;     // chunks [first_full, last_full) are complete
+    for (uint32_t c = first_full + tid; c < last_full; c += HUF_T) ((uint4*)dal)[c] = ((const uint4*)sout)[c];
+    if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HUF_T) dal[k] = sout[k]; }
+    if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
+        for (uint32_t k = (last_full << 4) + tid; k < endb; k += HUF_T) dal[k] = sout[k];
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -414,7 +536,16 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
     NAF_LAUNCH(k_build_tables, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, (J.n_frames + 63) / 64, 64, 0, st, J); launches++; ev->mark();
-    NAF_LAUNCH(k_huf_decode, J.n_blocks, 128, 0, st, J); launches++; ev->mark();
+    if (J.n_huf_big) {       // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams, one warp each
+        const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
+        NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);
+        NAF_LAUNCH((k_huf_decode<HUF_T_BIG>), J.n_huf_big, HUF_T_BIG, smem, st, J, J.huf_items); launches++;
+    }
+    if (J.n_huf_items > J.n_huf_big) {
+        const uint32_t smem = huf_fixed_smem(HUF_T_SMALL) + ((J.max_huf_small + 15 + 16 + 16 + 15) & ~15u);
+        NAF_LAUNCH((k_huf_decode<HUF_T_SMALL>), J.n_huf_items - J.n_huf_big, HUF_T_SMALL, smem, st, J, J.huf_items + J.n_huf_big); launches++;
+    }
+    ev->mark();
     NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
         const uint32_t warps = 8;

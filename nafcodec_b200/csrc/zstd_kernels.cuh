@@ -8,7 +8,8 @@
 
 namespace zk {
 
-constexpr int LZ_PASSES = 6;          // dependency-resolving passes before the ordered fallback
+constexpr int LZ_PASSES = 6;
+constexpr uint32_t HUF_SMALL_SYMBOLS = 2048;   // streams regenerating <= this many symbols are decoded by one warp          // dependency-resolving passes before the ordered fallback
 
 // Everything the zstd kernels need, by value.  All pointers are device pointers.
 struct JobDev {
@@ -31,6 +32,9 @@ struct JobDev {
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
     uint32_t* remaining;              // [LZ_PASSES + 2] matches still pending after pass p
+    const zf::HufItem* huf_items;     // one per Huffman bitstream
+    uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
+    uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
     uint32_t n_frames, n_blocks, n_slots;
     uint64_t n_seq;
 };

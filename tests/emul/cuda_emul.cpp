@@ -2,7 +2,6 @@
 #include "cuda_emul.h"
 
 #include <time.h>
-#include <ucontext.h>
 #include <vector>
 
 namespace emul {
@@ -13,8 +12,34 @@ unsigned char* g_dyn_smem = nullptr;
 
 enum State { RUNNABLE, WAIT_CTA, WAIT_WARP, DONE };
 
+// Minimal x86-64 SysV context switch (callee-saved registers + stack pointer); ~20x cheaper than swapcontext,
+// which makes two sigprocmask system calls per switch.
+extern "C" void emul_switch(void** from_sp, void* to_sp);
+asm(R"(
+.text
+.globl emul_switch
+.type emul_switch,@function
+emul_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emul_switch,.-emul_switch
+)");
+
 struct Fiber {
-    ucontext_t ctx;
+    void* sp;
     State st;
     Idx tid;
     int warp;
@@ -23,14 +48,17 @@ struct Fiber {
 static const size_t STACK = 128 * 1024;
 static std::vector<Fiber> g_fibers;
 static std::vector<unsigned char> g_stacks;
-static ucontext_t g_sched;
+static void* g_sched_sp = nullptr;
 static int g_cur = -1;
 static const std::function<void()>* g_body = nullptr;
 static int g_cta_arrived = 0, g_cta_live = 0;
 static std::vector<int> g_warp_arrived, g_warp_live;
 static std::vector<uint64_t> g_xchg;      // per thread exchange slot
+int g_vote_slot[3] = {0, 0, 0};
+static std::vector<int> g_vote_calls;
+int vote_enter() { return g_vote_calls[g_cur]++; }
 
-static void yield_to_sched() { swapcontext(&g_fibers[g_cur].ctx, &g_sched); }
+static void yield_to_sched() { emul_switch(&g_fibers[g_cur].sp, g_sched_sp); }
 
 static void fiber_main() {
     (*g_body)();
@@ -38,7 +66,8 @@ static void fiber_main() {
     f.st = DONE;
     g_cta_live--;
     g_warp_live[f.warp]--;
-    swapcontext(&f.ctx, &g_sched);
+    emul_switch(&f.sp, g_sched_sp);
+    abort();     // a finished fiber is never resumed
 }
 
 void sync_cta() {
@@ -97,6 +126,8 @@ static void run_cta(dim3 block) {
     g_fibers.resize(n);
     if (g_stacks.size() < n * STACK) g_stacks.resize(n * STACK);
     g_xchg.assign(n, 0);
+    g_vote_calls.assign(n, 0);
+    g_vote_slot[0] = g_vote_slot[1] = g_vote_slot[2] = 0;
     size_t nw = (n + 31) / 32;
     g_warp_arrived.assign(nw, 0);
     g_warp_live.assign(nw, 0);
@@ -110,11 +141,12 @@ static void run_cta(dim3 block) {
         f.tid.z = (unsigned)(t / ((size_t)block.x * block.y));
         f.warp = (int)(t / 32);
         g_warp_live[f.warp]++;
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = g_stacks.data() + t * STACK;
-        f.ctx.uc_stack.ss_size = STACK;
-        f.ctx.uc_link = nullptr;
-        makecontext(&f.ctx, fiber_main, 0);
+        uintptr_t top = ((uintptr_t)(g_stacks.data() + (t + 1) * STACK)) & ~(uintptr_t)15;
+        void** sp = (void**)top;
+        *--sp = nullptr;                       // alignment slot: rsp == 8 (mod 16) when fiber_main starts
+        *--sp = (void*)fiber_main;             // "return address" of the first switch
+        for (int k = 0; k < 6; k++) *--sp = nullptr;   // rbp rbx r12 r13 r14 r15
+        f.sp = (void*)sp;
     }
     size_t done = 0;
     while (done < n) {
@@ -124,7 +156,7 @@ static void run_cta(dim3 block) {
             if (f.st != RUNNABLE) continue;
             g_cur = (int)t;
             g_threadIdx = f.tid;
-            swapcontext(&g_sched, &f.ctx);
+            emul_switch(&g_sched_sp, f.sp);
             progressed = true;
             if (f.st == DONE) done++;
             release_barriers();
@@ -166,3 +198,15 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = now_ms(); return 0; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return 0; }
+
+// CTA-wide vote barriers.  Each fiber counts its own vote calls; call k accumulates in slot k%3 and clears slot
+// (k+1)%3, which no fiber can still be using (barriers keep fibers within one call of each other).
+int __syncthreads_count(int pred) {
+    int k = emul::vote_enter();
+    emul::g_vote_slot[(k + 1) % 3] = 0;
+    if (pred) emul::g_vote_slot[k % 3] += 1;
+    emul::sync_cta();
+    return emul::g_vote_slot[k % 3];
+}
+int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
+int __syncthreads_and(int pred) { return __syncthreads_count(!pred) == 0; }

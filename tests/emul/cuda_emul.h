@@ -43,6 +43,8 @@ void sync_warp();
 uint64_t warp_exchange(uint64_t v, int src_lane);      // value of src_lane (all live lanes of the warp must call)
 uint32_t warp_ballot(int pred);
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+extern int g_vote_slot[3];
+int vote_enter();
 }  // namespace emul
 
 #define threadIdx emul::g_threadIdx
@@ -53,6 +55,9 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 
 static inline void __syncthreads() { emul::sync_cta(); }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emul::sync_warp(); }
+int __syncthreads_or(int pred);
+int __syncthreads_and(int pred);
+int __syncthreads_count(int pred);
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
