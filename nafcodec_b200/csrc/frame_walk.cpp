@@ -48,7 +48,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
     fd.first_block = (uint32_t)plan.blocks.size(); fd.first_seq = (uint32_t)plan.seq_total; fd.window = window;
     uint32_t frame_idx = (uint32_t)plan.frames.size();
 
-    uint32_t last_huf = zf::NO_BLOCK;
+    uint32_t last_huf = zf::NO_BLOCK, last_huf_slot = 0;
     uint32_t cur_tbl[3] = {zf::NO_SLOT, zf::NO_SLOT, zf::NO_SLOT};
     uint64_t known_total = 0;
     for (;;) {
@@ -97,10 +97,10 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
             if (regen > zf::BLOCK_MAX) FAIL(ERR_INVALID, "zstd literals: regenerated size %u too large", regen);
             if ((uint64_t)hdr + csize > bsize) FAIL(ERR_INVALID, "zstd literals: section exceeds the block");
             b.lit_type = (uint8_t)lt; b.n_streams = (uint8_t)streams; b.lit_regen = regen; b.lit_csize = csize; b.lit_src = hdr;
-            if (lt == zf::LT_HUF) { last_huf = self; b.huf_block = self; }
+            if (lt == zf::LT_HUF) { last_huf = self; b.huf_block = self; last_huf_slot = plan.n_huf_slots++; b.huf_slot = last_huf_slot; }
             else if (lt == zf::LT_TREELESS) {
                 if (last_huf == zf::NO_BLOCK) FAIL(ERR_INVALID, "zstd literals: treeless block without a previous tree");
-                b.huf_block = last_huf;
+                b.huf_block = last_huf; b.huf_slot = last_huf_slot;
             }
             if (lt >= zf::LT_HUF) {
                 plan.n_huf_blocks++;

@@ -3,6 +3,7 @@
 // reader parameter of nafcodec/src/decoder/reader.rs instantiated with ZstdDecoder in setup_block!
 // (nafcodec/src/decoder/mod.rs:32,218-226) and consumed by next_record / mask_sequence (mod.rs:356-441).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -65,7 +66,7 @@ struct nafgpu_ctx {
     int device = 0;
     cudaStream_t st = 0;
     std::string err;
-    DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, tables, table_al, seq32, seq64, misc, nafdev, flush;
+    DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, hufw, debug, tables, table_al, seq32, seq64, misc, nafdev, flush;
     PinBuf stage, result, misc_host;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -149,7 +150,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     c->misc_words = 1 + (zk::LZ_PASSES + 2) + nf + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 4 * 7 + 64) && c->seq64.ensure(nseq * 8 + 64) && c->misc.ensure(c->misc_words * 4) &&
               c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
@@ -187,7 +188,14 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.match_pos = (uint64_t*)c->seq64.p;
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.remaining = misc + 1; J.frame_bad = misc + 1 + (zk::LZ_PASSES + 2);
+    J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
+    J.debug = nullptr;
+    if (getenv("NAFGPU_DEBUG_HUF") && nh) {
+        if (!c->debug.ensure(nh * 64)) return fail(c, NAFGPU_ERR_NOMEM, "debug buffer");
+        cudaMemsetAsync(c->debug.p, 0, nh * 64, c->st);
+        J.debug = (unsigned long long*)c->debug.p;
+    }
     J.n_frames = (uint32_t)nf; J.n_blocks = (uint32_t)nb; J.n_slots = pl.n_slots; J.n_seq = nseq;
 
     c->stats.n_archives = n; c->stats.n_frames = nf; c->stats.n_blocks = nb; c->stats.n_sequences = nseq;
@@ -224,7 +232,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->hufitems, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->hufitems, &c->hufw, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i <= N_STAGES; i++) cudaEventDestroy(c->ev[i]);
@@ -425,6 +433,21 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
     CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
     CUDA_TRY(c, cudaStreamSynchronize(c->st));
     CUDA_TRY(c, cudaGetLastError());
+    if (c->J.debug) {
+        size_t nh = c->J.n_huf_items;
+        std::vector<unsigned long long> d(nh * 8);
+        cudaMemcpy(d.data(), c->J.debug, nh * 64, cudaMemcpyDeviceToHost);
+        double ph[6] = {0, 0, 0, 0, 0, 0}, iters = 0, maxit = 0;
+        size_t cnt = 0;
+        for (size_t i = 0; i < c->J.n_huf_big; i++) {
+            if (!d[i * 8 + 6]) continue;
+            for (int k = 0; k < 6; k++) ph[k] += (double)(d[i * 8 + k + 1] - d[i * 8 + k]);
+            iters += (double)d[i * 8 + 7]; if ((double)d[i * 8 + 7] > maxit) maxit = (double)d[i * 8 + 7];
+            cnt++;
+        }
+        if (cnt) fprintf(stderr, "[huf debug] big CTAs %zu: cycles stage+weights %.0f, table %.0f, sync %.0f (iters avg %.2f max %.0f), scan %.0f, write %.0f, flush %.0f\n",
+                         cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
+    }
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
     const uint8_t* R = (const uint8_t*)c->result.p;
     std::string msg;

@@ -25,7 +25,23 @@ __device__ __forceinline__ void flag_error(const JobDev& J, uint32_t frame, uint
 
 // --------------------------------------------------------------------------------------------------------------
 // k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
-__global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
+__global__ void __launch_bounds__(64) k_build_tables(JobDev J) {
+    if (threadIdx.x >= 32) {
+        // warp 1: the block's Huffman tree description -> 256 weights, decoded ONCE per tree (streams and treeless
+        // blocks that reuse the tree read the weights back and build their decode table in parallel).
+        if (threadIdx.x != 32 || blockIdx.x >= J.n_blocks) return;
+        const BlockDesc& B = J.blocks[blockIdx.x];
+        if (B.btype != BT_COMPRESSED || B.lit_type != LT_HUF) return;
+        uint8_t w[256];
+        int mb = 0;
+        int ns = zc::huf_read_weights(J.comp + B.src_off + B.lit_src, B.lit_csize, w, &mb);
+        uint8_t* gw = J.huf_weights + (size_t)B.huf_slot * 256;
+        for (int i = 0; i < 256; i += 4) *(uint32_t*)(gw + i) = w[i] | (w[i + 1] << 8) | (w[i + 2] << 16) | ((uint32_t)w[i + 3] << 24);
+        J.huf_meta[(size_t)B.huf_slot * 2] = (uint8_t)(ns ? ns - 1 : 0);
+        J.huf_meta[(size_t)B.huf_slot * 2 + 1] = (uint8_t)(ns ? mb : 0);
+        if (ns == 0) flag_error(J, B.frame, zc::E_HUF_TREE);
+        return;
+    }
     __shared__ int16_t norm[3][56];
     __shared__ uint8_t cell_sym[3][512];
     __shared__ uint16_t cnt[3][56];
@@ -213,26 +229,29 @@ __global__ void k_frame_scan(JobDev J) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// k_huf_decode: one CTA per Huffman bitstream, intra-stream parallel by self-synchronisation.
+// k_huf_decode: one CTA per Huffman bitstream, intra-stream parallel.
 //
-// A zstd Huffman stream is one serial bitstream of up to 32 Ki symbols, read backwards.  Decoding it with one thread
-// leaves a 5 Mbp genome with ~80 active lanes.  Instead the stream is cut into HUF_T equal bit ranges; every thread
-// starts decoding at the top of its range as if that were a codeword boundary and runs until it crosses into the next
-// range, publishing where it landed.  Prefix codes resynchronise within a few symbols, so after thread i adopts the
-// landing point of thread i-1 and re-decodes, the landing points stop changing after 2-3 rounds.  The fixpoint is
-// exact, not probabilistic: thread 0 starts on the true first codeword, and start[i+1] == landing(start[i]) for all i
-// implies by induction that every start is a true boundary.  Then: count symbols per thread, block-scan, decode once
-// more writing bytes into a shared-memory image of the output, and flush it with 16-byte stores.
+// A zstd Huffman stream is one serial bitstream of up to 32 Ki symbols, read backwards; with one thread per stream a
+// 5 Mbp genome keeps ~80 lanes busy.  Here the stream is cut into HUF_T equal bit ranges, one per thread.  A thread
+// does not know where the first codeword of its range starts, but it must be one of the `max_bits` positions at the
+// top of the range.  So it follows ALL candidates ("tracks") through its range: tracks that reach the same bit
+// position merge (prefix codes usually resynchronise within a few symbols, so one track survives; near-fixed-length
+// codes such as 4-bit packed uniform DNA never resynchronise and keep one track per phase, 4 of them).  The result is
+// a transition map candidate -> (candidate of the next range, symbols decoded).  Composing the maps along the stream
+// (a scan over function composition, maps packed as 4-bit fields of a u64) gives every thread its true start, exactly:
+// thread 0 starts on the stream's first codeword.  Then: block-scan the symbol counts, decode once more from the true
+// start into a shared-memory image of the output, flush with 16-byte stores.
 //
-// Shared memory: decode table (4 KB) | weights | per-thread landing points | compressed stream (16 B-aligned image of
-// global memory, preceded by >= 16 zero bytes so that reads below bit 0 see zeros) | output image (same 16 B phase as
-// the destination so the flush is vector-aligned on both sides).
+// Shared memory: decode table 4 KB | weights | scratch | compressed stream (16 B-aligned image of global memory,
+// preceded by >= 16 zero bytes so reads below bit 0 see zeros) | output image (same 16 B phase as the destination).
 constexpr int HUF_T_BIG = 512;                    // threads per stream for 4-stream blocks (up to 32 Ki symbols)
 constexpr int HUF_T_SMALL = 32;                   // one warp for short streams (1-stream blocks, tiny flushed blocks)
-constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;      // streams regenerating at most this many symbols use the warp variant
+constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
+constexpr int HUF_SEG = 64;                       // tracks are compared for merging every HUF_SEG bits
+constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
 __host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : HUF_SMALL_MAX_SYM) + 64u; }
-// table 4096 | weights 256 | wcnt 256 | misc 256 | landing points 4*T | output image | (dynamic) compressed stream image
-__host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 256u + 256u + 256u + 4u * T + huf_sout_bytes(T); }
+// table 4096 | weights 256 | wcnt 256 | misc 256 | output image | (dynamic) compressed stream image
+__host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 256u + 256u + 256u + huf_sout_bytes(T); }
 
 struct SpanResult { int end; int cnt; };
 
@@ -266,41 +285,53 @@ __device__ __forceinline__ SpanResult huf_span(const uint32_t* sw, const uint16_
     return r;
 }
 
+// maps over candidate indices 0..15 packed as 4-bit fields; compose(g, f)(k) = g(f(k))
+__device__ __forceinline__ uint64_t map_compose(uint64_t g, uint64_t f) {
+    uint64_t r = 0;
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) {
+        uint32_t fk = (uint32_t)(f >> (4 * k)) & 15u;
+        r |= ((g >> (4 * fk)) & 15ull) << (4 * k);
+    }
+    return r;
+}
+constexpr uint64_t MAP_IDENTITY = 0xFEDCBA9876543210ull;
+
 template <int HUF_T>
 __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* items) {
     NAF_DYN_SMEM(unsigned char, smem);
     constexpr uint32_t HUF_FIXED_SMEM = huf_fixed_smem(HUF_T);
+    constexpr int NWARPS = HUF_T / 32;
     uint16_t* table = (uint16_t*)smem;
     uint8_t* weights = smem + 4096;
     uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);                    // [8 symbol groups][16 weights]
-    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] scan, [40] nsym, [41] maxbits
-    int* ends = (int*)(smem + 4096 + 768);
-    uint8_t* sout = smem + 4096 + 768 + 4 * HUF_T;
+    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] count scan, [34..49] warp start candidates
+    uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [NWARPS] composed map of each warp; reuses wcnt after the table build
+    uint8_t* sout = smem + 4096 + 768;
     uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     const HufItem it = items[blockIdx.x];
     const BlockDesc& B = J.blocks[it.block];
     if (J.frame_bad[B.frame]) return;
-
-    // ---- stage the compressed stream (coalesced 16 B loads of the aligned image) ----------------------------------
+#if defined(__CUDA_ARCH__)
+#define HUF_TICK(k) do { if (J.debug && tid == 0) J.debug[(size_t)blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#else
+#define HUF_TICK(k) ((void)0)
+#endif
+    HUF_TICK(0);
+    // ---- stage the compressed stream (coalesced 16 B loads of the aligned image) and the weights -------------------
     const uint8_t* g = J.comp + B.src_off + it.src_off;
     const uint32_t a = (uint32_t)((uintptr_t)g & 15);
     const uint4* gbase = (const uint4*)(g - a);
     const uint32_t nchunks = (a + it.src_size + 15) >> 4;
     for (uint32_t c = tid; c < nchunks; c += HUF_T) ((uint4*)scomp)[1 + c] = gbase[c];
-    // ---- Huffman tree: weights (serial, thread 0) ------------------------------------------------------------------
-    if (tid == 0) {
-        const BlockDesc& D = J.blocks[B.huf_block];
-        int mb = 0;
-        int ns = zc::huf_read_weights(J.comp + D.src_off + D.lit_src, D.lit_csize, weights, &mb);
-        misc[40] = (uint32_t)ns;
-        misc[41] = (uint32_t)mb;
-    }
+    for (int i = tid; i < 64; i += HUF_T) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)B.huf_slot * 256))[i];
+    const int nsym = (int)J.huf_meta[(size_t)B.huf_slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)B.huf_slot * 2 + 1];
+    if (maxbits == 0) return;                                           // bad tree: already flagged by k_build_tables
     __syncthreads();
-    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;                       // bits below the stream start read as zero
-    const int nsym = (int)misc[40], maxbits = (int)misc[41];
-    if (nsym == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_TREE); return; }
+    HUF_TICK(1);
+    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;              // bits below the stream start read as zero
     // ---- decode table, built in parallel: ascending weight, then ascending symbol (RFC 8878 4.2.1) ----------------
     // symbols are handled in 8 groups of 32 (group g = symbols 32g..32g+31); wcnt[g][w] = symbols of weight w in group g
     constexpr int GROUPS_PER_PASS = HUF_T >= 256 ? 8 : HUF_T / 32;
@@ -339,50 +370,120 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
         }
     }
     __syncthreads();
+    HUF_TICK(2);
 
-    // ---- self-synchronisation ----------------------------------------------------------------------------------------
+    // ---- phase 1: transition map of every range -------------------------------------------------------------------------
+    // q = distance (in bits) from the top of the stream; smem bit position x = XTOP - q.
     const int Z = (int)(16 + a) * 8;                                    // smem bit position of stream bit 0
     const uint8_t last = ((const uint8_t*)scomp)[16 + a + it.src_size - 1];
     if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
     const int P0 = 8 * (int)(it.src_size - 1) + zc::highbit32(last);
+    const int XTOP = Z + P0;
     int S = (P0 + HUF_T - 1) / HUF_T;
-    if (S < 16) S = 16;
-    int start = Z + P0 - tid * S;
-    if (start < Z) start = Z;
-    if (tid == 0) start = Z + P0;
-    int bound = Z + P0 - (tid + 1) * S;
-    if (bound < Z || tid == HUF_T - 1) bound = Z;
-    bool need = true;
-    SpanResult sr;
-    sr.end = start; sr.cnt = 0;
-    for (int iter = 0; iter <= HUF_T; iter++) {
-        if (need) sr = huf_span<false>(scomp, table, maxbits, start, bound, nullptr);
-        ends[tid] = sr.end;
-        __syncthreads();
-        int ns = tid == 0 ? Z + P0 : ends[tid - 1];
-        need = ns != start;
-        start = ns;
-        if (!__syncthreads_or(need)) break;
+    if (S < 2 * MAXC) S = 2 * MAXC;
+    const int q0 = tid * S;                                             // top of this thread's range
+    const int qe = (q0 + S < P0) ? q0 + S : P0;                         // end of the range (exclusive)
+    const bool active = q0 < P0;
+    // track k: pc[k] = (q - q0) | (symbols << 16); merged tracks: mg[k] = (count offset & 0xFFFF) | (representative << 16)
+    uint32_t pc[MAXC], mg[MAXC];
+    uint32_t live = active ? ((1u << maxbits) - 1u) : 0u;
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) { pc[k] = (uint32_t)k; mg[k] = 0; }
+    if (active) {
+        for (int lim = q0 + HUF_SEG;; lim += HUF_SEG) {
+            const int l = lim < qe ? lim : qe;
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) {
+                if (live & (1u << k)) {
+                    const int q = q0 + (int)(pc[k] & 0xFFFFu);
+                    SpanResult r = huf_span<false>(scomp, table, maxbits, XTOP - q, XTOP - l, nullptr);
+                    pc[k] = (uint32_t)((XTOP - r.end) - q0) | ((pc[k] & 0xFFFF0000u) + ((uint32_t)r.cnt << 16));
+                }
+            }
+            if (live & (live - 1)) {                                    // more than one live track: merge equal positions
+#pragma unroll
+                for (int k = 1; k < MAXC; k++) {
+                    if (live & (1u << k)) {
+#pragma unroll
+                        for (int j = 0; j < k; j++) {
+                            if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
+                                live &= ~(1u << k);
+                                mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
+                            }
+                        }
+                    }
+                }
+            }
+            if (l >= qe) break;
+        }
     }
+    // resolve merged tracks (representatives always have a lower index): landing position and symbol count per candidate
+    uint64_t fmap = MAP_IDENTITY;
+    if (active) {
+        fmap = 0;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) {
+            if (!(live & (1u << k)) && k < maxbits) {
+                const uint32_t j = mg[k] >> 16;
+                uint32_t pj = 0;
+#pragma unroll
+                for (int t = 0; t < k; t++) if ((uint32_t)t == j) pj = pc[t];
+                pc[k] = (pj & 0xFFFFu) | ((((pj >> 16) + mg[k]) & 0xFFFFu) << 16);
+            }
+            int land = (int)(pc[k] & 0xFFFFu) - S;                      // candidate index in the next range
+            if (land < 0 || land > 15) land = 15;                       // only garbage tracks or the last range get here
+            fmap |= (uint64_t)land << (4 * k);
+        }
+    }
+    HUF_TICK(3);
+    // ---- compose the maps along the stream: inclusive scan in the warp, then warp totals serially ------------------------
+    uint64_t inc_map = fmap;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t o = __shfl_up_sync(0xFFFFFFFFu, inc_map, d);
+        if (lane >= d) inc_map = map_compose(inc_map, o);
+    }
+    uint64_t exc_map = __shfl_up_sync(0xFFFFFFFFu, inc_map, 1);
+    if (lane == 0) exc_map = MAP_IDENTITY;
+    if (lane == 31) wmap[warp] = inc_map;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t k = 0;
+        for (int w = 0; w < NWARPS; w++) { misc[34 + w] = k; k = (uint32_t)(wmap[w] >> (4 * k)) & 15u; }
+    }
+    __syncthreads();
+    const uint32_t kw = misc[34 + warp];
+    const uint32_t ktrue = (uint32_t)(exc_map >> (4 * kw)) & 15u;      // this thread's true candidate
+    uint32_t mypc = 0;
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) if ((uint32_t)k == ktrue) mypc = pc[k];
+    const uint32_t mycnt = active && ktrue < (uint32_t)maxbits ? (mypc >> 16) : 0u;
+    const int myland = q0 + (int)(mypc & 0xFFFFu);
+    // the stream must end exactly on its first bit: the last active range's true track lands on P0
+    const bool bad_end = active && qe == P0 && (ktrue >= (uint32_t)maxbits || myland != P0);
     // ---- count, scan, write ------------------------------------------------------------------------------------------
-    uint32_t inc = (uint32_t)sr.cnt;
+    uint32_t inc = mycnt;
+#pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
     if (lane == 31) misc[warp] = inc;
-    __syncthreads();
+    const int any_bad = __syncthreads_or(bad_end);
     if (warp == 0) {
-        uint32_t x = lane < (HUF_T >> 5) ? misc[lane] : 0, o = x;
+        uint32_t x = lane < NWARPS ? misc[lane] : 0, o = x;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
         misc[lane] = x - o;
         if (lane == 31) misc[32] = x;
     }
     __syncthreads();
-    const uint32_t off = inc - (uint32_t)sr.cnt + misc[warp];
+    const uint32_t off = inc - mycnt + misc[warp];
     const uint32_t total = misc[32];
-    if (total != it.n_sym || ends[HUF_T - 1] != Z) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+    if (any_bad || total != it.n_sym) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
     uint8_t* dst = ((B.n_seq == 0) ? (J.out + J.bstate[it.block].out_off) : (J.lit + B.lit_base)) + it.dst_off;
     const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
-    huf_span<true>(scomp, table, maxbits, start, bound, sout + a2 + off);
+    HUF_TICK(4);
+    if (mycnt) huf_span<true>(scomp, table, maxbits, XTOP - (q0 + (int)ktrue), XTOP - qe, sout + a2 + off);
     __syncthreads();
+    HUF_TICK(5);
     // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends --------------------
     const uint32_t n = it.n_sym, endb = a2 + n;
     uint8_t* dal = dst - a2;
@@ -391,6 +492,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HUF_T) dal[k] = sout[k]; }
     if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
         for (uint32_t k = (last_full << 4) + tid; k < endb; k += HUF_T) dal[k] = sout[k];
+    HUF_TICK(6);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -533,7 +635,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
     if (!ev) ev = &none;
     int launches = 0;
     if (J.n_blocks == 0) { for (int i = 0; i < ZSTD_STAGES; i++) ev->mark(); return 0; }
-    NAF_LAUNCH(k_build_tables, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_build_tables, J.n_blocks + 1, 64, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, (J.n_frames + 63) / 64, 64, 0, st, J); launches++; ev->mark();
     if (J.n_huf_big) {       // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams, one warp each

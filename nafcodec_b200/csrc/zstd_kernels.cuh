@@ -21,6 +21,8 @@ struct JobDev {
     zf::BlockState* bstate;
     zc::SeqCell* tables;              // n_slots * FSE_SLOT_CELLS
     uint8_t* table_al;                // accuracy log per slot
+    uint8_t* huf_weights;             // n_huf_slots x 256 weights (k_build_tables decodes every tree description once)
+    uint8_t* huf_meta;                // n_huf_slots x {n_symbols - 1, max_bits}; max_bits == 0: bad tree
     uint32_t* seq_ll;
     uint32_t* seq_ml;
     uint32_t* seq_off;                // resolved offset, or symbolic (zf::OFF_SYMBOLIC)
@@ -31,6 +33,7 @@ struct JobDev {
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
+    unsigned long long* debug;        // optional per-CTA phase clocks of k_huf_decode (NAFGPU_DEBUG_HUF=1), else null
     uint32_t* remaining;              // [LZ_PASSES + 2] matches still pending after pass p
     const zf::HufItem* huf_items;     // one per Huffman bitstream
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
