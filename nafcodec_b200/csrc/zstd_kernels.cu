@@ -247,38 +247,68 @@ __global__ void k_frame_scan(JobDev J) {
 constexpr int HUF_T_BIG = 512;                    // threads per stream for 4-stream blocks (up to 32 Ki symbols)
 constexpr int HUF_T_SMALL = 32;                   // one warp for short streams (1-stream blocks, tiny flushed blocks)
 constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
-constexpr int HUF_SEG = 64;                       // tracks are compared for merging every HUF_SEG bits
+constexpr int HUF_SEG = 96;                       // tracks are compared for merging every HUF_SEG bits
 constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
 __host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : HUF_SMALL_MAX_SYM) + 64u; }
-// table 4096 | weights 256 | wcnt 256 | misc 256 | output image | (dynamic) compressed stream image
-__host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 256u + 256u + 256u + huf_sout_bytes(T); }
+// t1 4096 | weights 256 | wcnt 256 | misc 256 | [big only: tl 4096 | t3 16384] | output image | (dynamic) compressed stream image
+__host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return T == HUF_T_BIG ? 4096u + 16384u : 0u; }
+__host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 768u + huf_multi_bytes(T) + huf_sout_bytes(T); }
 
 struct SpanResult { int end; int cnt; };
 
+constexpr int HUF_W = 12;                          // index width of the multi-symbol tables
+
 // Decodes from absolute smem bit position x_start down to the first codeword boundary <= x_bound.
-// sw: stream image as 32-bit words.  out (nullable): destination bytes.
-template <bool WRITE>
-__device__ __forceinline__ SpanResult huf_span(const uint32_t* sw, const uint16_t* table, int maxbits, int x_start, int x_bound, uint8_t* out) {
+//   t1 : base table, index = next max_bits bits, entry = symbol << 8 | length
+//   tl : (MULTI, counting)  index = next 12 bits, entry = symbols that fit << 4 | their total length
+//   t3 : (MULTI, writing)   index = next 12 bits, entry = sym1 | sym2 << 8 | sym3 << 16 | total length << 24 | n << 28
+// Multi-symbol steps are only taken while more than 12 bits remain before the bound, so the landing point is always
+// the FIRST codeword boundary at or below the bound (single steps finish the span).
+template <bool WRITE, bool MULTI>
+__device__ __forceinline__ SpanResult huf_span(const uint32_t* sw, const uint16_t* t1, const uint8_t* tl, const uint32_t* t3, int maxbits,
+                                               int x_start, int x_bound, uint8_t* out) {
     SpanResult r;
     r.cnt = 0;
     r.end = x_start;
     int rem = x_start - x_bound;
     if (rem <= 0) return r;
-    // window {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q kept in [maxbits, maxbits + 32)
-    int qi = ((x_start - maxbits) >> 5);
+    // window {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q kept in [12, 44)
+    int qi = ((x_start - HUF_W) >> 5);
     int rr = x_start - (qi << 5);
     uint32_t lo = sw[qi], hi = sw[qi + 1];
-    const uint32_t mask = (1u << maxbits) - 1u;
+    const int sh1 = HUF_W - maxbits;
     int cnt = 0;
+    if (MULTI) {
+        while (rem > HUF_W) {
+            const uint32_t idx = __funnelshift_r(lo, hi, rr - HUF_W) & 0xFFFu;
+            int len;
+            if (WRITE) {
+                const uint32_t e = t3[idx];
+                const int n = (int)(e >> 28);
+                len = (int)(e >> 24) & 15;
+                out[cnt] = (uint8_t)e;
+                if (n > 1) out[cnt + 1] = (uint8_t)(e >> 8);
+                if (n > 2) out[cnt + 2] = (uint8_t)(e >> 16);
+                cnt += n;
+            } else {
+                const uint32_t e = tl[idx];
+                len = (int)(e & 15u);
+                cnt += (int)(e >> 4);
+            }
+            rr -= len;
+            rem -= len;
+            if (rr < HUF_W) { hi = lo; lo = sw[--qi]; rr += 32; }
+        }
+    }
     while (rem > 0) {
-        uint32_t idx = __funnelshift_r(lo, hi, rr - maxbits) & mask;
-        uint32_t e = table[idx];
-        int len = e & 0xFF;
+        const uint32_t idx = (__funnelshift_r(lo, hi, rr - HUF_W) & 0xFFFu) >> sh1;
+        const uint32_t e = t1[idx];
+        const int len = (int)(e & 0xFFu);
         if (WRITE) out[cnt] = (uint8_t)(e >> 8);
         cnt++;
         rr -= len;
         rem -= len;
-        if (rr < maxbits) { hi = lo; lo = sw[--qi]; rr += 32; }
+        if (rr < HUF_W) { hi = lo; lo = sw[--qi]; rr += 32; }
     }
     r.cnt = cnt;
     r.end = x_bound + rem;
@@ -307,7 +337,10 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);                    // [8 symbol groups][16 weights]
     uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] count scan, [34..49] warp start candidates
     uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [NWARPS] composed map of each warp; reuses wcnt after the table build
-    uint8_t* sout = smem + 4096 + 768;
+    constexpr bool MULTI = HUF_T == HUF_T_BIG;
+    uint8_t* tl = smem + 4096 + 768;                                     // MULTI only
+    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768 + 4096);               // MULTI only
+    uint8_t* sout = smem + 4096 + 768 + huf_multi_bytes(HUF_T);
     uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -370,6 +403,25 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
         }
     }
     __syncthreads();
+    if (MULTI) {
+        // multi-symbol tables over 12-bit windows: decode the window with the base table while whole codewords fit
+        const int sh1 = HUF_W - maxbits;
+        for (uint32_t i = tid; i < (1u << HUF_W); i += HUF_T) {
+            uint32_t used = 0, n = 0, syms = 0, used3 = 0, n3 = 0;
+            for (;;) {
+                const uint32_t e = table[((i << used) & 0xFFFu) >> sh1];
+                const uint32_t len = e & 0xFFu;
+                if (used + len > (uint32_t)HUF_W) break;
+                if (n < 3) { syms |= (e >> 8) << (8 * n); used3 = used + len; n3 = n + 1; }
+                used += len; n++;
+                if (used == (uint32_t)HUF_W) break;
+            }
+            // every window holds at least one whole codeword (max_bits <= 11 < 12)
+            tl[i] = (uint8_t)((n << 4) | used);
+            t3[i] = syms | (used3 << 24) | (n3 << 28);
+        }
+        __syncthreads();
+    }
     HUF_TICK(2);
 
     // ---- phase 1: transition map of every range -------------------------------------------------------------------------
@@ -396,7 +448,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
             for (int k = 0; k < MAXC; k++) {
                 if (live & (1u << k)) {
                     const int q = q0 + (int)(pc[k] & 0xFFFFu);
-                    SpanResult r = huf_span<false>(scomp, table, maxbits, XTOP - q, XTOP - l, nullptr);
+                    SpanResult r = huf_span<false, MULTI>(scomp, table, tl, t3, maxbits, XTOP - q, XTOP - l, nullptr);
                     pc[k] = (uint32_t)((XTOP - r.end) - q0) | ((pc[k] & 0xFFFF0000u) + ((uint32_t)r.cnt << 16));
                 }
             }
@@ -481,7 +533,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     uint8_t* dst = ((B.n_seq == 0) ? (J.out + J.bstate[it.block].out_off) : (J.lit + B.lit_base)) + it.dst_off;
     const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
     HUF_TICK(4);
-    if (mycnt) huf_span<true>(scomp, table, maxbits, XTOP - (q0 + (int)ktrue), XTOP - qe, sout + a2 + off);
+    if (mycnt) huf_span<true, MULTI>(scomp, table, tl, t3, maxbits, XTOP - (q0 + (int)ktrue), XTOP - qe, sout + a2 + off);
     __syncthreads();
     HUF_TICK(5);
     // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends --------------------
