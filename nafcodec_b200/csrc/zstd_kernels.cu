@@ -120,70 +120,124 @@ __device__ __forceinline__ uint32_t encode_off(RepSym r) {
     return r.src < 0 ? r.val : (OFF_SYMBOLIC | ((uint32_t)r.src << 29) | (r.val & 0x1FFFFFFFu));
 }
 
+// Backward bit reader over a shared-memory image of the bitstream (32-bit words; >= 16 zero bytes below bit 0).
+// 64-bit register window, refilled 32 bits at a time; read(k) for k <= 32.
+struct SmemBits {
+    const uint32_t* sw;
+    uint64_t w;          // stream bits [32*qi, 32*qi + 64)
+    int qi, rr;          // rr = x - 32*qi, position of the next unread bit inside the window (kept in [32, 64] before a read)
+    int x_zero;          // smem bit position of stream bit 0
+    __device__ __forceinline__ void init(const uint32_t* words, int x, int xz) {
+        sw = words; x_zero = xz;
+        qi = (x >> 5) - 1;
+        rr = x - (qi << 5);
+        w = ((uint64_t)sw[qi + 1] << 32) | sw[qi];
+    }
+    __device__ __forceinline__ uint32_t read(int k) {
+        if (rr < k) { w = (w << 32) | sw[--qi]; rr += 32; }
+        rr -= k;
+        return k ? (uint32_t)(w >> rr) & (k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u)) : 0u;
+    }
+    __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
+};
+
+constexpr uint32_t SEQ_STAGE_BYTES = 12 * 1024;   // sequence bitstreams up to this size are staged in shared memory
+
 __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
+    __shared__ __align__(16) uint32_t sbits[SEQ_STAGE_BYTES / 4 + 16];
+    __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
     if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
-    if (threadIdx.x != 0) return;
     if (J.frame_bad[B.frame]) return;
+    const int lane = threadIdx.x;
     BlockState& S = J.bstate[bi];
     const uint8_t* src = J.comp + B.src_off;
-    BackBits bb;
-    if (S.seq_bits_off >= B.src_size || !bb.init(src + S.seq_bits_off, B.src_size - S.seq_bits_off)) {
-        flag_error(J, B.frame, zc::E_SEQ_STREAM);
-        return;
+    if (S.seq_bits_off >= B.src_size) { if (lane == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    const uint32_t nbytes = B.src_size - S.seq_bits_off;
+    const uint8_t* g = src + S.seq_bits_off;
+    const bool staged = nbytes <= SEQ_STAGE_BYTES - 48;
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    int al[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        al[k] = J.table_al[B.tbl[k]];
+        const uint2* T = (const uint2*)(J.tables + (size_t)B.tbl[k] * FSE_SLOT_CELLS);
+        for (int i = lane; i < (1 << al[k]); i += 32) ((uint2*)stab[k])[i] = T[i];
     }
-    const SeqCell* TLL = J.tables + (size_t)B.tbl[0] * FSE_SLOT_CELLS;
-    const SeqCell* TOF = J.tables + (size_t)B.tbl[1] * FSE_SLOT_CELLS;
-    const SeqCell* TML = J.tables + (size_t)B.tbl[2] * FSE_SLOT_CELLS;
-    uint32_t sLL = bb.read(J.table_al[B.tbl[0]]);
-    uint32_t sOF = bb.read(J.table_al[B.tbl[1]]);
-    uint32_t sML = bb.read(J.table_al[B.tbl[2]]);
+    if (staged) {
+        const uint4* gbase = (const uint4*)(g - a);
+        const uint32_t nchunks = (a + nbytes + 15) >> 4;
+        for (uint32_t c = lane; c < nchunks; c += 32) ((uint4*)sbits)[1 + c] = gbase[c];
+        __syncwarp();
+        if ((uint32_t)lane < 16 + a) ((uint8_t*)sbits)[lane] = 0;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    const uint8_t last = g[nbytes - 1];
+    if (last == 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    const int P0 = 8 * (int)(nbytes - 1) + zc::highbit32(last);
+    const SeqCell* TLL = stab[0];
+    const SeqCell* TOF = stab[1];
+    const SeqCell* TML = stab[2];
     RepSym rep[3] = {{0, 0}, {1, 0}, {2, 0}};
     uint32_t litpos = 0, outpos = 0;
     const uint32_t n = B.n_seq, base = B.seq_base;
     bool bad = false;
-    for (uint32_t i = 0; i < n; i++) {
-        SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];
-        uint32_t ov = cOF.base_value + bb.read(cOF.add_bits);
-        uint32_t ml = cML.base_value + bb.read(cML.add_bits);
-        uint32_t ll = cLL.base_value + bb.read(cLL.add_bits);
-        RepSym off;
-        if (ov > 3) {
-            off.src = -1; off.val = ov - 3;
-            rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-        } else {
-            uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
-            if (idx == 0) {
-                off = rep[0];
-            } else if (idx == 1) {
-                off = rep[1]; rep[1] = rep[0]; rep[0] = off;
-            } else if (idx == 2) {
-                off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-            } else {
-                off = rep[0];
-                if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; }
-                else off.val += 1;
-                rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-            }
-        }
-        if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
-        if (i + 1 < n) {
-            sLL = cLL.next_base + bb.read(cLL.nb);
-            sML = cML.next_base + bb.read(cML.nb);
-            sOF = cOF.next_base + bb.read(cOF.nb);
-        }
-        J.seq_ll[base + i] = ll;
-        J.seq_ml[base + i] = ml;
-        J.seq_off[base + i] = encode_off(off);
-        J.seq_litpos[base + i] = litpos;
-        J.seq_outpos[base + i] = outpos;
-        J.seq_block[base + i] = bi;
-        litpos += ll;
-        outpos += ll + ml;
-        if (bb.P < 0 || outpos > BLOCK_MAX) { bad = true; break; }
+    int left;
+    // the loop body is written once over a reader type: shared-memory window (common) or global memory (huge sections)
+#define SEQ_LOOP(RD)                                                                                       \
+    uint32_t sLL = RD.read(al[0]), sOF = RD.read(al[1]), sML = RD.read(al[2]);                             \
+    for (uint32_t i = 0; i < n; i++) {                                                                     \
+        const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];                                      \
+        const uint32_t ov = cOF.base_value + RD.read(cOF.add_bits);                                        \
+        const uint32_t ml = cML.base_value + RD.read(cML.add_bits);                                        \
+        const uint32_t ll = cLL.base_value + RD.read(cLL.add_bits);                                        \
+        RepSym off;                                                                                        \
+        if (ov > 3) {                                                                                      \
+            off.src = -1; off.val = ov - 3;                                                                \
+            rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;                                                \
+        } else {                                                                                           \
+            const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);                                             \
+            if (idx == 0) { off = rep[0]; }                                                                \
+            else if (idx == 1) { off = rep[1]; rep[1] = rep[0]; rep[0] = off; }                            \
+            else if (idx == 2) { off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }           \
+            else {                                                                                         \
+                off = rep[0];                                                                              \
+                if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; } else off.val += 1;        \
+                rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;                                            \
+            }                                                                                              \
+        }                                                                                                  \
+        if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;                                             \
+        if (i + 1 < n) {                                                                                   \
+            sLL = cLL.next_base + RD.read(cLL.nb);                                                         \
+            sML = cML.next_base + RD.read(cML.nb);                                                         \
+            sOF = cOF.next_base + RD.read(cOF.nb);                                                         \
+        }                                                                                                  \
+        J.seq_ll[base + i] = ll;                                                                           \
+        J.seq_ml[base + i] = ml;                                                                           \
+        J.seq_off[base + i] = encode_off(off);                                                             \
+        J.seq_litpos[base + i] = litpos;                                                                   \
+        J.seq_outpos[base + i] = outpos;                                                                   \
+        J.seq_block[base + i] = bi;                                                                        \
+        litpos += ll;                                                                                      \
+        outpos += ll + ml;                                                                                 \
+        if (outpos > BLOCK_MAX) { bad = true; break; }                                                     \
     }
-    if (bad || bb.P != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    if (staged) {
+        SmemBits rd;
+        const int xz = (int)(16 + a) * 8;
+        rd.init(sbits, xz + P0, xz);
+        SEQ_LOOP(rd)
+        left = rd.remaining();
+    } else {
+        BackBits rd;
+        rd.init(g, nbytes);
+        SEQ_LOOP(rd)
+        left = (int)rd.P;
+    }
+#undef SEQ_LOOP
+    if (bad || left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
     if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
     uint32_t regen = outpos + (B.lit_regen - litpos);
     if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
@@ -530,20 +584,48 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     const uint32_t off = inc - mycnt + misc[warp];
     const uint32_t total = misc[32];
     if (any_bad || total != it.n_sym) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
-    uint8_t* dst = ((B.n_seq == 0) ? (J.out + J.bstate[it.block].out_off) : (J.lit + B.lit_base)) + it.dst_off;
-    const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
+    // destination: literal-only blocks are contiguous output; blocks with sequences get every literal run scattered to
+    // its final position right here (no literal staging buffer, no separate copy pass)
+    const bool scatter = B.n_seq != 0;
+    uint8_t* blk_out = J.out + J.bstate[it.block].out_off;
+    uint8_t* dst = blk_out + it.dst_off;
+    const uint32_t a2 = scatter ? 0u : (uint32_t)((uintptr_t)dst & 15);
     HUF_TICK(4);
     if (mycnt) huf_span<true, MULTI>(scomp, table, tl, t3, maxbits, XTOP - (q0 + (int)ktrue), XTOP - qe, sout + a2 + off);
     __syncthreads();
     HUF_TICK(5);
-    // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends --------------------
-    const uint32_t n = it.n_sym, endb = a2 + n;
-    uint8_t* dal = dst - a2;
-    const uint32_t first_full = a2 ? 1u : 0u, last_full = endb >> 4;     // chunks [first_full, last_full) are complete
-    for (uint32_t c = first_full + tid; c < last_full; c += HUF_T) ((uint4*)dal)[c] = ((const uint4*)sout)[c];
-    if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HUF_T) dal[k] = sout[k]; }
-    if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
-        for (uint32_t k = (last_full << 4) + tid; k < endb; k += HUF_T) dal[k] = sout[k];
+    if (!scatter) {
+        // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends ----------------
+        const uint32_t n = it.n_sym, endb = a2 + n;
+        uint8_t* dal = dst - a2;
+        const uint32_t first_full = a2 ? 1u : 0u, last_full = endb >> 4;     // chunks [first_full, last_full) are complete
+        for (uint32_t c = first_full + tid; c < last_full; c += HUF_T) ((uint4*)dal)[c] = ((const uint4*)sout)[c];
+        if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HUF_T) dal[k] = sout[k]; }
+        if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
+            for (uint32_t k = (last_full << 4) + tid; k < endb; k += HUF_T) dal[k] = sout[k];
+    } else {
+        // this stream holds literals [L0, L1) of the block; sequence j owns literals [lp_j, lp_j + ll_j) -> output outpos_j
+        const uint32_t L0 = it.dst_off, L1 = it.dst_off + it.n_sym;
+        const uint32_t nseq = B.n_seq, sb = B.seq_base;
+        uint32_t lo = 0, hi = nseq;                                      // first sequence whose literals end after L0
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (J.seq_litpos[sb + mid] + J.seq_ll[sb + mid] > L0) hi = mid; else lo = mid + 1;
+        }
+        for (uint32_t j = lo + warp; j <= nseq; j += NWARPS) {            // j == nseq: the literals after the last sequence
+            uint32_t lp, ll, op;
+            if (j < nseq) { lp = J.seq_litpos[sb + j]; ll = J.seq_ll[sb + j]; op = J.seq_outpos[sb + j]; }
+            else {
+                const uint32_t t = sb + nseq - 1;
+                lp = J.seq_litpos[t] + J.seq_ll[t]; ll = B.lit_regen - lp; op = J.seq_outpos[t] + J.seq_ll[t] + J.seq_ml[t];
+            }
+            if (lp >= L1) break;
+            const uint32_t b0 = lp > L0 ? lp : L0, b1 = (lp + ll < L1) ? lp + ll : L1;
+            uint8_t* o = blk_out + op + (b0 - lp);
+            const uint8_t* sp = sout + (b0 - L0);
+            for (uint32_t k = lane; b0 + k < b1; k += 32) o[k] = sp[k];
+        }
+    }
     HUF_TICK(6);
 }
 
@@ -567,15 +649,15 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         for (uint32_t i = tid; i < B.src_size; i += nt) out[i] = v;
         return;
     }
+    const bool huf = B.lit_type >= LT_HUF;           // Huffman literals were placed by k_huf_decode
     const uint8_t* lsrc = nullptr;
     uint8_t rle = 0;
     if (B.lit_type == LT_RAW) lsrc = J.comp + B.src_off + B.lit_src;
     else if (B.lit_type == LT_RLE) rle = J.comp[B.src_off + B.lit_src];
-    else lsrc = J.lit + B.lit_base;
     if (B.n_seq == 0) {
         if (B.lit_type == LT_RAW) copy_bytes(out, lsrc, B.lit_regen, tid, nt);
         else if (B.lit_type == LT_RLE) for (uint32_t i = tid; i < B.lit_regen; i += nt) out[i] = rle;
-        return;                                        // Huffman literals were decoded in place
+        return;
     }
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     const uint32_t n = B.n_seq, base = B.seq_base;
@@ -583,13 +665,14 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         uint32_t lp, op, ll;
         if (i < n) {
             lp = J.seq_litpos[base + i]; op = J.seq_outpos[base + i]; ll = J.seq_ll[base + i];
-            if (lane == 0) J.match_pos[base + i] = S.out_off + op + ll;
+            if (lane == 0) J.match_pos[base + i] = S.out_off + op + ll;     // absolute destination of the match
         } else {                                       // literals after the last sequence
             uint32_t j = base + n - 1;
             lp = J.seq_litpos[j] + J.seq_ll[j];
             op = J.seq_outpos[j] + J.seq_ll[j] + J.seq_ml[j];
             ll = B.lit_regen - lp;
         }
+        if (huf) continue;
         if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += 32) out[op + k] = rle;
         else for (uint32_t k = lane; k < ll; k += 32) out[op + k] = lsrc[lp + k];
     }
@@ -606,55 +689,73 @@ __device__ __forceinline__ uint32_t resolve_offset(const JobDev& J, uint32_t v, 
 
 // bytes [d, d+ml) <- periodic extension of [d-off, d): byte k comes from d-off + (k mod off); all sources lie
 // strictly below d, so the copy has no intra-match hazard even when off < ml.
-__device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t off, uint32_t ml, int lane) {
+__device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t off, uint32_t ml, int lane, int nlanes) {
     const uint8_t* s = out + d - off;
     if (off >= ml) {
-        for (uint32_t k = lane; k < ml; k += 32) out[d + k] = s[k];
+        for (uint32_t k = lane; k < ml; k += nlanes) out[d + k] = s[k];
     } else {
-        for (uint32_t k = lane; k < ml; k += 32) out[d + k] = s[k % off];
+        for (uint32_t k = lane; k < ml; k += nlanes) out[d + k] = s[k % off];
     }
 }
 
-// k_lz_pass: one warp per pending match.  A match may run in pass p if every earlier match whose destination
-// intersects its source range finished in a pass < p (literals are all final before pass 1).
-__global__ void __launch_bounds__(256) k_lz_pass(JobDev J, uint32_t pass) {
+// k_lz_pass: ONE THREAD per pending match.  A match may run in pass p if every earlier match whose destination
+// intersects its source range finished in a pass < p (all literals are final before pass 1).  Short matches (the
+// common case: a few tens of bytes) are copied by their own thread; long ones (N stretches: offset 1, ~100 KB) are
+// queued in shared memory and copied by the whole CTA.
+constexpr uint32_t LZ_SHORT = 64;
+constexpr int LZ_CTA = 256;
+
+__global__ void __launch_bounds__(LZ_CTA) k_lz_pass(JobDev J, uint32_t pass) {
     if (pass > 1 && J.remaining[pass - 1] == 0) return;
-    const int lane = threadIdx.x & 31;
-    const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= J.n_seq) return;
-    if (J.seq_done[i]) return;
-    const uint32_t bi = J.seq_block[i];
-    const BlockDesc& B = J.blocks[bi];
-    if (J.frame_bad[B.frame]) return;
-    const FrameDesc& F = J.frames[B.frame];
-    const uint32_t ml = J.seq_ml[i];
-    const uint32_t off = resolve_offset(J, J.seq_off[i], bi);
-    const uint64_t d = J.match_pos[i];
-    if (off == 0 || (uint64_t)off > d - F.dst_off) {
-        __syncwarp();                                     // every lane has read seq_done[i] before lane 0 rewrites it
-        if (lane == 0) { flag_error(J, B.frame, zc::E_OFFSET); J.seq_done[i] = pass; }
-        return;
+    __shared__ uint32_t q_n;
+    __shared__ uint64_t q_d[LZ_CTA];
+    __shared__ uint32_t q_off[LZ_CTA], q_ml[LZ_CTA], q_i[LZ_CTA];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) q_n = 0;
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * LZ_CTA + tid;
+    bool pending = false;
+    if (i < J.n_seq && J.seq_done[i] == 0) {
+        const uint32_t bi = J.seq_block[i];
+        const BlockDesc& B = J.blocks[bi];
+        if (!J.frame_bad[B.frame]) {
+            const FrameDesc& F = J.frames[B.frame];
+            const uint32_t ml = J.seq_ml[i];
+            const uint32_t off = resolve_offset(J, J.seq_off[i], bi);
+            const uint64_t d = J.match_pos[i];
+            if (off == 0 || (uint64_t)off > d - F.dst_off) {
+                flag_error(J, B.frame, zc::E_OFFSET);
+                J.seq_done[i] = pass;
+            } else {
+                const uint64_t s = d - off;
+                const uint64_t e = (off < ml) ? d : s + ml;           // external source range [s, e)
+                uint64_t lo = F.first_seq, hi = i;                    // first earlier match (same frame) ending after s
+                while (lo < hi) {
+                    uint64_t mid = (lo + hi) >> 1;
+                    if (J.match_pos[mid] + J.seq_ml[mid] > s) hi = mid; else lo = mid + 1;
+                }
+                bool ready = true;
+                for (uint64_t j = lo; j < i && J.match_pos[j] < e; j++) {
+                    uint32_t dn = J.seq_done[j];
+                    if (dn == 0 || dn >= pass) { ready = false; break; }
+                }
+                if (!ready) pending = true;
+                else if (ml <= LZ_SHORT) {
+                    copy_match(J.out, d, off, ml, 0, 1);
+                    J.seq_done[i] = pass;
+                } else {
+                    uint32_t slot = atomicAdd(&q_n, 1u);
+                    q_d[slot] = d; q_off[slot] = off; q_ml[slot] = ml; q_i[slot] = (uint32_t)i;
+                }
+            }
+        }
     }
-    const uint64_t s = d - off;
-    const uint64_t e = (off < ml) ? d : s + ml;           // external source range [s, e)
-    // first earlier match j (same frame) whose destination ends after s
-    uint64_t lo = F.first_seq, hi = i;
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (J.match_pos[mid] + J.seq_ml[mid] > s) hi = mid; else lo = mid + 1;
-    }
-    bool ready = true;
-    for (uint64_t j = lo; j < i && J.match_pos[j] < e; j++) {
-        uint32_t dn = J.seq_done[j];
-        if (dn == 0 || dn >= pass) { ready = false; break; }
-    }
-    if (!ready) {
-        if (lane == 0) atomicAdd(&J.remaining[pass], 1u);
-        return;
-    }
-    copy_match(J.out, d, off, ml, lane);
-    __syncwarp();                                         // (also orders the lanes' reads of seq_done[i] before the write)
-    if (lane == 0) J.seq_done[i] = pass;
+    const uint32_t pb = __ballot_sync(0xFFFFFFFFu, pending);
+    if (lane == 0 && pb) atomicAdd(&J.remaining[pass], (uint32_t)__popc(pb));
+    __syncthreads();
+    const uint32_t nq = q_n;
+    for (uint32_t k = 0; k < nq; k++) copy_match(J.out, q_d[k], q_off[k], q_ml[k], tid, LZ_CTA);
+    if ((uint32_t)tid < nq) J.seq_done[q_i[tid]] = pass;
 }
 
 // k_lz_sequential: ordered fallback, one warp per frame, for dependency chains deeper than LZ_PASSES.
@@ -674,7 +775,7 @@ __global__ void __launch_bounds__(32) k_lz_sequential(JobDev J) {
             if (lane == 0) flag_error(J, f, zc::E_OFFSET);
             return;
         }
-        copy_match(J.out, d, off, ml, lane);
+        copy_match(J.out, d, off, ml, lane, 32);
         __syncwarp();
         if (lane == 0) J.seq_done[i] = LZ_PASSES + 1;
         __syncwarp();
@@ -702,9 +803,8 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
     ev->mark();
     NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
-        const uint32_t warps = 8;
-        uint32_t grid = (uint32_t)((J.n_seq + warps - 1) / warps);
-        for (uint32_t p = 1; p <= (uint32_t)LZ_PASSES; p++) { NAF_LAUNCH(k_lz_pass, grid, warps * 32, 0, st, J, p); launches++; }
+        uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
+        for (uint32_t p = 1; p <= (uint32_t)LZ_PASSES; p++) { NAF_LAUNCH(k_lz_pass, grid, LZ_CTA, 0, st, J, p); launches++; }
         ev->mark();
         NAF_LAUNCH(k_lz_sequential, J.n_frames, 32, 0, st, J); launches++; ev->mark();
     } else { ev->mark(); ev->mark(); }
