@@ -369,6 +369,27 @@ __device__ __forceinline__ SpanResult huf_span(const uint32_t* sw, const uint16_
     return r;
 }
 
+// Warp-cooperative copy of n bytes from shared memory (any alignment) to global memory: destination-aligned 16-byte
+// stores, each assembled from five shared-memory words with funnel shifts; ragged ends go byte-wise.
+// The shared buffer must be readable 20 bytes past the last source byte.
+__device__ __forceinline__ void warp_copy_s2g(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane) {
+    if (n < 48) { for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k]; return; }
+    const uint32_t h = (uint32_t)(-(intptr_t)dst) & 15u;
+    if ((uint32_t)lane < h) dst[lane] = src[lane];
+    const uint32_t body = (n - h) >> 4;
+    const uintptr_t sa = (uintptr_t)(src + h);
+    const uint32_t* sw = (const uint32_t*)(sa & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(sa & 3) * 8;
+    uint4* d4 = (uint4*)(dst + h);
+    for (uint32_t c = lane; c < body; c += 32) {
+        const uint32_t* p = sw + 4 * c;
+        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
+        d4[c] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    const uint32_t done = h + (body << 4);
+    for (uint32_t k = done + lane; k < n; k += 32) dst[k] = src[k];
+}
+
 // maps over candidate indices 0..15 packed as 4-bit fields; compose(g, f)(k) = g(f(k))
 __device__ __forceinline__ uint64_t map_compose(uint64_t g, uint64_t f) {
     uint64_t r = 0;
@@ -496,7 +517,8 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
 #pragma unroll
     for (int k = 0; k < MAXC; k++) { pc[k] = (uint32_t)k; mg[k] = 0; }
     if (active) {
-        for (int lim = q0 + HUF_SEG;; lim += HUF_SEG) {
+        // first stop right below the candidate window: tracks on the same codeword chain coincide there
+        for (int lim = q0 + HUF_W;; lim += HUF_SEG) {
             const int l = lim < qe ? lim : qe;
 #pragma unroll
             for (int k = 0; k < MAXC; k++) {
@@ -506,7 +528,18 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
                     pc[k] = (uint32_t)((XTOP - r.end) - q0) | ((pc[k] & 0xFFFF0000u) + ((uint32_t)r.cnt << 16));
                 }
             }
-            if (live & (live - 1)) {                                    // more than one live track: merge equal positions
+            if ((live & (live - 1)) && !(live & ~15u)) {                // common steady state: at most tracks 0..3 alive
+#pragma unroll
+                for (int k = 1; k < 4; k++) {
+#pragma unroll
+                    for (int j = 0; j < k; j++) {
+                        if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
+                            live &= ~(1u << k);
+                            mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
+                        }
+                    }
+                }
+            } else if (live & (live - 1)) {                             // more than one live track: merge equal positions
 #pragma unroll
                 for (int k = 1; k < MAXC; k++) {
                     if (live & (1u << k)) {
@@ -621,9 +654,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
             }
             if (lp >= L1) break;
             const uint32_t b0 = lp > L0 ? lp : L0, b1 = (lp + ll < L1) ? lp + ll : L1;
-            uint8_t* o = blk_out + op + (b0 - lp);
-            const uint8_t* sp = sout + (b0 - L0);
-            for (uint32_t k = lane; b0 + k < b1; k += 32) o[k] = sp[k];
+            if (b1 > b0) warp_copy_s2g(blk_out + op + (b0 - lp), sout + (b0 - L0), b1 - b0, lane);
         }
     }
     HUF_TICK(6);
