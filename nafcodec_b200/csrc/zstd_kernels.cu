@@ -304,69 +304,106 @@ constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
 constexpr int HUF_SEG = 96;                       // tracks are compared for merging every HUF_SEG bits
 constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
 __host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : HUF_SMALL_MAX_SYM) + 64u; }
-// t1 4096 | weights 256 | wcnt 256 | misc 256 | [big only: tl 4096 | t3 16384] | output image | (dynamic) compressed stream image
-__host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return T == HUF_T_BIG ? 4096u + 16384u : 0u; }
+// t1 4096 | weights 256 | wcnt 256 | misc 256 | bm 8192 | [big only: t3 16384] | output image | (dynamic) compressed stream image
+__host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return 8192u + (T == HUF_T_BIG ? 16384u : 0u); }
 __host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 768u + huf_multi_bytes(T) + huf_sout_bytes(T); }
 
-struct SpanResult { int end; int cnt; };
+// ---- shared-memory access by explicit shared-space address ---------------------------------------------------------
+// The hot loops below address shared memory through 32-bit shared-space addresses and ld.shared PTX: with generic
+// pointers nvcc re-derives the shared window base inside the loops (S2R SR_CgaCtaId + LEA per access, seen in SASS).
+#if defined(__CUDA_ARCH__)
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t to_saddr(const void* p) { return (saddr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(saddr_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+#else
+typedef uintptr_t saddr_t;
+static inline saddr_t to_saddr(const void* p) { return (saddr_t)p; }
+static inline uint32_t lds32(saddr_t a) { return *(const uint32_t*)a; }
+static inline uint32_t lds16(saddr_t a) { return *(const uint16_t*)a; }
+static inline void sts8(saddr_t a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
+#endif
 
 constexpr int HUF_W = 12;                          // index width of the multi-symbol tables
 
-// Decodes from absolute smem bit position x_start down to the first codeword boundary <= x_bound.
-//   t1 : base table, index = next max_bits bits, entry = symbol << 8 | length
-//   tl : (MULTI, counting)  index = next 12 bits, entry = symbols that fit << 4 | their total length
-//   t3 : (MULTI, writing)   index = next 12 bits, entry = sym1 | sym2 << 8 | sym3 << 16 | total length << 24 | n << 28
-// Multi-symbol steps are only taken while more than 12 bits remain before the bound, so the landing point is always
-// the FIRST codeword boundary at or below the bound (single steps finish the span).
-template <bool WRITE, bool MULTI>
-__device__ __forceinline__ SpanResult huf_span(const uint32_t* sw, const uint16_t* t1, const uint8_t* tl, const uint32_t* t3, int maxbits,
-                                               int x_start, int x_bound, uint8_t* out) {
-    SpanResult r;
-    r.cnt = 0;
-    r.end = x_start;
-    int rem = x_start - x_bound;
-    if (rem <= 0) return r;
-    // window {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q kept in [12, 44)
-    int qi = ((x_start - HUF_W) >> 5);
-    int rr = x_start - (qi << 5);
-    uint32_t lo = sw[qi], hi = sw[qi + 1];
-    const int sh1 = HUF_W - maxbits;
+// 64-bit register window over the stream image: {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q in [12, 44).
+struct Win {
+    saddr_t waddr;      // shared address of the `lo` word
+    uint32_t lo, hi;
+    int rr;
+};
+__device__ __forceinline__ void win_init(Win& w, saddr_t comp, int x) {
+    const int qi = (x - HUF_W) >> 5;
+    w.waddr = comp + 4 * qi;
+    w.lo = lds32(w.waddr);
+    w.hi = lds32(w.waddr + 4);
+    w.rr = x - (qi << 5);
+}
+__device__ __forceinline__ uint32_t win_peek(const Win& w) { return __funnelshift_r(w.lo, w.hi, w.rr - HUF_W) & 0xFFFu; }
+__device__ __forceinline__ void win_consume(Win& w, int len) {
+    w.rr -= len;
+    if (w.rr < HUF_W) { w.hi = w.lo; w.waddr -= 4; w.lo = lds32(w.waddr); w.rr += 32; }
+}
+
+// Follows one track from q (bits below the top of the stream) to the FIRST codeword boundary >= lim, counting symbols.
+// bm: boundary-mask table, index = next 12 bits, bit j set <=> j+1 bits is a cumulative length of whole codewords.
+__device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, int& q, int& cnt, int lim) {
+    int rem = lim - q;
+    if (rem <= 0) return;
+    Win w;
+    win_init(w, comp, xtop - q);
+    for (;;) {
+        const uint32_t m = lds16(bm + 2 * win_peek(w));
+        if (rem <= HUF_W) {
+            const uint32_t t = m >> (rem - 1);                 // boundaries at or past the limit
+            if (t) {
+                const int j = __ffs((int)t) - 1 + rem - 1;
+                cnt += __popc(m & ((2u << j) - 1u));
+                rem -= j + 1;
+                break;
+            }
+        }
+        const int used = 32 - __clz((int)m);                   // every window holds >= 1 whole codeword (max_bits <= 11)
+        cnt += __popc(m);
+        rem -= used;
+        win_consume(w, used);
+    }
+    q = lim - rem;
+}
+
+// Write pass: decodes from q to the first boundary >= lim, storing symbols at out.. (shared address). Returns the count.
+//   t3: index = next 12 bits, entry = sym1 | sym2 << 8 | sym3 << 16 | total length << 24 | n << 28
+//   t1: index = next max_bits bits, entry = symbol << 8 | length
+template <bool MULTI>
+__device__ __forceinline__ int track_write(saddr_t comp, saddr_t t3, saddr_t t1, int maxbits, int xtop, int q, int lim, saddr_t out) {
+    int rem = lim - q;
+    if (rem <= 0) return 0;
+    Win w;
+    win_init(w, comp, xtop - q);
     int cnt = 0;
     if (MULTI) {
         while (rem > HUF_W) {
-            const uint32_t idx = __funnelshift_r(lo, hi, rr - HUF_W) & 0xFFFu;
-            int len;
-            if (WRITE) {
-                const uint32_t e = t3[idx];
-                const int n = (int)(e >> 28);
-                len = (int)(e >> 24) & 15;
-                out[cnt] = (uint8_t)e;
-                if (n > 1) out[cnt + 1] = (uint8_t)(e >> 8);
-                if (n > 2) out[cnt + 2] = (uint8_t)(e >> 16);
-                cnt += n;
-            } else {
-                const uint32_t e = tl[idx];
-                len = (int)(e & 15u);
-                cnt += (int)(e >> 4);
-            }
-            rr -= len;
+            const uint32_t e = lds32(t3 + 4 * win_peek(w));
+            const int n = (int)(e >> 28), len = (int)(e >> 24) & 15;
+            sts8(out + cnt, e);
+            if (n > 1) sts8(out + cnt + 1, e >> 8);
+            if (n > 2) sts8(out + cnt + 2, e >> 16);
+            cnt += n;
             rem -= len;
-            if (rr < HUF_W) { hi = lo; lo = sw[--qi]; rr += 32; }
+            win_consume(w, len);
         }
     }
+    const int sh1 = HUF_W - maxbits;
     while (rem > 0) {
-        const uint32_t idx = (__funnelshift_r(lo, hi, rr - HUF_W) & 0xFFFu) >> sh1;
-        const uint32_t e = t1[idx];
+        const uint32_t e = lds16(t1 + 2 * (win_peek(w) >> sh1));
         const int len = (int)(e & 0xFFu);
-        if (WRITE) out[cnt] = (uint8_t)(e >> 8);
+        sts8(out + cnt, e >> 8);
         cnt++;
-        rr -= len;
         rem -= len;
-        if (rr < HUF_W) { hi = lo; lo = sw[--qi]; rr += 32; }
+        win_consume(w, len);
     }
-    r.cnt = cnt;
-    r.end = x_bound + rem;
-    return r;
+    return cnt;
 }
 
 // Warp-cooperative copy of n bytes from shared memory (any alignment) to global memory: destination-aligned 16-byte
@@ -413,8 +450,8 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] count scan, [34..49] warp start candidates
     uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [NWARPS] composed map of each warp; reuses wcnt after the table build
     constexpr bool MULTI = HUF_T == HUF_T_BIG;
-    uint8_t* tl = smem + 4096 + 768;                                     // MULTI only
-    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768 + 4096);               // MULTI only
+    uint16_t* bm = (uint16_t*)(smem + 4096 + 768);                      // boundary masks of 12-bit windows
+    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768 + 8192);               // MULTI only: 3-symbol write table
     uint8_t* sout = smem + 4096 + 768 + huf_multi_bytes(HUF_T);
     uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -478,22 +515,22 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
         }
     }
     __syncthreads();
-    if (MULTI) {
-        // multi-symbol tables over 12-bit windows: decode the window with the base table while whole codewords fit
+    {
+        // tables over 12-bit windows: decode the window with the base table while whole codewords fit
         const int sh1 = HUF_W - maxbits;
         for (uint32_t i = tid; i < (1u << HUF_W); i += HUF_T) {
-            uint32_t used = 0, n = 0, syms = 0, used3 = 0, n3 = 0;
+            uint32_t used = 0, n = 0, syms = 0, used3 = 0, mask = 0;
             for (;;) {
                 const uint32_t e = table[((i << used) & 0xFFFu) >> sh1];
                 const uint32_t len = e & 0xFFu;
                 if (used + len > (uint32_t)HUF_W) break;
-                if (n < 3) { syms |= (e >> 8) << (8 * n); used3 = used + len; n3 = n + 1; }
-                used += len; n++;
+                if (n < 3) { syms |= (e >> 8) << (8 * n); used3 = used + len; n++; }
+                used += len;
+                mask |= 1u << (used - 1);
                 if (used == (uint32_t)HUF_W) break;
             }
-            // every window holds at least one whole codeword (max_bits <= 11 < 12)
-            tl[i] = (uint8_t)((n << 4) | used);
-            t3[i] = syms | (used3 << 24) | (n3 << 28);
+            bm[i] = (uint16_t)mask;
+            if (MULTI) t3[i] = syms | (used3 << 24) | (n << 28);
         }
         __syncthreads();
     }
@@ -516,19 +553,32 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     uint32_t live = active ? ((1u << maxbits) - 1u) : 0u;
 #pragma unroll
     for (int k = 0; k < MAXC; k++) { pc[k] = (uint32_t)k; mg[k] = 0; }
+    const saddr_t s_comp = to_saddr(scomp), s_bm = to_saddr(bm);
     if (active) {
-        // first stop right below the candidate window: tracks on the same codeword chain coincide there
-        for (int lim = q0 + HUF_W;; lim += HUF_SEG) {
+        // stops: right below the candidate window (tracks on the same codeword chain coincide there), one more after
+        // HUF_SEG bits (codes that resynchronise have merged by then), then the end of the range
+        int lim = q0 + HUF_W;
+        for (int stop = 0;; stop++) {
             const int l = lim < qe ? lim : qe;
+            if ((live & (live - 1)) == 0) {                              // a single track left: straight to the end
+                const int k0 = __ffs((int)live) - 1;
+                int q = 0, c = 0;
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) if (k == k0) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
+                track_advance(s_comp, s_bm, XTOP, q, c, qe);
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) if (k == k0) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
+                break;
+            }
 #pragma unroll
             for (int k = 0; k < MAXC; k++) {
                 if (live & (1u << k)) {
-                    const int q = q0 + (int)(pc[k] & 0xFFFFu);
-                    SpanResult r = huf_span<false, MULTI>(scomp, table, tl, t3, maxbits, XTOP - q, XTOP - l, nullptr);
-                    pc[k] = (uint32_t)((XTOP - r.end) - q0) | ((pc[k] & 0xFFFF0000u) + ((uint32_t)r.cnt << 16));
+                    int q = q0 + (int)(pc[k] & 0xFFFFu), c = (int)(pc[k] >> 16);
+                    track_advance(s_comp, s_bm, XTOP, q, c, l);
+                    pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
                 }
             }
-            if ((live & (live - 1)) && !(live & ~15u)) {                // common steady state: at most tracks 0..3 alive
+            if (!(live & ~15u)) {                                        // common steady state: at most tracks 0..3 alive
 #pragma unroll
                 for (int k = 1; k < 4; k++) {
 #pragma unroll
@@ -539,7 +589,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
                         }
                     }
                 }
-            } else if (live & (live - 1)) {                             // more than one live track: merge equal positions
+            } else {
 #pragma unroll
                 for (int k = 1; k < MAXC; k++) {
                     if (live & (1u << k)) {
@@ -554,6 +604,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
                 }
             }
             if (l >= qe) break;
+            lim = stop == 0 ? lim + HUF_SEG : qe;
         }
     }
     // resolve merged tracks (representatives always have a lower index): landing position and symbol count per candidate
@@ -624,7 +675,7 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     uint8_t* dst = blk_out + it.dst_off;
     const uint32_t a2 = scatter ? 0u : (uint32_t)((uintptr_t)dst & 15);
     HUF_TICK(4);
-    if (mycnt) huf_span<true, MULTI>(scomp, table, tl, t3, maxbits, XTOP - (q0 + (int)ktrue), XTOP - qe, sout + a2 + off);
+    if (mycnt) track_write<MULTI>(s_comp, to_saddr(t3), to_saddr(table), maxbits, XTOP, q0 + (int)ktrue, qe, to_saddr(sout) + a2 + off);
     __syncthreads();
     HUF_TICK(5);
     if (!scatter) {
