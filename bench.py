@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--unique", type=int, default=8, help="distinct generated archives per GPU (cycled to fill the batch)")
     ap.add_argument("--residues", type=int, default=5_000_000)
     ap.add_argument("--level", type=int, default=19)
-    ap.add_argument("--single", action="store_true", help="also report single-archive latency")
+    ap.add_argument("--lanes", type=int, default=4, help="contexts (streams) used by the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -272,14 +272,16 @@ def main():
     path_gbs = st.algorithmic_bytes * args.steps / (dev_ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI: pinned host in, pinned host out ------------------------------------------------
-    n = len(archives)
-    arr = (_ffi.Archive * n)(*archives)
-    res = (_ffi.Result * n)()
+    # The batch is split over `--lanes` contexts driven from host threads (the public Pipeline API), so that H2D, kernels
+    # and D2H of different sub-batches overlap; every byte of input and output still crosses PCIe inside the timed region.
+    pipe = N.Pipeline(local, args.lanes, lib)
+    seen = [0]
+
+    def consume(i, r):
+        seen[0] += int(r.total_residues)          # touch the result struct: the pinned output is ready here
 
     def e2e_step():
-        rc = lib.dll.nafgpu_decode_batch(ctx._ctx, arr, n, want, res)
-        if rc:
-            raise RuntimeError(lib.dll.nafgpu_last_error(ctx._ctx).decode())
+        pipe.decode(archives, want, consume)
 
     for _ in range(args.warmup):
         e2e_step()
@@ -291,7 +293,10 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_s = max_over_ranks(e2e_s)
-    st2 = ctx.stats()
+    lane_stats = pipe.stats()
+    h2d_step = sum(int(s.h2d_bytes) for s in lane_stats)
+    d2h_step = sum(int(s.d2h_bytes) for s in lane_stats)
+    assert seen[0] == (args.steps + args.warmup) * ascii_bytes, (seen[0], ascii_bytes)
     e2e_val = world * ascii_bytes * args.steps / e2e_s / 1e9
     clocks = sampler.summary()
 
@@ -327,7 +332,7 @@ def main():
                 "dtype": "u8", "data": "synthetic", "config": workload_config(args, args.batch),
                 "compressed_in_GBps": world * st.compressed_bytes * args.steps / (dev_ms * 1e-3) / 1e9,
                 "path_algorithmic_GBps": path_gbs, "path_frac_of_hbm_peak": path_gbs / peak,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes), "d2h_bytes_per_step": int(st2.d2h_bytes),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "lanes": args.lanes,
                         "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": int(st.kernel_launches) * args.steps,
                 "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -377,6 +377,54 @@ class DecoderBuilder:
         return Decoder(reader, **self._kw())
 
 
+class Pipeline:
+    """Several contexts (CUDA streams) on one GPU fed from host threads: the H2D copy of one sub-batch, the kernels of
+    another and the D2H copy of a third overlap.  This is the intended way to drive a collection of archives through the
+    C ABI ("distinct contexts may be used concurrently from distinct threads", include/nafgpu.h)."""
+
+    def __init__(self, device: int = 0, lanes: int = 3, library: Optional[_ffi.Library] = None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.lib = library or _ffi.default_library()
+        self.ctxs = [Context(device, self.lib) for _ in range(lanes)]
+        self.pool = ThreadPoolExecutor(max_workers=lanes)
+
+    def decode(self, archives, want: int = _ffi.WANT_ALL, consume=None):
+        """Decodes `archives` (list of _ffi.Archive) in len(ctxs) interleaved sub-batches.  `consume(index, result_struct)`
+        is called on the worker thread for every archive while its pinned buffers are valid; without it the results are
+        copied out as ArchiveResult objects."""
+        n, lanes = len(archives), len(self.ctxs)
+        bounds = [(n * k) // lanes for k in range(lanes + 1)]
+        out = [None] * n
+
+        def work(k):
+            lo, hi = bounds[k], bounds[k + 1]
+            if hi == lo:
+                return
+            ctx = self.ctxs[k]
+            cnt = hi - lo
+            arr = (_ffi.Archive * cnt)(*archives[lo:hi])
+            res = (_ffi.Result * cnt)()
+            with ctx._lock:
+                rc = self.lib.dll.nafgpu_decode_batch(ctx._ctx, arr, cnt, want, res)
+                raise_for_status(self.lib, rc, ctx._ctx)
+                for i in range(cnt):
+                    if consume is not None:
+                        consume(lo + i, res[i])
+                    else:
+                        out[lo + i] = ArchiveResult._copy_from(archives[lo + i].header, res[i])
+
+        list(self.pool.map(work, range(lanes)))
+        return out
+
+    def stats(self):
+        return [c.stats() for c in self.ctxs]
+
+    def close(self):
+        self.pool.shutdown()
+        for c in self.ctxs:
+            c.close()
+
+
 def decode_batch(files: Iterable, *, id=True, comment=True, sequence=True, quality=True, mask=True, device: int = 0,
                  _library=None) -> List[ArchiveResult]:
     """Decode many independent archives in one set of kernel launches (the RefSeq-collection shape)."""

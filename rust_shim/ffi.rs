@@ -1,0 +1,100 @@
+//! ffi.rs -- `extern "C"` declarations mirroring include/nafgpu.h 1:1.
+//!
+//! UNBUILT: the build image has no cargo/rustc.  This file documents the binding a maintainer of
+//! althonos/nafcodec would add as `nafcodec/src/decoder/device/ffi.rs` (feature `cuda`).
+#![allow(non_camel_case_types, dead_code)]
+
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const NAFGPU_OK: c_int = 0;
+pub const NAFGPU_ERR_UNEXPECTED_EOF: c_int = -1;
+pub const NAFGPU_ERR_INVALID_DATA: c_int = -2;
+pub const NAFGPU_ERR_PARSE: c_int = -3;
+pub const NAFGPU_ERR_UTF8: c_int = -4;
+pub const NAFGPU_ERR_CUDA: c_int = -5;
+pub const NAFGPU_ERR_NOMEM: c_int = -6;
+pub const NAFGPU_ERR_ARGUMENT: c_int = -7;
+pub const NAFGPU_ERR_NO_DEVICE: c_int = -8;
+pub const NAFGPU_ERR_UNSUPPORTED: c_int = -9;
+
+pub const NAFGPU_WANT_ID: u32 = 1;
+pub const NAFGPU_WANT_COMMENT: u32 = 2;
+pub const NAFGPU_WANT_SEQUENCE: u32 = 4;
+pub const NAFGPU_WANT_QUALITY: u32 = 8;
+pub const NAFGPU_WANT_MASK: u32 = 16;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct nafgpu_header {
+    pub format_version: i32,
+    pub sequence_type: i32,
+    pub flags: u32,
+    pub name_separator: i32,
+    pub line_length: u64,
+    pub number_of_sequences: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct nafgpu_section {
+    pub data: *const u8,
+    pub compressed_size: u64,
+    pub original_size: u64,
+    pub present: i32,
+    pub _pad: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct nafgpu_archive {
+    pub header: nafgpu_header,
+    /// Id, Comment, Length, Mask, Sequence, Quality (decoder/mod.rs:237-242)
+    pub sections: [nafgpu_section; 6],
+}
+
+#[repr(C)]
+pub struct nafgpu_result {
+    pub n_records: u64,
+    pub n_ids: u64,
+    pub n_comments: u64,
+    pub n_lengths: u64,
+    pub total_residues: u64,
+    pub ids: *const u8,
+    pub id_offsets: *const u64,
+    pub comments: *const u8,
+    pub comment_offsets: *const u64,
+    pub lengths: *const u64,
+    pub record_offsets: *const u64,
+    pub sequence: *const u8,
+    pub quality: *const u8,
+    pub first_bad_record: u64,
+    pub record_status: i32,
+    pub _pad: i32,
+}
+
+#[repr(C)]
+pub struct nafgpu_ctx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn nafgpu_ctx_create(device: c_int, out: *mut *mut nafgpu_ctx) -> c_int;
+    pub fn nafgpu_ctx_destroy(ctx: *mut nafgpu_ctx);
+    pub fn nafgpu_last_error(ctx: *const nafgpu_ctx) -> *const c_char;
+    pub fn nafgpu_strerror(status: c_int) -> *const c_char;
+    pub fn nafgpu_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn nafgpu_host_free(p: *mut c_void);
+    pub fn nafgpu_decode(
+        ctx: *mut nafgpu_ctx,
+        archive: *const nafgpu_archive,
+        want: u32,
+        out: *mut nafgpu_result,
+    ) -> c_int;
+    pub fn nafgpu_decode_batch(
+        ctx: *mut nafgpu_ctx,
+        archives: *const nafgpu_archive,
+        n: u32,
+        want: u32,
+        out: *mut nafgpu_result,
+    ) -> c_int;
+}

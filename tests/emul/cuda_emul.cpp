@@ -2,6 +2,7 @@
 #include "cuda_emul.h"
 
 #include <time.h>
+#include <mutex>
 #include <vector>
 
 namespace emul {
@@ -175,6 +176,8 @@ static void run_cta(dim3 block) {
 }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+    static std::mutex mu;                       // the emulator state is global: one kernel at a time
+    std::lock_guard<std::mutex> lock(mu);
     static std::vector<unsigned char> dyn;
     if (dyn.size() < smem + 16) dyn.resize(smem + 16);
     g_dyn_smem = dyn.data();

@@ -202,3 +202,18 @@ def test_batch_of_archives(backend):
     from _harness import assert_same_as_oracle
     for i, (r, a) in enumerate(zip(res, arcs)):
         assert_same_as_oracle(r, O.decode(a), f"archive {i}")
+
+
+def test_pipeline_lanes(backend):
+    """Several contexts driven from host threads (the e2e path of bench.py) give the same results as one context."""
+    lib = library(backend)
+    arcs = [K.genome(300 + i, 25_000 + 999 * i, level=3) for i in range(5)] + [read_golden("phix.naf")]
+    parsed = [N.parse_archive(a, lib) for a in arcs]
+    pipe = N.Pipeline(0, 3, lib)
+    try:
+        res = pipe.decode(parsed)
+    finally:
+        pipe.close()
+    from _harness import assert_same_as_oracle
+    for i, (r, a) in enumerate(zip(res, arcs)):
+        assert_same_as_oracle(r, O.decode(a), f"archive {i}")
