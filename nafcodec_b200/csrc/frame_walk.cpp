@@ -165,6 +165,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                 plan.seq_total += nseq;
                 if (plan.seq_total > 0xFFFFFFF0ull) FAIL(ERR_UNSUPPORTED, "job has too many sequences");
                 plan.n_seq_blocks++;
+                if (bsize - q > plan.max_seq_section) plan.max_seq_section = bsize - q;
                 if (lt >= zf::LT_HUF) { b.lit_base = plan.lit_total; plan.lit_total += (regen + 15u) & ~15u; }
             }
             b.seq_src = q;

@@ -152,7 +152,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
-              c->seq32.ensure(nseq * 4 * 7 + 64) && c->seq64.ensure(nseq * 8 + 64) && c->misc.ensure(c->misc_words * 4) &&
+              c->seq32.ensure(nseq * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
               c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     const size_t nh = pl.huf_items.size();
@@ -182,10 +182,9 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.comp = (const uint8_t*)c->comp.p; J.out = (uint8_t*)c->arena.p; J.lit = (uint8_t*)c->lit.p;
     J.frames = (const zf::FrameDesc*)c->frames.p; J.blocks = (const zf::BlockDesc*)c->blocks.p;
     J.bstate = (zf::BlockState*)c->bstate.p; J.tables = (zc::SeqCell*)c->tables.p; J.table_al = (uint8_t*)c->table_al.p;
-    uint32_t* s32 = (uint32_t*)c->seq32.p;
-    J.seq_ll = s32; J.seq_ml = s32 + nseq; J.seq_off = s32 + 2 * nseq; J.seq_litpos = s32 + 3 * nseq;
-    J.seq_outpos = s32 + 4 * nseq; J.seq_block = s32 + 5 * nseq; J.seq_done = s32 + 6 * nseq;
-    J.match_pos = (uint64_t*)c->seq64.p;
+    J.seq_done = (uint32_t*)c->seq32.p;
+    J.seq = (zf::SeqRec*)c->seq64.p;
+    J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.remaining = misc + 1; J.frame_bad = misc + 1 + (zk::LZ_PASSES + 2);
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;

@@ -29,12 +29,19 @@ __global__ void __launch_bounds__(64) k_build_tables(JobDev J) {
     if (threadIdx.x >= 32) {
         // warp 1: the block's Huffman tree description -> 256 weights, decoded ONCE per tree (streams and treeless
         // blocks that reuse the tree read the weights back and build their decode table in parallel).
-        if (threadIdx.x != 32 || blockIdx.x >= J.n_blocks) return;
+        if (blockIdx.x >= J.n_blocks) return;
         const BlockDesc& B = J.blocks[blockIdx.x];
         if (B.btype != BT_COMPRESSED || B.lit_type != LT_HUF) return;
+        // stage the tree description (<= 129 bytes) in shared memory: the weight decode is a serial chain of bit reads
+        __shared__ __align__(16) uint8_t tree[176];
+        const int l1 = threadIdx.x - 32;
+        const uint32_t tsize = B.lit_csize < 130u ? B.lit_csize : 130u;
+        for (uint32_t i = l1; i < 176; i += 32) tree[i] = i < tsize ? J.comp[B.src_off + B.lit_src + i] : 0;
+        __syncwarp();
+        if (l1 != 0) return;
         uint8_t w[256];
         int mb = 0;
-        int ns = zc::huf_read_weights(J.comp + B.src_off + B.lit_src, B.lit_csize, w, &mb);
+        int ns = zc::huf_read_weights(tree, tsize, w, &mb);
         uint8_t* gw = J.huf_weights + (size_t)B.huf_slot * 256;
         for (int i = 0; i < 256; i += 4) *(uint32_t*)(gw + i) = w[i] | (w[i + 1] << 8) | (w[i + 2] << 16) | ((uint32_t)w[i + 3] << 24);
         J.huf_meta[(size_t)B.huf_slot * 2] = (uint8_t)(ns ? ns - 1 : 0);
@@ -67,13 +74,19 @@ __global__ void __launch_bounds__(64) k_build_tables(JobDev J) {
         if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
         frame = B.frame;
         slot[0] = B.tbl[0]; slot[1] = B.tbl[1]; slot[2] = B.tbl[2];
+        // stage the table descriptions (at most ~3 x 64 bytes) in shared memory for the serial bit parser
+        __shared__ __align__(16) uint8_t desc[256];
+        const uint32_t dsize = (B.src_size - B.seq_src) < 240u ? (B.src_size - B.seq_src) : 240u;
+        for (uint32_t i = lane; i < 256; i += 32) desc[i] = i < dsize ? J.comp[B.src_off + B.seq_src + i] : 0;
+        __syncwarp();
         if (lane == 0) {
             ok = 1;
-            const uint8_t* src = J.comp + B.src_off;
+            const uint8_t* src = desc - B.seq_src;      // so that src[p] addresses the staged copy for p >= seq_src
             uint32_t p = B.seq_src;
             for (int k = 0; k < 3; k++) {
                 int m = (B.modes >> (6 - 2 * k)) & 3;
                 mode[k] = (B.defines >> k) & 1 ? m : -1;
+                if (p - B.seq_src + 80 > 256 && (m == SM_RLE || m == SM_FSE)) src = J.comp + B.src_off;   // oversized: read global memory
                 if (m == SM_RLE) {
                     if (p >= B.src_size) { ok = 0; break; }
                     rle_sym[k] = src[p++];
@@ -141,10 +154,9 @@ struct SmemBits {
     __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
 };
 
-constexpr uint32_t SEQ_STAGE_BYTES = 12 * 1024;   // sequence bitstreams up to this size are staged in shared memory
 
 __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
-    __shared__ __align__(16) uint32_t sbits[SEQ_STAGE_BYTES / 4 + 16];
+    NAF_DYN_SMEM(uint32_t, sbits);                       // staged bitstream: J.seq_stage_bytes (job maximum, capped)
     __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
     if (S.seq_bits_off >= B.src_size) { if (lane == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
     const uint32_t nbytes = B.src_size - S.seq_bits_off;
     const uint8_t* g = src + S.seq_bits_off;
-    const bool staged = nbytes <= SEQ_STAGE_BYTES - 48;
+    const bool staged = nbytes + 48 <= J.seq_stage_bytes;
     const uint32_t a = (uint32_t)((uintptr_t)g & 15);
     int al[3];
 #pragma unroll
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
     RepSym rep[3] = {{0, 0}, {1, 0}, {2, 0}};
     uint32_t litpos = 0, outpos = 0;
     const uint32_t n = B.n_seq, base = B.seq_base;
+    uint4* rec = (uint4*)(J.seq + base);
     bool bad = false;
     int left;
     // the loop body is written once over a reader type: shared-memory window (common) or global memory (huge sections)
@@ -191,8 +204,9 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
     for (uint32_t i = 0; i < n; i++) {                                                                     \
         const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];                                      \
         const uint32_t ov = cOF.base_value + RD.read(cOF.add_bits);                                        \
-        const uint32_t ml = cML.base_value + RD.read(cML.add_bits);                                        \
-        const uint32_t ll = cLL.base_value + RD.read(cLL.add_bits);                                        \
+        const uint32_t xb = RD.read(cML.add_bits + cLL.add_bits);        /* ML then LL extra bits, one read */ \
+        const uint32_t ml = cML.base_value + (xb >> cLL.add_bits);                                         \
+        const uint32_t ll = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));                           \
         RepSym off;                                                                                        \
         if (ov > 3) {                                                                                      \
             off.src = -1; off.val = ov - 3;                                                                \
@@ -209,17 +223,15 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
             }                                                                                              \
         }                                                                                                  \
         if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;                                             \
-        if (i + 1 < n) {                                                                                   \
-            sLL = cLL.next_base + RD.read(cLL.nb);                                                         \
-            sML = cML.next_base + RD.read(cML.nb);                                                         \
-            sOF = cOF.next_base + RD.read(cOF.nb);                                                         \
+        if (i + 1 < n) {                                     /* LL, ML, OF state bits (<= 27) in one read */  \
+            const uint32_t sb = RD.read(cLL.nb + cML.nb + cOF.nb);                                         \
+            sOF = cOF.next_base + (sb & ((1u << cOF.nb) - 1u));                                            \
+            sML = cML.next_base + ((sb >> cOF.nb) & ((1u << cML.nb) - 1u));                                \
+            sLL = cLL.next_base + (sb >> (cOF.nb + cML.nb));                                               \
         }                                                                                                  \
-        J.seq_ll[base + i] = ll;                                                                           \
-        J.seq_ml[base + i] = ml;                                                                           \
-        J.seq_off[base + i] = encode_off(off);                                                             \
-        J.seq_litpos[base + i] = litpos;                                                                   \
-        J.seq_outpos[base + i] = outpos;                                                                   \
-        J.seq_block[base + i] = bi;                                                                        \
+        rec[0] = make_uint4(ll, ml, encode_off(off), litpos);                                              \
+        rec[1] = make_uint4(outpos, bi, 0u, 0u);                                                           \
+        rec += 2;                                                                                          \
         litpos += ll;                                                                                      \
         outpos += ll + ml;                                                                                 \
         if (outpos > BLOCK_MAX) { bad = true; break; }                                                     \
@@ -248,38 +260,58 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
 // --------------------------------------------------------------------------------------------------------------
 // k_frame_scan: one thread per frame.  Exclusive prefix sum of regenerated block sizes -> out_off; composes the
 // repeat-offset transfer functions -> rep_in per block; checks the total against the size the container states.
-__global__ void k_frame_scan(JobDev J) {
-    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_frame_scan(JobDev J) {
+    // one warp per frame; 32 blocks per step: lanes load in parallel, offsets by a shuffle scan, the repeat-offset chain
+    // is walked lane by lane through shuffles (no global-memory latency inside the dependent chain)
+    const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (f >= J.n_frames) return;
+    if (J.frame_bad[f]) return;
     const FrameDesc& F = J.frames[f];
     uint64_t off = F.dst_off;
-    uint32_t rep[3] = {1, 4, 8};
-    if (J.frame_bad[f]) return;
+    uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
     bool bad = false;
-    for (uint32_t b = F.first_block; b < F.first_block + F.n_blocks && !bad; b++) {
-        const BlockDesc& B = J.blocks[b];
-        BlockState& S = J.bstate[b];
-        uint32_t regen = (B.btype != BT_COMPRESSED || B.n_seq == 0) ? B.known_regen : S.regen;
-        S.regen = regen;
-        S.out_off = off;
-        off += regen;
-        if (off - F.dst_off > F.dst_size) { bad = true; break; }
-        if (B.btype == BT_COMPRESSED && B.n_seq > 0) {
-            uint32_t nr[3];
-            for (int k = 0; k < 3; k++) {
-                S.rep_in[k] = rep[k];
-                if (S.rep_src[k] < 0) nr[k] = S.rep_val[k];
-                else {
-                    uint32_t v = rep[S.rep_src[k]];
-                    if (v <= S.rep_val[k]) { bad = true; nr[k] = 1; }
-                    else nr[k] = v - S.rep_val[k];
-                }
-            }
-            rep[0] = nr[0]; rep[1] = nr[1]; rep[2] = nr[2];
+    for (uint32_t b0 = 0; b0 < F.n_blocks; b0 += 32) {
+        const uint32_t b = F.first_block + b0 + lane;
+        const bool valid = b0 + lane < F.n_blocks;
+        uint32_t regen = 0;
+        bool has_seq = false;
+        int32_t rs0 = 0, rs1 = 1, rs2 = 2;
+        uint32_t rv0 = 0, rv1 = 0, rv2 = 0;
+        if (valid) {
+            const BlockDesc& B = J.blocks[b];
+            has_seq = B.btype == BT_COMPRESSED && B.n_seq > 0;
+            if (has_seq) {
+                const BlockState& S = J.bstate[b];
+                regen = S.regen;
+                rs0 = S.rep_src[0]; rs1 = S.rep_src[1]; rs2 = S.rep_src[2];
+                rv0 = S.rep_val[0]; rv1 = S.rep_val[1]; rv2 = S.rep_val[2];
+            } else regen = B.known_regen;
         }
+        uint32_t inc = regen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+        if (valid) { J.bstate[b].regen = regen; J.bstate[b].out_off = off + (inc - regen); }
+        off += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        // repeat offsets: apply the blocks' transfer functions in order (uniform across the warp)
+        const uint32_t seqmask = __ballot_sync(0xFFFFFFFFu, has_seq);
+        uint32_t in0 = 0, in1 = 0, in2 = 0;
+        for (uint32_t m = seqmask; m; m &= m - 1) {
+            const int l = __ffs((int)m) - 1;
+            const int32_t s0 = __shfl_sync(0xFFFFFFFFu, rs0, l), s1 = __shfl_sync(0xFFFFFFFFu, rs1, l), s2 = __shfl_sync(0xFFFFFFFFu, rs2, l);
+            const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rv0, l), v1 = __shfl_sync(0xFFFFFFFFu, rv1, l), v2 = __shfl_sync(0xFFFFFFFFu, rv2, l);
+            if (lane == l) { in0 = rep0; in1 = rep1; in2 = rep2; }
+            const uint32_t r[3] = {rep0, rep1, rep2};
+            uint32_t n0, n1, n2;
+            if (s0 < 0) n0 = v0; else { uint32_t x = r[s0]; if (x <= v0) { bad = true; n0 = 1; } else n0 = x - v0; }
+            if (s1 < 0) n1 = v1; else { uint32_t x = r[s1]; if (x <= v1) { bad = true; n1 = 1; } else n1 = x - v1; }
+            if (s2 < 0) n2 = v2; else { uint32_t x = r[s2]; if (x <= v2) { bad = true; n2 = 1; } else n2 = x - v2; }
+            rep0 = n0; rep1 = n1; rep2 = n2;
+        }
+        if (valid && has_seq) { BlockState& S = J.bstate[b]; S.rep_in[0] = in0; S.rep_in[1] = in1; S.rep_in[2] = in2; }
     }
-    if (!bad && off - F.dst_off != F.dst_size) bad = true;
-    if (bad) flag_error(J, f, zc::E_SIZE);
+    if (off - F.dst_off != F.dst_size) bad = true;
+    if (bad && lane == 0) flag_error(J, f, zc::E_SIZE);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -694,14 +726,14 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
         uint32_t lo = 0, hi = nseq;                                      // first sequence whose literals end after L0
         while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
-            if (J.seq_litpos[sb + mid] + J.seq_ll[sb + mid] > L0) hi = mid; else lo = mid + 1;
+            if (J.seq[sb + mid].litpos + J.seq[sb + mid].ll > L0) hi = mid; else lo = mid + 1;
         }
         for (uint32_t j = lo + warp; j <= nseq; j += NWARPS) {            // j == nseq: the literals after the last sequence
             uint32_t lp, ll, op;
-            if (j < nseq) { lp = J.seq_litpos[sb + j]; ll = J.seq_ll[sb + j]; op = J.seq_outpos[sb + j]; }
+            if (j < nseq) { lp = J.seq[sb + j].litpos; ll = J.seq[sb + j].ll; op = J.seq[sb + j].outpos; }
             else {
                 const uint32_t t = sb + nseq - 1;
-                lp = J.seq_litpos[t] + J.seq_ll[t]; ll = B.lit_regen - lp; op = J.seq_outpos[t] + J.seq_ll[t] + J.seq_ml[t];
+                lp = J.seq[t].litpos + J.seq[t].ll; ll = B.lit_regen - lp; op = J.seq[t].outpos + J.seq[t].ll + J.seq[t].ml;
             }
             if (lp >= L1) break;
             const uint32_t b0 = lp > L0 ? lp : L0, b1 = (lp + ll < L1) ? lp + ll : L1;
@@ -746,12 +778,12 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     for (uint32_t i = warp; i <= n; i += nw) {
         uint32_t lp, op, ll;
         if (i < n) {
-            lp = J.seq_litpos[base + i]; op = J.seq_outpos[base + i]; ll = J.seq_ll[base + i];
-            if (lane == 0) J.match_pos[base + i] = S.out_off + op + ll;     // absolute destination of the match
+            lp = J.seq[base + i].litpos; op = J.seq[base + i].outpos; ll = J.seq[base + i].ll;
+            if (lane == 0) J.seq[base + i].match_pos = S.out_off + op + ll;     // absolute destination of the match
         } else {                                       // literals after the last sequence
             uint32_t j = base + n - 1;
-            lp = J.seq_litpos[j] + J.seq_ll[j];
-            op = J.seq_outpos[j] + J.seq_ll[j] + J.seq_ml[j];
+            lp = J.seq[j].litpos + J.seq[j].ll;
+            op = J.seq[j].outpos + J.seq[j].ll + J.seq[j].ml;
             ll = B.lit_regen - lp;
         }
         if (huf) continue;
@@ -798,13 +830,13 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_pass(JobDev J, uint32_t pass) {
     const uint64_t i = (uint64_t)blockIdx.x * LZ_CTA + tid;
     bool pending = false;
     if (i < J.n_seq && J.seq_done[i] == 0) {
-        const uint32_t bi = J.seq_block[i];
+        const uint32_t bi = J.seq[i].block;
         const BlockDesc& B = J.blocks[bi];
         if (!J.frame_bad[B.frame]) {
             const FrameDesc& F = J.frames[B.frame];
-            const uint32_t ml = J.seq_ml[i];
-            const uint32_t off = resolve_offset(J, J.seq_off[i], bi);
-            const uint64_t d = J.match_pos[i];
+            const uint32_t ml = J.seq[i].ml;
+            const uint32_t off = resolve_offset(J, J.seq[i].off, bi);
+            const uint64_t d = J.seq[i].match_pos;
             if (off == 0 || (uint64_t)off > d - F.dst_off) {
                 flag_error(J, B.frame, zc::E_OFFSET);
                 J.seq_done[i] = pass;
@@ -814,10 +846,10 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_pass(JobDev J, uint32_t pass) {
                 uint64_t lo = F.first_seq, hi = i;                    // first earlier match (same frame) ending after s
                 while (lo < hi) {
                     uint64_t mid = (lo + hi) >> 1;
-                    if (J.match_pos[mid] + J.seq_ml[mid] > s) hi = mid; else lo = mid + 1;
+                    if (J.seq[mid].match_pos + J.seq[mid].ml > s) hi = mid; else lo = mid + 1;
                 }
                 bool ready = true;
-                for (uint64_t j = lo; j < i && J.match_pos[j] < e; j++) {
+                for (uint64_t j = lo; j < i && J.seq[j].match_pos < e; j++) {
                     uint32_t dn = J.seq_done[j];
                     if (dn == 0 || dn >= pass) { ready = false; break; }
                 }
@@ -849,10 +881,10 @@ __global__ void __launch_bounds__(32) k_lz_sequential(JobDev J) {
     const int lane = threadIdx.x;
     for (uint64_t i = F.first_seq; i < (uint64_t)F.first_seq + F.n_seq; i++) {
         if (J.seq_done[i]) continue;
-        const uint32_t bi = J.seq_block[i];
-        const uint32_t ml = J.seq_ml[i];
-        const uint32_t off = resolve_offset(J, J.seq_off[i], bi);
-        const uint64_t d = J.match_pos[i];
+        const uint32_t bi = J.seq[i].block;
+        const uint32_t ml = J.seq[i].ml;
+        const uint32_t off = resolve_offset(J, J.seq[i].off, bi);
+        const uint64_t d = J.seq[i].match_pos;
         if (off == 0 || (uint64_t)off > d - F.dst_off) {
             if (lane == 0) flag_error(J, f, zc::E_OFFSET);
             return;
@@ -871,8 +903,8 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
     int launches = 0;
     if (J.n_blocks == 0) { for (int i = 0; i < ZSTD_STAGES; i++) ev->mark(); return 0; }
     NAF_LAUNCH(k_build_tables, J.n_blocks + 1, 64, 0, st, J); launches++; ev->mark();
-    NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, 0, st, J); launches++; ev->mark();
-    NAF_LAUNCH(k_frame_scan, (J.n_frames + 63) / 64, 64, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, J.seq_stage_bytes, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_frame_scan, (J.n_frames + 3) / 4, 128, 0, st, J); launches++; ev->mark();
     if (J.n_huf_big) {       // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams, one warp each
         const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
         NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);

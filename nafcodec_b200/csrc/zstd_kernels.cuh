@@ -23,13 +23,8 @@ struct JobDev {
     uint8_t* table_al;                // accuracy log per slot
     uint8_t* huf_weights;             // n_huf_slots x 256 weights (k_build_tables decodes every tree description once)
     uint8_t* huf_meta;                // n_huf_slots x {n_symbols - 1, max_bits}; max_bits == 0: bad tree
-    uint32_t* seq_ll;
-    uint32_t* seq_ml;
-    uint32_t* seq_off;                // resolved offset, or symbolic (zf::OFF_SYMBOLIC)
-    uint32_t* seq_litpos;             // start of the sequence's literals inside the block's literals
-    uint32_t* seq_outpos;             // start of the sequence's output inside the block
-    uint32_t* seq_block;              // owning block
-    uint64_t* match_pos;              // absolute position of the match destination in `out`
+    zf::SeqRec* seq;                  // one 32-byte record per sequence (written by k_decode_sequences / k_lz_literals)
+    uint32_t seq_stage_bytes;         // shared-memory staging size of k_decode_sequences (largest sequence bitstream, capped)
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
