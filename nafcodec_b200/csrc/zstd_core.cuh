@@ -181,25 +181,43 @@ ZHD bool fse_build(const int16_t* norm, int max_symbol, int al, uint8_t* cell_sy
     return true;
 }
 
-// Code -> (baseline, extra bits) tables (RFC 8878 3.1.1.3.2.1.1)
-ZHD uint32_t ll_base(int c) {
-    const uint32_t t[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
-    return t[c];
-}
-ZHD int ll_bits(int c) {
-    const uint8_t t[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-    return t[c];
-}
-ZHD uint32_t ml_base(int c) {
-    const uint32_t t[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34,
-                            35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
-    return t[c];
-}
-ZHD int ml_bits(int c) {
-    const uint8_t t[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                           1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-    return t[c];
-}
+// Code -> (baseline, extra bits) tables (RFC 8878 3.1.1.3.2.1.1).  In device code they live in constant memory
+// (a function-local array would be rebuilt on the thread's stack at every call).
+#define ZC_LL_BASE {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536}
+#define ZC_LL_BITS {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16}
+#define ZC_ML_BASE {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, \
+                    35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539}
+#define ZC_ML_BITS {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, \
+                    1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16}
+#define ZC_PRE_LL {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1}
+#define ZC_PRE_OF {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1}
+#define ZC_PRE_ML {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, \
+                   1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1}
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t d_ll_base[36] = ZC_LL_BASE;
+__device__ __constant__ uint8_t d_ll_bits[36] = ZC_LL_BITS;
+__device__ __constant__ uint32_t d_ml_base[53] = ZC_ML_BASE;
+__device__ __constant__ uint8_t d_ml_bits[53] = ZC_ML_BITS;
+__device__ __constant__ int8_t d_pre_ll[36] = ZC_PRE_LL;
+__device__ __constant__ int8_t d_pre_of[29] = ZC_PRE_OF;
+__device__ __constant__ int8_t d_pre_ml[53] = ZC_PRE_ML;
+#endif
+static const uint32_t h_ll_base[36] = ZC_LL_BASE;
+static const uint8_t h_ll_bits[36] = ZC_LL_BITS;
+static const uint32_t h_ml_base[53] = ZC_ML_BASE;
+static const uint8_t h_ml_bits[53] = ZC_ML_BITS;
+static const int8_t h_pre_ll[36] = ZC_PRE_LL;
+static const int8_t h_pre_of[29] = ZC_PRE_OF;
+static const int8_t h_pre_ml[53] = ZC_PRE_ML;
+#if defined(__CUDA_ARCH__)
+#define ZC_TAB(name) d_##name
+#else
+#define ZC_TAB(name) h_##name
+#endif
+ZHD uint32_t ll_base(int c) { return ZC_TAB(ll_base)[c]; }
+ZHD int ll_bits(int c) { return ZC_TAB(ll_bits)[c]; }
+ZHD uint32_t ml_base(int c) { return ZC_TAB(ml_base)[c]; }
+ZHD int ml_bits(int c) { return ZC_TAB(ml_bits)[c]; }
 
 enum { KIND_LL = 0, KIND_OF = 1, KIND_ML = 2 };
 ZHD int kind_max_symbol(int k) { return k == KIND_LL ? MAX_LL : (k == KIND_OF ? MAX_OF : MAX_ML); }
@@ -216,13 +234,9 @@ ZHD SeqCell make_seq_cell(int kind, int sym, int nb, int base) {
 
 // Predefined distributions (RFC 8878 3.1.1.3.2.2)
 ZHD int16_t predef_norm(int kind, int s) {
-    const int8_t ll[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
-    const int8_t of[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
-    const int8_t ml[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
-                           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
-    if (kind == KIND_LL) return ll[s];
-    if (kind == KIND_OF) return s < 29 ? of[s] : 0;
-    return ml[s];
+    if (kind == KIND_LL) return ZC_TAB(pre_ll)[s];
+    if (kind == KIND_OF) return s < 29 ? ZC_TAB(pre_of)[s] : 0;
+    return ZC_TAB(pre_ml)[s];
 }
 ZHD int predef_al(int kind) { return kind == KIND_OF ? 5 : 6; }
 
