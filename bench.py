@@ -263,7 +263,7 @@ def main():
         "huf_decode": st.compressed_bytes + lits,
         "unpack": lits + st.ascii_bytes,
         "decode_sequences": st.compressed_bytes,
-        "lz_literals": 2 * lits, "lz_passes": 2 * lits, "lz_sequential": 2 * lits,
+        "lz_literals": 2 * lits, "lz_first": 2 * lits, "lz_resolve": 2 * lits,
     }
     dom_name = stage_names[dom]
     dom_bytes = kernel_bytes.get(dom_name, st.algorithmic_bytes)

@@ -7,8 +7,18 @@
     emul::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define NAF_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul::g_dyn_smem)
 #define NAF_SET_MAX_SMEM(kernel, bytes) ((void)0)
+// cooperative (grid-synchronising) kernels run as ONE CTA under the emulator, so a grid barrier is a CTA barrier
+#define NAF_LAUNCH_COOP(kernel, grid, block, stream, arg) emul::launch(dim3(1), dim3(block), 0, [=]() { kernel(arg); })
+#define NAF_GRID_SYNC() __syncthreads()
 #else
 #include <cuda_runtime.h>
+#if defined(__CUDACC__)
+#include <cooperative_groups.h>
+#define NAF_GRID_SYNC() cooperative_groups::this_grid().sync()
+#endif
+// one by-value argument; all CTAs must be co-resident (grid <= occupancy x SMs)
+#define NAF_LAUNCH_COOP(kernel, grid, block, stream, arg) \
+    do { void* _args[] = {(void*)&(arg)}; cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(block), _args, 0, (stream)); } while (0)
 #define NAF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define NAF_SET_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #define NAF_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _naf_dyn_smem[]; type* name = reinterpret_cast<type*>(_naf_dyn_smem)

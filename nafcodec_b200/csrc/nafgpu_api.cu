@@ -76,6 +76,7 @@ struct nafgpu_ctx {
     uint64_t max_records = 0, max_text = 0;
     uint32_t max_chunks = 0;
     bool any_mask = false;
+    uint32_t coop_ctas = 1;
     size_t misc_words = 0;
     nafgpu_job_stats stats;
     bool prepared = false, ran = false;
@@ -147,12 +148,12 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     const uint64_t nseq = pl.seq_total;
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
-    c->misc_words = 1 + (zk::LZ_PASSES + 2) + nf + 8;
+    c->misc_words = 1 + 2 + nf + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
-              c->seq32.ensure(nseq * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
+              c->seq32.ensure(nseq * 4 * 3 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
               c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     const size_t nh = pl.huf_items.size();
@@ -183,10 +184,12 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.frames = (const zf::FrameDesc*)c->frames.p; J.blocks = (const zf::BlockDesc*)c->blocks.p;
     J.bstate = (zf::BlockState*)c->bstate.p; J.tables = (zc::SeqCell*)c->tables.p; J.table_al = (uint8_t*)c->table_al.p;
     J.seq_done = (uint32_t*)c->seq32.p;
+    J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq;
     J.seq = (zf::SeqRec*)c->seq64.p;
     J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
-    J.status = misc; J.remaining = misc + 1; J.frame_bad = misc + 1 + (zk::LZ_PASSES + 2);
+    J.status = misc; J.lz_count = misc + 1; J.frame_bad = misc + 3;
+    J.coop_ctas = c->coop_ctas;
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
     J.debug = nullptr;
@@ -222,6 +225,7 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     for (int i = 0; i <= N_STAGES; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     c->ev_ok = true;
+    c->coop_ctas = zk::lz_resolve_max_ctas(device);
     *out = c;
     return NAFGPU_OK;
 }
@@ -555,8 +559,8 @@ int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
 }
 
 const char* nafgpu_stage_name(uint32_t s) {
-    static const char* names[N_STAGES] = {"memset+build_tables", "decode_sequences", "frame_scan", "huf_decode", "lz_literals", "lz_passes",
-                                          "lz_sequential", "naf_scan", "mask_fix", "mask_parity", "unpack", "utf8_check"};
+    static const char* names[N_STAGES] = {"memset+build_tables", "decode_sequences", "frame_scan", "huf_decode", "lz_literals", "lz_first",
+                                          "lz_resolve", "naf_scan", "mask_fix", "mask_parity", "unpack", "utf8_check"};
     return s < (uint32_t)N_STAGES ? names[s] : "?";
 }
 

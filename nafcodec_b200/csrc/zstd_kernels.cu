@@ -8,8 +8,8 @@
 //   k_frame_scan        per frame: block output offsets (prefix sum) + repeat-offset carry across blocks
 //   k_huf_decode        per block: Huffman literals (1/4 streams), straight into the output when n_seq == 0
 //   k_lz_literals       per block: raw/RLE blocks, literal runs -> output positions
-//   k_lz_pass x N       per match: dependency-resolving passes (a match runs once its source bytes are final)
-//   k_lz_sequential     per frame: ordered fallback for whatever dependency chains remain
+//   k_lz_first          per match: round 1 of the dependency-resolving match execution (+ redirect through copies)
+//   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, grid barrier between rounds
 #include "zstd_kernels.cuh"
 
 namespace zk {
@@ -812,91 +812,140 @@ __device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t of
     }
 }
 
-// k_lz_pass: ONE THREAD per pending match.  A match may run in pass p if every earlier match whose destination
-// intersects its source range finished in a pass < p (all literals are final before pass 1).  Short matches (the
-// common case: a few tens of bytes) are copied by their own thread; long ones (N stretches: offset 1, ~100 KB) are
-// queued in shared memory and copied by the whole CTA.
+// Match resolution.
+//
+// A match may run once every earlier match whose destination intersects its source range has finished in an EARLIER
+// round (all literals are final before round 1).  Two mechanisms keep the number of rounds small:
+//   * redirect ("pointer jumping"): if the whole source range lies inside the destination of ONE unfinished match j,
+//     the bytes wanted are by definition equal to those `off_j` further back (out[p] == out[p - off_j] for every p in
+//     j's destination, also for overlapping j).  So the match rewrites its own offset, off += off_j, and looks again:
+//     chains of copies-of-copies (repeat families, reads sampled from one genome) collapse in a few hops.
+//   * rounds are driven by a persistent cooperative kernel over a compacted worklist of the matches still pending,
+//     with a grid-wide barrier between rounds: deep chains (text-like sections) cost one barrier per level instead of
+//     one kernel launch, and there is no serial fallback.
+// Short matches (the common case: a few tens of bytes) are copied by their own thread; long ones (N stretches:
+// offset 1, ~100 KB) are queued in shared memory and copied by the whole CTA.
 constexpr uint32_t LZ_SHORT = 64;
 constexpr int LZ_CTA = 256;
+constexpr int LZ_HOPS = 8;
 
-__global__ void __launch_bounds__(LZ_CTA) k_lz_pass(JobDev J, uint32_t pass) {
-    if (pass > 1 && J.remaining[pass - 1] == 0) return;
-    __shared__ uint32_t q_n;
-    __shared__ uint64_t q_d[LZ_CTA];
-    __shared__ uint32_t q_off[LZ_CTA], q_ml[LZ_CTA], q_i[LZ_CTA];
+// Returns 1 when match i may be copied now (d/off/ml filled), 0 when it has to wait, 2 when it was rejected.
+__device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t round, uint64_t& d, uint32_t& off, uint32_t& ml) {
+    SeqRec& R = J.seq[i];
+    const uint32_t bi = R.block;
+    const BlockDesc& B = J.blocks[bi];
+    if (J.frame_bad[B.frame]) { J.seq_done[i] = round; return 2; }
+    const FrameDesc& F = J.frames[B.frame];
+    ml = R.ml;
+    const uint32_t off0 = resolve_offset(J, R.off, bi);
+    off = off0;
+    d = R.match_pos;
+    int verdict = 0;
+    for (int hop = 0; hop <= LZ_HOPS; hop++) {
+        if (off == 0 || (uint64_t)off > d - F.dst_off) {
+            flag_error(J, B.frame, zc::E_OFFSET);
+            J.seq_done[i] = round;
+            return 2;
+        }
+        const uint64_t s = d - off;
+        const uint64_t e = (off < ml) ? d : s + ml;                   // external source range [s, e)
+        uint32_t lo = F.first_seq, hi = i;                            // first earlier match (same frame) ending after s
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (J.seq[mid].match_pos + J.seq[mid].ml > s) hi = mid; else lo = mid + 1;
+        }
+        uint32_t blocker = 0xFFFFFFFFu;
+        for (uint32_t j = lo; j < i && J.seq[j].match_pos < e; j++) {
+            const uint32_t dn = J.seq_done[j];
+            if (dn == 0 || dn >= round) { blocker = j; break; }
+        }
+        if (blocker == 0xFFFFFFFFu) { verdict = 1; break; }
+        const SeqRec& Q = J.seq[blocker];
+        if (hop == LZ_HOPS || off < ml || Q.match_pos > s || e > Q.match_pos + Q.ml) break;      // cannot redirect: wait
+        off += resolve_offset(J, Q.off, Q.block);
+    }
+    if (off != off0) R.off = off;                                      // keep the shortcut for later rounds (and for others)
+    return verdict;
+}
+
+// One round over a list of matches: items [0, n) of `list` (or the identity when list == nullptr).  Matches that still
+// have to wait are appended to `next` (count in *next_n).
+__device__ __forceinline__ void lz_round(const JobDev& J, const uint32_t* list, uint32_t n, uint32_t round, uint32_t* next, uint32_t* next_n,
+                                         uint32_t first, uint32_t stride,
+                                         uint32_t* q_n, uint64_t* q_d, uint32_t* q_off, uint32_t* q_ml, uint32_t* q_i) {
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) q_n = 0;
-    __syncthreads();
-    const uint64_t i = (uint64_t)blockIdx.x * LZ_CTA + tid;
-    bool pending = false;
-    if (i < J.n_seq && J.seq_done[i] == 0) {
-        const uint32_t bi = J.seq[i].block;
-        const BlockDesc& B = J.blocks[bi];
-        if (!J.frame_bad[B.frame]) {
-            const FrameDesc& F = J.frames[B.frame];
-            const uint32_t ml = J.seq[i].ml;
-            const uint32_t off = resolve_offset(J, J.seq[i].off, bi);
-            const uint64_t d = J.seq[i].match_pos;
-            if (off == 0 || (uint64_t)off > d - F.dst_off) {
-                flag_error(J, B.frame, zc::E_OFFSET);
-                J.seq_done[i] = pass;
-            } else {
-                const uint64_t s = d - off;
-                const uint64_t e = (off < ml) ? d : s + ml;           // external source range [s, e)
-                uint64_t lo = F.first_seq, hi = i;                    // first earlier match (same frame) ending after s
-                while (lo < hi) {
-                    uint64_t mid = (lo + hi) >> 1;
-                    if (J.seq[mid].match_pos + J.seq[mid].ml > s) hi = mid; else lo = mid + 1;
-                }
-                bool ready = true;
-                for (uint64_t j = lo; j < i && J.seq[j].match_pos < e; j++) {
-                    uint32_t dn = J.seq_done[j];
-                    if (dn == 0 || dn >= pass) { ready = false; break; }
-                }
-                if (!ready) pending = true;
-                else if (ml <= LZ_SHORT) {
-                    copy_match(J.out, d, off, ml, 0, 1);
-                    J.seq_done[i] = pass;
-                } else {
-                    uint32_t slot = atomicAdd(&q_n, 1u);
-                    q_d[slot] = d; q_off[slot] = off; q_ml[slot] = ml; q_i[slot] = (uint32_t)i;
+    for (uint32_t base = first; base < n; base += stride) {          // `base` is CTA-uniform
+        if (tid == 0) *q_n = 0;
+        __syncthreads();
+        const uint32_t k = base + tid;
+        bool pending = false;
+        uint32_t i = 0;
+        if (k < n) {
+            i = list ? list[k] : k;
+            if (J.seq_done[i] == 0) {
+                uint64_t d; uint32_t off, ml;
+                const int v = lz_try(J, i, round, d, off, ml);
+                if (v == 0) pending = true;
+                else if (v == 1) {
+                    if (ml <= LZ_SHORT) { copy_match(J.out, d, off, ml, 0, 1); J.seq_done[i] = round; }
+                    else { const uint32_t slot = atomicAdd(q_n, 1u); q_d[slot] = d; q_off[slot] = off; q_ml[slot] = ml; q_i[slot] = i; }
                 }
             }
         }
+        const uint32_t pb = __ballot_sync(0xFFFFFFFFu, pending);
+        uint32_t wbase = 0;
+        if (lane == 0 && pb) wbase = atomicAdd(next_n, (uint32_t)__popc(pb));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (pending) next[wbase + __popc(pb & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        const uint32_t nq = *q_n;
+        for (uint32_t t = 0; t < nq; t++) copy_match(J.out, q_d[t], q_off[t], q_ml[t], tid, LZ_CTA);
+        if ((uint32_t)tid < nq) J.seq_done[q_i[tid]] = round;
+        __syncthreads();
     }
-    const uint32_t pb = __ballot_sync(0xFFFFFFFFu, pending);
-    if (lane == 0 && pb) atomicAdd(&J.remaining[pass], (uint32_t)__popc(pb));
-    __syncthreads();
-    const uint32_t nq = q_n;
-    for (uint32_t k = 0; k < nq; k++) copy_match(J.out, q_d[k], q_off[k], q_ml[k], tid, LZ_CTA);
-    if ((uint32_t)tid < nq) J.seq_done[q_i[tid]] = pass;
 }
 
-// k_lz_sequential: ordered fallback, one warp per frame, for dependency chains deeper than LZ_PASSES.
-__global__ void __launch_bounds__(32) k_lz_sequential(JobDev J) {
-    if (J.remaining[LZ_PASSES] == 0) return;
-    const uint32_t f = blockIdx.x;
-    if (J.frame_bad[f]) return;
-    const FrameDesc& F = J.frames[f];
-    const int lane = threadIdx.x;
-    for (uint64_t i = F.first_seq; i < (uint64_t)F.first_seq + F.n_seq; i++) {
-        if (J.seq_done[i]) continue;
-        const uint32_t bi = J.seq[i].block;
-        const uint32_t ml = J.seq[i].ml;
-        const uint32_t off = resolve_offset(J, J.seq[i].off, bi);
-        const uint64_t d = J.seq[i].match_pos;
-        if (off == 0 || (uint64_t)off > d - F.dst_off) {
-            if (lane == 0) flag_error(J, f, zc::E_OFFSET);
-            return;
-        }
-        copy_match(J.out, d, off, ml, lane, 32);
-        __syncwarp();
-        if (lane == 0) J.seq_done[i] = LZ_PASSES + 1;
-        __syncwarp();
+#define LZ_SHARED_QUEUE \
+    __shared__ uint32_t q_n; __shared__ uint64_t q_d[LZ_CTA]; __shared__ uint32_t q_off[LZ_CTA], q_ml[LZ_CTA], q_i[LZ_CTA]
+
+// Round 1: every match of the job, one thread each.
+__global__ void __launch_bounds__(LZ_CTA) k_lz_first(JobDev J) {
+    LZ_SHARED_QUEUE;
+    lz_round(J, nullptr, (uint32_t)J.n_seq, 1u, J.lz_list[0], &J.lz_count[0], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
+             &q_n, q_d, q_off, q_ml, q_i);
+}
+
+// Rounds 2..: persistent cooperative kernel over the worklist, ping-ponging between the two lists.
+__global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
+    LZ_SHARED_QUEUE;
+    uint32_t cur = 0;
+    for (uint32_t round = 2;; round++) {
+        const uint32_t n = J.lz_count[cur];                          // stable: written before the last grid barrier
+        if (n == 0) break;
+        lz_round(J, J.lz_list[cur], n, round, J.lz_list[cur ^ 1], &J.lz_count[cur ^ 1], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
+                 &q_n, q_d, q_off, q_ml, q_i);
+        NAF_GRID_SYNC();                                             // all copies and list appends of this round are visible
+        if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[cur] = 0; // becomes the append target of the round after next
+        cur ^= 1;
+        NAF_GRID_SYNC();
+        if (round > J.n_seq + 2) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(J.status, zc::E_INTERNAL); break; }   // cannot happen: >= 1 match finishes per round
     }
 }
 
 // --------------------------------------------------------------------------------------------------------------
+uint32_t lz_resolve_max_ctas(int device) {
+#if defined(NAFGPU_EMULATE)
+    (void)device;
+    return 1;
+#else
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz_resolve, LZ_CTA, 0);
+    if (per_sm > 4) per_sm = 4;
+    return (uint32_t)(sms > 0 && per_sm > 0 ? sms * per_sm : 1);
+#endif
+}
+
 int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
     StageEvents none;
     if (!ev) ev = &none;
@@ -918,9 +967,13 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
     NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
         uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
-        for (uint32_t p = 1; p <= (uint32_t)LZ_PASSES; p++) { NAF_LAUNCH(k_lz_pass, grid, LZ_CTA, 0, st, J, p); launches++; }
+        if (grid > 148u * 64u) grid = 148u * 64u;
+        NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();
-        NAF_LAUNCH(k_lz_sequential, J.n_frames, 32, 0, st, J); launches++; ev->mark();
+        uint32_t cg = J.coop_ctas ? J.coop_ctas : 1u;                 // co-resident CTAs for the grid barrier (queried by the API)
+        JobDev Jc = J;
+        NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
+        ev->mark();
     } else { ev->mark(); ev->mark(); }
     return launches;
 }

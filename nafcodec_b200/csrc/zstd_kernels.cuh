@@ -8,7 +8,6 @@
 
 namespace zk {
 
-constexpr int LZ_PASSES = 6;
 constexpr uint32_t HUF_SMALL_SYMBOLS = 2048;   // streams regenerating <= this many symbols are decoded by one warp          // dependency-resolving passes before the ordered fallback
 
 // Everything the zstd kernels need, by value.  All pointers are device pointers.
@@ -29,7 +28,9 @@ struct JobDev {
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
     unsigned long long* debug;        // optional per-CTA phase clocks of k_huf_decode (NAFGPU_DEBUG_HUF=1), else null
-    uint32_t* remaining;              // [LZ_PASSES + 2] matches still pending after pass p
+    uint32_t* lz_list[2];             // ping-pong worklists of matches still pending (n_seq entries each)
+    uint32_t* lz_count;               // [2] their lengths
+    uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
     const zf::HufItem* huf_items;     // one per Huffman bitstream
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
     uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
@@ -40,6 +41,8 @@ struct JobDev {
 // Enqueues the whole zstd stage for a job on `stream` (no host synchronisation).
 // Returns the number of kernels launched.  `ev` (optional) gets one mark per stage (7 stages).
 int launch_zstd_stage(const JobDev& job, cudaStream_t stream, StageEvents* ev);
+// Co-resident CTAs (whole device) for the cooperative match-resolution kernel.
+uint32_t lz_resolve_max_ctas(int device);
 constexpr int ZSTD_STAGES = 7;
 
 }  // namespace zk
