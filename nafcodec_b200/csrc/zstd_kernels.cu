@@ -10,6 +10,7 @@
 //   k_lz_literals       per block: raw/RLE blocks, literal runs -> output positions
 //   k_lz_first          per match: round 1 of the dependency-resolving match execution (+ redirect through copies)
 //   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, grid barrier between rounds
+//   k_lz_finish         per frame: ordered finisher when chains are deeper than LZ_MAX_ROUNDS (text-like sections)
 #include "zstd_kernels.cuh"
 
 namespace zk {
@@ -828,6 +829,7 @@ __device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t of
 constexpr uint32_t LZ_SHORT = 64;
 constexpr int LZ_CTA = 256;
 constexpr int LZ_HOPS = 8;
+constexpr uint32_t LZ_MAX_ROUNDS = 48;
 
 // Returns 1 when match i may be copied now (d/off/ml filled), 0 when it has to wait, 2 when it was rejected.
 __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t round, uint64_t& d, uint32_t& off, uint32_t& ml) {
@@ -928,7 +930,35 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[cur] = 0; // becomes the append target of the round after next
         cur ^= 1;
         NAF_GRID_SYNC();
-        if (round > J.n_seq + 2) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(J.status, zc::E_INTERNAL); break; }   // cannot happen: >= 1 match finishes per round
+        if (round >= LZ_MAX_ROUNDS) break;        // very deep chains (text-like sections): hand over to the ordered finisher
+    }
+}
+
+// k_lz_finish: ordered finisher for what k_lz_resolve left behind (dependency chains deeper than LZ_MAX_ROUNDS, i.e.
+// text-like sections where nearly every match feeds the next one).  One warp per frame walks the frame's matches in
+// order, 32 done-flags per step, and copies the pending ones cooperatively; in order, every source byte is final.
+__global__ void __launch_bounds__(32) k_lz_finish(JobDev J) {
+    if (J.lz_count[0] == 0 && J.lz_count[1] == 0) return;
+    const uint32_t f = blockIdx.x;
+    if (J.frame_bad[f]) return;
+    const FrameDesc& F = J.frames[f];
+    const int lane = threadIdx.x;
+    const uint32_t end = F.first_seq + F.n_seq;
+    for (uint32_t base = F.first_seq; base < end; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t pend = __ballot_sync(0xFFFFFFFFu, i < end && J.seq_done[i] == 0);
+        while (pend) {
+            const uint32_t k = base + (uint32_t)__ffs((int)pend) - 1;
+            pend &= pend - 1;
+            const SeqRec& R = J.seq[k];
+            const uint32_t off = resolve_offset(J, R.off, R.block);
+            const uint64_t d = R.match_pos;
+            if (off == 0 || (uint64_t)off > d - F.dst_off) { if (lane == 0) flag_error(J, f, zc::E_OFFSET); return; }
+            copy_match(J.out, d, off, R.ml, lane, 32);
+            __syncwarp();
+            if (lane == 0) J.seq_done[k] = LZ_MAX_ROUNDS + 1;
+            __syncwarp();
+        }
     }
 }
 
@@ -973,6 +1003,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
         uint32_t cg = J.coop_ctas ? J.coop_ctas : 1u;                 // co-resident CTAs for the grid barrier (queried by the API)
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
+        NAF_LAUNCH(k_lz_finish, J.n_frames, 32, 0, st, J); launches++;
         ev->mark();
     } else { ev->mark(); ev->mark(); }
     return launches;
