@@ -10,7 +10,7 @@
 //   k_lz_literals       per block: raw/RLE blocks, literal runs -> output positions
 //   k_lz_first          per match: round 1 of the dependency-resolving match execution (+ redirect through copies)
 //   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, grid barrier between rounds
-//   k_lz_finish         per frame: ordered finisher when chains are deeper than LZ_MAX_ROUNDS (text-like sections)
+//   k_lz_finish         per frame: ordered finisher when the rounds stop making progress (text-like sections)
 #include "zstd_kernels.cuh"
 
 namespace zk {
@@ -294,25 +294,55 @@ __global__ void __launch_bounds__(128) k_frame_scan(JobDev J) {
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
         if (valid) { J.bstate[b].regen = regen; J.bstate[b].out_off = off + (inc - regen); }
         off += __shfl_sync(0xFFFFFFFFu, inc, 31);
-        // repeat offsets: apply the blocks' transfer functions in order (uniform across the warp)
-        const uint32_t seqmask = __ballot_sync(0xFFFFFFFFu, has_seq);
-        uint32_t in0 = 0, in1 = 0, in2 = 0;
-        for (uint32_t m = seqmask; m; m &= m - 1) {
-            const int l = __ffs((int)m) - 1;
-            const int32_t s0 = __shfl_sync(0xFFFFFFFFu, rs0, l), s1 = __shfl_sync(0xFFFFFFFFu, rs1, l), s2 = __shfl_sync(0xFFFFFFFFu, rs2, l);
-            const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rv0, l), v1 = __shfl_sync(0xFFFFFFFFu, rv1, l), v2 = __shfl_sync(0xFFFFFFFFu, rv2, l);
-            if (lane == l) { in0 = rep0; in1 = rep1; in2 = rep2; }
-            const uint32_t r[3] = {rep0, rep1, rep2};
-            uint32_t n0, n1, n2;
-            if (s0 < 0) n0 = v0; else { uint32_t x = r[s0]; if (x <= v0) { bad = true; n0 = 1; } else n0 = x - v0; }
-            if (s1 < 0) n1 = v1; else { uint32_t x = r[s1]; if (x <= v1) { bad = true; n1 = 1; } else n1 = x - v1; }
-            if (s2 < 0) n2 = v2; else { uint32_t x = r[s2]; if (x <= v2) { bad = true; n2 = 1; } else n2 = x - v2; }
-            rep0 = n0; rep1 = n1; rep2 = n2;
+        // repeat offsets: inclusive scan over function composition of the blocks' transfer functions
+        // (slot k = constant v, or incoming slot s minus v); blocks without sequences are the identity
+        int32_t cs[3] = {rs0, rs1, rs2};
+        uint32_t cv[3] = {rv0, rv1, rv2};
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int32_t fs[3]; uint32_t fv[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { fs[k] = __shfl_up_sync(0xFFFFFFFFu, cs[k], d); fv[k] = __shfl_up_sync(0xFFFFFFFFu, cv[k], d); }
+            if (lane >= d) {                              // (mine) after (earlier f)
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (cs[k] >= 0) {
+                        const int sk = cs[k];
+                        const int32_t es = sk == 0 ? fs[0] : (sk == 1 ? fs[1] : fs[2]);
+                        const uint32_t ev = sk == 0 ? fv[0] : (sk == 1 ? fv[1] : fv[2]);
+                        if (es < 0) { if (ev <= cv[k]) { bad = true; cv[k] = 1; } else cv[k] = ev - cv[k]; cs[k] = -1; }
+                        else { cs[k] = es; cv[k] = ev + cv[k]; }
+                    }
+                }
+            }
         }
+        // exclusive map of this lane applied to the repeat offsets entering this group of 32 blocks
+        int32_t xs[3]; uint32_t xv[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { xs[k] = __shfl_up_sync(0xFFFFFFFFu, cs[k], 1); xv[k] = __shfl_up_sync(0xFFFFFFFFu, cv[k], 1); }
+        if (lane == 0) { xs[0] = 0; xs[1] = 1; xs[2] = 2; xv[0] = xv[1] = xv[2] = 0; }
+        const uint32_t rin[3] = {rep0, rep1, rep2};
+        uint32_t inr[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (xs[k] < 0) inr[k] = xv[k];
+            else { const uint32_t x = xs[k] == 0 ? rin[0] : (xs[k] == 1 ? rin[1] : rin[2]); if (x <= xv[k]) { if (has_seq) bad = true; inr[k] = 1; } else inr[k] = x - xv[k]; }
+        }
+        const uint32_t in0 = inr[0], in1 = inr[1], in2 = inr[2];
+        // repeat offsets leaving the group = lane 31's inclusive map applied to the incoming ones
+        uint32_t outr[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int32_t ls = __shfl_sync(0xFFFFFFFFu, cs[k], 31);
+            const uint32_t lv = __shfl_sync(0xFFFFFFFFu, cv[k], 31);
+            if (ls < 0) outr[k] = lv;
+            else { const uint32_t x = ls == 0 ? rin[0] : (ls == 1 ? rin[1] : rin[2]); if (x <= lv) { bad = true; outr[k] = 1; } else outr[k] = x - lv; }
+        }
+        rep0 = outr[0]; rep1 = outr[1]; rep2 = outr[2];
         if (valid && has_seq) { BlockState& S = J.bstate[b]; S.rep_in[0] = in0; S.rep_in[1] = in1; S.rep_in[2] = in2; }
     }
     if (off - F.dst_off != F.dst_size) bad = true;
-    if (bad && lane == 0) flag_error(J, f, zc::E_SIZE);
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) flag_error(J, f, zc::E_SIZE);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -829,7 +859,7 @@ __device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t of
 constexpr uint32_t LZ_SHORT = 64;
 constexpr int LZ_CTA = 256;
 constexpr int LZ_HOPS = 8;
-constexpr uint32_t LZ_MAX_ROUNDS = 48;
+constexpr uint32_t LZ_MIN_ROUNDS = 12, LZ_MIN_PROGRESS = 24;
 
 // Returns 1 when match i may be copied now (d/off/ml filled), 0 when it has to wait, 2 when it was rejected.
 __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t round, uint64_t& d, uint32_t& off, uint32_t& ml) {
@@ -927,14 +957,17 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         lz_round(J, J.lz_list[cur], n, round, J.lz_list[cur ^ 1], &J.lz_count[cur ^ 1], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
                  &q_n, q_d, q_off, q_ml, q_i);
         NAF_GRID_SYNC();                                             // all copies and list appends of this round are visible
+        const uint32_t n_next = J.lz_count[cur ^ 1];
         if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[cur] = 0; // becomes the append target of the round after next
         cur ^= 1;
         NAF_GRID_SYNC();
-        if (round >= LZ_MAX_ROUNDS) break;        // very deep chains (text-like sections): hand over to the ordered finisher
+        // A round costs two grid barriers (~5 us) whatever it resolves; the ordered finisher copies ~2 matches/us.  When a
+        // round resolves only a handful of matches the section is one long dependency chain (text-like): hand it over.
+        if (round >= LZ_MIN_ROUNDS && n - n_next < LZ_MIN_PROGRESS && n_next > 8 * LZ_MIN_PROGRESS) break;
     }
 }
 
-// k_lz_finish: ordered finisher for what k_lz_resolve left behind (dependency chains deeper than LZ_MAX_ROUNDS, i.e.
+// k_lz_finish: ordered finisher for what k_lz_resolve left behind (rounds that stop making progress, i.e.
 // text-like sections where nearly every match feeds the next one).  One warp per frame walks the frame's matches in
 // order, 32 done-flags per step, and copies the pending ones cooperatively; in order, every source byte is final.
 __global__ void __launch_bounds__(32) k_lz_finish(JobDev J) {
@@ -956,7 +989,7 @@ __global__ void __launch_bounds__(32) k_lz_finish(JobDev J) {
             if (off == 0 || (uint64_t)off > d - F.dst_off) { if (lane == 0) flag_error(J, f, zc::E_OFFSET); return; }
             copy_match(J.out, d, off, R.ml, lane, 32);
             __syncwarp();
-            if (lane == 0) J.seq_done[k] = LZ_MAX_ROUNDS + 1;
+            if (lane == 0) J.seq_done[k] = 0x7FFFFFFFu;
             __syncwarp();
         }
     }
