@@ -148,12 +148,12 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     const uint64_t nseq = pl.seq_total;
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
-    c->misc_words = 1 + 2 + nf + 8;
+    c->misc_words = 1 + 3 + nf + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
-              c->seq32.ensure(nseq * 4 * 3 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
+              c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
               c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     const size_t nh = pl.huf_items.size();
@@ -184,11 +184,11 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.frames = (const zf::FrameDesc*)c->frames.p; J.blocks = (const zf::BlockDesc*)c->blocks.p;
     J.bstate = (zf::BlockState*)c->bstate.p; J.tables = (zc::SeqCell*)c->tables.p; J.table_al = (uint8_t*)c->table_al.p;
     J.seq_done = (uint32_t*)c->seq32.p;
-    J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq;
+    J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq; J.lz_list[2] = J.seq_done + 3 * nseq;
     J.seq = (zf::SeqRec*)c->seq64.p;
     J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
-    J.status = misc; J.lz_count = misc + 1; J.frame_bad = misc + 3;
+    J.status = misc; J.lz_count = misc + 1; J.frame_bad = misc + 4;
     J.coop_ctas = c->coop_ctas;
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;

@@ -947,21 +947,22 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_first(JobDev J) {
              &q_n, q_d, q_off, q_ml, q_i);
 }
 
-// Rounds 2..: persistent cooperative kernel over the worklist, ping-ponging between the two lists.
+// Rounds 2..: persistent cooperative kernel over the worklist.  Three lists rotate (read / append / being cleared), so a
+// round needs a single grid barrier.
 __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
     LZ_SHARED_QUEUE;
     uint32_t cur = 0;
     for (uint32_t round = 2;; round++) {
+        const uint32_t nxt = cur == 2 ? 0 : cur + 1, clr = nxt == 2 ? 0 : nxt + 1;
         const uint32_t n = J.lz_count[cur];                          // stable: written before the last grid barrier
         if (n == 0) break;
-        lz_round(J, J.lz_list[cur], n, round, J.lz_list[cur ^ 1], &J.lz_count[cur ^ 1], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
+        if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[clr] = 0; // append target of the NEXT round; idle in this one
+        lz_round(J, J.lz_list[cur], n, round, J.lz_list[nxt], &J.lz_count[nxt], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
                  &q_n, q_d, q_off, q_ml, q_i);
-        NAF_GRID_SYNC();                                             // all copies and list appends of this round are visible
-        const uint32_t n_next = J.lz_count[cur ^ 1];
-        if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[cur] = 0; // becomes the append target of the round after next
-        cur ^= 1;
-        NAF_GRID_SYNC();
-        // A round costs two grid barriers (~5 us) whatever it resolves; the ordered finisher copies ~2 matches/us.  When a
+        NAF_GRID_SYNC();                                             // copies, list appends and the cleared counter are visible
+        const uint32_t n_next = J.lz_count[nxt];
+        cur = nxt;
+        // A round costs a grid barrier (~3 us) whatever it resolves; the ordered finisher copies ~2 matches/us.  When a
         // round resolves only a handful of matches the section is one long dependency chain (text-like): hand it over.
         if (round >= LZ_MIN_ROUNDS && n - n_next < LZ_MIN_PROGRESS && n_next > 8 * LZ_MIN_PROGRESS) break;
     }
@@ -971,7 +972,7 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
 // text-like sections where nearly every match feeds the next one).  One warp per frame walks the frame's matches in
 // order, 32 done-flags per step, and copies the pending ones cooperatively; in order, every source byte is final.
 __global__ void __launch_bounds__(32) k_lz_finish(JobDev J) {
-    if (J.lz_count[0] == 0 && J.lz_count[1] == 0) return;
+    // (lists that were consumed keep a stale count; scanning the done flags is cheap when nothing is pending)
     const uint32_t f = blockIdx.x;
     if (J.frame_bad[f]) return;
     const FrameDesc& F = J.frames[f];
@@ -1004,7 +1005,7 @@ uint32_t lz_resolve_max_ctas(int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz_resolve, LZ_CTA, 0);
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 2) per_sm = 2;
     return (uint32_t)(sms > 0 && per_sm > 0 ? sms * per_sm : 1);
 #endif
 }
@@ -1034,6 +1035,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
         NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();
         uint32_t cg = J.coop_ctas ? J.coop_ctas : 1u;                 // co-resident CTAs for the grid barrier (queried by the API)
+        (void)cg;
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
         NAF_LAUNCH(k_lz_finish, J.n_frames, 32, 0, st, J); launches++;

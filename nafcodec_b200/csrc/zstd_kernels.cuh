@@ -28,8 +28,8 @@ struct JobDev {
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
     unsigned long long* debug;        // optional per-CTA phase clocks of k_huf_decode (NAFGPU_DEBUG_HUF=1), else null
-    uint32_t* lz_list[2];             // ping-pong worklists of matches still pending (n_seq entries each)
-    uint32_t* lz_count;               // [2] their lengths
+    uint32_t* lz_list[3];             // rotating worklists of matches still pending (n_seq entries each)
+    uint32_t* lz_count;               // [3] their lengths
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
     const zf::HufItem* huf_items;     // one per Huffman bitstream
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
