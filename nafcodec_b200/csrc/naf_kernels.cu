@@ -2,7 +2,7 @@
 //   CStringReader::next   reader.rs:20-31    -> k_naf_scan task 0/1 (NUL positions -> string offsets)
 //   LengthReader::next    reader.rs:46-68    -> k_naf_scan task 2   (u32 words, 0xFFFFFFFF continues a length)
 //   MaskReader::next      reader.rs:196-231  -> k_naf_scan task 3   (byte RLE, 0xFF continues a run)
-//   Decoder::mask_sequence mod.rs:402-441    -> toggle bitmap + k_mask_fix (the record-tail quirk) + k_unpack
+//   Decoder::mask_sequence mod.rs:402-441    -> toggle bitmap (+ per-chunk parity) + k_mask_fix (the record-tail quirk) + k_unpack
 //   SequenceReader::read_nucleotide / decode reader.rs:121-172 -> k_unpack (4-bit -> IUPAC, low nibble first)
 //   String::from_utf8     reader.rs:108-109  -> k_ascii_check + k_utf8_validate
 #include "naf_kernels.cuh"
@@ -50,7 +50,12 @@ __device__ __forceinline__ CS block_excl_scan(uint32_t c, uint64_t s, CS* total)
     return r;
 }
 
-__device__ __forceinline__ void toggle_bit(uint32_t* bits, uint64_t pos) { atomicXor(&bits[pos >> 5], 1u << (pos & 31)); }
+// Flips the mask state from residue `pos` on; the parity of the toggles of every CHUNK_RESIDUES chunk is kept beside the
+// bitmap (two toggles on the same bit cancel in both), so k_unpack gets its carry-in without a separate parity pass.
+__device__ __forceinline__ void toggle_bit(uint32_t* bits, uint32_t* chunk_par, uint64_t pos) {
+    atomicXor(&bits[pos >> 5], 1u << (pos & 31));
+    atomicXor(&chunk_par[pos / CHUNK_RESIDUES], 1u);
+}
 
 // --------------------------------------------------------------------------------------------------------------
 // k_naf_scan: grid (4 tasks, n_archives), 1024 threads.  One CTA streams its section with a running carry.
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
         const uint64_t size = A.mask_size;
         uint64_t* bounds = (uint64_t*)(arena + A.mask_bounds_off);
         uint32_t* bits = (uint32_t*)(arena + A.mask_bits_off);
+        uint32_t* cpar = (uint32_t*)(arena + A.chunk_par_off);
         uint64_t carry_c = 0, carry_s = 0;
         for (uint64_t base = 0; base < size; base += 1024 * 16) {
             uint64_t p0 = base + (uint64_t)tid * 16;
@@ -160,14 +166,14 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
             for (uint32_t j = 0; j < nvalid; j++) {
                 uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFF;
                 S += b;
-                if (b != 0xFF) { bounds[k++] = S; if (S <= A.seq_residues) toggle_bit(bits, S); }
+                if (b != 0xFF) { bounds[k++] = S; if (S <= A.seq_residues) toggle_bit(bits, cpar, S); }
             }
             carry_c += tot.c; carry_s += tot.s;
         }
         if (tid == 0) {
             if (size > 0 && src[size - 1] == 0xFF) {        // trailing 0xFF bytes at EOF still form a unit (reader.rs:206-209)
                 bounds[carry_c++] = carry_s;
-                if (carry_s <= A.seq_residues) toggle_bit(bits, carry_s);
+                if (carry_s <= A.seq_residues) toggle_bit(bits, cpar, carry_s);
             }
             counts->n_mask_runs = carry_c;
             counts->mask_sum = carry_s;
@@ -199,43 +205,9 @@ __global__ void __launch_bounds__(256) k_mask_fix(uint8_t* arena, const NafDev* 
     if (lo == n_runs) { atomicOr(status, zc::E_MASK); return; }      // "failed to get mask unit" (mod.rs:429-434)
     if (lo & 1) {
         uint64_t a = lo ? bounds[lo - 1] : 0;
-        toggle_bit(bits, a > S ? a : S);
-        toggle_bit(bits, E);
-    }
-}
-
-// k_mask_parity: parity of the toggle bits of every chunk (grid: max_chunks x n_archives, 1024 threads).
-__global__ void __launch_bounds__(1024) k_mask_parity(uint8_t* arena, const NafDev* archives) {
-    const NafDev& A = archives[blockIdx.y];
-    if (!(A.has & HAS_MASK) || !(A.has & HAS_SEQUENCE) || blockIdx.x >= A.n_chunks) return;
-    __shared__ uint32_t wp[32];
-    const uint32_t* bits = (const uint32_t*)(arena + A.mask_bits_off);
-    uint32_t* par = (uint32_t*)(arena + A.chunk_par_off);
-    const uint64_t n_words = (A.seq_residues + 32) / 32;
-    const uint64_t wi = (uint64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x;
-    uint32_t p = wi < n_words ? (__popc(bits[wi]) & 1) : 0;
-    uint32_t b = __ballot_sync(FULL, p);
-    if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = __popc(b) & 1;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t bb = __ballot_sync(FULL, wp[threadIdx.x]);
-        if (threadIdx.x == 0) par[blockIdx.x] = __popc(bb) & 1;
-    }
-}
-
-// k_mask_parity_scan: exclusive XOR scan of the chunk parities, in place (grid: 1 x n_archives).
-__global__ void __launch_bounds__(1024) k_mask_parity_scan(uint8_t* arena, const NafDev* archives) {
-    const NafDev& A = archives[blockIdx.y];
-    if (!(A.has & HAS_MASK) || !(A.has & HAS_SEQUENCE)) return;
-    uint32_t* par = (uint32_t*)(arena + A.chunk_par_off);
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < A.n_chunks; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t p = i < A.n_chunks ? par[i] : 0;
-        CS tot;
-        CS ex = block_excl_scan(p, 0, &tot);
-        if (i < A.n_chunks) par[i] = (carry + ex.c) & 1;
-        carry += tot.c;
+        uint32_t* cpar = (uint32_t*)(arena + A.chunk_par_off);
+        toggle_bit(bits, cpar, a > S ? a : S);
+        toggle_bit(bits, cpar, E);
     }
 }
 
@@ -267,8 +239,8 @@ __device__ __forceinline__ uint32_t spread4_x20(uint32_t q) {        // 4 mask b
 __global__ void __launch_bounds__(1024) k_unpack(uint8_t* arena, const NafDev* archives) {
     const NafDev& A = archives[blockIdx.y];
     if (!(A.has & HAS_SEQUENCE) || A.seq_type > 1 || blockIdx.x >= A.n_chunks) return;
-    __shared__ uint32_t wp[32];
-    __shared__ uint32_t wball;
+    __shared__ uint32_t wp[32], wp2[32];
+    __shared__ uint32_t wball, cball;
     const NafCounts* counts = (const NafCounts*)(arena + A.counts_off);
     const uint64_t total = counts->total_residues;
     const uint64_t wi = (uint64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x;
@@ -286,8 +258,16 @@ __global__ void __launch_bounds__(1024) k_unpack(uint8_t* arena, const NafDev* a
         __syncthreads();
         if (warp == 0) { uint32_t bb = __ballot_sync(FULL, wp[lane]); if (lane == 0) wball = bb; }
         __syncthreads();
-        uint32_t carry = ((const uint32_t*)(arena + A.chunk_par_off))[blockIdx.x]
-                       ^ (__popc(wball & ((1u << warp) - 1u)) & 1) ^ (__popc(b & ((1u << lane) - 1u)) & 1);
+        // carry into this chunk = parity of all toggles in the chunks before it
+        const uint32_t* cpar = (const uint32_t*)(arena + A.chunk_par_off);
+        uint32_t cp = 0;
+        for (uint32_t c = threadIdx.x; c < blockIdx.x; c += blockDim.x) cp ^= cpar[c];
+        const uint32_t cb = __ballot_sync(FULL, cp & 1);
+        if (lane == 0) wp2[warp] = __popc(cb) & 1;
+        __syncthreads();
+        if (warp == 0) { uint32_t bb = __ballot_sync(FULL, wp2[lane]); if (lane == 0) cball = bb; }
+        __syncthreads();
+        uint32_t carry = (__popc(cball) & 1) ^ (__popc(wball & ((1u << warp) - 1u)) & 1) ^ (__popc(b & ((1u << lane) - 1u)) & 1);
         mask = carry ? ~m : m;
     }
     if (r0 >= total) return;
@@ -318,7 +298,8 @@ __global__ void __launch_bounds__(1024) k_text_mask(uint8_t* arena, const NafDev
     const uint64_t n_words = (A.seq_residues + 32) / 32;
     if (wi >= n_words) return;
     // carry: chunk carry ^ parity of the words of this chunk before wi (serial: this path is rare)
-    uint32_t carry = par[blockIdx.x];
+    uint32_t carry = 0;
+    for (uint32_t c = 0; c < blockIdx.x; c++) carry ^= par[c] & 1;
     for (uint64_t j = (uint64_t)blockIdx.x * CHUNK_WORDS; j < wi; j++) carry ^= __popc(bits[j]) & 1;
     uint32_t m = bits[wi];
     m ^= m << 1; m ^= m << 2; m ^= m << 4; m ^= m << 8; m ^= m << 16;
@@ -409,7 +390,7 @@ __global__ void __launch_bounds__(256) k_utf8_validate(uint8_t* arena, const Naf
 
 // --------------------------------------------------------------------------------------------------------------
 int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives, uint64_t max_records,
-                     uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, uint32_t* status, cudaStream_t st,
+                     uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, bool any_text_mask, uint32_t* status, cudaStream_t st,
                      StageEvents* ev) {
     StageEvents none;
     if (!ev) ev = &none;
@@ -420,13 +401,11 @@ int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives
     if (max_chunks > 0 && any_mask) {
         if (rec_grid) { NAF_LAUNCH(k_mask_fix, dim3(rec_grid, n_archives), 256, 0, st, arena, archives, status); launches++; }
         ev->mark();
-        NAF_LAUNCH(k_mask_parity, dim3(max_chunks, n_archives), 1024, 0, st, arena, archives); launches++;
-        NAF_LAUNCH(k_mask_parity_scan, dim3(1, n_archives), 1024, 0, st, arena, archives); launches++;
         ev->mark();
     } else { ev->mark(); ev->mark(); }
     if (max_chunks > 0) {
         NAF_LAUNCH(k_unpack, dim3(max_chunks, n_archives), 1024, 0, st, arena, archives); launches++;
-        if (any_mask) { NAF_LAUNCH(k_text_mask, dim3(max_chunks, n_archives), 1024, 0, st, arena, archives); launches++; }
+        if (any_text_mask) { NAF_LAUNCH(k_text_mask, dim3(max_chunks, n_archives), 1024, 0, st, arena, archives); launches++; }
     }
     ev->mark();
     if (max_text_bytes > 0) {

@@ -40,9 +40,9 @@ struct NafDev {
 
 // Enqueues the NAF stage for n_archives archives on `stream`.  max_* are maxima over the archives (grid sizing).
 // Returns the number of kernels launched; `ev` (optional) gets one mark per stage (NAF_STAGES).
-// any_mask: some archive decodes sequence + mask.
+// any_mask: some archive decodes sequence + mask; any_text_mask: one of those is protein/text.
 int launch_naf_stage(uint8_t* arena, const NafDev* archives_dev, uint32_t n_archives, uint64_t max_records,
-                     uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, uint32_t* status, cudaStream_t stream,
+                     uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, bool any_text_mask, uint32_t* status, cudaStream_t stream,
                      StageEvents* ev);
 constexpr int NAF_STAGES = 5;
 

@@ -75,7 +75,7 @@ struct nafgpu_ctx {
     uint64_t z1_size = 0, z2_off = 0, z2_size = 0, arena_size = 0, counts_size = 0;
     uint64_t max_records = 0, max_text = 0;
     uint32_t max_chunks = 0;
-    bool any_mask = false;
+    bool any_mask = false, any_text_mask = false;
     uint32_t coop_ctas = 1;
     size_t misc_words = 0;
     nafgpu_job_stats stats;
@@ -114,7 +114,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     int launches = zk::launch_zstd_stage(c->J, st, ev);
     launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)c->nafdev.p, (uint32_t)c->arch.size(), c->max_records,
-                                     c->max_chunks, c->max_text, c->any_mask, c->J.status, st, ev);
+                                     c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
     CUDA_TRY(c, cudaGetLastError());
     c->ran = true;
@@ -148,7 +148,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     const uint64_t nseq = pl.seq_total;
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
-    c->misc_words = 1 + 3 + nf + 8;
+    c->misc_words = 1 + 3 + 1 + nf + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
@@ -188,7 +188,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.seq = (zf::SeqRec*)c->seq64.p;
     J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
-    J.status = misc; J.lz_count = misc + 1; J.frame_bad = misc + 4;
+    J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.frame_bad = misc + 5;
     J.coop_ctas = c->coop_ctas;
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
@@ -271,7 +271,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     c->counts_size = align_up((uint64_t)n * sizeof(nk::NafCounts));
     off = c->counts_size;
     uint64_t comp_off = 0;
-    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false; c->any_text_mask = false;
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
@@ -316,7 +316,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         if (P.dec[4]) {
             D.n_chunks = (uint32_t)((residues + 1 + nk::CHUNK_RESIDUES - 1) / nk::CHUNK_RESIDUES);
             c->max_chunks = std::max(c->max_chunks, D.n_chunks);
-            if (P.dec[3]) c->any_mask = true;
+            if (P.dec[3]) { c->any_mask = true; if (!P.nucleotide) c->any_text_mask = true; }
             if (!P.nucleotide) c->max_text = std::max(c->max_text, P.blob_size[4]);
         }
         if (P.dec[5]) c->max_text = std::max(c->max_text, P.blob_size[5]);
@@ -333,6 +333,8 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         nk::NafDev& D = c->arch[a];
         D.mask_bits_off = off;
         if (P.dec[3]) off = align_up(off + 4 * ((D.seq_residues + 32) / 32 + 1));
+        D.chunk_par_off = off;
+        if (P.dec[3]) off = align_up(off + 4 * ((uint64_t)D.n_chunks + 1));
     }
     c->z2_size = off - c->z2_off;
     for (uint32_t a = 0; a < n; a++) {
@@ -343,7 +345,6 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         if (P.dec[3]) place(3);
         if (P.dec[4] && P.nucleotide) place(4);
         D.mask_bounds_off = off; if (P.dec[3]) off = align_up(off + 8 * (P.blob_size[3] + 2));
-        D.chunk_par_off = off; if (P.dec[3]) off = align_up(off + 4 * ((uint64_t)D.n_chunks + 1));
         D.ids_off = P.blob_off[0]; D.ids_size = P.blob_size[0];
         D.com_off = P.blob_off[1]; D.com_size = P.blob_size[1];
         D.len_off = P.blob_off[2]; D.len_size = P.blob_size[2];
@@ -392,7 +393,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->z1_size = align_up(ALIGN + regen_size + 32);
     c->z2_off = c->z1_size; c->z2_size = 0;
     c->arena_size = c->z1_size + 256;
-    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false; c->any_text_mask = false;
     std::string e;
     int rc = fw::walk_frame(frame, 0, frame_size, ALIGN, regen_size, c->plan, e);
     if (rc) return fail(c, rc, e);
@@ -560,7 +561,7 @@ int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
 
 const char* nafgpu_stage_name(uint32_t s) {
     static const char* names[N_STAGES] = {"memset+build_tables", "decode_sequences", "frame_scan", "huf_decode", "lz_literals", "lz_first",
-                                          "lz_resolve", "naf_scan", "mask_fix", "mask_parity", "unpack", "utf8_check"};
+                                          "lz_resolve", "naf_scan", "mask_fix", "-", "unpack", "utf8_check"};
     return s < (uint32_t)N_STAGES ? names[s] : "?";
 }
 

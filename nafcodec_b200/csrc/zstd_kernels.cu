@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128) k_frame_scan(JobDev J) {
 // Shared memory: decode table 4 KB | weights | scratch | compressed stream (16 B-aligned image of global memory,
 // preceded by >= 16 zero bytes so reads below bit 0 see zeros) | output image (same 16 B phase as the destination).
 constexpr int HUF_T_BIG = 512;                    // threads per stream for 4-stream blocks (up to 32 Ki symbols)
-constexpr int HUF_T_SMALL = 32;                   // one warp for short streams (1-stream blocks, tiny flushed blocks)
+constexpr int HUF_T_SMALL = 128;                  // four warps for short streams (1-stream blocks, tiny flushed blocks)
 constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
 constexpr int HUF_SEG = 96;                       // tracks are compared for merging every HUF_SEG bits
 constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
@@ -964,7 +964,10 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         cur = nxt;
         // A round costs a grid barrier (~3 us) whatever it resolves; the ordered finisher copies ~2 matches/us.  When a
         // round resolves only a handful of matches the section is one long dependency chain (text-like): hand it over.
-        if (round >= LZ_MIN_ROUNDS && n - n_next < LZ_MIN_PROGRESS && n_next > 8 * LZ_MIN_PROGRESS) break;
+        if (round >= LZ_MIN_ROUNDS && n - n_next < LZ_MIN_PROGRESS && n_next > 8 * LZ_MIN_PROGRESS) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = 1;
+            break;
+        }
     }
 }
 
@@ -972,7 +975,7 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
 // text-like sections where nearly every match feeds the next one).  One warp per frame walks the frame's matches in
 // order, 32 done-flags per step, and copies the pending ones cooperatively; in order, every source byte is final.
 __global__ void __launch_bounds__(32) k_lz_finish(JobDev J) {
-    // (lists that were consumed keep a stale count; scanning the done flags is cheap when nothing is pending)
+    if (*J.lz_handover == 0) return;                // the rounds finished everything (the normal case)
     const uint32_t f = blockIdx.x;
     if (J.frame_bad[f]) return;
     const FrameDesc& F = J.frames[f];
