@@ -38,6 +38,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.  Keep a private copy
+# of the real stdout for that line and point fd 1 at stderr for everything else.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # workload: cfg2 archives, generated with the oracle's restatement of the reference encoder (+ mask section)
 def make_archive(seed, n_res, level):
@@ -149,7 +160,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample_n} cfg2 archives per step, one archive per core, {cores} threads; oracle/naf_oracle.c on libzstd {O.lib().nafo_zstd_version().decode()} (the Rust reference cannot be built in this image: no cargo/rustc)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, batch):
@@ -341,7 +352,7 @@ def main():
                 "cpu_baseline": cpu, "clocks": clocks, "single_archive": single,
                 "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences),
                         "compressed_bytes": int(st.compressed_bytes), "ascii_bytes": int(st.ascii_bytes), "algorithmic_bytes": int(st.algorithmic_bytes)}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
