@@ -12,6 +12,8 @@
 //   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, grid barrier between rounds
 //   k_lz_finish         per frame: ordered finisher when the rounds stop making progress (text-like sections)
 #include "zstd_kernels.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace zk {
 
@@ -411,6 +413,10 @@ __device__ __forceinline__ void win_consume(Win& w, int len) {
 
 // 16-entry nibble predicate held in four registers (one byte per nibble value, bit 0 set = "NOT a complete 4-bit
 // codeword"): lets the 4-bit fast path test eight consecutive codewords of a track with a handful of prmt instructions.
+#if defined(NAFGPU_EMULATE)
+static long g_dbg_fast = 0, g_dbg_generic = 0;
+struct DbgPrinter { ~DbgPrinter() { if (getenv("NAFGPU_DEBUG_HUF")) fprintf(stderr, "[emul] fast4 words %ld, generic lookups %ld\n", g_dbg_fast, g_dbg_generic); } } g_dbg_printer;
+#endif
 struct Nib4 { uint32_t k0, k1, k2, k3; };
 __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
@@ -433,7 +439,7 @@ __device__ __forceinline__ uint32_t nib4_flags(const Nib4& n, uint32_t x16) {
 // bm: boundary-mask table, index = next 12 bits, bit j set <=> j+1 bits is a cumulative length of whole codewords.
 // fast4 != 0: most codewords are 4 bits long (4-bit packed DNA with near-uniform composition): while the next 32 bits
 // are eight complete 4-bit codewords the track advances a whole word at a time without touching the tables.
-__device__ __noinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, int& q, int& cnt, int lim, Nib4 nib, int fast4) {
+__device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, int& q, int& cnt, int lim, const Nib4& nib, int fast4) {
     int rem = lim - q;
     if (rem <= 0) return;
     int x = xtop - q;
@@ -448,13 +454,16 @@ __device__ __noinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, i
                 const uint32_t w32 = __funnelshift_r(lo, hi, rr - 32);
                 if ((nib4_flags(nib, w32 & 0xFFFFu) | nib4_flags(nib, w32 >> 16)) & 0x01010101u) break;
                 cnt += 8; rem -= 32; x -= 32;
+#if defined(NAFGPU_EMULATE)
+                g_dbg_fast++;
+#endif
                 hi = lo; wa -= 4; lo = lds32(wa);
             }
         }
         Win w;
         win_init(w, comp, x);
         bool landed = false;
-        for (int step = 0; step < (fast4 ? 2 : 0x7FFFFFFF); step++) {
+        for (int step = 0; step < (fast4 && rem > 44 ? 1 : 0x7FFFFFFF); step++) {
             const uint32_t m = lds16(bm + 2 * win_peek(w));
             if (rem <= HUF_W) {
                 const uint32_t t = m >> (rem - 1);                 // boundaries at or past the limit
@@ -467,6 +476,9 @@ __device__ __noinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, i
                 }
             }
             const int used = 32 - __clz((int)m);                   // every window holds >= 1 whole codeword (max_bits <= 11)
+#if defined(NAFGPU_EMULATE)
+            g_dbg_generic++;
+#endif
             cnt += __popc(m);
             rem -= used;
             x -= used;
@@ -678,32 +690,21 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
         fast4 = (MULTI && n4 >= 8) ? 1 : 0;
     }
     if (active) {
-        // stops: right below the candidate window (tracks on the same codeword chain coincide there), one more after
-        // HUF_SEG bits (codes that resynchronise have merged by then), then the end of the range
-        int lim = q0 + HUF_W;
-        for (int stop = 0;; stop++) {
-            const int l = lim < qe ? lim : qe;
-            if ((live & (live - 1)) == 0) {                              // a single track left: straight to the end
-                const int k0 = __ffs((int)live) - 1;
-                int q = 0, c = 0;
-#pragma unroll
-                for (int k = 0; k < MAXC; k++) if (k == k0) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
-                track_advance(s_comp, s_bm, XTOP, q, c, qe, nib, fast4);
-#pragma unroll
-                for (int k = 0; k < MAXC; k++) if (k == k0) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
-                break;
-            }
+        // (1) first stop right below the candidate window: one boundary-mask lookup per candidate lands every track on
+        //     its first codeword boundary >= q0 + 12; tracks on the same codeword chain coincide there
+        {
+            const int l = (q0 + HUF_W < qe) ? q0 + HUF_W : qe;
 #pragma unroll
             for (int k = 0; k < MAXC; k++) {
                 if (live & (1u << k)) {
-                    int q = q0 + (int)(pc[k] & 0xFFFFu), c = (int)(pc[k] >> 16);
-                    track_advance(s_comp, s_bm, XTOP, q, c, l, nib, fast4);
+                    int q = q0 + k, c = 0;
+                    track_advance(s_comp, s_bm, XTOP, q, c, l, nib, 0);
                     pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
                 }
             }
-            if (!(live & ~15u)) {                                        // common steady state: at most tracks 0..3 alive
 #pragma unroll
-                for (int k = 1; k < 4; k++) {
+            for (int k = 1; k < MAXC; k++) {
+                if (live & (1u << k)) {
 #pragma unroll
                     for (int j = 0; j < k; j++) {
                         if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
@@ -712,22 +713,68 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
                         }
                     }
                 }
-            } else {
+            }
+        }
+        // (2) the survivors (1 for codes that resynchronise, one per phase -- 4 -- for uniform 4-bit codes) go into four
+        //     register slots and run to the end of the range; further survivors (rare) take the generic loop below
+        uint32_t sp[4] = {0, 0, 0, 0};
+        int sk[4] = {-1, -1, -1, -1};
+        uint32_t rest = live;
+        {
+            int ns = 0;
 #pragma unroll
-                for (int k = 1; k < MAXC; k++) {
-                    if (live & (1u << k)) {
+            for (int k = 0; k < MAXC; k++) {
+                if ((live & (1u << k)) && ns < 4) {
 #pragma unroll
-                        for (int j = 0; j < k; j++) {
-                            if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
-                                live &= ~(1u << k);
-                                mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
-                            }
-                        }
+                    for (int t = 0; t < 4; t++) if (t == ns) { sp[t] = pc[k]; sk[t] = k; }
+                    ns++;
+                    rest &= ~(1u << k);
+                }
+            }
+        }
+        const int mid = q0 + HUF_W + HUF_SEG;
+        if (!fast4 && sk[1] >= 0 && mid < qe) {
+            // codes that resynchronise: one more stop, then merge what has met (saves following twins to the end)
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (sk[t] >= 0) {
+                    int q = q0 + (int)(sp[t] & 0xFFFFu), c = (int)(sp[t] >> 16);
+                    track_advance(s_comp, s_bm, XTOP, q, c, mid, nib, 0);
+                    sp[t] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
+                }
+            }
+#pragma unroll
+            for (int t = 1; t < 4; t++) {
+#pragma unroll
+                for (int u = 0; u < t; u++) {
+                    if (sk[t] >= 0 && sk[u] >= 0 && ((sp[t] ^ sp[u]) & 0xFFFFu) == 0) {
+                        const uint32_t m = (((sp[t] >> 16) - (sp[u] >> 16)) & 0xFFFFu) | ((uint32_t)sk[u] << 16);
+#pragma unroll
+                        for (int k = 0; k < MAXC; k++) if (k == sk[t]) { mg[k] = m; pc[k] = sp[t]; }
+                        live &= ~(1u << sk[t]);
+                        sk[t] = -1;
                     }
                 }
             }
-            if (l >= qe) break;
-            lim = stop == 0 ? lim + HUF_SEG : qe;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (sk[t] >= 0) {
+                int q = q0 + (int)(sp[t] & 0xFFFFu), c = (int)(sp[t] >> 16);
+                track_advance(s_comp, s_bm, XTOP, q, c, qe, nib, fast4);
+                sp[t] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) if (k == sk[t]) pc[k] = sp[t];
+            }
+        }
+        for (uint32_t m = rest; m; m &= m - 1) {
+            const int kk = __ffs((int)m) - 1;
+            int q = 0, c = 0;
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) if (k == kk) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
+            track_advance(s_comp, s_bm, XTOP, q, c, qe, nib, 0);
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) if (k == kk) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
         }
     }
     // resolve merged tracks (representatives always have a lower index): landing position and symbol count per candidate
