@@ -12,8 +12,6 @@
 //   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, grid barrier between rounds
 //   k_lz_finish         per frame: ordered finisher when the rounds stop making progress (text-like sections)
 #include "zstd_kernels.cuh"
-#include <stdio.h>
-#include <stdlib.h>
 
 namespace zk {
 
@@ -411,80 +409,28 @@ __device__ __forceinline__ void win_consume(Win& w, int len) {
     if (w.rr < HUF_W) { w.hi = w.lo; w.waddr -= 4; w.lo = lds32(w.waddr); w.rr += 32; }
 }
 
-// 16-entry nibble predicate held in four registers (one byte per nibble value, bit 0 set = "NOT a complete 4-bit
-// codeword"): lets the 4-bit fast path test eight consecutive codewords of a track with a handful of prmt instructions.
-#if defined(NAFGPU_EMULATE)
-static long g_dbg_fast = 0, g_dbg_generic = 0;
-struct DbgPrinter { ~DbgPrinter() { if (getenv("NAFGPU_DEBUG_HUF")) fprintf(stderr, "[emul] fast4 words %ld, generic lookups %ld\n", g_dbg_fast, g_dbg_generic); } } g_dbg_printer;
-#endif
-struct Nib4 { uint32_t k0, k1, k2, k3; };
-__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
-#if defined(__CUDA_ARCH__)
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-#else
-    return __byte_perm(a, b, sel);
-#endif
-}
-// flags (bit 0 of each byte) of the four nibbles packed in x16
-__device__ __forceinline__ uint32_t nib4_flags(const Nib4& n, uint32_t x16) {
-    const uint32_t sel = x16 & 0x7777u;
-    const uint32_t lo = prmt_b32(n.k0, n.k1, sel), hi = prmt_b32(n.k2, n.k3, sel);
-    const uint32_t m = prmt_b32(0x80808080u, 0u, x16 & 0x8888u);       // 0xFF where nibble >= 8, else 0x80 (flags live in bit 0)
-    return (lo & ~m) | (hi & m);
-}
-
 // Follows one track from q (bits below the top of the stream) to the FIRST codeword boundary >= lim, counting symbols.
 // bm: boundary-mask table, index = next 12 bits, bit j set <=> j+1 bits is a cumulative length of whole codewords.
-// fast4 != 0: most codewords are 4 bits long (4-bit packed DNA with near-uniform composition): while the next 32 bits
-// are eight complete 4-bit codewords the track advances a whole word at a time without touching the tables.
-__device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, int& q, int& cnt, int lim, const Nib4& nib, int fast4) {
+__device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, int& q, int& cnt, int lim) {
     int rem = lim - q;
     if (rem <= 0) return;
-    int x = xtop - q;
+    Win w;
+    win_init(w, comp, xtop - q);
     for (;;) {
-        if (fast4 && rem > 32) {
-            // window {hi:lo} = bits [32*qi, 32*qi + 64), rr = x - 32*qi in [32, 64)
-            int qi = (x >> 5) - 1;
-            saddr_t wa = comp + 4 * qi;
-            uint32_t lo = lds32(wa), hi = lds32(wa + 4);
-            const int rr = x - (qi << 5);
-            while (rem > 32) {
-                const uint32_t w32 = __funnelshift_r(lo, hi, rr - 32);
-                if ((nib4_flags(nib, w32 & 0xFFFFu) | nib4_flags(nib, w32 >> 16)) & 0x01010101u) break;
-                cnt += 8; rem -= 32; x -= 32;
-#if defined(NAFGPU_EMULATE)
-                g_dbg_fast++;
-#endif
-                hi = lo; wa -= 4; lo = lds32(wa);
+        const uint32_t m = lds16(bm + 2 * win_peek(w));
+        if (rem <= HUF_W) {
+            const uint32_t t = m >> (rem - 1);                 // boundaries at or past the limit
+            if (t) {
+                const int j = __ffs((int)t) - 1 + rem - 1;
+                cnt += __popc(m & ((2u << j) - 1u));
+                rem -= j + 1;
+                break;
             }
         }
-        Win w;
-        win_init(w, comp, x);
-        bool landed = false;
-        for (int step = 0; step < (fast4 && rem > 44 ? 1 : 0x7FFFFFFF); step++) {
-            const uint32_t m = lds16(bm + 2 * win_peek(w));
-            if (rem <= HUF_W) {
-                const uint32_t t = m >> (rem - 1);                 // boundaries at or past the limit
-                if (t) {
-                    const int j = __ffs((int)t) - 1 + rem - 1;
-                    cnt += __popc(m & ((2u << j) - 1u));
-                    rem -= j + 1;
-                    landed = true;
-                    break;
-                }
-            }
-            const int used = 32 - __clz((int)m);                   // every window holds >= 1 whole codeword (max_bits <= 11)
-#if defined(NAFGPU_EMULATE)
-            g_dbg_generic++;
-#endif
-            cnt += __popc(m);
-            rem -= used;
-            x -= used;
-            win_consume(w, used);
-        }
-        if (landed) break;
+        const int used = 32 - __clz((int)m);                   // every window holds >= 1 whole codeword (max_bits <= 11)
+        cnt += __popc(m);
+        rem -= used;
+        win_consume(w, used);
     }
     q = lim - rem;
 }
@@ -671,40 +617,33 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
 #pragma unroll
     for (int k = 0; k < MAXC; k++) { pc[k] = (uint32_t)k; mg[k] = 0; }
     const saddr_t s_comp = to_saddr(scomp), s_bm = to_saddr(bm);
-    // nibble predicate of the 4-bit fast path: nibble v is a complete codeword iff the base-table entry of "v followed by
-    // zeros" has length 4.  Enabled when at least 8 of the 16 nibbles are (4-bit packed DNA: all 16 of them, typically).
-    Nib4 nib;
-    int fast4 = 0;
-    {
-        uint32_t kk[4] = {0, 0, 0, 0};
-        int n4 = 0;
-        if (maxbits >= 4) {
-#pragma unroll
-            for (int v = 0; v < 16; v++) {
-                const bool is4 = (table[v << (maxbits - 4)] & 0xFFu) == 4u;
-                n4 += is4;
-                if (!is4) kk[v >> 2] |= 1u << (8 * (v & 3));
-            }
-        }
-        nib.k0 = kk[0]; nib.k1 = kk[1]; nib.k2 = kk[2]; nib.k3 = kk[3];
-        fast4 = (MULTI && n4 >= 8) ? 1 : 0;
-    }
     if (active) {
-        // (1) first stop right below the candidate window: one boundary-mask lookup per candidate lands every track on
-        //     its first codeword boundary >= q0 + 12; tracks on the same codeword chain coincide there
-        {
-            const int l = (q0 + HUF_W < qe) ? q0 + HUF_W : qe;
+        // stops: right below the candidate window (tracks on the same codeword chain coincide there), one more after
+        // HUF_SEG bits (codes that resynchronise have merged by then), then the end of the range
+        int lim = q0 + HUF_W;
+        for (int stop = 0;; stop++) {
+            const int l = lim < qe ? lim : qe;
+            if ((live & (live - 1)) == 0) {                              // a single track left: straight to the end
+                const int k0 = __ffs((int)live) - 1;
+                int q = 0, c = 0;
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) if (k == k0) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
+                track_advance(s_comp, s_bm, XTOP, q, c, qe);
+#pragma unroll
+                for (int k = 0; k < MAXC; k++) if (k == k0) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
+                break;
+            }
 #pragma unroll
             for (int k = 0; k < MAXC; k++) {
                 if (live & (1u << k)) {
-                    int q = q0 + k, c = 0;
-                    track_advance(s_comp, s_bm, XTOP, q, c, l, nib, 0);
+                    int q = q0 + (int)(pc[k] & 0xFFFFu), c = (int)(pc[k] >> 16);
+                    track_advance(s_comp, s_bm, XTOP, q, c, l);
                     pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
                 }
             }
+            if (!(live & ~15u)) {                                        // common steady state: at most tracks 0..3 alive
 #pragma unroll
-            for (int k = 1; k < MAXC; k++) {
-                if (live & (1u << k)) {
+                for (int k = 1; k < 4; k++) {
 #pragma unroll
                     for (int j = 0; j < k; j++) {
                         if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
@@ -713,68 +652,22 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
                         }
                     }
                 }
-            }
-        }
-        // (2) the survivors (1 for codes that resynchronise, one per phase -- 4 -- for uniform 4-bit codes) go into four
-        //     register slots and run to the end of the range; further survivors (rare) take the generic loop below
-        uint32_t sp[4] = {0, 0, 0, 0};
-        int sk[4] = {-1, -1, -1, -1};
-        uint32_t rest = live;
-        {
-            int ns = 0;
+            } else {
 #pragma unroll
-            for (int k = 0; k < MAXC; k++) {
-                if ((live & (1u << k)) && ns < 4) {
+                for (int k = 1; k < MAXC; k++) {
+                    if (live & (1u << k)) {
 #pragma unroll
-                    for (int t = 0; t < 4; t++) if (t == ns) { sp[t] = pc[k]; sk[t] = k; }
-                    ns++;
-                    rest &= ~(1u << k);
-                }
-            }
-        }
-        const int mid = q0 + HUF_W + HUF_SEG;
-        if (!fast4 && sk[1] >= 0 && mid < qe) {
-            // codes that resynchronise: one more stop, then merge what has met (saves following twins to the end)
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (sk[t] >= 0) {
-                    int q = q0 + (int)(sp[t] & 0xFFFFu), c = (int)(sp[t] >> 16);
-                    track_advance(s_comp, s_bm, XTOP, q, c, mid, nib, 0);
-                    sp[t] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
-                }
-            }
-#pragma unroll
-            for (int t = 1; t < 4; t++) {
-#pragma unroll
-                for (int u = 0; u < t; u++) {
-                    if (sk[t] >= 0 && sk[u] >= 0 && ((sp[t] ^ sp[u]) & 0xFFFFu) == 0) {
-                        const uint32_t m = (((sp[t] >> 16) - (sp[u] >> 16)) & 0xFFFFu) | ((uint32_t)sk[u] << 16);
-#pragma unroll
-                        for (int k = 0; k < MAXC; k++) if (k == sk[t]) { mg[k] = m; pc[k] = sp[t]; }
-                        live &= ~(1u << sk[t]);
-                        sk[t] = -1;
+                        for (int j = 0; j < k; j++) {
+                            if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
+                                live &= ~(1u << k);
+                                mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
+                            }
+                        }
                     }
                 }
             }
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            if (sk[t] >= 0) {
-                int q = q0 + (int)(sp[t] & 0xFFFFu), c = (int)(sp[t] >> 16);
-                track_advance(s_comp, s_bm, XTOP, q, c, qe, nib, fast4);
-                sp[t] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
-#pragma unroll
-                for (int k = 0; k < MAXC; k++) if (k == sk[t]) pc[k] = sp[t];
-            }
-        }
-        for (uint32_t m = rest; m; m &= m - 1) {
-            const int kk = __ffs((int)m) - 1;
-            int q = 0, c = 0;
-#pragma unroll
-            for (int k = 0; k < MAXC; k++) if (k == kk) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
-            track_advance(s_comp, s_bm, XTOP, q, c, qe, nib, 0);
-#pragma unroll
-            for (int k = 0; k < MAXC; k++) if (k == kk) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
+            if (l >= qe) break;
+            lim = stop == 0 ? lim + HUF_SEG : qe;
         }
     }
     // resolve merged tracks (representatives always have a lower index): landing position and symbol count per candidate
