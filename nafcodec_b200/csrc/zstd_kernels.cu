@@ -366,9 +366,10 @@ constexpr int HUF_T_SMALL = 128;                  // four warps for short stream
 constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
 constexpr int HUF_SEG = 96;                       // tracks are compared for merging every HUF_SEG bits
 constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
-__host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : HUF_SMALL_MAX_SYM) + 64u; }
-// t1 4096 | weights 256 | wcnt 256 | misc 256 | bm 8192 | [big only: t3 16384] | output image | (dynamic) compressed stream image
-__host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return 8192u + (T == HUF_T_BIG ? 16384u : 0u); }
+__host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : (HUF_SMALL_MAX_SYM < 8192u ? 8192u : HUF_SMALL_MAX_SYM)) + 64u; }
+// t1 4096 | weights 256 | wcnt 256 | misc 256 | [big only: t3 16384] | output image / boundary masks | (dynamic) compressed stream image
+// the boundary-mask table (8 KB, phase 1 only) shares its space with the output image (phase 2 and flush only)
+__host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return T == HUF_T_BIG ? 16384u : 0u; }
 __host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 768u + huf_multi_bytes(T) + huf_sout_bytes(T); }
 
 // ---- shared-memory access by explicit shared-space address ---------------------------------------------------------
@@ -503,7 +504,7 @@ __device__ __forceinline__ uint64_t map_compose(uint64_t g, uint64_t f) {
 constexpr uint64_t MAP_IDENTITY = 0xFEDCBA9876543210ull;
 
 template <int HUF_T>
-__global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* items) {
+__global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobDev J, const HufItem* items) {
     NAF_DYN_SMEM(unsigned char, smem);
     constexpr uint32_t HUF_FIXED_SMEM = huf_fixed_smem(HUF_T);
     constexpr int NWARPS = HUF_T / 32;
@@ -513,9 +514,9 @@ __global__ void __launch_bounds__(HUF_T) k_huf_decode(JobDev J, const HufItem* i
     uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] count scan, [34..49] warp start candidates
     uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [NWARPS] composed map of each warp; reuses wcnt after the table build
     constexpr bool MULTI = HUF_T == HUF_T_BIG;
-    uint16_t* bm = (uint16_t*)(smem + 4096 + 768);                      // boundary masks of 12-bit windows
-    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768 + 8192);               // MULTI only: 3-symbol write table
-    uint8_t* sout = smem + 4096 + 768 + huf_multi_bytes(HUF_T);
+    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768);                      // MULTI only: 3-symbol write table
+    uint8_t* sout = smem + 4096 + 768 + huf_multi_bytes(HUF_T);         // output image (phase 2, flush)
+    uint16_t* bm = (uint16_t*)sout;                                     // boundary masks of 12-bit windows (phase 1): same space
     uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
