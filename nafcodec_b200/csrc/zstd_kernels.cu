@@ -156,6 +156,51 @@ struct SmemBits {
 };
 
 
+// The sequence loop, written once over a reader type: shared-memory window (common) or global memory (huge sections).
+template <class RD>
+__device__ __forceinline__ bool seq_loop(RD& rd, const SeqCell* TLL, const SeqCell* TOF, const SeqCell* TML, const int* al, uint32_t n,
+                                         uint32_t bi, uint32_t lit_regen, uint4* rec, RepSym* rep, uint32_t& litpos, uint32_t& outpos) {
+    (void)lit_regen;
+    bool bad = false;
+    uint32_t sLL = rd.read(al[0]), sOF = rd.read(al[1]), sML = rd.read(al[2]);
+    for (uint32_t i = 0; i < n; i++) {
+        const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];
+        const uint32_t ov = cOF.base_value + rd.read(cOF.add_bits);
+        const uint32_t xb = rd.read(cML.add_bits + cLL.add_bits);        // ML then LL extra bits, one read
+        const uint32_t ml = cML.base_value + (xb >> cLL.add_bits);
+        const uint32_t ll = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));
+        RepSym off;
+        if (ov > 3) {
+            off.src = -1; off.val = ov - 3;
+            rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+        } else {
+            const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+            if (idx == 0) { off = rep[0]; }
+            else if (idx == 1) { off = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+            else if (idx == 2) { off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+            else {
+                off = rep[0];
+                if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; } else off.val += 1;
+                rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+            }
+        }
+        if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
+        if (i + 1 < n) {                                     // LL, ML, OF state bits (<= 27) in one read
+            const uint32_t sb = rd.read(cLL.nb + cML.nb + cOF.nb);
+            sOF = cOF.next_base + (sb & ((1u << cOF.nb) - 1u));
+            sML = cML.next_base + ((sb >> cOF.nb) & ((1u << cML.nb) - 1u));
+            sLL = cLL.next_base + (sb >> (cOF.nb + cML.nb));
+        }
+        rec[0] = make_uint4(ll, ml, encode_off(off), litpos);
+        rec[1] = make_uint4(outpos, bi, 0u, 0u);
+        rec += 2;
+        litpos += ll;
+        outpos += ll + ml;
+        if (outpos > BLOCK_MAX) { bad = true; break; }
+    }
+    return bad;
+}
+
 __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
     NAF_DYN_SMEM(uint32_t, sbits);                       // staged bitstream: J.seq_stage_bytes (job maximum, capped)
     __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
@@ -199,57 +244,18 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
     uint4* rec = (uint4*)(J.seq + base);
     bool bad = false;
     int left;
-    // the loop body is written once over a reader type: shared-memory window (common) or global memory (huge sections)
-#define SEQ_LOOP(RD)                                                                                       \
-    uint32_t sLL = RD.read(al[0]), sOF = RD.read(al[1]), sML = RD.read(al[2]);                             \
-    for (uint32_t i = 0; i < n; i++) {                                                                     \
-        const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];                                      \
-        const uint32_t ov = cOF.base_value + RD.read(cOF.add_bits);                                        \
-        const uint32_t xb = RD.read(cML.add_bits + cLL.add_bits);        /* ML then LL extra bits, one read */ \
-        const uint32_t ml = cML.base_value + (xb >> cLL.add_bits);                                         \
-        const uint32_t ll = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));                           \
-        RepSym off;                                                                                        \
-        if (ov > 3) {                                                                                      \
-            off.src = -1; off.val = ov - 3;                                                                \
-            rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;                                                \
-        } else {                                                                                           \
-            const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);                                             \
-            if (idx == 0) { off = rep[0]; }                                                                \
-            else if (idx == 1) { off = rep[1]; rep[1] = rep[0]; rep[0] = off; }                            \
-            else if (idx == 2) { off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }           \
-            else {                                                                                         \
-                off = rep[0];                                                                              \
-                if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; } else off.val += 1;        \
-                rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;                                            \
-            }                                                                                              \
-        }                                                                                                  \
-        if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;                                             \
-        if (i + 1 < n) {                                     /* LL, ML, OF state bits (<= 27) in one read */  \
-            const uint32_t sb = RD.read(cLL.nb + cML.nb + cOF.nb);                                         \
-            sOF = cOF.next_base + (sb & ((1u << cOF.nb) - 1u));                                            \
-            sML = cML.next_base + ((sb >> cOF.nb) & ((1u << cML.nb) - 1u));                                \
-            sLL = cLL.next_base + (sb >> (cOF.nb + cML.nb));                                               \
-        }                                                                                                  \
-        rec[0] = make_uint4(ll, ml, encode_off(off), litpos);                                              \
-        rec[1] = make_uint4(outpos, bi, 0u, 0u);                                                           \
-        rec += 2;                                                                                          \
-        litpos += ll;                                                                                      \
-        outpos += ll + ml;                                                                                 \
-        if (outpos > BLOCK_MAX) { bad = true; break; }                                                     \
-    }
     if (staged) {
         SmemBits rd;
         const int xz = (int)(16 + a) * 8;
         rd.init(sbits, xz + P0, xz);
-        SEQ_LOOP(rd)
+        bad = seq_loop(rd, TLL, TOF, TML, al, n, bi, B.lit_regen, rec, rep, litpos, outpos);
         left = rd.remaining();
     } else {
         BackBits rd;
         rd.init(g, nbytes);
-        SEQ_LOOP(rd)
+        bad = seq_loop(rd, TLL, TOF, TML, al, n, bi, B.lit_regen, rec, rep, litpos, outpos);
         left = (int)rd.P;
     }
-#undef SEQ_LOOP
     if (bad || left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
     if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
     uint32_t regen = outpos + (B.lit_regen - litpos);
@@ -575,7 +581,13 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
             for (int k = 0; k < grp; k++) rank += wcnt[k * 16 + w];
             uint32_t pos = start + ((uint32_t)rank << (w - 1)), n = 1u << (w - 1);
             uint16_t e = (uint16_t)((sym << 8) | (maxbits + 1 - w));
-            for (uint32_t i = 0; i < n; i++) table[pos + i] = e;
+            if (n >= 8) {                                        // groups start on multiples of their size: 16-byte stores
+                const uint32_t e2 = (uint32_t)e | ((uint32_t)e << 16);
+                const uint4 v = make_uint4(e2, e2, e2, e2);
+                for (uint32_t i = 0; i < n; i += 8) *(uint4*)(table + pos + i) = v;
+            } else {
+                for (uint32_t i = 0; i < n; i++) table[pos + i] = e;
+            }
         }
     }
     __syncthreads();
@@ -755,11 +767,17 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
         // this stream holds literals [L0, L1) of the block; sequence j owns literals [lp_j, lp_j + ll_j) -> output outpos_j
         const uint32_t L0 = it.dst_off, L1 = it.dst_off + it.n_sym;
         const uint32_t nseq = B.n_seq, sb = B.seq_base;
-        uint32_t lo = 0, hi = nseq;                                      // first sequence whose literals end after L0
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (J.seq[sb + mid].litpos + J.seq[sb + mid].ll > L0) hi = mid; else lo = mid + 1;
-        }
+        // first sequence whose literals end after L0 = number of sequences whose literals end at or before L0
+        // (literal ends are non-decreasing): counted by the whole CTA, one coalesced probe per thread and pass
+        uint32_t mine = 0;
+        for (uint32_t j = tid; j < nseq; j += HUF_T) mine += (J.seq[sb + j].litpos + J.seq[sb + j].ll <= L0) ? 1u : 0u;
+        uint32_t wsum = mine;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, d);
+        if (lane == 0) misc[warp] = wsum;
+        __syncthreads();
+        uint32_t lo = 0;
+        for (int k = 0; k < NWARPS; k++) lo += misc[k];
         for (uint32_t j = lo + warp; j <= nseq; j += NWARPS) {            // j == nseq: the literals after the last sequence
             uint32_t lp, ll, op;
             if (j < nseq) { lp = J.seq[sb + j].litpos; ll = J.seq[sb + j].ll; op = J.seq[sb + j].outpos; }
