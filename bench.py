@@ -271,14 +271,24 @@ def main():
     dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
     lits = st.section_bytes                # every regenerated section byte is produced once by the zstd stage
     kernel_bytes = {                       # algorithmic bytes per launch of each stage (DESIGN.md "Kernels")
-        "huf_decode": st.compressed_bytes + lits,
+        "memset+huf_decode": st.compressed_bytes + lits,
         "unpack": lits + st.ascii_bytes,
         "decode_sequences": st.compressed_bytes,
         "lz_literals": 2 * lits, "lz_first": 2 * lits, "lz_resolve": 2 * lits,
     }
     dom_name = stage_names[dom]
+    kernel_of = {"memset+huf_decode": "k_huf_decode<512>", "decode_sequences": "k_decode_sequences", "unpack": "k_unpack",
+                 "lz_resolve": "k_lz_resolve", "lz_first": "k_lz_first", "lz_literals": "k_lz_literals", "build_tables": "k_build_tables<0>"}
     dom_bytes = kernel_bytes.get(dom_name, st.algorithmic_bytes)
     peak, peak_src = measured_peak()
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture (profiles/r1_traffic.json)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        ent = tj.get(kernel_of.get(dom_name, dom_name))
+        if ent and ent.get("archives") == args.batch:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     path_gbs = st.algorithmic_bytes * args.steps / (dev_ms * 1e-3) / 1e9
 
@@ -346,8 +356,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "lanes": args.lanes,
                         "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": int(st.kernel_launches) * args.steps,
-                "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "algorithmic_bytes_per_launch": int(dom_bytes),
+                "roofline": {"bound": "hbm", "kernel": kernel_of.get(dom_name, dom_name), "stage": dom_name, "traffic_source": traffic_src, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "algorithmic_bytes_per_launch": int(dom_bytes),
                              "stage_ms": {nm: round(ms, 4) for nm, ms in zip(stage_names, stage_ms)}},
                 "cpu_baseline": cpu, "clocks": clocks, "single_archive": single,
                 "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences),

@@ -104,6 +104,8 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
             }
             if (lt >= zf::LT_HUF) {
                 plan.n_huf_blocks++;
+                b.lit_base = plan.lit_total;              // every Huffman block decodes into the literal staging buffer
+                plan.lit_total += (regen + 15u + 16u) & ~15u;
                 // locate the bitstreams: [tree description][jump table (4 streams)] streams...
                 uint32_t pay = hdr, pay_size = csize;
                 if (lt == zf::LT_HUF) {
@@ -166,7 +168,6 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                 if (plan.seq_total > 0xFFFFFFF0ull) FAIL(ERR_UNSUPPORTED, "job has too many sequences");
                 plan.n_seq_blocks++;
                 if (bsize - q > plan.max_seq_section) plan.max_seq_section = bsize - q;
-                if (lt >= zf::LT_HUF) { b.lit_base = plan.lit_total; plan.lit_total += (regen + 15u) & ~15u; }
             }
             b.seq_src = q;
         }

@@ -64,7 +64,8 @@ struct ArchPlan {
 
 struct nafgpu_ctx {
     int device = 0;
-    cudaStream_t st = 0;
+    cudaStream_t st = 0, st2 = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, hufw, debug, tables, table_al, seq32, seq64, misc, nafdev, flush;
     PinBuf stage, result, misc_host;
@@ -112,7 +113,8 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     if (c->J.n_seq) CUDA_TRY(c, cudaMemsetAsync(c->J.seq_done, 0, c->J.n_seq * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(c->arena.p, 0, c->counts_size, st));
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
-    int launches = zk::launch_zstd_stage(c->J, st, ev);
+    // profiled runs (ev != null) are serial so that every stage has its own interval
+    int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev);
     launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)c->nafdev.p, (uint32_t)c->arch.size(), c->max_records,
                                      c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
@@ -223,6 +225,8 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->J, 0, sizeof c->J);
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     for (int i = 0; i <= N_STAGES; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     c->ev_ok = true;
     c->coop_ctas = zk::lz_resolve_max_ctas(device);
@@ -239,6 +243,9 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i <= N_STAGES; i++) cudaEventDestroy(c->ev[i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->st2);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -560,7 +567,7 @@ int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
 }
 
 const char* nafgpu_stage_name(uint32_t s) {
-    static const char* names[N_STAGES] = {"memset+build_tables", "decode_sequences", "frame_scan", "huf_decode", "lz_literals", "lz_first",
+    static const char* names[N_STAGES] = {"memset+huf_decode", "build_tables", "decode_sequences", "frame_scan", "lz_literals", "lz_first",
                                           "lz_resolve", "naf_scan", "mask_fix", "-", "unpack", "utf8_check"};
     return s < (uint32_t)N_STAGES ? names[s] : "?";
 }

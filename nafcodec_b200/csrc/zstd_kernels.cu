@@ -26,8 +26,11 @@ __device__ __forceinline__ void flag_error(const JobDev& J, uint32_t frame, uint
 
 // --------------------------------------------------------------------------------------------------------------
 // k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
-__global__ void __launch_bounds__(64) k_build_tables(JobDev J) {
-    if (threadIdx.x >= 32) {
+// part 0: FSE tables (32 threads, grid n_blocks + 1); part 1: Huffman weights (32 threads, grid n_blocks).  Two launches so
+// that the Huffman branch and the FSE branch of the zstd stage can run on different streams.
+template <int PART>
+__global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
+    if (PART == 1) {
         // warp 1: the block's Huffman tree description -> 256 weights, decoded ONCE per tree (streams and treeless
         // blocks that reuse the tree read the weights back and build their decode table in parallel).
         if (blockIdx.x >= J.n_blocks) return;
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(64) k_build_tables(JobDev J) {
         if (B.btype != BT_COMPRESSED || B.lit_type != LT_HUF) return;
         // stage the tree description (<= 129 bytes) in shared memory: the weight decode is a serial chain of bit reads
         __shared__ __align__(16) uint8_t tree[176];
-        const int l1 = threadIdx.x - 32;
+        const int l1 = threadIdx.x;
         const uint32_t tsize = B.lit_csize < 130u ? B.lit_csize : 130u;
         for (uint32_t i = l1; i < 176; i += 32) tree[i] = i < tsize ? J.comp[B.src_off + B.lit_src + i] : 0;
         __syncwarp();
@@ -744,17 +747,15 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
     const uint32_t off = inc - mycnt + misc[warp];
     const uint32_t total = misc[32];
     if (any_bad || total != it.n_sym) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
-    // destination: literal-only blocks are contiguous output; blocks with sequences get every literal run scattered to
-    // its final position right here (no literal staging buffer, no separate copy pass)
-    const bool scatter = B.n_seq != 0;
-    uint8_t* blk_out = J.out + J.bstate[it.block].out_off;
-    uint8_t* dst = blk_out + it.dst_off;
-    const uint32_t a2 = scatter ? 0u : (uint32_t)((uintptr_t)dst & 15);
+    // destination: the block's slot in the literal staging buffer (k_lz_literals places the runs; the Huffman branch of
+    // the stage does not depend on the FSE branch, so the two run on different streams)
+    uint8_t* dst = J.lit + B.lit_base + it.dst_off;
+    const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
     HUF_TICK(4);
     if (mycnt) track_write<MULTI>(s_comp, to_saddr(t3), to_saddr(table), maxbits, XTOP, q0 + (int)ktrue, qe, to_saddr(sout) + a2 + off);
     __syncthreads();
     HUF_TICK(5);
-    if (!scatter) {
+    {
         // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends ----------------
         const uint32_t n = it.n_sym, endb = a2 + n;
         uint8_t* dal = dst - a2;
@@ -763,32 +764,6 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
         if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HUF_T) dal[k] = sout[k]; }
         if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
             for (uint32_t k = (last_full << 4) + tid; k < endb; k += HUF_T) dal[k] = sout[k];
-    } else {
-        // this stream holds literals [L0, L1) of the block; sequence j owns literals [lp_j, lp_j + ll_j) -> output outpos_j
-        const uint32_t L0 = it.dst_off, L1 = it.dst_off + it.n_sym;
-        const uint32_t nseq = B.n_seq, sb = B.seq_base;
-        // first sequence whose literals end after L0 = number of sequences whose literals end at or before L0
-        // (literal ends are non-decreasing): counted by the whole CTA, one coalesced probe per thread and pass
-        uint32_t mine = 0;
-        for (uint32_t j = tid; j < nseq; j += HUF_T) mine += (J.seq[sb + j].litpos + J.seq[sb + j].ll <= L0) ? 1u : 0u;
-        uint32_t wsum = mine;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, d);
-        if (lane == 0) misc[warp] = wsum;
-        __syncthreads();
-        uint32_t lo = 0;
-        for (int k = 0; k < NWARPS; k++) lo += misc[k];
-        for (uint32_t j = lo + warp; j <= nseq; j += NWARPS) {            // j == nseq: the literals after the last sequence
-            uint32_t lp, ll, op;
-            if (j < nseq) { lp = J.seq[sb + j].litpos; ll = J.seq[sb + j].ll; op = J.seq[sb + j].outpos; }
-            else {
-                const uint32_t t = sb + nseq - 1;
-                lp = J.seq[t].litpos + J.seq[t].ll; ll = B.lit_regen - lp; op = J.seq[t].outpos + J.seq[t].ll + J.seq[t].ml;
-            }
-            if (lp >= L1) break;
-            const uint32_t b0 = lp > L0 ? lp : L0, b1 = (lp + ll < L1) ? lp + ll : L1;
-            if (b1 > b0) warp_copy_s2g(blk_out + op + (b0 - lp), sout + (b0 - L0), b1 - b0, lane);
-        }
     }
     HUF_TICK(6);
 }
@@ -798,6 +773,31 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
 // blocks with sequences every literal run goes to its final position and match destinations are published.
 __device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, int tid, int nthreads) {
     for (uint32_t i = tid; i < n; i += nthreads) d[i] = s[i];
+}
+
+// Cooperative global -> global copy of n bytes with arbitrary alignments by `nlanes` threads (a warp or a CTA):
+// destination-aligned 16-byte stores; each is assembled from the two aligned 16-byte source words that span it.
+// The source must be readable up to 31 bytes past its end (staging buffers are padded).
+__device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
+    if (n < 64) { for (uint32_t k = lane; k < n; k += nlanes) dst[k] = src[k]; return; }
+    const uint32_t h = (uint32_t)(-(intptr_t)dst) & 15u;
+    if ((uint32_t)lane < h) dst[lane] = src[lane];
+    const uint32_t body = (n - h) >> 4;
+    const uintptr_t sa = (uintptr_t)(src + h);
+    const uint4* sw = (const uint4*)(sa & ~(uintptr_t)15);
+    const uint32_t mis = (uint32_t)(sa & 15), q = mis >> 2, sh = (mis & 3) * 8;
+    uint4* d4 = (uint4*)(dst + h);
+    for (uint32_t c = lane; c < body; c += nlanes) {
+        const uint4 A = sw[c], B = sw[c + 1];
+        uint32_t w0, w1, w2, w3, w4;                   // the five words starting at word q of {A, B}
+        if (q == 0) { w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; }
+        else if (q == 1) { w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; }
+        else if (q == 2) { w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; }
+        else { w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; }
+        d4[c] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    const uint32_t done = h + (body << 4);
+    for (uint32_t k = done + lane; k < n; k += nlanes) dst[k] = src[k];
 }
 
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
@@ -813,14 +813,14 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         for (uint32_t i = tid; i < B.src_size; i += nt) out[i] = v;
         return;
     }
-    const bool huf = B.lit_type >= LT_HUF;           // Huffman literals were placed by k_huf_decode
-    const uint8_t* lsrc = nullptr;
+    const uint8_t* lsrc = nullptr;                   // raw literals sit in the compressed block, Huffman literals in the staging buffer
     uint8_t rle = 0;
     if (B.lit_type == LT_RAW) lsrc = J.comp + B.src_off + B.lit_src;
     else if (B.lit_type == LT_RLE) rle = J.comp[B.src_off + B.lit_src];
+    else lsrc = J.lit + B.lit_base;
     if (B.n_seq == 0) {
-        if (B.lit_type == LT_RAW) copy_bytes(out, lsrc, B.lit_regen, tid, nt);
-        else if (B.lit_type == LT_RLE) for (uint32_t i = tid; i < B.lit_regen; i += nt) out[i] = rle;
+        if (B.lit_type == LT_RLE) for (uint32_t i = tid; i < B.lit_regen; i += nt) out[i] = rle;
+        else copy_g2g(out, lsrc, B.lit_regen, tid, nt);
         return;
     }
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
@@ -836,9 +836,8 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
             op = J.seq[j].outpos + J.seq[j].ll + J.seq[j].ml;
             ll = B.lit_regen - lp;
         }
-        if (huf) continue;
         if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += 32) out[op + k] = rle;
-        else for (uint32_t k = lane; k < ll; k += 32) out[op + k] = lsrc[lp + k];
+        else copy_g2g(out + op, lsrc + lp, ll, lane, 32);
     }
 }
 
@@ -1032,24 +1031,33 @@ uint32_t lz_resolve_max_ctas(int device) {
 #endif
 }
 
-int launch_zstd_stage(const JobDev& J, cudaStream_t st, StageEvents* ev) {
+int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev) {
     StageEvents none;
     if (!ev) ev = &none;
     int launches = 0;
     if (J.n_blocks == 0) { for (int i = 0; i < ZSTD_STAGES; i++) ev->mark(); return 0; }
-    NAF_LAUNCH(k_build_tables, J.n_blocks + 1, 64, 0, st, J); launches++; ev->mark();
+    // Two independent branches: (A) FSE tables -> sequences -> frame scan on `st`; (B) Huffman weights -> Huffman decode into
+    // the literal staging buffer on `st2` (when given).  They join before k_lz_literals.
+    cudaStream_t sb = st2 ? st2 : st;
+    if (st2) { cudaEventRecord(fork, st); cudaStreamWaitEvent(st2, fork, 0); }
+    if (J.n_huf_items) {
+        NAF_LAUNCH(k_build_tables<1>, J.n_blocks, 32, 0, sb, J); launches++;
+        if (J.n_huf_big) {   // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams
+            const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
+            NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);
+            NAF_LAUNCH((k_huf_decode<HUF_T_BIG>), J.n_huf_big, HUF_T_BIG, smem, sb, J, J.huf_items); launches++;
+        }
+        if (J.n_huf_items > J.n_huf_big) {
+            const uint32_t smem = huf_fixed_smem(HUF_T_SMALL) + ((J.max_huf_small + 15 + 16 + 16 + 15) & ~15u);
+            NAF_LAUNCH((k_huf_decode<HUF_T_SMALL>), J.n_huf_items - J.n_huf_big, HUF_T_SMALL, smem, sb, J, J.huf_items + J.n_huf_big); launches++;
+        }
+    }
+    if (st2) cudaEventRecord(join, st2);
+    else ev->mark();                                  // serial (profiled) order: the Huffman branch first
+    NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, J.seq_stage_bytes, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, (J.n_frames + 3) / 4, 128, 0, st, J); launches++; ev->mark();
-    if (J.n_huf_big) {       // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams, one warp each
-        const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
-        NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);
-        NAF_LAUNCH((k_huf_decode<HUF_T_BIG>), J.n_huf_big, HUF_T_BIG, smem, st, J, J.huf_items); launches++;
-    }
-    if (J.n_huf_items > J.n_huf_big) {
-        const uint32_t smem = huf_fixed_smem(HUF_T_SMALL) + ((J.max_huf_small + 15 + 16 + 16 + 15) & ~15u);
-        NAF_LAUNCH((k_huf_decode<HUF_T_SMALL>), J.n_huf_items - J.n_huf_big, HUF_T_SMALL, smem, st, J, J.huf_items + J.n_huf_big); launches++;
-    }
-    ev->mark();
+    if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
         uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);

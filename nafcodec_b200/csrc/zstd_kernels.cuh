@@ -41,7 +41,8 @@ struct JobDev {
 
 // Enqueues the whole zstd stage for a job on `stream` (no host synchronisation).
 // Returns the number of kernels launched.  `ev` (optional) gets one mark per stage (7 stages).
-int launch_zstd_stage(const JobDev& job, cudaStream_t stream, StageEvents* ev);
+// st2 (optional) runs the Huffman branch concurrently with the FSE branch; fork/join are events owned by the caller.
+int launch_zstd_stage(const JobDev& job, cudaStream_t stream, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev);
 // Co-resident CTAs (whole device) for the cooperative match-resolution kernel.
 uint32_t lz_resolve_max_ctas(int device);
 constexpr int ZSTD_STAGES = 7;
