@@ -129,7 +129,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                 }
                 for (int k = 0; k < streams; k++) {
                     if (ss[k] == 0) FAIL(ERR_INVALID, "zstd literals: empty Huffman stream");
-                    zf::HufItem it{self, so[k], ss[k], dof[k], dn[k], 0};
+                    zf::HufItem it{self, so[k], ss[k], dof[k], dn[k], 0u};
                     plan.huf_items.push_back(it);
                 }
             }
@@ -193,6 +193,14 @@ void JobPlan::finalize(uint32_t small_max_symbols) {
     for (size_t i = 0; i < huf_items.size(); i++) {
         uint32_t& m = i < n_huf_big ? max_huf_stream : max_huf_small;
         m = std::max(m, huf_items[i].src_size);
+    }
+    // trees whose tables the big streams need: built once each by k_huf_tables
+    big_tree_slots.clear();
+    std::vector<uint32_t> index_of(n_huf_slots, 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < n_huf_big; i++) {
+        const uint32_t slot = blocks[huf_items[i].block].huf_slot;
+        if (index_of[slot] == 0xFFFFFFFFu) { index_of[slot] = (uint32_t)big_tree_slots.size(); big_tree_slots.push_back(slot); }
+        huf_items[i].tab = index_of[slot];
     }
 }
 

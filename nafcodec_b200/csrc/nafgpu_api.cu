@@ -67,7 +67,7 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, hufw, debug, tables, table_al, seq32, seq64, misc, nafdev, flush;
+    DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, nafdev, flush;
     PinBuf stage, result, misc_host;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -153,13 +153,13 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     c->misc_words = 1 + 3 + 1 + nf + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) && c->huftabs.ensure(pl.big_tree_slots.size() * (28672 + 4) + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
               c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
-    const size_t nh = pl.huf_items.size();
-    size_t stage_bytes = nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev) + nh * sizeof(zf::HufItem);
+    const size_t nh = pl.huf_items.size(), nbt = pl.big_tree_slots.size();
+    size_t stage_bytes = nbt * 4 + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev) + nh * sizeof(zf::HufItem);
     if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
         return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
 
@@ -174,6 +174,11 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     {
         uint8_t* hp = sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev);
         if (nh) { memcpy(hp, pl.huf_items.data(), nh * sizeof(zf::HufItem)); CUDA_TRY(c, cudaMemcpyAsync(c->hufitems.p, hp, nh * sizeof(zf::HufItem), cudaMemcpyHostToDevice, c->st)); }
+    }
+    if (nbt) {
+        uint8_t* bp = sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev) + nh * sizeof(zf::HufItem);
+        memcpy(bp, pl.big_tree_slots.data(), nbt * 4);
+        CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->huftabs.p + nbt * 28672, bp, nbt * 4, cudaMemcpyHostToDevice, c->st));
     }
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
@@ -193,6 +198,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.frame_bad = misc + 5;
     J.coop_ctas = c->coop_ctas;
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
+    J.huf_tabs = (uint8_t*)c->huftabs.p; J.big_tree_slots = (const uint32_t*)((uint8_t*)c->huftabs.p + nbt * 28672); J.n_big_trees = (uint32_t)nbt;
     J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
     J.debug = nullptr;
     if (getenv("NAFGPU_DEBUG_HUF") && nh) {
@@ -239,7 +245,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->hufitems, &c->hufw, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->hufitems, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i <= N_STAGES; i++) cudaEventDestroy(c->ev[i]);

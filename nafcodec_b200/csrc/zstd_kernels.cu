@@ -512,45 +512,14 @@ __device__ __forceinline__ uint64_t map_compose(uint64_t g, uint64_t f) {
 }
 constexpr uint64_t MAP_IDENTITY = 0xFEDCBA9876543210ull;
 
-template <int HUF_T>
-__global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobDev J, const HufItem* items) {
-    NAF_DYN_SMEM(unsigned char, smem);
-    constexpr uint32_t HUF_FIXED_SMEM = huf_fixed_smem(HUF_T);
-    constexpr int NWARPS = HUF_T / 32;
-    uint16_t* table = (uint16_t*)smem;
-    uint8_t* weights = smem + 4096;
-    uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);                    // [8 symbol groups][16 weights]
-    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] count scan, [34..49] warp start candidates
-    uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [NWARPS] composed map of each warp; reuses wcnt after the table build
-    constexpr bool MULTI = HUF_T == HUF_T_BIG;
-    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768);                      // MULTI only: 3-symbol write table
-    uint8_t* sout = smem + 4096 + 768 + huf_multi_bytes(HUF_T);         // output image (phase 2, flush)
-    uint16_t* bm = (uint16_t*)sout;                                     // boundary masks of 12-bit windows (phase 1): same space
-    uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    const HufItem it = items[blockIdx.x];
-    const BlockDesc& B = J.blocks[it.block];
-    if (J.frame_bad[B.frame]) return;
-#if defined(__CUDA_ARCH__)
-#define HUF_TICK(k) do { if (J.debug && tid == 0) J.debug[(size_t)blockIdx.x * 8 + (k)] = clock64(); } while (0)
-#else
-#define HUF_TICK(k) ((void)0)
-#endif
-    HUF_TICK(0);
-    // ---- stage the compressed stream (coalesced 16 B loads of the aligned image) and the weights -------------------
-    const uint8_t* g = J.comp + B.src_off + it.src_off;
-    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
-    const uint4* gbase = (const uint4*)(g - a);
-    const uint32_t nchunks = (a + it.src_size + 15) >> 4;
-    for (uint32_t c = tid; c < nchunks; c += HUF_T) ((uint4*)scomp)[1 + c] = gbase[c];
-    for (int i = tid; i < 64; i += HUF_T) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)B.huf_slot * 256))[i];
-    const int nsym = (int)J.huf_meta[(size_t)B.huf_slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)B.huf_slot * 2 + 1];
-    if (maxbits == 0) return;                                           // bad tree: already flagged by k_build_tables
-    __syncthreads();
-    HUF_TICK(1);
-    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;              // bits below the stream start read as zero
-    // ---- decode table, built in parallel: ascending weight, then ascending symbol (RFC 8878 4.2.1) ----------------
+// Builds the three decode tables of one Huffman tree in shared memory (all HUF_T threads of the CTA must call):
+//   table: base table, index = next max_bits bits -> symbol << 8 | length (RFC 8878 4.2.1: ascending weight, then symbol)
+//   bm   : boundary masks of 12-bit windows;  t3 (WITH_T3): 3-symbol write table of 12-bit windows
+template <int HUF_T, bool WITH_T3>
+__device__ __forceinline__ void huf_build_tables(const uint8_t* weights, int nsym, int maxbits, uint16_t* table, uint16_t* bm, uint32_t* t3,
+                                                 uint16_t* wcnt) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr bool MULTI = WITH_T3;
     // symbols are handled in 8 groups of 32 (group g = symbols 32g..32g+31); wcnt[g][w] = symbols of weight w in group g
     constexpr int GROUPS_PER_PASS = HUF_T >= 256 ? 8 : HUF_T / 32;
     int wreg[8 / GROUPS_PER_PASS], rankreg[8 / GROUPS_PER_PASS];
@@ -612,6 +581,79 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
             if (MULTI) t3[i] = syms | (used3 << 24) | (n << 28);
         }
         __syncthreads();
+    }
+}
+
+constexpr uint32_t HUF_TAB_BYTES = 4096u + 8192u + 16384u;        // t1 | bm | t3 of one tree in global memory
+
+// k_huf_tables: one CTA per Huffman tree that big streams use: the tables are built ONCE per tree (a 4-stream block, and
+// every treeless block after it, share them) and the stream CTAs just copy 28 KB in.
+__global__ void __launch_bounds__(512) k_huf_tables(JobDev J) {
+    __shared__ __align__(16) uint16_t table[2048];
+    __shared__ __align__(16) uint16_t bm[4096];
+    __shared__ __align__(16) uint32_t t3[4096];
+    __shared__ __align__(16) uint8_t weights[256];
+    __shared__ uint16_t wcnt[128];
+    const int tid = threadIdx.x;
+    const uint32_t slot = J.big_tree_slots[blockIdx.x];
+    for (int i = tid; i < 64; i += 512) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)slot * 256))[i];
+    const int nsym = (int)J.huf_meta[(size_t)slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)slot * 2 + 1];
+    if (maxbits == 0) return;                                           // bad tree: flagged by k_build_tables<1>
+    __syncthreads();
+    huf_build_tables<512, true>(weights, nsym, maxbits, table, bm, t3, wcnt);
+    uint4* g = (uint4*)(J.huf_tabs + (size_t)blockIdx.x * HUF_TAB_BYTES);
+    for (int i = tid; i < 256; i += 512) g[i] = ((const uint4*)table)[i];
+    for (int i = tid; i < 512; i += 512) g[256 + i] = ((const uint4*)bm)[i];
+    for (int i = tid; i < 1024; i += 512) g[768 + i] = ((const uint4*)t3)[i];
+}
+
+template <int HUF_T>
+__global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobDev J, const HufItem* items) {
+    NAF_DYN_SMEM(unsigned char, smem);
+    constexpr uint32_t HUF_FIXED_SMEM = huf_fixed_smem(HUF_T);
+    constexpr int NWARPS = HUF_T / 32;
+    uint16_t* table = (uint16_t*)smem;
+    uint8_t* weights = smem + 4096;
+    uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);                    // [8 symbol groups][16 weights]
+    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..32] count scan, [34..49] warp start candidates
+    uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [NWARPS] composed map of each warp; reuses wcnt after the table build
+    constexpr bool MULTI = HUF_T == HUF_T_BIG;
+    uint32_t* t3 = (uint32_t*)(smem + 4096 + 768);                      // MULTI only: 3-symbol write table
+    uint8_t* sout = smem + 4096 + 768 + huf_multi_bytes(HUF_T);         // output image (phase 2, flush)
+    uint16_t* bm = (uint16_t*)sout;                                     // boundary masks of 12-bit windows (phase 1): same space
+    uint32_t* scomp = (uint32_t*)(smem + HUF_FIXED_SMEM);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const HufItem it = items[blockIdx.x];
+    const BlockDesc& B = J.blocks[it.block];
+    if (J.frame_bad[B.frame]) return;
+#if defined(__CUDA_ARCH__)
+#define HUF_TICK(k) do { if (J.debug && tid == 0) J.debug[(size_t)blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#else
+#define HUF_TICK(k) ((void)0)
+#endif
+    HUF_TICK(0);
+    // ---- stage the compressed stream (coalesced 16 B loads of the aligned image) and the weights -------------------
+    const uint8_t* g = J.comp + B.src_off + it.src_off;
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    const uint4* gbase = (const uint4*)(g - a);
+    const uint32_t nchunks = (a + it.src_size + 15) >> 4;
+    for (uint32_t c = tid; c < nchunks; c += HUF_T) ((uint4*)scomp)[1 + c] = gbase[c];
+    for (int i = tid; i < 64; i += HUF_T) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)B.huf_slot * 256))[i];
+    const int nsym = (int)J.huf_meta[(size_t)B.huf_slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)B.huf_slot * 2 + 1];
+    if (maxbits == 0) return;                                           // bad tree: already flagged by k_build_tables
+    __syncthreads();
+    HUF_TICK(1);
+    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;              // bits below the stream start read as zero
+    if (MULTI) {
+        // the tree's tables were built once by k_huf_tables: copy 28 KB (t1 | bm | t3) from global memory
+        const uint4* g = (const uint4*)(J.huf_tabs + (size_t)it.tab * HUF_TAB_BYTES);
+        for (int i = tid; i < 256; i += HUF_T) ((uint4*)table)[i] = g[i];
+        for (int i = tid; i < 512; i += HUF_T) ((uint4*)bm)[i] = g[256 + i];
+        for (int i = tid; i < 1024; i += HUF_T) ((uint4*)t3)[i] = g[768 + i];
+        __syncthreads();
+    } else {
+        huf_build_tables<HUF_T, false>(weights, nsym, maxbits, table, bm, t3, wcnt);
     }
     HUF_TICK(2);
 
@@ -1042,6 +1084,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) { cudaEventRecord(fork, st); cudaStreamWaitEvent(st2, fork, 0); }
     if (J.n_huf_items) {
         NAF_LAUNCH(k_build_tables<1>, J.n_blocks, 32, 0, sb, J); launches++;
+        if (J.n_big_trees) { NAF_LAUNCH(k_huf_tables, J.n_big_trees, 512, 0, sb, J); launches++; }
         if (J.n_huf_big) {   // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams
             const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
             NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);

@@ -32,6 +32,9 @@ struct JobDev {
     uint32_t* lz_count;               // [3] their lengths
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
+    uint8_t* huf_tabs;                // n_big_trees x 28 KB prebuilt decode tables (t1 | bm | t3) of trees used by big streams
+    const uint32_t* big_tree_slots;   // weight-record slot of each of them
+    uint32_t n_big_trees;
     const zf::HufItem* huf_items;     // one per Huffman bitstream
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
     uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
