@@ -375,7 +375,8 @@ constexpr int HUF_T_SMALL = 128;                  // four warps for short stream
 constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
 constexpr int HUF_SEG = 96;                       // tracks are compared for merging every HUF_SEG bits
 constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
-__host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : (HUF_SMALL_MAX_SYM < 8192u ? 8192u : HUF_SMALL_MAX_SYM)) + 64u; }
+// output image (phase 2) / boundary masks 8 KB + track queue 32 B per thread (phase 1)
+__host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_T_BIG ? 32768u : 8192u + 32u * (uint32_t)T) + 64u; }
 // t1 4096 | weights 256 | wcnt 256 | misc 256 | [big only: t3 16384] | output image / boundary masks | (dynamic) compressed stream image
 // the boundary-mask table (8 KB, phase 1 only) shares its space with the output image (phase 2 and flush only)
 __host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return T == HUF_T_BIG ? 16384u : 0u; }
@@ -675,58 +676,98 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
 #pragma unroll
     for (int k = 0; k < MAXC; k++) { pc[k] = (uint32_t)k; mg[k] = 0; }
     const saddr_t s_comp = to_saddr(scomp), s_bm = to_saddr(bm);
+    // Merge of tracks that reached the same position (the representative always has the lower index).
+    auto dedupe = [&]() {
+        if (!(live & (live - 1))) return;
+#pragma unroll
+        for (int k = 1; k < MAXC; k++) {
+            if (live & (1u << k)) {
+#pragma unroll
+                for (int j = 0; j < k; j++) {
+                    if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
+                        live &= ~(1u << k);
+                        mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
+                    }
+                }
+            }
+        }
+    };
+    // (1) first stop right below the candidate window: one boundary-mask lookup per candidate lands every track on its
+    //     first codeword boundary >= q0 + 12; candidates on the same codeword chain coincide there and merge.
     if (active) {
-        // stops: right below the candidate window (tracks on the same codeword chain coincide there), one more after
-        // HUF_SEG bits (codes that resynchronise have merged by then), then the end of the range
-        int lim = q0 + HUF_W;
-        for (int stop = 0;; stop++) {
-            const int l = lim < qe ? lim : qe;
-            if ((live & (live - 1)) == 0) {                              // a single track left: straight to the end
-                const int k0 = __ffs((int)live) - 1;
+        const int l = (q0 + HUF_W < qe) ? q0 + HUF_W : qe;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) {
+            if (live & (1u << k)) {
+                int q = q0 + k, c = 0;
+                track_advance(s_comp, s_bm, XTOP, q, c, l);
+                pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
+            }
+        }
+        dedupe();
+    }
+    // (2) the surviving tracks of ALL ranges (1 per range for codes that resynchronise, up to one per phase otherwise)
+    //     become work items in a shared-memory queue and are spread evenly over the CTA: following tracks thread-by-
+    //     thread leaves lanes with fewer survivors idle (45 % thread efficiency measured); the queue keeps every lane on
+    //     one track of equal length.  Two legs: to 96 bits past the first stop (twins merge), then to the range end.
+    constexpr int HUF_QCAP = 4 * HUF_T;
+    uint32_t* q_owner = (uint32_t*)(sout + 8192);                        // [HUF_QCAP] owner thread | track << 16 (after the boundary masks)
+    uint32_t* q_pc = q_owner + HUF_QCAP;                                 // [HUF_QCAP] position | symbols << 16
+    for (int leg = 0; leg < 2; leg++) {
+        uint32_t l4 = 0;                                                 // up to four lowest live tracks go to the queue
+        { uint32_t t = live; for (int i = 0; i < 4 && t; i++) { l4 |= t & (0u - t); t &= t - 1; } }
+        const uint32_t n_mine = (uint32_t)__popc(l4);
+        uint32_t inc = n_mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) misc[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t x = lane < NWARPS ? misc[lane] : 0, o = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += t; }
+            misc[lane] = x - o;
+            if (lane == 31) misc[32] = x;
+        }
+        __syncthreads();
+        const uint32_t qbase = inc - n_mine + misc[warp], qtotal = misc[32];
+        {
+            uint32_t idx = qbase;
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) if (l4 & (1u << k)) { q_owner[idx] = (uint32_t)tid | ((uint32_t)k << 16); q_pc[idx] = pc[k]; idx++; }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < qtotal; i += HUF_T) {
+            const int ot = (int)(q_owner[i] & 0xFFFFu);
+            const int oq0 = ot * S, oqe = (oq0 + S < P0) ? oq0 + S : P0;
+            const int mid = oq0 + HUF_W + HUF_SEG;
+            const int lim = (leg == 0 && mid < oqe) ? mid : oqe;
+            const uint32_t p = q_pc[i];
+            int q = oq0 + (int)(p & 0xFFFFu), c = (int)(p >> 16);
+            track_advance(s_comp, s_bm, XTOP, q, c, lim);
+            q_pc[i] = (uint32_t)(q - oq0) | ((uint32_t)c << 16);
+        }
+        __syncthreads();
+        {
+            uint32_t idx = qbase;
+#pragma unroll
+            for (int k = 0; k < MAXC; k++) if (l4 & (1u << k)) { pc[k] = q_pc[idx]; idx++; }
+        }
+        {
+            const int mid = q0 + HUF_W + HUF_SEG;
+            const int lim = (leg == 0 && mid < qe) ? mid : qe;
+            for (uint32_t m = live & ~l4; m; m &= m - 1) {               // more than four survivors (rare): the owner follows them
+                const int kk = __ffs((int)m) - 1;
                 int q = 0, c = 0;
 #pragma unroll
-                for (int k = 0; k < MAXC; k++) if (k == k0) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
-                track_advance(s_comp, s_bm, XTOP, q, c, qe);
+                for (int k = 0; k < MAXC; k++) if (k == kk) { q = q0 + (int)(pc[k] & 0xFFFFu); c = (int)(pc[k] >> 16); }
+                track_advance(s_comp, s_bm, XTOP, q, c, lim);
 #pragma unroll
-                for (int k = 0; k < MAXC; k++) if (k == k0) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
-                break;
+                for (int k = 0; k < MAXC; k++) if (k == kk) pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
             }
-#pragma unroll
-            for (int k = 0; k < MAXC; k++) {
-                if (live & (1u << k)) {
-                    int q = q0 + (int)(pc[k] & 0xFFFFu), c = (int)(pc[k] >> 16);
-                    track_advance(s_comp, s_bm, XTOP, q, c, l);
-                    pc[k] = (uint32_t)(q - q0) | ((uint32_t)c << 16);
-                }
-            }
-            if (!(live & ~15u)) {                                        // common steady state: at most tracks 0..3 alive
-#pragma unroll
-                for (int k = 1; k < 4; k++) {
-#pragma unroll
-                    for (int j = 0; j < k; j++) {
-                        if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
-                            live &= ~(1u << k);
-                            mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 1; k < MAXC; k++) {
-                    if (live & (1u << k)) {
-#pragma unroll
-                        for (int j = 0; j < k; j++) {
-                            if ((live & (1u << j)) && (live & (1u << k)) && ((pc[j] ^ pc[k]) & 0xFFFFu) == 0) {
-                                live &= ~(1u << k);
-                                mg[k] = (((pc[k] >> 16) - (pc[j] >> 16)) & 0xFFFFu) | ((uint32_t)j << 16);
-                            }
-                        }
-                    }
-                }
-            }
-            if (l >= qe) break;
-            lim = stop == 0 ? lim + HUF_SEG : qe;
         }
+        dedupe();
+        __syncthreads();                                                 // the queue is rewritten by the next leg
     }
     // resolve merged tracks (representatives always have a lower index): landing position and symbol count per candidate
     uint64_t fmap = MAP_IDENTITY;
