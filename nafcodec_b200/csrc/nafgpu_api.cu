@@ -283,7 +283,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     uint64_t off = 0;
     c->counts_size = align_up((uint64_t)n * sizeof(nk::NafCounts));
     off = c->counts_size;
-    uint64_t comp_off = 0;
+    uint64_t comp_off = 16;          // gathers may read up to 15 bytes below a literal run: keep them inside the allocation
     c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false; c->any_text_mask = false;
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
@@ -408,12 +408,12 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->arena_size = c->z1_size + 256;
     c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false; c->any_text_mask = false;
     std::string e;
-    int rc = fw::walk_frame(frame, 0, frame_size, ALIGN, regen_size, c->plan, e);
+    int rc = fw::walk_frame(frame, 16, frame_size, ALIGN, regen_size, c->plan, e);
     if (rc) return fail(c, rc, e);
-    std::vector<Copy> copies{{frame, 0, frame_size}};
+    std::vector<Copy> copies{{frame, 16, frame_size}};
     c->stats.compressed_bytes = frame_size; c->stats.section_bytes = regen_size;
     c->stats.algorithmic_bytes = frame_size + regen_size;
-    rc = finish_prepare(c, copies, align_up(frame_size + zf::COMP_PAD, 16), 0);
+    rc = finish_prepare(c, copies, 16 + align_up(frame_size + zf::COMP_PAD, 16), 0);
     if (rc) return rc;
     rc = enqueue_run(c, nullptr);
     if (rc) return rc;

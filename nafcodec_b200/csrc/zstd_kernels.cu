@@ -971,10 +971,38 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
                 *(uint4*)(out + p0) = v;
                 continue;
             }
-            for (uint32_t p = p0; p < p1; p++) {                          // ragged chunk: byte by byte, skipping match bytes
-                while (j + 1 < nruns && s_out[j + 1] <= p) j++;
+            // ragged chunk (touches run boundaries): assemble it from one 16-byte gather per overlapping literal run,
+            // merged under a byte mask; match bytes stay zero and are rewritten by the match kernels anyway
+            uint32_t v[4] = {0, 0, 0, 0};
+            const int64_t org = (c == 0) ? (int64_t)p1 - 16 : (int64_t)p0;   // output position of byte 0 of the 16-byte image (the head chunk is right-aligned)
+            for (; j < nruns && s_out[j] < p1; j++) {
                 const uint32_t lj = (j + 1 <= tn ? s_lit[j + 1] : lit_end) - s_lit[j];
-                if (p >= s_out[j] && p - s_out[j] < lj) out[p] = is_rle ? (uint8_t)rle4 : lsrc[s_lit[j] + (p - s_out[j])];
+                const uint32_t r0 = s_out[j] > p0 ? s_out[j] : p0, r1 = (s_out[j] + lj < p1) ? s_out[j] + lj : p1;
+                if (r0 >= r1) continue;
+                uint4 g;
+                if (is_rle) g = make_uint4(rle4, rle4, rle4, rle4);
+                else g = load16_unaligned(lsrc + ((int64_t)s_lit[j] + org - (int64_t)s_out[j]));   // image byte k <-> output position org + k
+                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+                const int b0 = (int)((int64_t)r0 - org), b1 = (int)((int64_t)r1 - org);   // byte range [b0, b1) of the image
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int lo = b0 - 4 * w, hi = b1 - 4 * w;
+                    const uint32_t mh = hi >= 4 ? 0xFFFFFFFFu : (hi <= 0 ? 0u : ((1u << (8 * hi)) - 1u));
+                    const uint32_t ml = lo >= 4 ? 0xFFFFFFFFu : (lo <= 0 ? 0u : ((1u << (8 * lo)) - 1u));
+                    const uint32_t m = mh & ~ml;
+                    v[w] = (v[w] & ~m) | (gw[w] & m);
+                }
+            }
+            if (p1 - p0 == 16) *(uint4*)(out + p0) = make_uint4(v[0], v[1], v[2], v[3]);
+            else {
+                // partial chunk at the edge of the tile: only literal bytes inside [p0, p1) may be written (the neighbours
+                // belong to other tiles / blocks): byte stores from the assembled image, run by run
+                uint32_t jj = a;
+                for (uint32_t p = p0; p < p1; p++) {
+                    while (jj + 1 < nruns && s_out[jj + 1] <= p) jj++;
+                    const uint32_t lj = (jj + 1 <= tn ? s_lit[jj + 1] : lit_end) - s_lit[jj];
+                    if (p >= s_out[jj] && p - s_out[jj] < lj) { const uint32_t k = (uint32_t)((int64_t)p - org); out[p] = (uint8_t)(v[k >> 2] >> (8 * (k & 3))); }
+                }
             }
         }
     }
