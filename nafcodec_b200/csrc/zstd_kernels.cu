@@ -883,128 +883,44 @@ __device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_
     for (uint32_t k = done + lane; k < n; k += nlanes) dst[k] = src[k];
 }
 
-// 16 source bytes starting at an arbitrary address (two aligned 16-byte loads + funnel shifts).
-__device__ __forceinline__ uint4 load16_unaligned(const uint8_t* src) {
-    const uintptr_t sa = (uintptr_t)src;
-    const uint4* sw = (const uint4*)(sa & ~(uintptr_t)15);
-    const uint32_t mis = (uint32_t)(sa & 15), q = mis >> 2, sh = (mis & 3) * 8;
-    const uint4 A = sw[0];
-    if (mis == 0) return A;
-    const uint4 B = sw[1];
-    uint32_t w0, w1, w2, w3, w4;
-    if (q == 0) { w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; }
-    else if (q == 1) { w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; }
-    else if (q == 2) { w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; }
-    else { w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; }
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-
-constexpr uint32_t LIT_TILE = 2048;      // sequences whose run table is staged in shared memory at a time
-
-// k_lz_literals: one CTA per block.  Raw / RLE blocks and literal-only blocks are plain copies or fills.  For blocks with
-// sequences the literal runs go to their final positions: the run table (output start, literal start of every
-// sequence) is staged in shared memory and the block's output is swept in destination-aligned 16-byte chunks; a chunk
-// inside one literal run is one unaligned 16-byte gather + one aligned store (its run found by binary search in shared
-// memory), a chunk that touches run boundaries is handled byte by byte.  Match bytes are left to the match kernels.
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
-    __shared__ uint32_t s_out[LIT_TILE + 2], s_lit[LIT_TILE + 2];
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
     if (J.frame_bad[B.frame]) return;
     const BlockState& S = J.bstate[bi];
     uint8_t* out = J.out + S.out_off;
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (B.btype == BT_RAW) { copy_g2g(out, J.comp + B.src_off, B.src_size, tid, nt); return; }
+    if (B.btype == BT_RAW) { copy_bytes(out, J.comp + B.src_off, B.src_size, tid, nt); return; }
     if (B.btype == BT_RLE) {
         uint8_t v = J.comp[B.src_off];
         for (uint32_t i = tid; i < B.src_size; i += nt) out[i] = v;
         return;
     }
     const uint8_t* lsrc = nullptr;                   // raw literals sit in the compressed block, Huffman literals in the staging buffer
-    uint32_t rle4 = 0;
-    const bool is_rle = B.lit_type == LT_RLE;
+    uint8_t rle = 0;
     if (B.lit_type == LT_RAW) lsrc = J.comp + B.src_off + B.lit_src;
-    else if (is_rle) rle4 = 0x01010101u * J.comp[B.src_off + B.lit_src];
+    else if (B.lit_type == LT_RLE) rle = J.comp[B.src_off + B.lit_src];
     else lsrc = J.lit + B.lit_base;
     if (B.n_seq == 0) {
-        if (is_rle) for (uint32_t i = tid; i < B.lit_regen; i += nt) out[i] = (uint8_t)rle4;
+        if (B.lit_type == LT_RLE) for (uint32_t i = tid; i < B.lit_regen; i += nt) out[i] = rle;
         else copy_g2g(out, lsrc, B.lit_regen, tid, nt);
         return;
     }
-    const uint32_t n = B.n_seq, base = B.seq_base, regen = S.regen;
-    for (uint32_t t0 = 0; t0 < n; t0 += LIT_TILE) {
-        const uint32_t tn = (n - t0 < LIT_TILE) ? n - t0 : LIT_TILE;      // runs t0 .. t0+tn-1 (+ the closing entry)
-        __syncthreads();
-        for (uint32_t i = tid; i <= tn; i += nt) {
-            const uint32_t j = t0 + i;
-            if (j < n) {
-                const SeqRec& R = J.seq[base + j];
-                s_out[i] = R.outpos; s_lit[i] = R.litpos;
-                if (i < tn) J.seq[base + j].match_pos = S.out_off + R.outpos + R.ll;   // absolute destination of the match
-            } else {                                   // the literals after the last sequence form the last run
-                const SeqRec& R = J.seq[base + n - 1];
-                s_out[i] = R.outpos + R.ll + R.ml; s_lit[i] = R.litpos + R.ll;
-            }
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const uint32_t n = B.n_seq, base = B.seq_base;
+    for (uint32_t i = warp; i <= n; i += nw) {
+        uint32_t lp, op, ll;
+        if (i < n) {
+            lp = J.seq[base + i].litpos; op = J.seq[base + i].outpos; ll = J.seq[base + i].ll;
+            if (lane == 0) J.seq[base + i].match_pos = S.out_off + op + ll;     // absolute destination of the match
+        } else {                                       // literals after the last sequence
+            uint32_t j = base + n - 1;
+            lp = J.seq[j].litpos + J.seq[j].ll;
+            op = J.seq[j].outpos + J.seq[j].ll + J.seq[j].ml;
+            ll = B.lit_regen - lp;
         }
-        __syncthreads();
-        const bool last_tile = t0 + tn == n;
-        const uint32_t nruns = last_tile ? tn + 1 : tn;                   // the closing entry is a real run only in the last tile
-        const uint32_t lo_pos = s_out[0];
-        const uint32_t hi_pos = last_tile ? regen : s_out[tn];           // output range covered by this tile
-        const uint32_t lit_end = B.lit_regen;
-        // run j of the tile: output [s_out[j], s_out[j] + len_j), literals from s_lit[j]; len_j = s_lit[j+1] - s_lit[j]
-        const uintptr_t abs0 = (uintptr_t)(out + lo_pos);
-        const uint32_t head = (uint32_t)(-(intptr_t)abs0) & 15u;         // bytes before the first aligned chunk
-        const uint32_t span = hi_pos - lo_pos;
-        const uint32_t nchunks = span > head ? (span - head + 15) / 16 + 1 : 1;   // chunk 0 = the ragged head
-        for (uint32_t c = tid; c < nchunks; c += nt) {
-            uint32_t p0 = c == 0 ? lo_pos : lo_pos + head + (c - 1) * 16;
-            uint32_t p1 = c == 0 ? lo_pos + head : p0 + 16;
-            if (p1 > hi_pos) p1 = hi_pos;
-            if (p0 >= p1) continue;
-            uint32_t a = 0, b = nruns;                                    // last run with s_out[j] <= p0
-            while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (s_out[m] <= p0) a = m; else b = m; }
-            uint32_t j = a;
-            const uint32_t len_j = (j + 1 <= tn ? s_lit[j + 1] : lit_end) - s_lit[j];
-            if (p1 - p0 == 16 && p0 >= s_out[j] && p1 <= s_out[j] + len_j) {
-                const uint4 v = is_rle ? make_uint4(rle4, rle4, rle4, rle4) : load16_unaligned(lsrc + s_lit[j] + (p0 - s_out[j]));
-                *(uint4*)(out + p0) = v;
-                continue;
-            }
-            // ragged chunk (touches run boundaries): assemble it from one 16-byte gather per overlapping literal run,
-            // merged under a byte mask; match bytes stay zero and are rewritten by the match kernels anyway
-            uint32_t v[4] = {0, 0, 0, 0};
-            const int64_t org = (c == 0) ? (int64_t)p1 - 16 : (int64_t)p0;   // output position of byte 0 of the 16-byte image (the head chunk is right-aligned)
-            for (; j < nruns && s_out[j] < p1; j++) {
-                const uint32_t lj = (j + 1 <= tn ? s_lit[j + 1] : lit_end) - s_lit[j];
-                const uint32_t r0 = s_out[j] > p0 ? s_out[j] : p0, r1 = (s_out[j] + lj < p1) ? s_out[j] + lj : p1;
-                if (r0 >= r1) continue;
-                uint4 g;
-                if (is_rle) g = make_uint4(rle4, rle4, rle4, rle4);
-                else g = load16_unaligned(lsrc + ((int64_t)s_lit[j] + org - (int64_t)s_out[j]));   // image byte k <-> output position org + k
-                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-                const int b0 = (int)((int64_t)r0 - org), b1 = (int)((int64_t)r1 - org);   // byte range [b0, b1) of the image
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int lo = b0 - 4 * w, hi = b1 - 4 * w;
-                    const uint32_t mh = hi >= 4 ? 0xFFFFFFFFu : (hi <= 0 ? 0u : ((1u << (8 * hi)) - 1u));
-                    const uint32_t ml = lo >= 4 ? 0xFFFFFFFFu : (lo <= 0 ? 0u : ((1u << (8 * lo)) - 1u));
-                    const uint32_t m = mh & ~ml;
-                    v[w] = (v[w] & ~m) | (gw[w] & m);
-                }
-            }
-            if (p1 - p0 == 16) *(uint4*)(out + p0) = make_uint4(v[0], v[1], v[2], v[3]);
-            else {
-                // partial chunk at the edge of the tile: only literal bytes inside [p0, p1) may be written (the neighbours
-                // belong to other tiles / blocks): byte stores from the assembled image, run by run
-                uint32_t jj = a;
-                for (uint32_t p = p0; p < p1; p++) {
-                    while (jj + 1 < nruns && s_out[jj + 1] <= p) jj++;
-                    const uint32_t lj = (jj + 1 <= tn ? s_lit[jj + 1] : lit_end) - s_lit[jj];
-                    if (p >= s_out[jj] && p - s_out[jj] < lj) { const uint32_t k = (uint32_t)((int64_t)p - org); out[p] = (uint8_t)(v[k >> 2] >> (8 * (k & 3))); }
-                }
-            }
-        }
+        if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += 32) out[op + k] = rle;
+        else copy_g2g(out + op, lsrc + lp, ll, lane, 32);
     }
 }
 
