@@ -268,6 +268,8 @@ def main():
         stage_acc = [x[1] for x in s] if stage_acc is None else [a + x[1] for a, x in zip(stage_acc, s)]
     stage_names = [x[0] for x in s]
     stage_ms = [a / reps for a in stage_acc]
+    kern_ms = dict(zip(stage_names, stage_ms)).get("k_huf_decode<512>", 0.0)     # the dominant kernel alone (own event pair)
+    stage_names, stage_ms = stage_names[:-1], stage_ms[:-1]
     dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
     lits = st.section_bytes                # every regenerated section byte is produced once by the zstd stage
     kernel_bytes = {                       # algorithmic bytes per launch of each stage (DESIGN.md "Kernels")
@@ -289,7 +291,8 @@ def main():
         ent = tj.get(kernel_of.get(dom_name, dom_name))
         if ent and ent.get("archives") == args.batch:
             traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
-    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    dom_ms = kern_ms if (dom_name == "memset+huf_decode" and kern_ms > 0) else stage_ms[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     path_gbs = st.algorithmic_bytes * args.steps / (dev_ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI: pinned host in, pinned host out ------------------------------------------------
@@ -357,7 +360,7 @@ def main():
                         "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": int(st.kernel_launches) * args.steps,
                 "roofline": {"bound": "hbm", "kernel": kernel_of.get(dom_name, dom_name), "stage": dom_name, "traffic_source": traffic_src, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "algorithmic_bytes_per_launch": int(dom_bytes),
+                             "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": int(dom_bytes),
                              "stage_ms": {nm: round(ms, 4) for nm, ms in zip(stage_names, stage_ms)}},
                 "cpu_baseline": cpu, "clocks": clocks, "single_archive": single,
                 "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences),

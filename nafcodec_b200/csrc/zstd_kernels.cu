@@ -1129,7 +1129,9 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         if (J.n_huf_big) {   // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams
             const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
             NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);
+            if (!st2) ev->kernel_begin();
             NAF_LAUNCH((k_huf_decode<HUF_T_BIG>), J.n_huf_big, HUF_T_BIG, smem, sb, J, J.huf_items); launches++;
+            if (!st2) ev->kernel_end();
         }
         if (J.n_huf_items > J.n_huf_big) {
             const uint32_t smem = huf_fixed_smem(HUF_T_SMALL) + ((J.max_huf_small + 15 + 16 + 16 + 15) & ~15u);
