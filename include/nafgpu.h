@@ -104,6 +104,8 @@ typedef struct nafgpu_job_stats {
     uint64_t h2d_bytes, d2h_bytes;      /* bytes copied per decode */
     uint32_t kernel_launches;           /* kernels enqueued by one nafgpu_job_run */
     uint32_t n_stages;                  /* entries nafgpu_job_run_profiled writes */
+    uint32_t lz_handover;               /* nonzero if the last fetched run left LZ matches to the ordered finisher (k_lz_finish): the round it gave up at */
+    uint32_t reserved;
 } nafgpu_job_stats;
 
 /* ---- host-only helpers -------------------------------------------------------------------------------- */

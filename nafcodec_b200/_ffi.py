@@ -46,7 +46,8 @@ class JobStats(C.Structure):
                 ("compressed_bytes", C.c_uint64), ("section_bytes", C.c_uint64), ("ascii_bytes", C.c_uint64),
                 ("quality_bytes", C.c_uint64), ("id_bytes", C.c_uint64), ("comment_bytes", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("n_stages", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("n_stages", C.c_uint32), ("lz_handover", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 # every symbol include/nafgpu.h declares (tests check the library exports all of them)

@@ -197,6 +197,11 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.frame_bad = misc + 5;
     J.coop_ctas = c->coop_ctas;
+    {   // k_lz_finish sweeps a frame in 64 KB chunks at ~90 us each (profiles/r1_summary.md), frames in parallel
+        uint64_t biggest = 0;
+        for (const auto& F : c->plan.frames) biggest = std::max<uint64_t>(biggest, F.dst_size);
+        J.fin_cost_us = (uint32_t)std::min<uint64_t>(200 + (biggest >> 16) * 90, 0x7FFFFFFFu);
+    }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_tabs = (uint8_t*)c->huftabs.p; J.big_tree_slots = (const uint32_t*)((uint8_t*)c->huftabs.p + nbt * 28672); J.n_big_trees = (uint32_t)nbt;
     J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
@@ -422,6 +427,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     CUDA_TRY(c, cudaStreamSynchronize(c->st));
     std::string msg;
     int code = status_to_code(*(const uint32_t*)c->misc_host.p, msg);
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
     if (code) return fail(c, code, msg);
     if (regen_size) memcpy(dst, (const uint8_t*)c->result.p + ALIGN, regen_size);
     return NAFGPU_OK;
@@ -466,6 +472,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
     const uint8_t* R = (const uint8_t*)c->result.p;
     std::string msg;
     int code = status_to_code(status & ~zc::E_UTF8, msg);
@@ -577,7 +584,7 @@ int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
 
 const char* nafgpu_stage_name(uint32_t s) {
     static const char* names[N_STAGES] = {"memset+huf_decode", "build_tables", "decode_sequences", "frame_scan", "lz_literals", "lz_first",
-                                          "lz_resolve", "naf_scan", "mask_fix", "-", "unpack", "utf8_check"};
+                                          "lz_resolve", "lz_finish", "naf_scan", "mask_fix", "-", "unpack", "utf8_check"};
     return s < (uint32_t)N_STAGES ? names[s] : (s == (uint32_t)N_STAGES ? "k_huf_decode<512>" : "?");
 }
 

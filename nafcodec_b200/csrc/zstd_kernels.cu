@@ -960,7 +960,7 @@ __device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t of
 constexpr uint32_t LZ_SHORT = 64;
 constexpr int LZ_CTA = 256;
 constexpr int LZ_HOPS = 8;
-constexpr uint32_t LZ_MIN_ROUNDS = 12, LZ_MIN_PROGRESS = 24;
+constexpr uint32_t LZ_MIN_ROUNDS = 12, LZ_MIN_PENDING = 192;
 
 // Returns 1 when match i may be copied now (d/off/ml filled), 0 when it has to wait, 2 when it was rejected.
 __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t round, uint64_t& d, uint32_t& off, uint32_t& ml) {
@@ -1063,44 +1063,159 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         NAF_GRID_SYNC();                                             // copies, list appends and the cleared counter are visible
         const uint32_t n_next = J.lz_count[nxt];
         cur = nxt;
-        // A round costs a grid barrier (~3 us) whatever it resolves; the ordered finisher copies ~2 matches/us.  When a
-        // round resolves only a handful of matches the section is one long dependency chain (text-like): hand it over.
-        if (round >= LZ_MIN_ROUNDS && n - n_next < LZ_MIN_PROGRESS && n_next > 8 * LZ_MIN_PROGRESS) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = 1;
+        // A round costs a grid barrier (~3 us) plus a pass over the worklist, whatever it resolves.  At the current rate
+        // the rest would take n_next / progress more rounds; when that costs more than k_lz_finish (whose cost depends on
+        // the bytes of the frame, not on the depth of the chain), the section is text-like: hand it over.
+        const uint32_t progress = n - n_next;
+        const uint64_t round_ns = 3000 + n_next / 5;                       // measured: ~250 us per round at 1.4 M entries
+        if (round >= LZ_MIN_ROUNDS && n_next > LZ_MIN_PENDING &&
+            (uint64_t)n_next * round_ns > (uint64_t)(progress ? progress : 1u) * J.fin_cost_us * 1000u) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = round;
             break;
         }
     }
 }
 
-// k_lz_finish: ordered finisher for what k_lz_resolve left behind (rounds that stop making progress, i.e.
-// text-like sections where nearly every match feeds the next one).  One warp per frame walks the frame's matches in
-// order, 32 done-flags per step, and copies the pending ones cooperatively; in order, every source byte is final.
-__global__ void __launch_bounds__(32) k_lz_finish(JobDev J) {
+// k_lz_finish: what k_lz_resolve leaves behind when its rounds stop paying (text-like sections -- quality strings,
+// ids -- where nearly every match feeds the next one: a dependency chain as long as the section has matches).  Walking
+// such a chain in order costs hundreds of cycles per match on a GPU; instead the chain is cut at BYTE level, where an
+// LZ77 stream is a forest: every byte of a pending match points at the byte `off` behind it, every other byte is a
+// root.  One CTA per frame sweeps the frame in 64 KB chunks held in shared memory: pointers (16-bit, chunk-relative)
+// are set up from the pending matches, pointer jumping (ptr[e] = ptr[ptr[e]], in place) reaches the roots in
+// log2(depth) steps, then every pending byte takes its root's value.  Sources below the chunk are final in global
+// memory (earlier chunks are complete), so those bytes are roots with the value read directly.
+constexpr uint32_t FIN_C = 65536;        // chunk bytes (16-bit pointers)
+constexpr uint32_t FIN_T = 1024;         // threads
+constexpr uint32_t FIN_U = 4;            // matches per thread and scan step (independent loads in flight)
+constexpr uint32_t FIN_INLINE = 64;      // longer pieces are set up by the whole CTA
+constexpr uint32_t FIN_SMEM = FIN_C + FIN_C * 2 + FIN_T * 20;
+
+// One byte of a pending match: chunk-relative e, parent at chunk-relative (signed) s.  The parent is the byte the
+// periodic extension names (k mod off for an overlapping match, so that a run does not become a chain of its own
+// bytes); parents below the chunk are final in global memory.
+__device__ __forceinline__ void fin_byte(uint8_t* val, uint16_t* ptr, uint8_t* out_c0, uint32_t e, int32_t s) {
+    if (s >= 0) ptr[e] = (uint16_t)s;
+    else out_c0[e] = val[e] = __ldcg(out_c0 + s);
+}
+
+__global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
     if (*J.lz_handover == 0) return;                // the rounds finished everything (the normal case)
+    NAF_DYN_SMEM(unsigned char, fin_smem);
+    uint8_t* val = fin_smem;                                   // [FIN_C] chunk bytes
+    uint16_t* ptr = (uint16_t*)(fin_smem + FIN_C);             // [FIN_C] chunk-relative parent; self = root
+    uint32_t* q_rel = (uint32_t*)(fin_smem + FIN_C * 3);       // [FIN_T] long pieces: first chunk-relative byte,
+    uint32_t* q_len = q_rel + FIN_T;                           //         length,
+    uint32_t* q_off = q_len + FIN_T;                           //         match offset,
+    uint32_t* q_m0 = q_off + FIN_T;                            //         first byte of the piece within the match,
+    uint32_t* q_ml = q_m0 + FIN_T;                             //         match length
+    __shared__ uint32_t s_first, s_next, s_q, s_bad;
     const uint32_t f = blockIdx.x;
     if (J.frame_bad[f]) return;
-    const FrameDesc& F = J.frames[f];
-    const int lane = threadIdx.x;
-    const uint32_t end = F.first_seq + F.n_seq;
-    for (uint32_t base = F.first_seq; base < end; base += 32) {
-        const uint32_t i = base + lane;
-        uint32_t pend = __ballot_sync(0xFFFFFFFFu, i < end && J.seq_done[i] == 0);
-        while (pend) {
-            const uint32_t k = base + (uint32_t)__ffs((int)pend) - 1;
-            pend &= pend - 1;
-            const SeqRec& R = J.seq[k];
-            const uint32_t off = resolve_offset(J, R.off, R.block);
-            const uint64_t d = R.match_pos;
-            if (off == 0 || (uint64_t)off > d - F.dst_off) { if (lane == 0) flag_error(J, f, zc::E_OFFSET); return; }
-            copy_match(J.out, d, off, R.ml, lane, 32);
-            __syncwarp();
-            if (lane == 0) J.seq_done[k] = 0x7FFFFFFFu;
-            __syncwarp();
+    const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
+    const uint32_t first = J.frames[f].first_seq, end = first + J.frames[f].n_seq;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+    // first pending match of the frame (most frames have none)
+    if (tid == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
+    __syncthreads();
+    for (uint32_t i = first + tid; i < end; i += FIN_T)
+        if (J.seq_done[i] == 0) { atomicMin(&s_first, i); break; }
+    __syncthreads();
+    uint32_t mi = s_first;
+    if (mi == 0xFFFFFFFFu) return;
+
+    for (uint64_t c0 = f0 + ((J.seq[mi].match_pos - f0) & ~(uint64_t)15); c0 < fend && mi < end; c0 += FIN_C) {
+        const uint64_t c1 = (c0 + FIN_C < fend) ? c0 + FIN_C : fend;
+        const uint32_t cn = (uint32_t)(c1 - c0);
+        uint8_t* out_c0 = J.out + c0;
+        // chunk bytes as they stand (literals and finished matches are final, pending bytes are garbage) + self pointers
+        for (uint32_t e = tid * 16; e < cn; e += FIN_T * 16) {
+            *(uint4*)(val + e) = __ldcg((const uint4*)(out_c0 + e));         // the arena is padded past the last frame
+            uint32_t* p2 = (uint32_t*)(ptr + e);
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) p2[k] = (e + 2 * k) | ((e + 2 * k + 1) << 16);
         }
+        if (tid == 0) s_next = end;
+        __syncthreads();
+        // pending matches that intersect the chunk (matches are ordered by position)
+        bool any = false;
+        for (uint32_t base = mi;; base += FIN_T * FIN_U) {
+            if (tid == 0) s_q = 0;
+            __syncthreads();
+            uint64_t pos[FIN_U];
+            uint32_t ml[FIN_U], ov[FIN_U], blk[FIN_U];
+            bool pend[FIN_U];
+#pragma unroll
+            for (uint32_t j = 0; j < FIN_U; j++) {
+                const uint32_t i = base + j * FIN_T + tid;
+                pos[j] = ~0ull; ml[j] = 0; ov[j] = 0; blk[j] = 0; pend[j] = false;
+                if (i < end) {
+                    const SeqRec& R = J.seq[i];
+                    pos[j] = R.match_pos; ml[j] = R.ml; ov[j] = R.off; blk[j] = R.block; pend[j] = J.seq_done[i] == 0;
+                }
+            }
+            bool stop = false;
+#pragma unroll
+            for (uint32_t j = 0; j < FIN_U; j++) {
+                const uint32_t i = base + j * FIN_T + tid;
+                const bool beyond = i < end && pos[j] + ml[j] > c1;         // the next chunk starts looking at the first of these
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, beyond);
+                if (bal && lane == (uint32_t)__ffs(bal) - 1u) atomicMin(&s_next, i);
+                if (i >= end || pos[j] >= c1) stop = true;
+                else if (pend[j] && pos[j] + ml[j] > c0) {
+                    const uint32_t off = resolve_offset(J, ov[j], blk[j]);
+                    if (off == 0 || (uint64_t)off > pos[j] - f0 || off > 0x7F000000u) { flag_error(J, f, zc::E_OFFSET); s_bad = 1; }
+                    else {
+                        const uint64_t b0 = pos[j] > c0 ? pos[j] : c0, b1 = pos[j] + ml[j] < c1 ? pos[j] + ml[j] : c1;
+                        const uint32_t rel = (uint32_t)(b0 - c0), len = (uint32_t)(b1 - b0), m0 = (uint32_t)(b0 - pos[j]);
+                        const int32_t srel = (int32_t)((int64_t)(pos[j] - off) - (int64_t)c0);   // |srel| < 2^31: offsets are capped below
+                        any = true;
+                        if (len > FIN_INLINE) {
+                            const uint32_t slot = atomicAdd(&s_q, 1u);
+                            q_rel[slot] = rel; q_len[slot] = len; q_off[slot] = off; q_m0[slot] = m0; q_ml[slot] = ml[j];
+                        } else if (off >= ml[j]) {
+                            int32_t sp = srel + (int32_t)m0;
+                            for (uint32_t k = 0; k < len; k++, sp++) fin_byte(val, ptr, out_c0, rel + k, sp);
+                        } else {
+                            uint32_t r = m0 % off;
+                            for (uint32_t k = 0; k < len; k++) { fin_byte(val, ptr, out_c0, rel + k, srel + (int32_t)r); if (++r == off) r = 0; }
+                        }
+                    }
+                }
+            }
+            const int all_stop = __syncthreads_or(stop);
+            const uint32_t nq = s_q;
+            for (uint32_t t = 0; t < nq; t++) {
+                const uint32_t rel = q_rel[t], len = q_len[t], off = q_off[t], m0 = q_m0[t], mlen = q_ml[t];
+                const int32_t srel = (int32_t)rel - (int32_t)m0 - (int32_t)off;
+                for (uint32_t k = tid; k < len; k += FIN_T)
+                    fin_byte(val, ptr, out_c0, rel + k, srel + (int32_t)(off < mlen ? (m0 + k) % off : m0 + k));
+            }
+            if (all_stop) break;
+            __syncthreads();                                                // queue drained before it is refilled
+        }
+        const int work = __syncthreads_or(any);
+        mi = s_next;
+        if (s_bad) return;                                                  // (uniform: set before the barrier above)
+        if (work) {
+            // pointer jumping, in place: a pointer only ever moves to an ancestor, roots never move
+            for (;;) {
+                bool changed = false;
+                for (uint32_t e = tid; e < cn; e += FIN_T) {
+                    const uint32_t p = ptr[e];
+                    if (p != e) { const uint32_t pp = ptr[p]; if (pp != p) { ptr[e] = (uint16_t)pp; changed = true; } }
+                }
+                if (!__syncthreads_or(changed)) break;
+            }
+            for (uint32_t e = tid; e < cn; e += FIN_T) {
+                const uint32_t p = ptr[e];
+                if (p != e) out_c0[e] = val[p];                              // roots are not written here: no hazard
+            }
+        }
+        __syncthreads();                                                    // chunk complete (and visible) before the next one reads it
     }
 }
 
-// --------------------------------------------------------------------------------------------------------------
 uint32_t lz_resolve_max_ctas(int device) {
 #if defined(NAFGPU_EMULATE)
     (void)device;
@@ -1154,9 +1269,11 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         (void)cg;
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
-        NAF_LAUNCH(k_lz_finish, J.n_frames, 32, 0, st, J); launches++;
         ev->mark();
-    } else { ev->mark(); ev->mark(); }
+        NAF_SET_MAX_SMEM(k_lz_finish, FIN_SMEM);
+        NAF_LAUNCH(k_lz_finish, J.n_frames, FIN_T, FIN_SMEM, st, J); launches++;
+        ev->mark();
+    } else { ev->mark(); ev->mark(); ev->mark(); }
     return launches;
 }
 

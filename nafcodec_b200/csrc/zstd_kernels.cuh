@@ -32,6 +32,7 @@ struct JobDev {
     uint32_t* lz_count;               // [3] their lengths
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
+    uint32_t fin_cost_us;             // estimated cost of k_lz_finish on this job's largest frame (hand-over decision)
     uint8_t* huf_tabs;                // n_big_trees x 28 KB prebuilt decode tables (t1 | bm | t3) of trees used by big streams
     const uint32_t* big_tree_slots;   // weight-record slot of each of them
     uint32_t n_big_trees;
@@ -48,6 +49,6 @@ struct JobDev {
 int launch_zstd_stage(const JobDev& job, cudaStream_t stream, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev);
 // Co-resident CTAs (whole device) for the cooperative match-resolution kernel.
 uint32_t lz_resolve_max_ctas(int device);
-constexpr int ZSTD_STAGES = 7;
+constexpr int ZSTD_STAGES = 8;
 
 }  // namespace zk

@@ -163,6 +163,46 @@ def test_zstd_boundary_generated(backend):
         assert ctx.zstd_decompress(frame, len(p)) == p, (name, "flushed")
 
 
+def _generations(rng, gens, blen, far_every=0, long_every=0):
+    """Text in which block k is block k-1 with one byte changed: every match feeds the next one (one dependency chain),
+    which is what quality strings and ids look like to the LZ stage.  `far_every` / `long_every` splice in references
+    far behind the current position and long matches."""
+    b = bytearray(rng.integers(33, 75, size=blen).astype(np.uint8).tobytes())
+    first = bytes(rng.integers(33, 75, size=5000).astype(np.uint8))
+    q = bytearray(first)
+    for g in range(gens):
+        b[int(rng.integers(blen))] = int(rng.integers(33, 75))
+        q += b
+        if far_every and g % far_every == far_every - 1:
+            k = int(rng.integers(0, 4000)); q += first[k:k + int(rng.integers(8, 600))]     # far reference
+        if long_every and g % long_every == long_every - 1:
+            q += bytes(b[:7]) * 4000                                                          # 28 kB periodic match
+    return bytes(q)
+
+
+def test_ordered_finisher_on_dependency_chains(backend):
+    """Sections that are one long LZ dependency chain are handed to k_lz_finish (shared-memory ring); the job stats
+    say so, and the bytes must still be libzstd's."""
+    ctx = N.shared_context(0, library(backend))
+    rng = np.random.default_rng(7)
+    gens = 3000 if backend == "emul" else 40000
+    for blen, far, lng, level in [(100, 0, 0, 3), (300, 0, 0, 19), (100, 50, 0, 3), (150, 40, 700, 19), (3000, 3, 0, 3)]:
+        p = _generations(rng, gens if blen < 1000 else gens // 20, blen, far, lng)
+        frame = K.zstd_frame(p, level)
+        assert O.zstd_decompress(frame) == p
+        assert ctx.zstd_decompress(frame, len(p)) == p, (blen, far, lng, level)
+        if blen < 1000:                                    # (few, long matches: the rounds stay cheaper than the finisher)
+            assert ctx.stats().lz_handover > 0, (blen, far, lng, level)
+    # a chain next to ordinary frames in one job: quality of a FASTQ archive whose reads descend from one another
+    qual = _generations(rng, 1500, 150)[5000:]
+    n = len(qual) // 150
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=150)) for _ in range(n)]
+    arc = O.encode(sequence_type=O.DNA, ids=[b"r%d" % i for i in range(n)], sequences=seqs,
+                   qualities=[qual[i * 150:(i + 1) * 150] for i in range(n)], level=3)
+    check_parity(backend, arc)
+    assert ctx.stats().lz_handover > 0
+
+
 def test_corrupt_input_never_hangs(backend):
     """Truncations and byte flips: the device path must return (error or data), never hang or fault."""
     data = bytearray(K.multi_record_dna(9, 20, 2000, level=3))
