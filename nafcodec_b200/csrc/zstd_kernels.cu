@@ -268,90 +268,131 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// k_frame_scan: one thread per frame.  Exclusive prefix sum of regenerated block sizes -> out_off; composes the
+// k_frame_scan: one CTA per frame.  Exclusive prefix sum of regenerated block sizes -> out_off; composes the
 // repeat-offset transfer functions -> rep_in per block; checks the total against the size the container states.
-__global__ void __launch_bounds__(128) k_frame_scan(JobDev J) {
-    // one warp per frame; 32 blocks per step: lanes load in parallel, offsets by a shuffle scan, the repeat-offset chain
-    // is walked lane by lane through shuffles (no global-memory latency inside the dependent chain)
-    const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= J.n_frames) return;
+//
+// A block's effect on the three repeat offsets is a map: slot k = constant v, or incoming slot s minus v (blocks
+// without sequences are the identity).  Maps compose associatively, so the chain across the blocks of a frame is a
+// scan: shuffles inside a warp, the warps' aggregates scanned once more by every warp; FSCAN_T blocks per step.
+// A genome frame has a handful of blocks; a FASTQ section flushed per record has 10^5 of them.
+constexpr int FSCAN_T = 512, FSCAN_W = FSCAN_T / 32;
+
+struct RepMap { int32_t s[3]; uint32_t v[3]; };
+
+__device__ __forceinline__ void rep_identity(RepMap& m) { m.s[0] = 0; m.s[1] = 1; m.s[2] = 2; m.v[0] = m.v[1] = m.v[2] = 0; }
+
+// m <- (m after f)
+__device__ __forceinline__ void rep_compose(RepMap& m, const RepMap& f, bool& bad) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (m.s[k] >= 0) {
+            const int sk = m.s[k];
+            const int32_t es = sk == 0 ? f.s[0] : (sk == 1 ? f.s[1] : f.s[2]);
+            const uint32_t ev = sk == 0 ? f.v[0] : (sk == 1 ? f.v[1] : f.v[2]);
+            if (es < 0) { if (ev <= m.v[k]) { bad = true; m.v[k] = 1; } else m.v[k] = ev - m.v[k]; m.s[k] = -1; }
+            else { m.s[k] = es; m.v[k] = ev + m.v[k]; }
+        }
+    }
+}
+
+// out <- m(in); returns false if an offset would not be positive
+__device__ __forceinline__ bool rep_apply(const RepMap& m, const uint32_t in[3], uint32_t out[3]) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (m.s[k] < 0) out[k] = m.v[k];
+        else {
+            const uint32_t x = m.s[k] == 0 ? in[0] : (m.s[k] == 1 ? in[1] : in[2]);
+            if (x <= m.v[k]) { ok = false; out[k] = 1; } else out[k] = x - m.v[k];
+        }
+    }
+    return ok;
+}
+
+// inclusive scan of maps over the lanes of a warp (lane i ends up with map_i after ... after map_0)
+__device__ __forceinline__ void rep_warp_scan(RepMap& m, int lane, bool& bad) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        RepMap f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { f.s[k] = __shfl_up_sync(0xFFFFFFFFu, m.s[k], d); f.v[k] = __shfl_up_sync(0xFFFFFFFFu, m.v[k], d); }
+        if (lane >= d) rep_compose(m, f, bad);
+    }
+}
+
+__device__ __forceinline__ void rep_shfl(RepMap& out, const RepMap& m, int src) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { out.s[k] = __shfl_sync(0xFFFFFFFFu, m.s[k], src); out.v[k] = __shfl_sync(0xFFFFFFFFu, m.v[k], src); }
+}
+
+__global__ void __launch_bounds__(FSCAN_T) k_frame_scan(JobDev J) {
+    __shared__ RepMap agg_map[2][FSCAN_W];
+    __shared__ uint32_t agg_regen[2][FSCAN_W];
+    const uint32_t f = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (J.frame_bad[f]) return;
     const FrameDesc& F = J.frames[f];
+    const uint32_t nb = F.n_blocks, fb = F.first_block;
     uint64_t off = F.dst_off;
-    uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
+    uint32_t rep[3] = {1, 4, 8};
     bool bad = false;
-    for (uint32_t b0 = 0; b0 < F.n_blocks; b0 += 32) {
-        const uint32_t b = F.first_block + b0 + lane;
-        const bool valid = b0 + lane < F.n_blocks;
+    int buf = 0;
+    for (uint32_t b0 = 0; b0 < nb; b0 += FSCAN_T, buf ^= 1) {
+        const uint32_t b = fb + b0 + threadIdx.x;
+        const bool valid = b0 + threadIdx.x < nb;
         uint32_t regen = 0;
         bool has_seq = false;
-        int32_t rs0 = 0, rs1 = 1, rs2 = 2;
-        uint32_t rv0 = 0, rv1 = 0, rv2 = 0;
+        RepMap m; rep_identity(m);
         if (valid) {
             const BlockDesc& B = J.blocks[b];
             has_seq = B.btype == BT_COMPRESSED && B.n_seq > 0;
             if (has_seq) {
                 const BlockState& S = J.bstate[b];
                 regen = S.regen;
-                rs0 = S.rep_src[0]; rs1 = S.rep_src[1]; rs2 = S.rep_src[2];
-                rv0 = S.rep_val[0]; rv1 = S.rep_val[1]; rv2 = S.rep_val[2];
+#pragma unroll
+                for (int k = 0; k < 3; k++) { m.s[k] = S.rep_src[k]; m.v[k] = S.rep_val[k]; }
             } else regen = B.known_regen;
         }
         uint32_t inc = regen;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
-        if (valid) { J.bstate[b].regen = regen; J.bstate[b].out_off = off + (inc - regen); }
-        off += __shfl_sync(0xFFFFFFFFu, inc, 31);
-        // repeat offsets: inclusive scan over function composition of the blocks' transfer functions
-        // (slot k = constant v, or incoming slot s minus v); blocks without sequences are the identity
-        int32_t cs[3] = {rs0, rs1, rs2};
-        uint32_t cv[3] = {rv0, rv1, rv2};
+        rep_warp_scan(m, lane, bad);
+        if (lane == 31) { agg_map[buf][w] = m; agg_regen[buf][w] = inc; }
+        __syncthreads();                                   // (aggregates are double-buffered: one barrier per step)
+        // the warps' aggregates, scanned by every warp for itself
+        RepMap a; rep_identity(a);
+        uint32_t ar = 0;
+        if (lane < FSCAN_W) { a = agg_map[buf][lane]; ar = agg_regen[buf][lane]; }
+        uint32_t ainc = ar;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int32_t fs[3]; uint32_t fv[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) { fs[k] = __shfl_up_sync(0xFFFFFFFFu, cs[k], d); fv[k] = __shfl_up_sync(0xFFFFFFFFu, cv[k], d); }
-            if (lane >= d) {                              // (mine) after (earlier f)
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (cs[k] >= 0) {
-                        const int sk = cs[k];
-                        const int32_t es = sk == 0 ? fs[0] : (sk == 1 ? fs[1] : fs[2]);
-                        const uint32_t ev = sk == 0 ? fv[0] : (sk == 1 ? fv[1] : fv[2]);
-                        if (es < 0) { if (ev <= cv[k]) { bad = true; cv[k] = 1; } else cv[k] = ev - cv[k]; cs[k] = -1; }
-                        else { cs[k] = es; cv[k] = ev + cv[k]; }
-                    }
-                }
-            }
+        for (int d = 1; d < FSCAN_W; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ainc, d); if (lane >= d) ainc += t; }
+        rep_warp_scan(a, lane, bad);
+        // everything before this thread's block: the warps before mine, then the lanes before mine
+        RepMap wp, x;
+        rep_shfl(wp, a, w ? w - 1 : 0);
+        uint32_t wregen = __shfl_sync(0xFFFFFFFFu, ainc, w ? w - 1 : 0);
+        if (w == 0) { rep_identity(wp); wregen = 0; }
+        rep_shfl(x, m, lane ? lane - 1 : 0);
+        if (lane == 0) rep_identity(x);
+        bool xbad = false;
+        rep_compose(x, wp, xbad);
+        uint32_t in[3];
+        const bool ok = rep_apply(x, rep, in);
+        if (valid) {
+            BlockState& S = J.bstate[b];
+            S.regen = regen; S.out_off = off + wregen + (inc - regen);
+            if (has_seq) { S.rep_in[0] = in[0]; S.rep_in[1] = in[1]; S.rep_in[2] = in[2]; if (!ok || xbad) bad = true; }
         }
-        // exclusive map of this lane applied to the repeat offsets entering this group of 32 blocks
-        int32_t xs[3]; uint32_t xv[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { xs[k] = __shfl_up_sync(0xFFFFFFFFu, cs[k], 1); xv[k] = __shfl_up_sync(0xFFFFFFFFu, cv[k], 1); }
-        if (lane == 0) { xs[0] = 0; xs[1] = 1; xs[2] = 2; xv[0] = xv[1] = xv[2] = 0; }
-        const uint32_t rin[3] = {rep0, rep1, rep2};
-        uint32_t inr[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            if (xs[k] < 0) inr[k] = xv[k];
-            else { const uint32_t x = xs[k] == 0 ? rin[0] : (xs[k] == 1 ? rin[1] : rin[2]); if (x <= xv[k]) { if (has_seq) bad = true; inr[k] = 1; } else inr[k] = x - xv[k]; }
-        }
-        const uint32_t in0 = inr[0], in1 = inr[1], in2 = inr[2];
-        // repeat offsets leaving the group = lane 31's inclusive map applied to the incoming ones
-        uint32_t outr[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int32_t ls = __shfl_sync(0xFFFFFFFFu, cs[k], 31);
-            const uint32_t lv = __shfl_sync(0xFFFFFFFFu, cv[k], 31);
-            if (ls < 0) outr[k] = lv;
-            else { const uint32_t x = ls == 0 ? rin[0] : (ls == 1 ? rin[1] : rin[2]); if (x <= lv) { bad = true; outr[k] = 1; } else outr[k] = x - lv; }
-        }
-        rep0 = outr[0]; rep1 = outr[1]; rep2 = outr[2];
-        if (valid && has_seq) { BlockState& S = J.bstate[b]; S.rep_in[0] = in0; S.rep_in[1] = in1; S.rep_in[2] = in2; }
+        // what leaves this group of blocks
+        RepMap tot;
+        rep_shfl(tot, a, FSCAN_W - 1);
+        uint32_t out[3];
+        if (!rep_apply(tot, rep, out)) bad = true;
+        rep[0] = out[0]; rep[1] = out[1]; rep[2] = out[2];
+        off += __shfl_sync(0xFFFFFFFFu, ainc, FSCAN_W - 1);
     }
     if (off - F.dst_off != F.dst_size) bad = true;
-    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) flag_error(J, f, zc::E_SIZE);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) flag_error(J, f, zc::E_SIZE);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -1257,7 +1298,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     else ev->mark();                                  // serial (profiled) order: the Huffman branch first
     NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, J.seq_stage_bytes, st, J); launches++; ev->mark();
-    NAF_LAUNCH(k_frame_scan, (J.n_frames + 3) / 4, 128, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++; ev->mark();
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
