@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -67,7 +68,8 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, blocks, frames, bstate, hufitems, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, nafdev, flush;
+    DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush;
+    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -115,7 +117,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     // profiled runs (ev != null) are serial so that every stage has its own interval
     int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev);
-    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)c->nafdev.p, (uint32_t)c->arch.size(), c->max_records,
+    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records,
                                      c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
     CUDA_TRY(c, cudaGetLastError());
@@ -140,6 +142,21 @@ int status_to_code(uint32_t s, std::string& msg) {
     return NAFGPU_ERR_INVALID_DATA;
 }
 
+// Result copies of concurrent contexts on one device take turns.  Issued together they share the PCIe link, every lane
+// finishes at the same time, and all of them then walk headers and run kernels together while the copy engine idles
+// (measured: 8.2 ms per 320 MB step whatever the number of lanes).  One at a time each copy runs at the full rate and
+// the lanes stay staggered, so the link is always busy (tools/e2e_probe.py).
+static std::mutex g_d2h_turn[16];
+
+static int d2h_results(nafgpu_ctx* c) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));                  // kernels first: do not hold the turn while they run
+    std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
+    CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    return NAFGPU_OK;
+}
+
 struct Copy { const uint8_t* src; uint64_t dst, size; };
 
 // Device allocation + H2D of descriptors and compressed frames for the plan in c->plan / c->arch.
@@ -151,35 +168,31 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
     c->misc_words = 1 + 3 + 1 + nf + 8;
-    bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
-              c->blocks.ensure(nb * sizeof(zf::BlockDesc) + 64) && c->frames.ensure(nf * sizeof(zf::FrameDesc) + 64) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufitems.ensure(pl.huf_items.size() * sizeof(zf::HufItem) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) && c->huftabs.ensure(pl.big_tree_slots.size() * (28672 + 4) + 64) &&
-              c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
-              c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4) &&
-              c->nafdev.ensure((size_t)n * sizeof(nk::NafDev) + 64);
-    if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     const size_t nh = pl.huf_items.size(), nbt = pl.big_tree_slots.size();
-    size_t stage_bytes = nbt * 4 + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev) + nh * sizeof(zf::HufItem);
+    // descriptors: [blocks | frames | NafDev | HufItem | big-tree slots], the same layout in pinned staging and on the device,
+    // so that they go up in ONE copy (a burst of small H2D copies is time-sliced against other contexts' result copies)
+    c->o_frames = align_up(nb * sizeof(zf::BlockDesc), 16);
+    c->o_naf = c->o_frames + align_up(nf * sizeof(zf::FrameDesc), 16);
+    c->o_huf = c->o_naf + align_up((size_t)n * sizeof(nk::NafDev), 16);
+    c->o_bt = c->o_huf + align_up(nh * sizeof(zf::HufItem), 16);
+    const size_t stage_bytes = c->o_bt + align_up(nbt * 4, 16);
+    bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
+              c->desc.ensure(stage_bytes + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) && c->huftabs.ensure(pl.big_tree_slots.size() * 28672 + 64) &&
+              c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
+              c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
+    if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
         return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
 
     // ---- H2D ---------------------------------------------------------------------------------------------------------
     uint8_t* sp = (uint8_t*)c->stage.p;
     if (nb) memcpy(sp, pl.blocks.data(), nb * sizeof(zf::BlockDesc));
-    if (nf) memcpy(sp + nb * sizeof(zf::BlockDesc), pl.frames.data(), nf * sizeof(zf::FrameDesc));
-    if (n) memcpy(sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc), c->arch.data(), (size_t)n * sizeof(nk::NafDev));
-    if (nb) CUDA_TRY(c, cudaMemcpyAsync(c->blocks.p, sp, nb * sizeof(zf::BlockDesc), cudaMemcpyHostToDevice, c->st));
-    if (nf) CUDA_TRY(c, cudaMemcpyAsync(c->frames.p, sp + nb * sizeof(zf::BlockDesc), nf * sizeof(zf::FrameDesc), cudaMemcpyHostToDevice, c->st));
-    if (n) CUDA_TRY(c, cudaMemcpyAsync(c->nafdev.p, sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc), (size_t)n * sizeof(nk::NafDev), cudaMemcpyHostToDevice, c->st));
-    {
-        uint8_t* hp = sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev);
-        if (nh) { memcpy(hp, pl.huf_items.data(), nh * sizeof(zf::HufItem)); CUDA_TRY(c, cudaMemcpyAsync(c->hufitems.p, hp, nh * sizeof(zf::HufItem), cudaMemcpyHostToDevice, c->st)); }
-    }
-    if (nbt) {
-        uint8_t* bp = sp + nb * sizeof(zf::BlockDesc) + nf * sizeof(zf::FrameDesc) + (size_t)n * sizeof(nk::NafDev) + nh * sizeof(zf::HufItem);
-        memcpy(bp, pl.big_tree_slots.data(), nbt * 4);
-        CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->huftabs.p + nbt * 28672, bp, nbt * 4, cudaMemcpyHostToDevice, c->st));
-    }
+    if (nf) memcpy(sp + c->o_frames, pl.frames.data(), nf * sizeof(zf::FrameDesc));
+    if (n) memcpy(sp + c->o_naf, c->arch.data(), (size_t)n * sizeof(nk::NafDev));
+    if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
+    if (nbt) memcpy(sp + c->o_bt, pl.big_tree_slots.data(), nbt * 4);
+    if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
         CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->comp.p + cp.dst, cp.src, cp.size, cudaMemcpyHostToDevice, c->st));
@@ -188,7 +201,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
 
     zk::JobDev& J = c->J;
     J.comp = (const uint8_t*)c->comp.p; J.out = (uint8_t*)c->arena.p; J.lit = (uint8_t*)c->lit.p;
-    J.frames = (const zf::FrameDesc*)c->frames.p; J.blocks = (const zf::BlockDesc*)c->blocks.p;
+    J.frames = (const zf::FrameDesc*)((const uint8_t*)c->desc.p + c->o_frames); J.blocks = (const zf::BlockDesc*)c->desc.p;
     J.bstate = (zf::BlockState*)c->bstate.p; J.tables = (zc::SeqCell*)c->tables.p; J.table_al = (uint8_t*)c->table_al.p;
     J.seq_done = (uint32_t*)c->seq32.p;
     J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq; J.lz_list[2] = J.seq_done + 3 * nseq;
@@ -203,8 +216,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         J.fin_cost_us = (uint32_t)std::min<uint64_t>(200 + (biggest >> 16) * 90, 0x7FFFFFFFu);
     }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
-    J.huf_tabs = (uint8_t*)c->huftabs.p; J.big_tree_slots = (const uint32_t*)((uint8_t*)c->huftabs.p + nbt * 28672); J.n_big_trees = (uint32_t)nbt;
-    J.huf_items = (const zf::HufItem*)c->hufitems.p; J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
+    J.huf_tabs = (uint8_t*)c->huftabs.p; J.big_tree_slots = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_bt); J.n_big_trees = (uint32_t)nbt;
+    J.huf_items = (const zf::HufItem*)((const uint8_t*)c->desc.p + c->o_huf); J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
     J.debug = nullptr;
     if (getenv("NAFGPU_DEBUG_HUF") && nh) {
         if (!c->debug.ensure(nh * 64)) return fail(c, NAFGPU_ERR_NOMEM, "debug buffer");
@@ -250,7 +263,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->blocks, &c->frames, &c->bstate, &c->hufitems, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->nafdev, &c->flush};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
@@ -381,19 +394,34 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
             if (!P.dec[s]) continue;
             const nafgpu_section& S = A.sections[s];
             std::string e;
+            // Sections that follow one another in the caller's buffer (the sections of a NAF file do, a few header bytes
+            // apart) keep their relative positions on the device and travel in one copy, gap bytes included.
+            bool merged = false;
+            if (!copies.empty()) {
+                Copy& L = copies.back();
+                const uint8_t* lend = L.src + L.size;
+                if (S.data >= lend && (uint64_t)(S.data - lend) <= 64) {
+                    comp_off = L.dst + (uint64_t)(S.data - L.src);
+                    L.size = (uint64_t)(S.data - L.src) + S.compressed_size;
+                    merged = true;
+                }
+            }
+            if (!merged) {
+                if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
+                copies.push_back({S.data, comp_off, S.compressed_size});
+            }
             int rc = fw::walk_frame(S.data, comp_off, S.compressed_size, P.blob_off[s], P.blob_size[s], c->plan, e);
             if (rc) {
                 static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
                 return fail(c, rc, std::string(names[s]) + " section: " + e);
             }
-            copies.push_back({S.data, comp_off, S.compressed_size});
-            comp_off = align_up(comp_off + S.compressed_size + zf::COMP_PAD, 16);
             c->stats.compressed_bytes += S.compressed_size;
             c->stats.section_bytes += P.blob_size[s];
         }
     }
     c->stats.algorithmic_bytes += c->stats.compressed_bytes;
     c->stats.algorithmic_bytes += c->stats.compressed_bytes;
+    if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
     return finish_prepare(c, copies, comp_off, n);
 }
 
@@ -422,9 +450,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     if (rc) return rc;
     rc = enqueue_run(c, nullptr);
     if (rc) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
-    CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
-    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    { int rc_d2h = d2h_results(c); if (rc_d2h) return rc_d2h; }
     std::string msg;
     int code = status_to_code(*(const uint32_t*)c->misc_host.p, msg);
     c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
@@ -452,9 +478,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
     if (!c->prepared || !c->ran) return fail(c, NAFGPU_ERR_ARGUMENT, "job has not been run");
     if (n != c->arch.size()) return fail(c, NAFGPU_ERR_ARGUMENT, "result count differs from the prepared job");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
-    CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
-    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    { int rc_d2h = d2h_results(c); if (rc_d2h) return rc_d2h; }
     CUDA_TRY(c, cudaGetLastError());
     if (c->J.debug) {
         size_t nh = c->J.n_huf_items;

@@ -416,6 +416,50 @@ class Pipeline:
         list(self.pool.map(work, range(lanes)))
         return out
 
+    def decode_stream(self, batches, want: int = _ffi.WANT_ALL, consume=None, sub_batch: Optional[int] = None):
+        """Decodes a sequence of batches (each a list of _ffi.Archive) as ONE stream of work: every batch is cut into
+        sub-batches, and the lanes pull them from a shared queue with no barrier between batches, so the header walk, H2D
+        and kernels of one sub-batch always overlap the D2H of another (a collection of archives is processed this way;
+        `decode` waits for every lane at the end of each batch).  `consume(batch_index, index, result_struct)` runs on
+        the worker thread while the pinned buffers of that sub-batch are valid.  Returns the number of archives decoded."""
+        import itertools
+        import threading
+        lanes = len(self.ctxs)
+        lock = threading.Lock()
+
+        def pieces():
+            for bi, archives in enumerate(batches):
+                n = len(archives)
+                step = sub_batch or max(1, -(-n // lanes))
+                for lo in range(0, n, step):
+                    yield bi, lo, archives[lo:lo + step]
+
+        it = pieces()
+        done = [0]
+
+        def work(k):
+            ctx = self.ctxs[k]
+            while True:
+                with lock:
+                    nxt = next(it, None)
+                if nxt is None:
+                    return
+                bi, lo, part = nxt
+                cnt = len(part)
+                arr = (_ffi.Archive * cnt)(*part)
+                res = (_ffi.Result * cnt)()
+                with ctx._lock:
+                    rc = self.lib.dll.nafgpu_decode_batch(ctx._ctx, arr, cnt, want, res)
+                    raise_for_status(self.lib, rc, ctx._ctx)
+                    if consume is not None:
+                        for i in range(cnt):
+                            consume(bi, lo + i, res[i])
+                with lock:
+                    done[0] += cnt
+
+        list(self.pool.map(work, range(lanes)))
+        return done[0]
+
     def stats(self):
         return [c.stats() for c in self.ctxs]
 

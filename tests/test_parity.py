@@ -250,10 +250,20 @@ def test_pipeline_lanes(backend):
     arcs = [K.genome(300 + i, 25_000 + 999 * i, level=3) for i in range(5)] + [read_golden("phix.naf")]
     parsed = [N.parse_archive(a, lib) for a in arcs]
     pipe = N.Pipeline(0, 3, lib)
+    from _harness import assert_same_as_oracle
+    got = {}
+
+    def consume(bi, i, r):                                   # runs on the lane's thread while its pinned buffers are valid
+        got[(bi, i)] = N.ArchiveResult._copy_from(parsed[i].header, r)
+
     try:
         res = pipe.decode(parsed)
+        n = pipe.decode_stream([parsed, parsed[:4], parsed], consume=consume, sub_batch=2)     # no barrier between batches
     finally:
         pipe.close()
-    from _harness import assert_same_as_oracle
-    for i, (r, a) in enumerate(zip(res, arcs)):
-        assert_same_as_oracle(r, O.decode(a), f"archive {i}")
+    want = [O.decode(a) for a in arcs]
+    for i, r in enumerate(res):
+        assert_same_as_oracle(r, want[i], f"archive {i}")
+    assert n == 16 and len(got) == 16
+    for (bi, i), r in got.items():
+        assert_same_as_oracle(r, want[i], f"stream batch {bi} archive {i}")
