@@ -105,7 +105,8 @@ typedef struct nafgpu_job_stats {
     uint32_t kernel_launches;           /* kernels enqueued by one nafgpu_job_run */
     uint32_t n_stages;                  /* entries nafgpu_job_run_profiled writes */
     uint32_t lz_handover;               /* nonzero if the last fetched run left LZ matches to the ordered finisher (k_lz_finish): the round it gave up at */
-    uint32_t reserved;
+    float text_kernel_ms;               /* device time of the last nafgpu_job_format's kernels (CUDA events on the context's stream) */
+    uint64_t text_bytes;                /* bytes of text the last nafgpu_job_format produced */
 } nafgpu_job_stats;
 
 /* ---- host-only helpers -------------------------------------------------------------------------------- */
@@ -161,6 +162,31 @@ int nafgpu_job_time(nafgpu_ctx* ctx, int iters, int flush_l2, float* total_ms);
  * stage_ms must hold stats.n_stages floats. Stage names: nafgpu_stage_name. */
 int nafgpu_job_run_profiled(nafgpu_ctx* ctx, float* stage_ms, uint32_t n_stages);
 const char* nafgpu_stage_name(uint32_t stage);
+
+/* ---- FASTA / FASTQ text --------------------------------------------------------------------------
+ * The reference crate yields Records and only CARRIES what a formatter needs, Header::line_length and
+ * Header::name_separator (nafcodec/src/data.rs:198-236; accessors decoder/mod.rs:319-328); the text is what upstream
+ * `unnaf` prints and the reference's fixtures hold (data/masked.fna, data/LuxC.faa, data/phix.fastq):
+ *   FASTA  '>' id [sep comment] '\n' sequence wrapped at line_length (0 = one line) '\n'
+ *   FASTQ  '@' id [sep comment] '\n' sequence '\n' '+' '\n' quality '\n'
+ * (separator + comment only when the comment is not empty; absent fields are empty).  Formatted on the device from the
+ * job that was just run; only the text is copied back. */
+enum { NAFGPU_TEXT_AUTO = 0 /* FASTQ iff quality was decoded */, NAFGPU_TEXT_FASTA = 1, NAFGPU_TEXT_FASTQ = 2 };
+#define NAFGPU_LINE_LENGTH_FROM_HEADER UINT64_MAX
+
+typedef struct nafgpu_text {
+    const uint8_t* data;                /* HOST pointer into pinned memory owned by the context (valid until its next call) */
+    uint64_t size;
+    int32_t format;                     /* NAFGPU_TEXT_FASTA | NAFGPU_TEXT_FASTQ, as written */
+    int32_t status;                     /* 0, or NAFGPU_ERR_UTF8: the reference fails AT first_bad_record (reader.rs:108-109) */
+    uint64_t first_bad_record;
+} nafgpu_text;
+
+/* After nafgpu_job_run: text of every archive of the job (sequence must have been decoded; FASTQ also needs quality). */
+int nafgpu_job_format(nafgpu_ctx* ctx, int format, uint64_t line_length, nafgpu_text* out, uint32_t n);
+/* prepare + run + format in one call. */
+int nafgpu_format_batch(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want, int format,
+                        uint64_t line_length, nafgpu_text* out);
 
 /* Device pointers of the last run's outputs, for callers that keep results in HBM (device-resident variant). */
 int nafgpu_job_device_result(nafgpu_ctx* ctx, uint32_t archive, const uint8_t** sequence_dev, uint64_t* capacity_bytes);

@@ -5,7 +5,8 @@ Decoder, DecoderBuilder, Record, Header, Flag, Flags, SequenceType, FormatVersio
 The compute runs in hand-written sm_100a kernels behind the C ABI of include/nafgpu.h; there is no CPU fallback.
 """
 from .data import Flag, Flags, FormatVersion, Header, Record, SequenceType
-from .decoder import ArchiveResult, Context, Decoder, DecoderBuilder, Pipeline, decode_batch, parse_archive, shared_context
+from .decoder import (ArchiveResult, Context, Decoder, DecoderBuilder, Pipeline, decode_batch, parse_archive, shared_context,
+                      to_fasta, to_fastq, to_text)
 from .errors import NafDeviceError, NafError, NafIoError, NafParseError, NafUnicodeError
 
 __version__ = "0.1.0"
@@ -29,5 +30,5 @@ def open(file, mode="r", **options):
 
 
 __all__ = ["Decoder", "DecoderBuilder", "Record", "Header", "Flag", "Flags", "SequenceType", "FormatVersion", "Encoder", "open",
-           "Context", "Pipeline", "ArchiveResult", "decode_batch", "parse_archive", "shared_context",
+           "Context", "Pipeline", "ArchiveResult", "decode_batch", "to_text", "to_fasta", "to_fastq", "parse_archive", "shared_context",
            "NafError", "NafIoError", "NafParseError", "NafUnicodeError", "NafDeviceError"]

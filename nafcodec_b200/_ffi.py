@@ -17,6 +17,8 @@ ERR_UNEXPECTED_EOF, ERR_INVALID_DATA, ERR_PARSE, ERR_UTF8, ERR_CUDA, ERR_NOMEM, 
 WANT_ID, WANT_COMMENT, WANT_SEQUENCE, WANT_QUALITY, WANT_MASK, WANT_ALL = 1, 2, 4, 8, 16, 31
 N_SECTIONS = 6
 NO_RECORD = 2 ** 64 - 1
+TEXT_AUTO, TEXT_FASTA, TEXT_FASTQ = 0, 1, 2
+LINE_LENGTH_FROM_HEADER = 2 ** 64 - 1
 
 
 class Header(C.Structure):
@@ -41,13 +43,18 @@ class Result(C.Structure):
                 ("first_bad_record", C.c_uint64), ("record_status", C.c_int32), ("_pad", C.c_int32)]
 
 
+class Text(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_uint64), ("format", C.c_int32), ("status", C.c_int32),
+                ("first_bad_record", C.c_uint64)]
+
+
 class JobStats(C.Structure):
     _fields_ = [("n_archives", C.c_uint64), ("n_frames", C.c_uint64), ("n_blocks", C.c_uint64), ("n_sequences", C.c_uint64),
                 ("compressed_bytes", C.c_uint64), ("section_bytes", C.c_uint64), ("ascii_bytes", C.c_uint64),
                 ("quality_bytes", C.c_uint64), ("id_bytes", C.c_uint64), ("comment_bytes", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("n_stages", C.c_uint32), ("lz_handover", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("text_kernel_ms", C.c_float), ("text_bytes", C.c_uint64)]
 
 
 # every symbol include/nafgpu.h declares (tests check the library exports all of them)
@@ -55,7 +62,7 @@ SYMBOLS = ["nafgpu_parse_archive", "nafgpu_variable_u64", "nafgpu_strerror", "na
            "nafgpu_ctx_destroy", "nafgpu_last_error", "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_decode",
            "nafgpu_decode_batch", "nafgpu_job_prepare", "nafgpu_job_run", "nafgpu_job_fetch", "nafgpu_job_sync",
            "nafgpu_job_get_stats", "nafgpu_job_time", "nafgpu_job_run_profiled", "nafgpu_stage_name",
-           "nafgpu_job_device_result", "nafgpu_zstd_decompress"]
+           "nafgpu_job_device_result", "nafgpu_zstd_decompress", "nafgpu_job_format", "nafgpu_format_batch"]
 
 
 class Library:
@@ -93,6 +100,8 @@ class Library:
         L.nafgpu_stage_name.restype = C.c_char_p
         L.nafgpu_stage_name.argtypes = [C.c_uint32]
         L.nafgpu_zstd_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.nafgpu_job_format.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(Text), C.c_uint32]
+        L.nafgpu_format_batch.argtypes = [C.c_void_p, C.POINTER(Archive), C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(Text)]
         L.nafgpu_job_device_result.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
 
     def strerror(self, code):

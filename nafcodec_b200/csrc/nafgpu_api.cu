@@ -15,6 +15,7 @@
 #include "cuda_compat.h"
 #include "frame_walk.h"
 #include "naf_kernels.cuh"
+#include "naf_text.cuh"
 #include "zstd_kernels.cuh"
 
 namespace {
@@ -59,6 +60,8 @@ struct ArchPlan {
     uint64_t blob_off[6] = {0, 0, 0, 0, 0, 0};   // arena offset of each regenerated section
     uint64_t blob_size[6] = {0, 0, 0, 0, 0, 0};
     bool nucleotide = true;
+    uint64_t line_length = 0;                    // Header::line_length / name_separator (data.rs:198-236): for the text formatter
+    uint32_t sep = ' ';
 };
 
 }  // namespace
@@ -68,9 +71,9 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush;
+    DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush, text;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
-    PinBuf stage, result, misc_host;
+    PinBuf stage, result, misc_host, text_host, text_stage;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
     std::vector<ArchPlan> aplan;
@@ -263,7 +266,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
@@ -311,6 +314,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         const uint64_t nrec = A.header.number_of_sequences;
         P.n_records = nrec;
         P.nucleotide = A.header.sequence_type <= 1;
+        P.line_length = A.header.line_length; P.sep = (uint32_t)(A.header.name_separator & 0xFF);
         if (A.header.sequence_type < 0 || A.header.sequence_type > 3) return fail(c, NAFGPU_ERR_ARGUMENT, "bad sequence type");
         for (int s = 0; s < 6; s++) if (A.sections[s].present && !A.sections[s].data) return fail(c, NAFGPU_ERR_ARGUMENT, "present section without data");
         const bool has_len = A.sections[NAFGPU_SEC_LENGTH].present;
@@ -521,6 +525,87 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
         r.record_status = (C->first_bad_record != nk::NO_RECORD) ? NAFGPU_ERR_UTF8 : 0;
     }
     return NAFGPU_OK;
+}
+
+// FASTA / FASTQ text of the job that was just run, formatted on the device (naf_text.cu); only the text crosses PCIe.
+int nafgpu_job_format(nafgpu_ctx* c, int format, uint64_t line_length, nafgpu_text* out, uint32_t n) {
+    if (!c || (!out && n)) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared || !c->ran) return fail(c, NAFGPU_ERR_ARGUMENT, "job has not been run");
+    if (n != c->arch.size()) return fail(c, NAFGPU_ERR_ARGUMENT, "result count differs from the prepared job");
+    if (format != NAFGPU_TEXT_AUTO && format != NAFGPU_TEXT_FASTA && format != NAFGPU_TEXT_FASTQ) return fail(c, NAFGPU_ERR_ARGUMENT, "bad text format");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    // layout of the text buffer: sizes[n] | text of every archive (copied back) | record offsets (device only)
+    std::vector<nk::TextDev> td(n);
+    uint64_t off = align_up((uint64_t)n * 8), max_cap = 0;
+    for (uint32_t a = 0; a < n; a++) {
+        const ArchPlan& P = c->aplan[a];
+        const nk::NafDev& D = c->arch[a];
+        if (!P.dec[NAFGPU_SEC_SEQUENCE]) return fail(c, NAFGPU_ERR_ARGUMENT, "text output needs the sequence (and lengths) decoded");
+        const bool fastq = format == NAFGPU_TEXT_FASTQ || (format == NAFGPU_TEXT_AUTO && P.dec[NAFGPU_SEC_QUALITY]);
+        if (fastq && !P.dec[NAFGPU_SEC_QUALITY]) return fail(c, NAFGPU_ERR_ARGUMENT, "FASTQ output needs the quality section decoded");
+        nk::TextDev& T = td[a];
+        T.fastq = fastq ? 1u : 0u;
+        T.sep = P.sep;
+        T.line_length = fastq ? 0 : (line_length == NAFGPU_LINE_LENGTH_FROM_HEADER ? P.line_length : line_length);
+        const uint64_t nrec = D.n_records, res = D.seq_residues;
+        T.cap = 3 * nrec + P.blob_size[0] + P.blob_size[1] +
+                (fastq ? 2 * res + 4 * nrec : res + (T.line_length ? res / T.line_length + nrec : nrec)) + 16;
+        T.text_off = off;
+        off = align_up(off + T.cap);
+        max_cap = std::max(max_cap, T.cap);
+    }
+    const uint64_t copy_size = off;
+    for (uint32_t a = 0; a < n; a++) { td[a].offs_off = off; off = align_up(off + 8 * (c->arch[a].n_records + 1)); }
+    if (!c->text.ensure(off + 64 + (uint64_t)n * sizeof(nk::TextDev))) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
+    if (!c->text_host.ensure(copy_size + 64) || !c->text_stage.ensure((uint64_t)n * sizeof(nk::TextDev) + 64) || !c->result.ensure(c->counts_size + 64))
+        return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));                  // text_stage may still feed an earlier call's copy
+    uint8_t* tdev = (uint8_t*)c->text.p + off;                  // descriptors behind the offsets (off is 128 B aligned)
+    if (n) {
+        memcpy(c->text_stage.p, td.data(), (size_t)n * sizeof(nk::TextDev));
+        CUDA_TRY(c, cudaMemcpyAsync(tdev, c->text_stage.p, (size_t)n * sizeof(nk::TextDev), cudaMemcpyHostToDevice, c->st));
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev[0], c->st));
+    nk::launch_text_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint8_t*)c->text.p,
+                          (const nk::TextDev*)tdev, n, max_cap, c->J.status, c->st);
+    CUDA_TRY(c, cudaEventRecord(c->ev[1], c->st));
+    CUDA_TRY(c, cudaGetLastError());
+    {
+        CUDA_TRY(c, cudaStreamSynchronize(c->st));
+        std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
+        CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->counts_size, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->text_host.p, c->text.p, copy_size, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    }
+    const uint32_t status = *(const uint32_t*)c->misc_host.p;
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
+    std::string msg;
+    int code = status_to_code(status & ~zc::E_UTF8, msg);
+    if (code) return fail(c, code, msg);
+    const uint8_t* H = (const uint8_t*)c->text_host.p;
+    c->stats.text_kernel_ms = 0; c->stats.text_bytes = 0;
+    cudaEventElapsedTime(&c->stats.text_kernel_ms, c->ev[0], c->ev[1]);
+    for (uint32_t a = 0; a < n; a++) c->stats.text_bytes += ((const uint64_t*)H)[a];
+    for (uint32_t a = 0; a < n; a++) {
+        const nk::NafCounts* C = (const nk::NafCounts*)((const uint8_t*)c->result.p + c->arch[a].counts_off);
+        nafgpu_text& t = out[a];
+        memset(&t, 0, sizeof t);
+        t.data = H + td[a].text_off;
+        t.size = ((const uint64_t*)H)[a];
+        t.format = td[a].fastq ? NAFGPU_TEXT_FASTQ : NAFGPU_TEXT_FASTA;
+        t.first_bad_record = C->first_bad_record;
+        t.status = (C->first_bad_record != nk::NO_RECORD) ? NAFGPU_ERR_UTF8 : 0;
+    }
+    return NAFGPU_OK;
+}
+
+int nafgpu_format_batch(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n, uint32_t want, int format, uint64_t line_length, nafgpu_text* out) {
+    int rc = nafgpu_job_prepare(c, archives, n, want);
+    if (rc) return rc;
+    rc = nafgpu_job_run(c);
+    if (rc) return rc;
+    return nafgpu_job_format(c, format, line_length, out, n);
 }
 
 int nafgpu_decode_batch(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n, uint32_t want, nafgpu_result* out) {

@@ -60,6 +60,23 @@ class Context:
             raise_for_status(self.lib, rc, self._ctx)
             return [ArchiveResult._copy_from(archives[i].header, res[i]) for i in range(n)]
 
+    def format(self, archives: List["_ffi.Archive"], want: int = _ffi.WANT_ALL, format: int = _ffi.TEXT_AUTO,
+               line_length: Optional[int] = None) -> List[bytes]:
+        """FASTA / FASTQ text of every archive, formatted on the device (nafgpu_format_batch): '>' / '@' + id + separator +
+        comment, the sequence wrapped at `line_length` (None: the header's; 0: one line), '+' and the quality for FASTQ."""
+        n = len(archives)
+        arr = (_ffi.Archive * n)(*archives)
+        res = (_ffi.Text * n)()
+        ll = _ffi.LINE_LENGTH_FROM_HEADER if line_length is None else int(line_length)
+        with self._lock:
+            rc = self.lib.dll.nafgpu_format_batch(self._ctx, arr, n, want, format, ll, res)
+            raise_for_status(self.lib, rc, self._ctx)
+            out = []
+            for i in range(n):
+                raise_for_status(self.lib, res[i].status, None, f"record {res[i].first_bad_record}")
+                out.append(C.string_at(res[i].data, int(res[i].size)) if res[i].size else b"")
+            return out
+
     def zstd_decompress(self, frame: bytes, regen_size: int) -> bytes:
         """One magicless zstd frame -> bytes (the pure-zstd boundary; used by the parity tests against libzstd)."""
         src = (C.c_uint8 * max(len(frame), 1)).from_buffer_copy(frame or b"\0")
@@ -484,3 +501,39 @@ def decode_batch(files: Iterable, *, id=True, comment=True, sequence=True, quali
                 data = fh.read()
         archives.append(parse_archive(data, lib))
     return shared_context(device, lib).decode(archives, _want_bits(id, comment, sequence, quality, mask))
+
+
+_TEXT_FORMATS = {"auto": _ffi.TEXT_AUTO, "fasta": _ffi.TEXT_FASTA, "fastq": _ffi.TEXT_FASTQ}
+
+
+def _read_all(f) -> bytes:
+    if isinstance(f, (bytes, bytearray, memoryview)):
+        return bytes(f)
+    if hasattr(f, "read"):
+        return f.read()
+    with open(os.fspath(f), "rb") as fh:
+        return fh.read()
+
+
+def to_text(files, format: str = "auto", *, line_length: Optional[int] = None, comment: bool = True, mask: bool = True,
+            device: int = 0, _library=None):
+    """Archive(s) -> FASTA / FASTQ text (bytes), formatted on the GPU; what upstream `unnaf` prints.  `files` is one
+    archive (bytes, path or file object) or a list of them (one set of kernel launches for the whole list).
+    format: "fasta", "fastq", or "auto" (FASTQ when the archive stores qualities).  line_length: None = the header's
+    (Header.line_length, data.rs:198-236), 0 = unwrapped.  mask=False gives upper-case sequences; comment=False names only."""
+    lib = _library or _ffi.default_library()
+    single = not isinstance(files, (list, tuple))
+    datas = [_read_all(f) for f in ([files] if single else files)]
+    archives = [parse_archive(d, lib) for d in datas]
+    fmt = _TEXT_FORMATS[format]
+    want = _want_bits(True, comment, True, fmt != _ffi.TEXT_FASTA, mask)
+    out = shared_context(device, lib).format(archives, want, fmt, line_length)
+    return out[0] if single else out
+
+
+def to_fasta(files, **kw):
+    return to_text(files, "fasta", **kw)
+
+
+def to_fastq(files, **kw):
+    return to_text(files, "fastq", **kw)

@@ -262,3 +262,32 @@ def time_decode(data: bytes, quality=True, mask=True, iters=1):
     if t < 0:
         raise OracleError(-1, lib().nafo_last_error().decode())
     return t, nb.value
+
+
+def format_text(data: bytes, fmt: str = "auto", line_length=None, comment=True, mask=True) -> bytes:
+    """FASTA / FASTQ text of an archive, restated on the CPU from the oracle's records.  The reference crate carries
+    line_length / name_separator (data.rs:198-236) but prints nothing itself; the text is pinned by the fixtures'
+    source files (masked.fna, LuxC.faa, phix.fastq; tests/test_oracle_golden.py)."""
+    lay = parse_header(data)
+    want_q = fmt != "fasta"
+    d = decode(data, comment=comment, quality=want_q, mask=mask)
+    has_q = bool(lay.flags & 0x01)
+    fastq = fmt == "fastq" or (fmt == "auto" and has_q)
+    if fastq and not has_q:
+        raise ValueError("FASTQ output needs qualities")
+    W = int(lay.line_length) if line_length is None else int(line_length)
+    sep = bytes([lay.name_separator & 0xFF])
+    out = []
+    for i in range(d.n):
+        name, com, seq = d.id(i) or b"", d.comment(i) or b"", d.seq(i) or b""
+        head = (b"@" if fastq else b">") + name + ((sep + com) if com else b"") + b"\n"
+        out.append(head)
+        if fastq:
+            q = d.qual(i) or b""
+            out += [seq, b"\n+\n", q, b"\n"]
+        elif W == 0:
+            out += [seq, b"\n"]
+        else:
+            for k in range(0, len(seq), W):
+                out += [seq[k:k + W], b"\n"]
+    return b"".join(out)
