@@ -40,7 +40,7 @@ __device__ __forceinline__ uint64_t block_excl_scan64(uint64_t v, uint64_t* tota
 // the end of their stream are absent (empty here).
 struct RecView {
     uint64_t id0, idlen, com0, comlen, seq0, L;
-    uint64_t hdr, total;
+    uint64_t hdr;
 };
 
 struct ArchView {
@@ -72,9 +72,13 @@ __device__ __forceinline__ RecView rec_view(const ArchView& V, uint64_t r) {
     if (r < V.n_com) { R.com0 = V.com_offs[r]; R.comlen = V.com_offs[r + 1] - R.com0 - 1; }
     if (r < V.n_len) { R.seq0 = V.rec_offs[r]; R.L = V.rec_offs[r + 1] - R.seq0; }
     R.hdr = 1 + R.idlen + (R.comlen ? 1 + R.comlen : 0) + 1;
-    if (V.fastq) R.total = R.hdr + 2 * R.L + 4;
-    else R.total = R.hdr + (V.W ? R.L + (R.L + V.W - 1) / V.W : R.L + 1);
     return R;
+}
+
+// bytes of text of the record (a 64-bit division: only where it is needed)
+__device__ __forceinline__ uint64_t rec_total(const ArchView& V, const RecView& R) {
+    if (V.fastq) return R.hdr + 2 * R.L + 4;
+    return R.hdr + (V.W ? R.L + (R.L + V.W - 1) / V.W : R.L + 1);
 }
 
 __global__ void __launch_bounds__(1024) k_text_layout(const uint8_t* arena, const NafDev* archives, uint8_t* text,
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(1024) k_text_layout(const uint8_t* arena, cons
     uint64_t carry = 0;
     for (uint64_t base = 0; base < V.n; base += 1024) {
         const uint64_t r = base + threadIdx.x;
-        const uint64_t sz = r < V.n ? rec_view(V, r).total : 0;
+        const uint64_t sz = r < V.n ? rec_total(V, rec_view(V, r)) : 0;
         uint64_t tot;
         const uint64_t ex = block_excl_scan64(sz, &tot);
         if (r < V.n) offs[r] = carry + ex;
@@ -107,15 +111,12 @@ __device__ __forceinline__ uint4 load16u(const uint8_t* p) {
     const uint4 lo = q[0];
     if (s == 0) return lo;
     const uint4 hi = q[1];
-    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    const uint32_t ws = s >> 2, bs = (s & 3) * 8;
-    uint32_t o[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t a0 = ws == 0 ? w[i] : (ws == 1 ? w[i + 1] : (ws == 2 ? w[i + 2] : w[i + 3]));
-        const uint32_t a1 = ws == 0 ? w[i + 1] : (ws == 1 ? w[i + 2] : (ws == 2 ? w[i + 3] : w[i + 4]));
-        o[i] = __funnelshift_r(a0, a1, bs);
-    }
+    // barrel shifter over the 8 words: by two words, by one word, then by bytes
+    const bool s2 = s & 8, s1 = s & 4;
+    const uint32_t a0 = s2 ? lo.z : lo.x, a1 = s2 ? lo.w : lo.y, a2 = s2 ? hi.x : lo.z, a3 = s2 ? hi.y : lo.w, a4 = s2 ? hi.z : hi.x, a5 = s2 ? hi.w : hi.y;
+    const uint32_t b0 = s1 ? a1 : a0, b1 = s1 ? a2 : a1, b2 = s1 ? a3 : a2, b3 = s1 ? a4 : a3, b4 = s1 ? a5 : a4;
+    const uint32_t bs = (s & 3) * 8;
+    const uint32_t o[4] = {__funnelshift_r(b0, b1, bs), __funnelshift_r(b1, b2, bs), __funnelshift_r(b2, b3, bs), __funnelshift_r(b3, b4, bs)};
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
@@ -148,65 +149,91 @@ __global__ void __launch_bounds__(TEXT_THREADS) k_text_write(const uint8_t* aren
         uint32_t v = TEXT_CHUNK;
         if (t <= TEXT_CHUNK / 2 && r < V.n) { const uint64_t o = offs[r]; if (o < p1) v = (uint32_t)(o - p0); }
         if (t <= TEXT_CHUNK / 2 + 1) starts[t] = v;
-        n_tab = b + TEXT_THREADS;
-        if (__syncthreads_or(v == TEXT_CHUNK)) break;
+        const uint32_t inside = (uint32_t)__syncthreads_count(v < TEXT_CHUNK);
+        n_tab += inside;                                                // entries [1, n_tab) start inside the chunk (sorted)
+        if (inside < TEXT_THREADS) break;
     }
-    if (n_tab > TEXT_CHUNK / 2 + 1) n_tab = TEXT_CHUNK / 2 + 1;         // entries [1, n_tab) are valid (sorted; TEXT_CHUNK = "not here")
-    const uint64_t p = p0 + (uint64_t)tid * 16;
-    if (p >= p1) return;
-    // my record: last t with starts[t] <= tid * 16 (t = 0: the record that began before the chunk)
-    uint32_t lo = 0, hi = n_tab;
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (starts[mid] <= tid * 16) lo = mid; else hi = mid; }
-    uint64_t r = r0 + lo;
-    RecView R = rec_view(V, r);
-    uint64_t q = lo == 0 ? p - offs[r0] : (uint64_t)(tid * 16 - starts[lo]);
-    // position inside the sequence for the FASTA body
-    uint64_t idx = 0, col = 0;
-    if (!V.fastq && q > R.hdr) {
-        const uint64_t qp = q - R.hdr;
-        if (V.W) { const uint64_t line = qp / (V.W + 1); col = qp - line * (V.W + 1); idx = line * V.W + col; }
-        else idx = qp;
-    }
-    const uint32_t nout = p1 - p >= 16 ? 16u : (uint32_t)(p1 - p);
-    uint8_t* dst = text + T.text_off + p;
-    // fast paths: 16 bytes from the inside of one line of sequence (or quality)
-    if (nout == 16 && q >= R.hdr) {
-        const uint8_t* src = nullptr;
-        if (!V.fastq) {
-            if (idx + 16 <= R.L && (V.W == 0 || col + 16 <= V.W)) src = V.seq + R.seq0 + idx;
-        } else {
+    for (uint32_t piece = tid; piece < TEXT_CHUNK / 16; piece += TEXT_THREADS) {
+        const uint64_t p = p0 + (uint64_t)piece * 16;
+        if (p >= p1) return;
+        // my record: last t with starts[t] <= piece * 16 (t = 0: the record that began before the chunk)
+        uint32_t lo = 0, hi = n_tab;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (starts[mid] <= piece * 16) lo = mid; else hi = mid; }
+        uint64_t r = r0 + lo;
+        RecView R = rec_view(V, r);
+        uint64_t q = lo == 0 ? p - offs[r0] : (uint64_t)(piece * 16 - starts[lo]);
+        // position inside the sequence for the FASTA body
+        uint64_t idx = 0, col = 0;
+        if (!V.fastq && q > R.hdr) {
             const uint64_t qp = q - R.hdr;
-            if (qp + 16 <= R.L) src = V.seq + R.seq0 + qp;
-            else if (qp >= R.L + 3 && qp + 16 <= 2 * R.L + 3) src = V.qual + R.seq0 + (qp - R.L - 3);
+            if (V.W == 0) idx = qp;
+            else if (((qp | V.W) >> 31) == 0) {                                // the usual case: 32-bit division
+                const uint32_t line = (uint32_t)qp / ((uint32_t)V.W + 1u);
+                col = (uint32_t)qp - line * ((uint32_t)V.W + 1u); idx = (uint64_t)line * V.W + col;
+            } else { const uint64_t line = qp / (V.W + 1); col = qp - line * (V.W + 1); idx = line * V.W + col; }
         }
-        if (src) { *(uint4*)dst = load16u(src); return; }
-    }
-    uint32_t o[4] = {0, 0, 0, 0};
-    for (uint32_t k = 0; k < nout; k++) {
-        if (q == R.total) { r++; R = rec_view(V, r); q = 0; idx = 0; col = 0; }
-        uint32_t b;
-        if (q < R.hdr) {
-            if (q == 0) b = V.fastq ? '@' : '>';
-            else if (q - 1 < R.idlen) b = V.ids[R.id0 + q - 1];
-            else if (q == R.hdr - 1) b = '\n';
-            else if (q == 1 + R.idlen) b = V.sep;                         // only reached when there is a comment
-            else b = V.com[R.com0 + (q - 2 - R.idlen)];
-        } else if (!V.fastq) {
-            if (idx == R.L || (V.W && col == V.W)) { b = '\n'; col = 0; }
-            else { b = V.seq[R.seq0 + idx]; idx++; col++; }
-        } else {
-            const uint64_t qp = q - R.hdr;
-            if (qp < R.L) b = V.seq[R.seq0 + qp];
-            else if (qp == R.L || qp == R.L + 2) b = '\n';
-            else if (qp == R.L + 1) b = '+';
-            else if (qp < 2 * R.L + 3) b = V.qual[R.seq0 + (qp - R.L - 3)];
-            else b = '\n';
+        const uint32_t nout = p1 - p >= 16 ? 16u : (uint32_t)(p1 - p);
+        uint8_t* dst = text + T.text_off + p;
+        // fast paths: 16 bytes from the inside of one line of sequence (or quality)
+        if (nout == 16 && q >= R.hdr) {
+            const uint8_t* src = nullptr;
+            if (!V.fastq) {
+                if (idx + 16 <= R.L && (V.W == 0 || col + 16 <= V.W)) src = V.seq + R.seq0 + idx;
+                else if (V.W >= 16 && V.W - col < 16 && idx + 15 <= R.L) {
+                    // exactly one line end inside the 16 bytes (a line and its '\n' are at least 17 bytes): 15 residues, with
+                    // '\n' inserted after the first j of them
+                    const uint32_t j = (uint32_t)(V.W - col);                   // 0..15
+                    const uint4 a = load16u(V.seq + R.seq0 + idx);
+                    const uint32_t A[4] = {a.x, a.y, a.z, a.w};
+                    const uint32_t B[4] = {a.x << 8, __funnelshift_l(a.x, a.y, 8), __funnelshift_l(a.y, a.z, 8), __funnelshift_l(a.z, a.w, 8)};   // bytes moved up by one
+                    uint32_t o4[4];
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; i++) {
+                        if (4 * i + 3 < j) o4[i] = A[i];
+                        else if (4 * i > j) o4[i] = B[i];
+                        else {
+                            const uint32_t sh = 8 * (j - 4 * i), low = (1u << sh) - 1u;      // bytes below j from A, byte j = '\n', above from B
+                            o4[i] = (A[i] & low) | (0x0Au << sh) | (B[i] & ~((low << 8) | 0xFFu));
+                        }
+                    }
+                    *(uint4*)dst = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                    continue;
+                }
+            } else {
+                const uint64_t qp = q - R.hdr;
+                if (qp + 16 <= R.L) src = V.seq + R.seq0 + qp;
+                else if (qp >= R.L + 3 && qp + 16 <= 2 * R.L + 3) src = V.qual + R.seq0 + (qp - R.L - 3);
+            }
+            if (src) { *(uint4*)dst = load16u(src); continue; }
         }
-        o[k >> 2] |= b << (8 * (k & 3));
-        q++;
+        uint32_t o[4] = {0, 0, 0, 0};
+        uint64_t rtotal = rec_total(V, R);
+        for (uint32_t k = 0; k < nout; k++) {
+            if (q == rtotal) { r++; R = rec_view(V, r); rtotal = rec_total(V, R); q = 0; idx = 0; col = 0; }
+            uint32_t b;
+            if (q < R.hdr) {
+                if (q == 0) b = V.fastq ? '@' : '>';
+                else if (q - 1 < R.idlen) b = V.ids[R.id0 + q - 1];
+                else if (q == R.hdr - 1) b = '\n';
+                else if (q == 1 + R.idlen) b = V.sep;                         // only reached when there is a comment
+                else b = V.com[R.com0 + (q - 2 - R.idlen)];
+            } else if (!V.fastq) {
+                if (idx == R.L || (V.W && col == V.W)) { b = '\n'; col = 0; }
+                else { b = V.seq[R.seq0 + idx]; idx++; col++; }
+            } else {
+                const uint64_t qp = q - R.hdr;
+                if (qp < R.L) b = V.seq[R.seq0 + qp];
+                else if (qp == R.L || qp == R.L + 2) b = '\n';
+                else if (qp == R.L + 1) b = '+';
+                else if (qp < 2 * R.L + 3) b = V.qual[R.seq0 + (qp - R.L - 3)];
+                else b = '\n';
+            }
+            o[k >> 2] |= b << (8 * (k & 3));
+            q++;
+        }
+        if (nout == 16) *(uint4*)dst = make_uint4(o[0], o[1], o[2], o[3]);
+        else for (uint32_t k = 0; k < nout; k++) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
     }
-    if (nout == 16) *(uint4*)dst = make_uint4(o[0], o[1], o[2], o[3]);
-    else for (uint32_t k = 0; k < nout; k++) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
 }
 
 int launch_text_stage(uint8_t* arena, const NafDev* archives, uint8_t* text, const TextDev* texts, uint32_t n_archives,

@@ -24,7 +24,7 @@ struct TextDev {
 };
 
 constexpr uint32_t TEXT_CHUNK = 8192;      // output bytes per CTA of k_text_write
-constexpr uint32_t TEXT_THREADS = 512;     // 16 output bytes per thread
+constexpr uint32_t TEXT_THREADS = 128;     // 4 x 16 output bytes per thread: small CTAs, many in flight (the set-up is a chain of dependent loads)
 
 // sizes[a] (u64 at the start of the text buffer) <- text bytes of archive a; then the text.  Returns kernels launched.
 int launch_text_stage(uint8_t* arena, const NafDev* archives, uint8_t* text, const TextDev* texts, uint32_t n_archives,
