@@ -7,6 +7,8 @@
 //   String::from_utf8     reader.rs:108-109  -> k_ascii_check + k_utf8_validate
 #include "naf_kernels.cuh"
 
+#include <algorithm>
+
 #include "zstd_core.cuh"
 
 namespace nk {
@@ -58,7 +60,8 @@ __device__ __forceinline__ void toggle_bit(uint32_t* bits, uint32_t* chunk_par, 
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// k_naf_scan: grid (4 tasks, n_archives), 1024 threads.  One CTA streams its section with a running carry.
+// k_naf_scan: grid (3 tasks + mask slices, n_archives), 1024 threads.  One CTA streams its section (or mask slice) with a
+// running carry.
 __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev* archives, uint32_t* status) {
     const NafDev& A = archives[blockIdx.y];
     const int task = blockIdx.x;
@@ -141,19 +144,47 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
         for (uint64_t k = tid; k < n_len; k += blockDim.x) lens[k] = rec[k + 1] - rec[k];
     } else {
         // ---- mask: run k ends at the inclusive byte sum at the k-th byte != 0xFF; toggle the bitmap there --------
-        if (!(A.has & HAS_MASK) || !(A.has & HAS_SEQUENCE)) { if (tid == 0) { counts->n_mask_runs = 0; counts->mask_sum = 0; } return; }
+        // The section is cut into MASK_SLICE-byte slices, one CTA each (a dense mask is ~1 byte per run, and every run
+        // costs atomics: one CTA for a 250 Mbp chromosome took 1.3 ms).  A run boundary is the plain sum of all bytes up to
+        // its terminator, so a slice's carry-in is the byte sum (and terminator count) of everything before it, which
+        // every CTA adds up for itself with wide loads (cheap next to its own atomics).
+        const uint32_t slice = (uint32_t)(task - 3);
+        if (!(A.has & HAS_MASK) || !(A.has & HAS_SEQUENCE)) { if (tid == 0 && slice == 0) { counts->n_mask_runs = 0; counts->mask_sum = 0; } return; }
         const uint8_t* src = arena + A.mask_off;
         const uint64_t size = A.mask_size;
+        const uint64_t s_begin = (uint64_t)slice * MASK_SLICE;
+        if (s_begin >= size && !(slice == 0 && size == 0)) return;
+        const uint64_t s_end = s_begin + MASK_SLICE < size ? s_begin + MASK_SLICE : size;
+        const bool last = s_end == size;
         uint64_t* bounds = (uint64_t*)(arena + A.mask_bounds_off);
         uint32_t* bits = (uint32_t*)(arena + A.mask_bits_off);
         uint32_t* cpar = (uint32_t*)(arena + A.chunk_par_off);
         uint64_t carry_c = 0, carry_s = 0;
-        for (uint64_t base = 0; base < size; base += 1024 * 16) {
+        if (s_begin) {
+            uint32_t c = 0;
+            uint64_t sm = 0;
+            for (uint64_t p = (uint64_t)tid * 16; p < s_begin; p += 1024 * 16) {       // s_begin is a multiple of 16
+                const uint4 v = *(const uint4*)(src + p);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t h = (w[j] & 0x00FF00FFu) + ((w[j] >> 8) & 0x00FF00FFu);
+                    sm += (h & 0xFFFFu) + (h >> 16);
+                    const uint32_t z = ~w[j];                                          // zero byte <=> 0xFF byte of the mask
+                    const uint32_t y = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);
+                    c += 4u - (uint32_t)__popc(y);
+                }
+            }
+            CS tot;
+            block_excl_scan(c, sm, &tot);
+            carry_c = tot.c; carry_s = tot.s;
+        }
+        for (uint64_t base = s_begin; base < s_end; base += 1024 * 16) {
             uint64_t p0 = base + (uint64_t)tid * 16;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (p0 < size) v = *(const uint4*)(src + p0);
+            if (p0 < s_end) v = *(const uint4*)(src + p0);
             uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t nvalid = p0 >= size ? 0 : (size - p0 >= 16 ? 16 : (uint32_t)(size - p0));
+            uint32_t nvalid = p0 >= s_end ? 0 : (s_end - p0 >= 16 ? 16 : (uint32_t)(s_end - p0));
             uint32_t c = 0;
             uint64_t s = 0;
             for (uint32_t j = 0; j < nvalid; j++) {
@@ -170,7 +201,7 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
             }
             carry_c += tot.c; carry_s += tot.s;
         }
-        if (tid == 0) {
+        if (tid == 0 && last) {
             if (size > 0 && src[size - 1] == 0xFF) {        // trailing 0xFF bytes at EOF still form a unit (reader.rs:206-209)
                 bounds[carry_c++] = carry_s;
                 if (carry_s <= A.seq_residues) toggle_bit(bits, cpar, carry_s);
@@ -389,14 +420,15 @@ __global__ void __launch_bounds__(256) k_utf8_validate(uint8_t* arena, const Naf
 }
 
 // --------------------------------------------------------------------------------------------------------------
-int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives, uint64_t max_records,
+int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives, uint64_t max_records, uint64_t max_mask_bytes,
                      uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, bool any_text_mask, uint32_t* status, cudaStream_t st,
                      StageEvents* ev) {
     StageEvents none;
     if (!ev) ev = &none;
     int launches = 0;
     if (n_archives == 0) { for (int i = 0; i < NAF_STAGES; i++) ev->mark(); return 0; }
-    NAF_LAUNCH(k_naf_scan, dim3(4, n_archives), 1024, 0, st, arena, archives, status); launches++; ev->mark();
+    const uint32_t mask_slices = (uint32_t)std::max<uint64_t>(1, (max_mask_bytes + MASK_SLICE - 1) / MASK_SLICE);
+    NAF_LAUNCH(k_naf_scan, dim3(3 + mask_slices, n_archives), 1024, 0, st, arena, archives, status); launches++; ev->mark();
     uint32_t rec_grid = (uint32_t)((max_records + 255) / 256);
     if (max_chunks > 0 && any_mask) {
         if (rec_grid) { NAF_LAUNCH(k_mask_fix, dim3(rec_grid, n_archives), 256, 0, st, arena, archives, status); launches++; }

@@ -11,6 +11,7 @@ enum : uint32_t { HAS_IDS = 1, HAS_COMMENTS = 2, HAS_LENGTHS = 4, HAS_MASK = 8, 
 constexpr uint32_t CHUNK_WORDS = 1024;                 // mask words (of 32 residues) per unpack CTA
 constexpr uint32_t CHUNK_RESIDUES = CHUNK_WORDS * 32;
 constexpr uint64_t NO_RECORD = ~0ull;
+constexpr uint32_t MASK_SLICE = 32768;                 // mask bytes per CTA of k_naf_scan's mask task
 
 // Per-archive counters, device-written, copied back with the results (64 bytes).
 struct NafCounts {
@@ -41,7 +42,7 @@ struct NafDev {
 // Enqueues the NAF stage for n_archives archives on `stream`.  max_* are maxima over the archives (grid sizing).
 // Returns the number of kernels launched; `ev` (optional) gets one mark per stage (NAF_STAGES).
 // any_mask: some archive decodes sequence + mask; any_text_mask: one of those is protein/text.
-int launch_naf_stage(uint8_t* arena, const NafDev* archives_dev, uint32_t n_archives, uint64_t max_records,
+int launch_naf_stage(uint8_t* arena, const NafDev* archives_dev, uint32_t n_archives, uint64_t max_records, uint64_t max_mask_bytes,
                      uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, bool any_text_mask, uint32_t* status, cudaStream_t stream,
                      StageEvents* ev);
 constexpr int NAF_STAGES = 5;

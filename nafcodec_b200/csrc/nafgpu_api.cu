@@ -79,7 +79,7 @@ struct nafgpu_ctx {
     std::vector<ArchPlan> aplan;
     zk::JobDev J;
     uint64_t z1_size = 0, z2_off = 0, z2_size = 0, arena_size = 0, counts_size = 0;
-    uint64_t max_records = 0, max_text = 0;
+    uint64_t max_records = 0, max_text = 0, max_mask = 0;
     uint32_t max_chunks = 0;
     bool any_mask = false, any_text_mask = false;
     uint32_t coop_ctas = 1;
@@ -120,7 +120,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     // profiled runs (ev != null) are serial so that every stage has its own interval
     int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev);
-    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records,
+    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records, c->max_mask,
                                      c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
     CUDA_TRY(c, cudaGetLastError());
@@ -305,7 +305,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     c->counts_size = align_up((uint64_t)n * sizeof(nk::NafCounts));
     off = c->counts_size;
     uint64_t comp_off = 16;          // gathers may read up to 15 bytes below a literal run: keep them inside the allocation
-    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false; c->any_text_mask = false;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
@@ -351,7 +351,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         if (P.dec[4]) {
             D.n_chunks = (uint32_t)((residues + 1 + nk::CHUNK_RESIDUES - 1) / nk::CHUNK_RESIDUES);
             c->max_chunks = std::max(c->max_chunks, D.n_chunks);
-            if (P.dec[3]) { c->any_mask = true; if (!P.nucleotide) c->any_text_mask = true; }
+            if (P.dec[3]) { c->any_mask = true; c->max_mask = std::max(c->max_mask, P.blob_size[3]); if (!P.nucleotide) c->any_text_mask = true; }
             if (!P.nucleotide) c->max_text = std::max(c->max_text, P.blob_size[4]);
         }
         if (P.dec[5]) c->max_text = std::max(c->max_text, P.blob_size[5]);
@@ -443,7 +443,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->z1_size = align_up(ALIGN + regen_size + 32);
     c->z2_off = c->z1_size; c->z2_size = 0;
     c->arena_size = c->z1_size + 256;
-    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->any_mask = false; c->any_text_mask = false;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
     std::string e;
     int rc = fw::walk_frame(frame, 16, frame_size, ALIGN, regen_size, c->plan, e);
     if (rc) return fail(c, rc, e);

@@ -413,7 +413,6 @@ __global__ void __launch_bounds__(FSCAN_T) k_frame_scan(JobDev J) {
 // preceded by >= 16 zero bytes so reads below bit 0 see zeros) | output image (same 16 B phase as the destination).
 constexpr int HUF_T_BIG = 512;                    // threads per stream for 4-stream blocks (up to 32 Ki symbols)
 constexpr int HUF_T_SMALL = 128;                  // four warps for short streams (1-stream blocks, tiny flushed blocks)
-constexpr uint32_t HUF_SMALL_MAX_SYM = HUF_SMALL_SYMBOLS;
 constexpr int HUF_SEG = 96;                       // tracks are compared for merging every HUF_SEG bits
 constexpr int MAXC = zc::HUF_MAX_BITS;            // candidates per range
 // output image (phase 2) / boundary masks 8 KB + track queue 32 B per thread (phase 1)
@@ -1278,6 +1277,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     // Two independent branches: (A) FSE tables -> sequences -> frame scan on `st`; (B) Huffman weights -> Huffman decode into
     // the literal staging buffer on `st2` (when given).  They join before k_lz_literals.
     cudaStream_t sb = st2 ? st2 : st;
+    (void)sb;                                          // (the emulator's launch macro ignores the stream)
     if (st2) { cudaEventRecord(fork, st); cudaStreamWaitEvent(st2, fork, 0); }
     if (J.n_huf_items) {
         NAF_LAUNCH(k_build_tables<1>, J.n_blocks, 32, 0, sb, J); launches++;

@@ -77,6 +77,26 @@ def test_mask_quirk_and_edges(backend):
         check_parity(backend, data, f"runs {runs} nomask", mask=False)
 
 
+def test_dense_mask_spans_several_scan_slices(backend):
+    """> 32 KiB of mask bytes: k_naf_scan cuts the mask into slices, one CTA each, every slice deriving its carry-in
+    (residue position, run index) from the bytes before it; runs of a few residues mixed with runs > 255 (0xFF
+    continuation bytes across slice boundaries)."""
+    rng = np.random.default_rng(11)
+    n = 360_000 if backend == "emul" else 3_000_000
+    runs, total = [], 0
+    while total < n:
+        r = int(rng.integers(1, 5)) if rng.random() > 0.002 else int(rng.integers(250, 2000))
+        r = min(r, n - total)
+        runs.append(r); total += r
+    seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n))
+    cuts = sorted(set(int(x) for x in rng.integers(1, n, size=6)))
+    cuts = [0] + cuts + [n]
+    seqs = [seq[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+    arc = O.encode(ids=[b"r%d" % i for i in range(len(seqs))], sequences=seqs, mask_runs_=runs, level=3)
+    assert O.parse(arc).sec[3].original_size > 2 * 32768
+    check_parity(backend, arc, "dense mask")
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 @pytest.mark.parametrize("level,flush", [(0, True), (3, False), (19, True)])
 def test_multi_record_dna(backend, seed, level, flush):
