@@ -256,7 +256,9 @@ def main():
     dev_ms = ctx.time_runs(args.steps, True)
     barrier()
     dev_ms = max_over_ranks(dev_ms)
+    ctx.fetch_raw()                        # (outside the timed region) brings back the LZ round statistics of the last run
     st = ctx.stats()                       # kernel_launches is filled by the runs
+    lz_rounds = int(st.lz_rounds)
     ascii_bytes = st.ascii_bytes
     value = world * ascii_bytes * args.steps / (dev_ms * 1e-3) / 1e9
 
@@ -376,7 +378,7 @@ def main():
                              "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": int(dom_bytes),
                              "stage_ms": {nm: round(ms, 4) for nm, ms in zip(stage_names, stage_ms)}},
                 "cpu_baseline": cpu, "clocks": clocks, "single_archive": single,
-                "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences),
+                "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences), "lz_rounds": lz_rounds,
                         "compressed_bytes": int(st.compressed_bytes), "ascii_bytes": int(st.ascii_bytes), "algorithmic_bytes": int(st.algorithmic_bytes)}}
         emit(line)
     if dist is not None:

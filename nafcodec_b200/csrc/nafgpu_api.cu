@@ -170,7 +170,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     const uint64_t nseq = pl.seq_total;
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
-    c->misc_words = 1 + 3 + 1 + nf + 8;
+    c->misc_words = 1 + 3 + 1 + 1 + nf + 8;
     const size_t nh = pl.huf_items.size(), nbt = pl.big_tree_slots.size();
     // descriptors: [blocks | frames | NafDev | HufItem | big-tree slots], the same layout in pinned staging and on the device,
     // so that they go up in ONE copy (a burst of small H2D copies is time-sliced against other contexts' result copies)
@@ -211,7 +211,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.seq = (zf::SeqRec*)c->seq64.p;
     J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
-    J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.frame_bad = misc + 5;
+    J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.frame_bad = misc + 6;
     J.coop_ctas = c->coop_ctas;
     {   // k_lz_finish sweeps a frame in 64 KB chunks at ~90 us each (profiles/r1_summary.md), frames in parallel
         uint64_t biggest = 0;
@@ -457,7 +457,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     { int rc_d2h = d2h_results(c); if (rc_d2h) return rc_d2h; }
     std::string msg;
     int code = status_to_code(*(const uint32_t*)c->misc_host.p, msg);
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5];
     if (code) return fail(c, code, msg);
     if (regen_size) memcpy(dst, (const uint8_t*)c->result.p + ALIGN, regen_size);
     return NAFGPU_OK;
@@ -500,7 +500,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5];
     const uint8_t* R = (const uint8_t*)c->result.p;
     std::string msg;
     int code = status_to_code(status & ~zc::E_UTF8, msg);
@@ -579,7 +579,7 @@ int nafgpu_job_format(nafgpu_ctx* c, int format, uint64_t line_length, nafgpu_te
         CUDA_TRY(c, cudaStreamSynchronize(c->st));
     }
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4];
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5];
     std::string msg;
     int code = status_to_code(status & ~zc::E_UTF8, msg);
     if (code) return fail(c, code, msg);

@@ -975,13 +975,46 @@ __device__ __forceinline__ uint32_t resolve_offset(const JobDev& J, uint32_t v, 
 
 // bytes [d, d+ml) <- periodic extension of [d-off, d): byte k comes from d-off + (k mod off); all sources lie
 // strictly below d, so the copy has no intra-match hazard even when off < ml.
+//
+// Loads and stores go to the same buffer, so the compiler keeps them in program order; a plain byte loop then has ONE
+// load in flight (every store waits for its load, every load for the store before it): ~0.5 us per byte, 30 us for a
+// 64-byte match, and a round lasts as long as its slowest copy.  The copies below issue 8 independent loads before the
+// first store.
 __device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t off, uint32_t ml, int lane, int nlanes) {
     const uint8_t* s = out + d - off;
-    if (off >= ml) {
-        for (uint32_t k = lane; k < ml; k += nlanes) out[d + k] = s[k];
-    } else {
-        for (uint32_t k = lane; k < ml; k += nlanes) out[d + k] = s[k % off];
+    uint8_t* o = out + d;
+    const bool periodic = off < ml;
+    for (uint32_t k0 = 0; k0 < ml; k0 += 8u * (uint32_t)nlanes) {
+        uint8_t t[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) {
+            const uint32_t k = k0 + j * (uint32_t)nlanes + (uint32_t)lane;
+            if (k < ml) t[j] = s[periodic ? k % off : k];
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) {
+            const uint32_t k = k0 + j * (uint32_t)nlanes + (uint32_t)lane;
+            if (k < ml) o[k] = t[j];
+        }
     }
+}
+
+// A run of one byte value (offset 1: N stretches, zero padding), n >= 1 bytes at dst, by `nlanes` threads: 16-byte stores.
+__device__ __forceinline__ void fill_run(uint8_t* dst, uint32_t v, uint32_t n, int lane, int nlanes) {
+    const uint32_t h = (uint32_t)(-(intptr_t)dst) & 15u;
+    if (n < 32u + h) { for (uint32_t k = lane; k < n; k += nlanes) dst[k] = (uint8_t)v; return; }
+    if ((uint32_t)lane < h) dst[lane] = (uint8_t)v;
+    const uint32_t body = (n - h) >> 4, w = v * 0x01010101u;
+    uint4* d4 = (uint4*)(dst + h);
+    for (uint32_t c = lane; c < body; c += nlanes) d4[c] = make_uint4(w, w, w, w);
+    for (uint32_t k = h + (body << 4) + lane; k < n; k += nlanes) dst[k] = (uint8_t)v;
+}
+
+// A long match by `nlanes` threads (a warp, or the CTA for the very long ones).
+__device__ __forceinline__ void copy_long_match(uint8_t* out, uint64_t d, uint32_t off, uint32_t ml, int lane, int nlanes) {
+    if (off >= ml) copy_g2g(out + d, out + d - off, ml, lane, nlanes);        // disjoint: 16-byte loads and stores
+    else if (off == 1) fill_run(out + d, out[d - 1], ml, lane, nlanes);
+    else copy_match(out, d, off, ml, lane, nlanes);
 }
 
 // Match resolution.
@@ -998,6 +1031,7 @@ __device__ __forceinline__ void copy_match(uint8_t* out, uint64_t d, uint32_t of
 // Short matches (the common case: a few tens of bytes) are copied by their own thread; long ones (N stretches:
 // offset 1, ~100 KB) are queued in shared memory and copied by the whole CTA.
 constexpr uint32_t LZ_SHORT = 64;
+constexpr uint32_t LZ_WARP_MAX = 4096;             // longer matches are copied by the whole CTA
 constexpr int LZ_CTA = 256;
 constexpr int LZ_HOPS = 8;
 constexpr uint32_t LZ_MIN_ROUNDS = 12, LZ_MIN_PENDING = 192;
@@ -1072,7 +1106,11 @@ __device__ __forceinline__ void lz_round(const JobDev& J, const uint32_t* list, 
         if (pending) next[wbase + __popc(pb & ((1u << lane) - 1u))] = i;
         __syncthreads();
         const uint32_t nq = *q_n;
-        for (uint32_t t = 0; t < nq; t++) copy_match(J.out, q_d[t], q_off[t], q_ml[t], tid, LZ_CTA);
+        // long matches: one warp each; the very long ones (N stretches: offset 1, ~100 KB) by the whole CTA
+        for (uint32_t t = (uint32_t)tid >> 5; t < nq; t += LZ_CTA / 32)
+            if (q_ml[t] <= LZ_WARP_MAX) copy_long_match(J.out, q_d[t], q_off[t], q_ml[t], lane, 32);
+        for (uint32_t t = 0; t < nq; t++)
+            if (q_ml[t] > LZ_WARP_MAX) copy_long_match(J.out, q_d[t], q_off[t], q_ml[t], tid, LZ_CTA);
         if ((uint32_t)tid < nq) J.seq_done[q_i[tid]] = round;
         __syncthreads();
     }
@@ -1082,7 +1120,7 @@ __device__ __forceinline__ void lz_round(const JobDev& J, const uint32_t* list, 
     __shared__ uint32_t q_n; __shared__ uint64_t q_d[LZ_CTA]; __shared__ uint32_t q_off[LZ_CTA], q_ml[LZ_CTA], q_i[LZ_CTA]
 
 // Round 1: every match of the job, one thread each.
-__global__ void __launch_bounds__(LZ_CTA) k_lz_first(JobDev J) {
+__global__ void __launch_bounds__(LZ_CTA, 4) k_lz_first(JobDev J) {
     LZ_SHARED_QUEUE;
     lz_round(J, nullptr, (uint32_t)J.n_seq, 1u, J.lz_list[0], &J.lz_count[0], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
              &q_n, q_d, q_off, q_ml, q_i);
@@ -1096,6 +1134,7 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
     for (uint32_t round = 2;; round++) {
         const uint32_t nxt = cur == 2 ? 0 : cur + 1, clr = nxt == 2 ? 0 : nxt + 1;
         const uint32_t n = J.lz_count[cur];                          // stable: written before the last grid barrier
+        if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_rounds = round - 1;
         if (n == 0) break;
         if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[clr] = 0; // append target of the NEXT round; idle in this one
         lz_round(J, J.lz_list[cur], n, round, J.lz_list[nxt], &J.lz_count[nxt], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,

@@ -30,6 +30,7 @@ struct JobDev {
     unsigned long long* debug;        // optional per-CTA phase clocks of k_huf_decode (NAFGPU_DEBUG_HUF=1), else null
     uint32_t* lz_list[3];             // rotating worklists of matches still pending (n_seq entries each)
     uint32_t* lz_count;               // [3] their lengths
+    uint32_t* lz_rounds;              // rounds k_lz_first + k_lz_resolve ran (statistics)
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
     uint32_t fin_cost_us;             // estimated cost of k_lz_finish on this job's largest frame (hand-over decision)
