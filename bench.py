@@ -338,6 +338,24 @@ def main():
     e2e_val = world * ascii_bytes * args.steps / e2e_s / 1e9
     clocks = sampler.summary()
 
+    # ---- FASTA text of the same batch, formatted on the device (reported beside the metric, not part of it) ----
+    text = None
+    if rank == 0:
+        n_arc = len(archives)
+        arr = (_ffi.Archive * n_arc)(*archives)
+        texts = (_ffi.Text * n_arc)()
+        tms = []
+        for _ in range(5):
+            rc = lib.dll.nafgpu_format_batch(ctx._ctx, arr, n_arc, want, _ffi.TEXT_FASTA, _ffi.LINE_LENGTH_FROM_HEADER, texts)
+            assert rc == 0, rc
+            tms.append(float(ctx.stats().text_kernel_ms))
+        ts = ctx.stats()
+        tmed = sorted(tms)[len(tms) // 2]
+        talg = int(ts.text_bytes) + int(ts.ascii_bytes) + int(ts.id_bytes) + int(ts.comment_bytes)
+        text = {"format": "fasta", "text_bytes": int(ts.text_bytes), "kernels": ["k_text_layout", "k_text_write"], "device_ms": tmed,
+                "text_GBps": int(ts.text_bytes) / (tmed * 1e-3) / 1e9, "algorithmic_bytes": talg,
+                "frac_of_hbm_peak": talg / (tmed * 1e-3) / 1e9 / peak}
+
     # ---- single archive latency (cfg2 as one archive) ------------------------------------------------------------------
     single = None
     if rank == 0:
@@ -377,7 +395,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": kernel_of.get(dom_name, dom_name), "stage": dom_name, "traffic_source": traffic_src, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": int(dom_bytes),
                              "stage_ms": {nm: round(ms, 4) for nm, ms in zip(stage_names, stage_ms)}},
-                "cpu_baseline": cpu, "clocks": clocks, "single_archive": single,
+                "cpu_baseline": cpu, "clocks": clocks, "single_archive": single, "text_formatter": text,
                 "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences), "lz_rounds": lz_rounds,
                         "compressed_bytes": int(st.compressed_bytes), "ascii_bytes": int(st.ascii_bytes), "algorithmic_bytes": int(st.algorithmic_bytes)}}
         emit(line)

@@ -139,7 +139,8 @@ void nafgpu_host_free(void* p);
 
 /* Whole path, host buffers in, host buffers out: walk frames, H2D, kernels, D2H, synchronise. */
 int nafgpu_decode(nafgpu_ctx* ctx, const nafgpu_archive* archive, uint32_t want, nafgpu_result* out);
-/* Same for n independent archives in ONE set of kernel launches (the batch / RefSeq-collection shape). */
+/* Same for n independent archives in ONE set of kernel launches (the batch / RefSeq-collection shape); n <= 65535 per
+ * call (larger collections: several calls, e.g. Pipeline.decode_stream). */
 int nafgpu_decode_batch(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want, nafgpu_result* out);
 
 /* One magicless zstd frame -> exactly regen_size bytes at dst (host memory).  The pure-zstd boundary: what

@@ -288,6 +288,7 @@ void nafgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n, uint32_t want) {
     if (!c || (!archives && n)) return NAFGPU_ERR_ARGUMENT;
+    if (n > 65535u) return fail(c, NAFGPU_ERR_ARGUMENT, "at most 65535 archives per job (the archive index is a grid dimension): split the batch");
     CUDA_TRY(c, cudaSetDevice(c->device));
     // the previous job may still be in flight on the stream and owns the staging buffers
     CUDA_TRY(c, cudaStreamSynchronize(c->st));
