@@ -106,7 +106,7 @@ typedef struct nafgpu_job_stats {
     uint32_t n_stages;                  /* entries nafgpu_job_run_profiled writes */
     uint32_t lz_handover;               /* nonzero if the last fetched run left LZ matches to the ordered finisher (k_lz_finish): the round it gave up at */
     uint32_t lz_rounds;                 /* dependency rounds the LZ stage of the last fetched run took */
-    uint32_t reserved;
+    uint32_t lz_unresolved;             /* bytes the finisher's first level left to its cross-chunk level (0 without a hand-over) */
     float text_kernel_ms;               /* device time of the last nafgpu_job_format's kernels (CUDA events on the context's stream) */
     uint64_t text_bytes;                /* bytes of text the last nafgpu_job_format produced */
 } nafgpu_job_stats;

@@ -54,7 +54,7 @@ class JobStats(C.Structure):
                 ("quality_bytes", C.c_uint64), ("id_bytes", C.c_uint64), ("comment_bytes", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("n_stages", C.c_uint32), ("lz_handover", C.c_uint32),
-                ("lz_rounds", C.c_uint32), ("reserved", C.c_uint32),
+                ("lz_rounds", C.c_uint32), ("lz_unresolved", C.c_uint32),
                 ("text_kernel_ms", C.c_float), ("text_bytes", C.c_uint64)]
 
 

@@ -71,8 +71,8 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush, text;
-    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
+    DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g;
+    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0, o_chunks = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -82,7 +82,7 @@ struct nafgpu_ctx {
     uint64_t max_records = 0, max_text = 0, max_mask = 0;
     uint32_t max_chunks = 0;
     bool any_mask = false, any_text_mask = false;
-    uint32_t coop_ctas = 1;
+    uint32_t coop_ctas = 1, fin_ctas = 1, fin2_ctas = 1;
     size_t misc_words = 0;
     nafgpu_job_stats stats;
     bool prepared = false, ran = false;
@@ -170,7 +170,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     const uint64_t nseq = pl.seq_total;
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
-    c->misc_words = 1 + 3 + 1 + 1 + nf + 8;
+    c->misc_words = 0;                                 // set below, once the number of finisher chunks is known
     const size_t nh = pl.huf_items.size(), nbt = pl.big_tree_slots.size();
     // descriptors: [blocks | frames | NafDev | HufItem | big-tree slots], the same layout in pinned staging and on the device,
     // so that they go up in ONE copy (a burst of small H2D copies is time-sliced against other contexts' result copies)
@@ -178,9 +178,19 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     c->o_naf = c->o_frames + align_up(nf * sizeof(zf::FrameDesc), 16);
     c->o_huf = c->o_naf + align_up((size_t)n * sizeof(nk::NafDev), 16);
     c->o_bt = c->o_huf + align_up(nh * sizeof(zf::HufItem), 16);
-    const size_t stage_bytes = c->o_bt + align_up(nbt * 4, 16);
+    c->o_chunks = c->o_bt + align_up(nbt * 4, 16);
+    // finisher chunk table: first 64 KB chunk of every frame (zstd_kernels.cu, k_lz_finish)
+    std::vector<uint32_t> chunk_first(nf + 1, 0);
+    for (size_t f = 0; f < nf; f++) {
+        const uint64_t nchunks = (pl.frames[f].dst_size + 65535) >> 16;
+        if ((uint64_t)chunk_first[f] + nchunks > 0x7FFFFFFFull) return fail(c, NAFGPU_ERR_UNSUPPORTED, "job too large for the chunk table");
+        chunk_first[f + 1] = chunk_first[f] + (uint32_t)nchunks;
+    }
+    const uint32_t total_chunks = chunk_first[nf];
+    const size_t stage_bytes = c->o_chunks + align_up((nf + 1) * 4, 16);
+    c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
-              c->desc.ensure(stage_bytes + 64) &&
+              c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)total_chunks * 65536 * 4 + 64) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) && c->huftabs.ensure(pl.big_tree_slots.size() * 28672 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
@@ -195,6 +205,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (n) memcpy(sp + c->o_naf, c->arch.data(), (size_t)n * sizeof(nk::NafDev));
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
     if (nbt) memcpy(sp + c->o_bt, pl.big_tree_slots.data(), nbt * 4);
+    memcpy(sp + c->o_chunks, chunk_first.data(), (nf + 1) * 4);
     if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
@@ -211,12 +222,17 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.seq = (zf::SeqRec*)c->seq64.p;
     J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
-    J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.frame_bad = misc + 6;
+    J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.fin_unresolved = misc + 6; J.fin_count = misc + 7;
+    J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf;
+    J.fin_chunk_first = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_chunks); J.fin_total_chunks = total_chunks;
+    J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p;
     J.coop_ctas = c->coop_ctas;
-    {   // k_lz_finish sweeps a frame in 64 KB chunks at ~90 us each (profiles/r1_summary.md), frames in parallel
+    {   // the finisher handles a 64 KB chunk in ~90 us on one SM, all SMs at once, then a few barrier rounds (profiles/r1_summary.md)
         uint64_t biggest = 0;
         for (const auto& F : c->plan.frames) biggest = std::max<uint64_t>(biggest, F.dst_size);
-        J.fin_cost_us = (uint32_t)std::min<uint64_t>(200 + (biggest >> 16) * 90, 0x7FFFFFFFu);
+        (void)biggest;
+        const uint64_t waves = ((uint64_t)total_chunks + c->fin_ctas - 1) / std::max<uint32_t>(c->fin_ctas, 1u);
+        J.fin_cost_us = (uint32_t)std::min<uint64_t>(150 + waves * 90, 0x7FFFFFFFu);
     }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_tabs = (uint8_t*)c->huftabs.p; J.big_tree_slots = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_bt); J.n_big_trees = (uint32_t)nbt;
@@ -257,6 +273,7 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     for (int i = 0; i < N_STAGES + 3; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     c->ev_ok = true;
     c->coop_ctas = zk::lz_resolve_max_ctas(device);
+    zk::lz_finish_ctas(device, &c->fin_ctas, &c->fin2_ctas);
     *out = c;
     return NAFGPU_OK;
 }
@@ -266,7 +283,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
@@ -458,7 +475,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     { int rc_d2h = d2h_results(c); if (rc_d2h) return rc_d2h; }
     std::string msg;
     int code = status_to_code(*(const uint32_t*)c->misc_host.p, msg);
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5];
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
     if (code) return fail(c, code, msg);
     if (regen_size) memcpy(dst, (const uint8_t*)c->result.p + ALIGN, regen_size);
     return NAFGPU_OK;
@@ -501,7 +518,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5];
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
     const uint8_t* R = (const uint8_t*)c->result.p;
     std::string msg;
     int code = status_to_code(status & ~zc::E_UTF8, msg);
@@ -580,7 +597,7 @@ int nafgpu_job_format(nafgpu_ctx* c, int format, uint64_t line_length, nafgpu_te
         CUDA_TRY(c, cudaStreamSynchronize(c->st));
     }
     const uint32_t status = *(const uint32_t*)c->misc_host.p;
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5];
+    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
     std::string msg;
     int code = status_to_code(status & ~zc::E_UTF8, msg);
     if (code) return fail(c, code, msg);

@@ -1155,26 +1155,39 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
     }
 }
 
-// k_lz_finish: what k_lz_resolve leaves behind when its rounds stop paying (text-like sections -- quality strings,
-// ids -- where nearly every match feeds the next one: a dependency chain as long as the section has matches).  Walking
-// such a chain in order costs hundreds of cycles per match on a GPU; instead the chain is cut at BYTE level, where an
-// LZ77 stream is a forest: every byte of a pending match points at the byte `off` behind it, every other byte is a
-// root.  One CTA per frame sweeps the frame in 64 KB chunks held in shared memory: pointers (16-bit, chunk-relative)
-// are set up from the pending matches, pointer jumping (ptr[e] = ptr[ptr[e]], in place) reaches the roots in
-// log2(depth) steps, then every pending byte takes its root's value.  Sources below the chunk are final in global
-// memory (earlier chunks are complete), so those bytes are roots with the value read directly.
-constexpr uint32_t FIN_C = 65536;        // chunk bytes (16-bit pointers)
+// k_lz_finish / k_lz_finish2: what k_lz_resolve leaves behind when its rounds stop paying (text-like sections -- quality
+// strings, ids -- where nearly every match feeds the next one: a dependency chain as long as the section has matches).
+// Walking such a chain in order costs hundreds of cycles per match on a GPU; instead the chain is cut at BYTE level, where
+// an LZ77 stream is a forest: every byte of a pending match points at the byte `off` behind it (the periodic extension
+// for an overlapping match), every other byte is a root.
+//
+// Level 1 (k_lz_finish): the frames are cut into 64 KB chunks, ALL chunks processed in parallel, one at a time per CTA in
+// shared memory: 16-bit chunk-relative parents, in-place pointer jumping (ptr[e] = ptr[ptr[e]]) to the roots in
+// log2(depth) steps.  A root is either final (literal, finished match): its bytes are written now; or it is a byte whose
+// source lies BELOW the chunk, which may itself still be unresolved: for every byte hanging off such a root the distance
+// back to that source goes to fin_g (u32 per byte of the chunk; 0 = final).
+// Level 2 (k_lz_finish2, cooperative): pointer jumping over fin_g across chunks.  A byte whose source is final takes its
+// value; otherwise it adopts its source's source (dist += dist[source]).  Sources always lie in an earlier chunk, so the
+// depth is at most the number of chunks of the frame: <= log2 of that many rounds, one grid barrier each.
+constexpr uint32_t FIN_C = 65536;        // chunk bytes (16-bit pointers); frame_walk.h uses the same value for the chunk table
 constexpr uint32_t FIN_T = 1024;         // threads
 constexpr uint32_t FIN_U = 4;            // matches per thread and scan step (independent loads in flight)
 constexpr uint32_t FIN_INLINE = 64;      // longer pieces are set up by the whole CTA
-constexpr uint32_t FIN_SMEM = FIN_C + FIN_C * 2 + FIN_T * 20;
+constexpr uint32_t FIN_SMEM = FIN_C + FIN_C * 2 + FIN_C / 8 + FIN_T * 20;
+constexpr int FIN2_T = 256;
 
-// One byte of a pending match: chunk-relative e, parent at chunk-relative (signed) s.  The parent is the byte the
-// periodic extension names (k mod off for an overlapping match, so that a run does not become a chain of its own
-// bytes); parents below the chunk are final in global memory.
-__device__ __forceinline__ void fin_byte(uint8_t* val, uint16_t* ptr, uint8_t* out_c0, uint32_t e, int32_t s) {
+// One byte of a pending match: chunk-relative e, parent at chunk-relative (signed) s.  Parents below the chunk: the byte
+// becomes an external root, its distance to the source goes to g[e].
+__device__ __forceinline__ void fin_byte(uint16_t* ptr, uint32_t* extbit, uint32_t* g, uint32_t e, int32_t s) {
     if (s >= 0) ptr[e] = (uint16_t)s;
-    else out_c0[e] = val[e] = __ldcg(out_c0 + s);
+    else { g[e] = (uint32_t)((int32_t)e - s); atomicOr(&extbit[e >> 5], 1u << (e & 31)); }
+}
+
+// frame that owns chunk c: last f with chunk_first[f] <= c < chunk_first[f + 1]
+__device__ __forceinline__ uint32_t fin_frame_of(const JobDev& J, uint32_t c) {
+    uint32_t lo = 0, hi = J.n_frames;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (J.fin_chunk_first[mid] <= c) lo = mid; else hi = mid; }
+    return lo;
 }
 
 __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
@@ -1182,42 +1195,62 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
     NAF_DYN_SMEM(unsigned char, fin_smem);
     uint8_t* val = fin_smem;                                   // [FIN_C] chunk bytes
     uint16_t* ptr = (uint16_t*)(fin_smem + FIN_C);             // [FIN_C] chunk-relative parent; self = root
-    uint32_t* q_rel = (uint32_t*)(fin_smem + FIN_C * 3);       // [FIN_T] long pieces: first chunk-relative byte,
+    uint32_t* extbit = (uint32_t*)(fin_smem + FIN_C * 3);      // [FIN_C / 32] roots whose source lies below the chunk
+    uint32_t* q_rel = extbit + FIN_C / 32;                     // [FIN_T] long pieces: first chunk-relative byte,
     uint32_t* q_len = q_rel + FIN_T;                           //         length,
     uint32_t* q_off = q_len + FIN_T;                           //         match offset,
     uint32_t* q_m0 = q_off + FIN_T;                            //         first byte of the piece within the match,
     uint32_t* q_ml = q_m0 + FIN_T;                             //         match length
-    __shared__ uint32_t s_first, s_next, s_q, s_bad;
-    const uint32_t f = blockIdx.x;
-    if (J.frame_bad[f]) return;
-    const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
-    const uint32_t first = J.frames[f].first_seq, end = first + J.frames[f].n_seq;
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint32_t s_f, s_mi, s_q, s_bad, s_unres;
+    const uint32_t tid = threadIdx.x;
 
-    // first pending match of the frame (most frames have none)
-    if (tid == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
-    __syncthreads();
-    for (uint32_t i = first + tid; i < end; i += FIN_T)
-        if (J.seq_done[i] == 0) { atomicMin(&s_first, i); break; }
-    __syncthreads();
-    uint32_t mi = s_first;
-    if (mi == 0xFFFFFFFFu) return;
-
-    for (uint64_t c0 = f0 + ((J.seq[mi].match_pos - f0) & ~(uint64_t)15); c0 < fend && mi < end; c0 += FIN_C) {
+    for (uint32_t c = blockIdx.x; c < J.fin_total_chunks; c += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t f = fin_frame_of(J, c);
+            s_f = f; s_bad = 0; s_unres = 0;
+            // first match of the frame that ends after the start of the chunk (matches are ordered by position)
+            const uint64_t cs = J.frames[f].dst_off + (uint64_t)(c - J.fin_chunk_first[f]) * FIN_C;
+            uint32_t lo = J.frames[f].first_seq, hi = lo + J.frames[f].n_seq;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (J.seq[mid].match_pos + J.seq[mid].ml > cs) hi = mid; else lo = mid + 1; }
+            s_mi = lo;
+        }
+        __syncthreads();
+        const uint32_t f = s_f, mi = s_mi;
+        if (J.frame_bad[f]) continue;
+        const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
+        const uint32_t end = J.frames[f].first_seq + J.frames[f].n_seq;
+        const uint64_t c0 = f0 + (uint64_t)(c - J.fin_chunk_first[f]) * FIN_C;
         const uint64_t c1 = (c0 + FIN_C < fend) ? c0 + FIN_C : fend;
         const uint32_t cn = (uint32_t)(c1 - c0);
         uint8_t* out_c0 = J.out + c0;
-        // chunk bytes as they stand (literals and finished matches are final, pending bytes are garbage) + self pointers
-        for (uint32_t e = tid * 16; e < cn; e += FIN_T * 16) {
-            *(uint4*)(val + e) = __ldcg((const uint4*)(out_c0 + e));         // the arena is padded past the last frame
+        uint32_t* g = J.fin_g + (size_t)c * FIN_C;
+        // any pending match in this chunk?  (most chunks of a job have none)
+        bool mine = false;
+        for (uint32_t base = mi;; base += FIN_T) {
+            const uint32_t i = base + tid;
+            bool stop = i >= end;
+            if (!stop) {
+                const SeqRec& R = J.seq[i];
+                if (R.match_pos >= c1) stop = true;
+                else if (J.seq_done[i] == 0) mine = true;
+            }
+            if (__syncthreads_or(stop || mine)) break;
+        }
+        if (!__syncthreads_or(mine)) continue;
+        // chunk bytes as they stand (literals and finished matches are final, pending bytes are garbage), self pointers,
+        // no external roots, all distances zero
+        for (uint32_t e = tid * 16; e < FIN_C; e += FIN_T * 16) {
+            if (e < cn) *(uint4*)(val + e) = __ldcg((const uint4*)(out_c0 + e));   // the arena is padded past the last frame
             uint32_t* p2 = (uint32_t*)(ptr + e);
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++) p2[k] = (e + 2 * k) | ((e + 2 * k + 1) << 16);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) ((uint4*)(g + e))[k] = make_uint4(0, 0, 0, 0);
         }
-        if (tid == 0) s_next = end;
+        for (uint32_t e = tid; e < FIN_C / 32; e += FIN_T) extbit[e] = 0;
         __syncthreads();
-        // pending matches that intersect the chunk (matches are ordered by position)
-        bool any = false;
+        // pending matches that intersect the chunk
         for (uint32_t base = mi;; base += FIN_T * FIN_U) {
             if (tid == 0) s_q = 0;
             __syncthreads();
@@ -1237,9 +1270,6 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
 #pragma unroll
             for (uint32_t j = 0; j < FIN_U; j++) {
                 const uint32_t i = base + j * FIN_T + tid;
-                const bool beyond = i < end && pos[j] + ml[j] > c1;         // the next chunk starts looking at the first of these
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, beyond);
-                if (bal && lane == (uint32_t)__ffs(bal) - 1u) atomicMin(&s_next, i);
                 if (i >= end || pos[j] >= c1) stop = true;
                 else if (pend[j] && pos[j] + ml[j] > c0) {
                     const uint32_t off = resolve_offset(J, ov[j], blk[j]);
@@ -1247,17 +1277,16 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
                     else {
                         const uint64_t b0 = pos[j] > c0 ? pos[j] : c0, b1 = pos[j] + ml[j] < c1 ? pos[j] + ml[j] : c1;
                         const uint32_t rel = (uint32_t)(b0 - c0), len = (uint32_t)(b1 - b0), m0 = (uint32_t)(b0 - pos[j]);
-                        const int32_t srel = (int32_t)((int64_t)(pos[j] - off) - (int64_t)c0);   // |srel| < 2^31: offsets are capped below
-                        any = true;
+                        const int32_t srel = (int32_t)((int64_t)(pos[j] - off) - (int64_t)c0);   // |srel| < 2^31: offsets are capped above
                         if (len > FIN_INLINE) {
                             const uint32_t slot = atomicAdd(&s_q, 1u);
                             q_rel[slot] = rel; q_len[slot] = len; q_off[slot] = off; q_m0[slot] = m0; q_ml[slot] = ml[j];
                         } else if (off >= ml[j]) {
                             int32_t sp = srel + (int32_t)m0;
-                            for (uint32_t k = 0; k < len; k++, sp++) fin_byte(val, ptr, out_c0, rel + k, sp);
+                            for (uint32_t k = 0; k < len; k++, sp++) fin_byte(ptr, extbit, g, rel + k, sp);
                         } else {
                             uint32_t r = m0 % off;
-                            for (uint32_t k = 0; k < len; k++) { fin_byte(val, ptr, out_c0, rel + k, srel + (int32_t)r); if (++r == off) r = 0; }
+                            for (uint32_t k = 0; k < len; k++) { fin_byte(ptr, extbit, g, rel + k, srel + (int32_t)r); if (++r == off) r = 0; }
                         }
                     }
                 }
@@ -1268,30 +1297,92 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
                 const uint32_t rel = q_rel[t], len = q_len[t], off = q_off[t], m0 = q_m0[t], mlen = q_ml[t];
                 const int32_t srel = (int32_t)rel - (int32_t)m0 - (int32_t)off;
                 for (uint32_t k = tid; k < len; k += FIN_T)
-                    fin_byte(val, ptr, out_c0, rel + k, srel + (int32_t)(off < mlen ? (m0 + k) % off : m0 + k));
+                    fin_byte(ptr, extbit, g, rel + k, srel + (int32_t)(off < mlen ? (m0 + k) % off : m0 + k));
             }
             if (all_stop) break;
             __syncthreads();                                                // queue drained before it is refilled
         }
-        const int work = __syncthreads_or(any);
-        mi = s_next;
-        if (s_bad) return;                                                  // (uniform: set before the barrier above)
-        if (work) {
-            // pointer jumping, in place: a pointer only ever moves to an ancestor, roots never move
-            for (;;) {
-                bool changed = false;
-                for (uint32_t e = tid; e < cn; e += FIN_T) {
-                    const uint32_t p = ptr[e];
-                    if (p != e) { const uint32_t pp = ptr[p]; if (pp != p) { ptr[e] = (uint16_t)pp; changed = true; } }
-                }
-                if (!__syncthreads_or(changed)) break;
-            }
+        __syncthreads();
+        if (s_bad) continue;                                                // (uniform; the frame is flagged)
+        // pointer jumping, in place: a pointer only ever moves to an ancestor, roots never move
+        for (;;) {
+            bool changed = false;
             for (uint32_t e = tid; e < cn; e += FIN_T) {
                 const uint32_t p = ptr[e];
-                if (p != e) out_c0[e] = val[p];                              // roots are not written here: no hazard
+                if (p != e) { const uint32_t pp = ptr[p]; if (pp != p) { ptr[e] = (uint16_t)pp; changed = true; } }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        // bytes under a final root take its value now; bytes under an external root get the distance to its source
+        uint32_t unres = 0;
+        for (uint32_t e = tid; e < cn; e += FIN_T) {
+            const uint32_t p = ptr[e];
+            const bool ext = (extbit[p >> 5] >> (p & 31)) & 1u;
+            if (p != e) {
+                if (ext) { g[e] = (e - p) + __ldcg(g + p); unres++; }       // (g[p] was written by this CTA before the barriers above)
+                else out_c0[e] = val[p];                                    // roots are not written here: no hazard
+            } else if (ext) unres++;
+        }
+        if (unres) atomicAdd(&s_unres, unres);
+        __syncthreads();
+        if (tid == 0 && s_unres) { J.fin_chunk_flag[c] = 1; atomicAdd(J.fin_unresolved, s_unres); }
+    }
+}
+
+// Level 2: see above.  Cooperative; every round scans the distances of the chunks that still have unresolved bytes.
+__global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
+    if (*J.lz_handover == 0 || *J.fin_unresolved == 0) return;
+    __shared__ uint32_t s_left;
+    const uint32_t tid = threadIdx.x;
+    volatile uint32_t* G = J.fin_g;
+    volatile uint32_t* flag = J.fin_chunk_flag;
+    for (uint32_t round = 0;; round++) {
+        const uint32_t cur = round % 3, clr = (round + 2) % 3;
+        if (blockIdx.x == 0 && tid == 0) J.fin_count[clr] = 0;             // the counter of the round after next; idle in this one
+        uint32_t left_total = 0;
+        for (uint32_t c = blockIdx.x; c < J.fin_total_chunks; c += gridDim.x) {
+            if (flag[c] == 0) continue;                                     // (uniform)
+            __syncthreads();
+            if (tid == 0) s_left = 0;
+            __syncthreads();
+            const uint32_t f = fin_frame_of(J, c);
+            const uint32_t cf = J.fin_chunk_first[f];
+            const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
+            const uint64_t crel = (uint64_t)(c - cf) * FIN_C;               // chunk start relative to the frame
+            const uint32_t cn = (uint32_t)((crel + FIN_C < fend - f0) ? FIN_C : fend - f0 - crel);
+            uint32_t left = 0;
+            for (uint32_t e = tid; e < cn; e += FIN2_T) {
+                const uint32_t dist = G[(size_t)c * FIN_C + e];
+                if (dist == 0) continue;
+                const uint64_t prel = crel + e;                             // my position and my source, relative to the frame
+                if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[(size_t)c * FIN_C + e] = 0; continue; }
+                const uint64_t srel = prel - dist;
+                const uint32_t sc = cf + (uint32_t)(srel >> 16);
+                uint32_t gs = 0;
+                if (flag[sc] != 0) gs = G[(size_t)sc * FIN_C + (uint32_t)(srel & (FIN_C - 1))];
+                if (gs == 0) {                                              // the source is final: take its value
+                    __threadfence();
+                    const uint8_t v = *(volatile const uint8_t*)(J.out + f0 + srel);
+                    J.out[f0 + prel] = v;
+                    __threadfence();
+                    G[(size_t)c * FIN_C + e] = 0;
+                } else {                                                    // adopt the source's source
+                    const uint64_t nd = (uint64_t)dist + gs;
+                    if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[(size_t)c * FIN_C + e] = 0; continue; }
+                    G[(size_t)c * FIN_C + e] = (uint32_t)nd;
+                    left++;
+                }
+            }
+            if (left) atomicAdd(&s_left, left);
+            __syncthreads();
+            if (tid == 0) {
+                if (s_left == 0) { __threadfence(); flag[c] = 0; }          // every byte of the chunk is final now
+                left_total += s_left;
             }
         }
-        __syncthreads();                                                    // chunk complete (and visible) before the next one reads it
+        if (tid == 0 && left_total) atomicAdd(&J.fin_count[cur], left_total);
+        NAF_GRID_SYNC();
+        if (J.fin_count[cur] == 0) break;
     }
 }
 
@@ -1305,6 +1396,21 @@ uint32_t lz_resolve_max_ctas(int device) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz_resolve, LZ_CTA, 0);
     if (per_sm > 2) per_sm = 2;
     return (uint32_t)(sms > 0 && per_sm > 0 ? sms * per_sm : 1);
+#endif
+}
+
+// CTAs for the two finisher kernels: level 1 is one 212 KB CTA per SM, level 2 is cooperative (co-resident CTAs).
+void lz_finish_ctas(int device, uint32_t* level1, uint32_t* level2) {
+#if defined(NAFGPU_EMULATE)
+    (void)device;
+    *level1 = 2; *level2 = 1;
+#else
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz_finish2, FIN2_T, 0);
+    if (per_sm > 4) per_sm = 4;
+    *level1 = (uint32_t)(sms > 0 ? sms : 1);
+    *level2 = (uint32_t)(sms > 0 && per_sm > 0 ? sms * per_sm : 1);
 #endif
 }
 
@@ -1351,7 +1457,13 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
         ev->mark();
         NAF_SET_MAX_SMEM(k_lz_finish, FIN_SMEM);
-        NAF_LAUNCH(k_lz_finish, J.n_frames, FIN_T, FIN_SMEM, st, J); launches++;
+        const uint32_t fin_grid = J.fin_total_chunks < J.fin_ctas ? J.fin_total_chunks : J.fin_ctas;
+        if (fin_grid) {
+            NAF_LAUNCH(k_lz_finish, fin_grid, FIN_T, FIN_SMEM, st, J); launches++;
+            const uint32_t cg2 = J.fin2_ctas ? J.fin2_ctas : 1u;
+            (void)cg2;
+            NAF_LAUNCH_COOP(k_lz_finish2, cg2, FIN2_T, st, Jc); launches++;
+        }
         ev->mark();
     } else { ev->mark(); ev->mark(); ev->mark(); }
     return launches;

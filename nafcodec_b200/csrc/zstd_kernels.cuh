@@ -33,7 +33,15 @@ struct JobDev {
     uint32_t* lz_rounds;              // rounds k_lz_first + k_lz_resolve ran (statistics)
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
-    uint32_t fin_cost_us;             // estimated cost of k_lz_finish on this job's largest frame (hand-over decision)
+    uint32_t fin_cost_us;             // estimated cost of the finisher kernels on this job (hand-over decision)
+    // finisher (k_lz_finish, k_lz_finish2): the frames cut into 64 KB chunks
+    const uint32_t* fin_chunk_first;  // [n_frames + 1] first chunk of every frame (host-filled)
+    uint32_t fin_total_chunks;
+    uint32_t fin_ctas, fin2_ctas;     // grid sizes (one CTA per SM; co-resident CTAs of the cooperative level 2)
+    uint32_t* fin_g;                  // [fin_total_chunks * 65536] distance of an unresolved byte to its source, 0 = final
+    uint32_t* fin_chunk_flag;         // [fin_total_chunks] chunk has unresolved bytes (zeroed every run)
+    uint32_t* fin_unresolved;         // unresolved bytes after level 1
+    uint32_t* fin_count;              // [3] rotating per-round counters of level 2
     uint8_t* huf_tabs;                // n_big_trees x 28 KB prebuilt decode tables (t1 | bm | t3) of trees used by big streams
     const uint32_t* big_tree_slots;   // weight-record slot of each of them
     uint32_t n_big_trees;
@@ -50,6 +58,7 @@ struct JobDev {
 int launch_zstd_stage(const JobDev& job, cudaStream_t stream, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev);
 // Co-resident CTAs (whole device) for the cooperative match-resolution kernel.
 uint32_t lz_resolve_max_ctas(int device);
+void lz_finish_ctas(int device, uint32_t* level1, uint32_t* level2);
 constexpr int ZSTD_STAGES = 8;
 
 }  // namespace zk

@@ -213,6 +213,7 @@ def test_ordered_finisher_on_dependency_chains(backend):
         assert ctx.zstd_decompress(frame, len(p)) == p, (blen, far, lng, level)
         if blen < 1000:                                    # (few, long matches: the rounds stay cheaper than the finisher)
             assert ctx.stats().lz_handover > 0, (blen, far, lng, level)
+            assert ctx.stats().lz_unresolved > 0, "chains cross the 64 KB chunks: the second level has work"
     # a chain next to ordinary frames in one job: quality of a FASTQ archive whose reads descend from one another
     qual = _generations(rng, 1500, 150)[5000:]
     n = len(qual) // 150

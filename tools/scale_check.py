@@ -39,7 +39,7 @@ def run(name, data, **fields):
     out_bytes = st.ascii_bytes + st.quality_bytes + st.id_bytes + st.comment_bytes
     print(f"{name}: PARITY OK | {len(data) / 1e6:.1f} MB archive, {st.n_blocks} zstd blocks, {st.n_sequences} sequences | device {ms:.3f} ms "
           f"({out_bytes / ms / 1e6:.1f} GB/s out, {st.algorithmic_bytes / ms / 1e6 / 6557.8 * 100:.2f}% of HBM peak) | host prepare {t_prep * 1e3:.1f} ms | "
-          f"cpu oracle {t_cpu * 1e3:.0f} ms ({out_bytes / t_cpu / 1e9:.2f} GB/s) | lz rounds {ctx.stats().lz_rounds}, handover at round {handover} | stages[ms]: {stages}", flush=True)
+          f"cpu oracle {t_cpu * 1e3:.0f} ms ({out_bytes / t_cpu / 1e9:.2f} GB/s) | lz rounds {ctx.stats().lz_rounds}, handover at round {handover} ({ctx.stats().lz_unresolved} bytes to level 2) | stages[ms]: {stages}", flush=True)
 
 
 t0 = time.time()
