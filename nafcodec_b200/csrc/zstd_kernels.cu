@@ -1337,8 +1337,10 @@ __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
     volatile uint32_t* G = J.fin_g;
     volatile uint32_t* flag = J.fin_chunk_flag;
     for (uint32_t round = 0;; round++) {
-        const uint32_t cur = round % 3, clr = (round + 2) % 3;
-        if (blockIdx.x == 0 && tid == 0) J.fin_count[clr] = 0;             // the counter of the round after next; idle in this one
+        // three counters rotate: this round adds to `cur` and reads it after the barrier (a slow CTA as late as during the next
+        // round); the NEXT round's counter is cleared now, while nobody reads it or adds to it
+        const uint32_t cur = round % 3, clr = (round + 1) % 3;
+        if (blockIdx.x == 0 && tid == 0) J.fin_count[clr] = 0;
         uint32_t left_total = 0;
         for (uint32_t c = blockIdx.x; c < J.fin_total_chunks; c += gridDim.x) {
             if (flag[c] == 0) continue;                                     // (uniform)
