@@ -1034,7 +1034,7 @@ constexpr uint32_t LZ_SHORT = 64;
 constexpr uint32_t LZ_WARP_MAX = 4096;             // longer matches are copied by the whole CTA
 constexpr int LZ_CTA = 256;
 constexpr int LZ_HOPS = 8;
-constexpr uint32_t LZ_MIN_ROUNDS = 12, LZ_MIN_PENDING = 192;
+constexpr uint32_t LZ_MIN_ROUNDS = 3, LZ_MIN_PENDING = 192;        // no hand-over before round 3 or for a handful of matches
 
 // Returns 1 when match i may be copied now (d/off/ml filled), 0 when it has to wait, 2 when it was rejected.
 __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t round, uint64_t& d, uint32_t& off, uint32_t& ml) {
