@@ -904,7 +904,7 @@ __device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ d, const uint8_
 __device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
     if (n < 64) { for (uint32_t k = lane; k < n; k += nlanes) dst[k] = src[k]; return; }
     const uint32_t h = (uint32_t)(-(intptr_t)dst) & 15u;
-    if ((uint32_t)lane < h) dst[lane] = src[lane];
+    for (uint32_t k = lane; k < h; k += nlanes) dst[k] = src[k];
     const uint32_t body = (n - h) >> 4;
     const uintptr_t sa = (uintptr_t)(src + h);
     const uint4* sw = (const uint4*)(sa & ~(uintptr_t)15);
@@ -923,13 +923,18 @@ __device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_
     for (uint32_t k = done + lane; k < n; k += nlanes) dst[k] = src[k];
 }
 
+constexpr int LZLIT_G = 32;                        // lanes per literal run (8-lane groups, four runs in flight per warp, measured no faster)
+constexpr int LZLIT_SPLIT = 4;                     // CTAs that share the runs of one block
+
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
     if (J.frame_bad[B.frame]) return;
     const BlockState& S = J.bstate[bi];
     uint8_t* out = J.out + S.out_off;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    // gridDim.y CTAs share a block: the time of this kernel is the time of the block with the most sequences (one literal
+    // run per warp and step, two dependent latencies each), so the runs of a block are dealt out to several CTAs
+    const int tid = threadIdx.x + blockIdx.y * blockDim.x, nt = blockDim.x * gridDim.y;
     if (B.btype == BT_RAW) { copy_bytes(out, J.comp + B.src_off, B.src_size, tid, nt); return; }
     if (B.btype == BT_RLE) {
         uint8_t v = J.comp[B.src_off];
@@ -946,9 +951,10 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         else copy_g2g(out, lsrc, B.lit_regen, tid, nt);
         return;
     }
-    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    // one literal run (a few hundred bytes) per group of LZLIT_G lanes
+    const int grp = tid / LZLIT_G, lane = tid % LZLIT_G, ng = nt / LZLIT_G;
     const uint32_t n = B.n_seq, base = B.seq_base;
-    for (uint32_t i = warp; i <= n; i += nw) {
+    for (uint32_t i = grp; i <= n; i += ng) {
         uint32_t lp, op, ll;
         if (i < n) {
             lp = J.seq[base + i].litpos; op = J.seq[base + i].outpos; ll = J.seq[base + i].ll;
@@ -959,8 +965,8 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
             op = J.seq[j].outpos + J.seq[j].ll + J.seq[j].ml;
             ll = B.lit_regen - lp;
         }
-        if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += 32) out[op + k] = rle;
-        else copy_g2g(out + op, lsrc + lp, ll, lane, 32);
+        if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += LZLIT_G) out[op + k] = rle;
+        else copy_g2g(out + op, lsrc + lp, ll, lane, LZLIT_G);
     }
 }
 
@@ -1447,7 +1453,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, J.seq_stage_bytes, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++; ev->mark();
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
-    NAF_LAUNCH(k_lz_literals, J.n_blocks, 256, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
         uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
         if (grid > 148u * 64u) grid = 148u * 64u;
