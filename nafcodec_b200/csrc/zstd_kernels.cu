@@ -1453,7 +1453,8 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, J.seq_stage_bytes, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++; ev->mark();
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
-    NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
+    // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
+    NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
         uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
         if (grid > 148u * 64u) grid = 148u * 64u;
