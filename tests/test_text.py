@@ -71,3 +71,24 @@ def test_text_raises_at_invalid_utf8(backend):
     arc = O.encode(sequence_type=O.TEXT, ids=[b"a", b"b"], sequences=[b"ok", b"\xff\xfe"], level=3)
     with pytest.raises(N.NafUnicodeError):
         N.to_fasta(arc, _library=lib)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_text_of_odd_archives(backend):
+    """Archives without ids / with empty records / whose header claims more records than the streams hold: absent fields are
+    empty in the text, exactly as in the CPU formatter."""
+    lib = library(backend)
+    arcs = [
+        O.encode(sequences=[b"ACGT" * 10, b"GG"], level=3),                                     # no ids: '>' alone
+        O.encode(ids=[b"x"], sequences=[b""], level=3, line_length=5),                          # an empty record: header line only
+        O.encode(ids=[b"a", b"b", b"c"], sequences=[b"", b"", b""], mask_runs_=[0, 0, 5]),
+        O.encode(ids=[b"r"], sequences=[b"ACGU" * 30], sequence_type=O.RNA, level=3, line_length=7),
+        O.encode(sequences=[b"ACGT", b"TT"], qualities=[b"IIII", b"##"], level=3),              # FASTQ without ids
+    ]
+    claimed = bytearray(O.encode(ids=[b"r1", b"r2"], comments=[b"c1", b"c2"], sequences=[b"ACGT", b"GG"]))
+    claimed[O.parse(bytes(claimed)).header_size - 1] = 5                                        # 5 records claimed, 2 stored
+    arcs.append(bytes(claimed))
+    for i, a in enumerate(arcs):
+        assert N.to_text(a, _library=lib) == O.format_text(a), i
+    with pytest.raises(ValueError):
+        N.to_fasta(O.encode(ids=[b"only", b"ids"]), _library=lib)                               # no sequence to print
