@@ -25,6 +25,27 @@ __device__ __forceinline__ void flag_error(const JobDev& J, uint32_t frame, uint
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// Backward bit reader over a shared-memory image of the bitstream (32-bit words; >= 16 zero bytes below bit 0).
+// 64-bit register window, refilled 32 bits at a time; read(k) for k <= 32.
+struct SmemBits {
+    const uint32_t* sw;
+    uint64_t w;          // stream bits [32*qi, 32*qi + 64)
+    int qi, rr;          // rr = x - 32*qi, position of the next unread bit inside the window (kept in [32, 64] before a read)
+    int x_zero;          // smem bit position of stream bit 0
+    __device__ __forceinline__ void init(const uint32_t* words, int x, int xz) {
+        sw = words; x_zero = xz;
+        qi = (x >> 5) - 1;
+        rr = x - (qi << 5);
+        w = ((uint64_t)sw[qi + 1] << 32) | sw[qi];
+    }
+    __device__ __forceinline__ uint32_t read(int k) {
+        if (rr < k) { w = (w << 32) | sw[--qi]; rr += 32; }
+        rr -= k;
+        return k ? (uint32_t)(w >> rr) & (k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u)) : 0u;
+    }
+    __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
+};
+
 // k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
 // part 0: FSE tables (32 threads, grid n_blocks + 1); part 1: Huffman weights (32 threads, grid n_blocks).  Two launches so
 // that the Huffman branch and the FSE branch of the zstd stage can run on different streams.
@@ -36,18 +57,95 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
         if (blockIdx.x >= J.n_blocks) return;
         const BlockDesc& B = J.blocks[blockIdx.x];
         if (B.btype != BT_COMPRESSED || B.lit_type != LT_HUF) return;
-        // stage the tree description (<= 129 bytes) in shared memory: the weight decode is a serial chain of bit reads
-        __shared__ __align__(16) uint8_t tree[176];
+        // The weight decode is a serial chain (FSE with two interleaved states): everything it touches sits in shared memory
+        // (tree description, packed table cells, weights) and it reads bits through a register window; what is not a
+        // chain (staging, zeroing, validation sums, the write-back) is done by the whole warp.  (A thread-local version
+        // -- zstd_core.cuh's huf_read_weights, still the host/test restatement -- took 67 us per tree, this one ~12.)
+        __shared__ __align__(16) uint8_t tree[192];         // the tree description (<= 129 bytes), zero padded
+        __shared__ __align__(16) uint32_t sb[48];           // the FSE bitstream of the weights behind 16 zero bytes
+        __shared__ uint32_t cells[64];                      // symbol | bits << 8 | base << 16
+        __shared__ uint8_t cell_sym[64];
+        __shared__ __align__(4) uint8_t w[256];
+        __shared__ int s_n, s_mode, s_start, s_nbytes, s_al;
         const int l1 = threadIdx.x;
         const uint32_t tsize = B.lit_csize < 130u ? B.lit_csize : 130u;
-        for (uint32_t i = l1; i < 176; i += 32) tree[i] = i < tsize ? J.comp[B.src_off + B.lit_src + i] : 0;
+        for (uint32_t i = l1; i < 192; i += 32) tree[i] = i < tsize ? J.comp[B.src_off + B.lit_src + i] : 0;
+        for (uint32_t i = l1; i < 64; i += 32) ((uint32_t*)w)[i] = 0;
+        for (uint32_t i = l1; i < 48; i += 32) sb[i] = 0;
+        if (l1 == 0) { s_n = 0; s_mode = -1; }
         __syncwarp();
+        const uint32_t h = tsize ? tree[0] : 0u;
+        if (l1 == 0 && tsize) {
+            if (h >= 128) { if (1u + (h - 127u + 1u) / 2u <= tsize) { s_mode = 0; s_n = (int)h - 127; } }
+            else if (h >= 2 && 1u + h <= tsize) {
+                int16_t norm[16];
+                uint16_t cnt[16];
+                int al = 0;
+                // weights are 0..11: at most 13 symbols, at most 64 cells
+                const uint32_t used = zc::fse_read_ncount(tree + 1, h, 12, zc::MAX_AL_HUF, norm, &al);
+                if (used != 0 && used < h &&
+                    zc::fse_build(norm, 12, al, cell_sym, cnt, [&](int i, int sy, int nb, int base) { cells[i] = (uint32_t)sy | ((uint32_t)nb << 8) | ((uint32_t)base << 16); })) {
+                    s_mode = 1; s_start = 1 + (int)used; s_nbytes = (int)(h - used); s_al = al;
+                }
+            }
+        }
+        __syncwarp();
+        int n = 0;
+        bool good = s_mode >= 0;
+        if (s_mode == 0) {
+            n = s_n;
+            for (int i = l1; i < n; i += 32) { const uint8_t b = tree[1 + (i >> 1)]; w[i] = (i & 1) ? (b & 15) : (b >> 4); }
+        } else if (s_mode == 1) {
+            for (int i = l1; i < s_nbytes; i += 32) ((uint8_t*)sb)[16 + i] = tree[s_start + i];
+            __syncwarp();
+            if (l1 == 0) {
+                const uint8_t last = ((const uint8_t*)sb)[16 + s_nbytes - 1];
+                bool ok = last != 0;
+                if (ok) {
+                    SmemBits rd;
+                    rd.init(sb, 128 + 8 * (s_nbytes - 1) + zc::highbit32(last), 128);
+                    uint32_t s1 = rd.read(s_al), s2 = rd.read(s_al);
+                    ok = rd.remaining() >= 0;
+                    int k = 0;
+                    while (ok) {
+                        if (k > 253) { ok = false; break; }
+                        const uint32_t c1 = cells[s1];
+                        w[k++] = (uint8_t)c1;
+                        s1 = (c1 >> 16) + rd.read((int)((c1 >> 8) & 0xFF));
+                        if (rd.remaining() < 0) { w[k++] = (uint8_t)cells[s2]; break; }
+                        if (k > 253) { ok = false; break; }
+                        const uint32_t c2 = cells[s2];
+                        w[k++] = (uint8_t)c2;
+                        s2 = (c2 >> 16) + rd.read((int)((c2 >> 8) & 0xFF));
+                        if (rd.remaining() < 0) { w[k++] = (uint8_t)cells[s1]; break; }
+                    }
+                    s_n = ok ? k : 0;
+                }
+                if (!ok) s_n = 0;
+            }
+            __syncwarp();
+            n = s_n;
+            good = n > 0;
+        }
+        __syncwarp();
+        // validation: weights <= 11, the sum of 2^(w-1) is short of a power of two by a power of two (the implied last weight)
+        uint32_t tot = 0, bad = 0;
+        for (int i = l1; i < n; i += 32) { const uint32_t x = w[i]; if (x > (uint32_t)zc::HUF_MAX_BITS) bad = 1; else if (x) tot += 1u << (x - 1); }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { tot += __shfl_xor_sync(0xFFFFFFFFu, tot, d); bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, d); }
+        int ns = 0, mb = 0;
+        if (good && !bad && tot != 0) {
+            mb = zc::highbit32(tot) + 1;
+            const uint32_t left = (1u << mb) - tot;
+            if (mb <= zc::HUF_MAX_BITS && (left & (left - 1)) == 0) {
+                if (l1 == 0) w[n] = (uint8_t)(zc::highbit32(left) + 1);
+                ns = n + 1;
+            }
+        }
+        __syncwarp();
+        uint32_t* gw = (uint32_t*)(J.huf_weights + (size_t)B.huf_slot * 256);
+        for (int i = l1; i < 64; i += 32) gw[i] = ((const uint32_t*)w)[i];
         if (l1 != 0) return;
-        uint8_t w[256];
-        int mb = 0;
-        int ns = zc::huf_read_weights(tree, tsize, w, &mb);
-        uint8_t* gw = J.huf_weights + (size_t)B.huf_slot * 256;
-        for (int i = 0; i < 256; i += 4) *(uint32_t*)(gw + i) = w[i] | (w[i + 1] << 8) | (w[i + 2] << 16) | ((uint32_t)w[i + 3] << 24);
         J.huf_meta[(size_t)B.huf_slot * 2] = (uint8_t)(ns ? ns - 1 : 0);
         J.huf_meta[(size_t)B.huf_slot * 2 + 1] = (uint8_t)(ns ? mb : 0);
         if (ns == 0) flag_error(J, B.frame, zc::E_HUF_TREE);
@@ -137,26 +235,6 @@ __device__ __forceinline__ uint32_t encode_off(RepSym r) {
     return r.src < 0 ? r.val : (OFF_SYMBOLIC | ((uint32_t)r.src << 29) | (r.val & 0x1FFFFFFFu));
 }
 
-// Backward bit reader over a shared-memory image of the bitstream (32-bit words; >= 16 zero bytes below bit 0).
-// 64-bit register window, refilled 32 bits at a time; read(k) for k <= 32.
-struct SmemBits {
-    const uint32_t* sw;
-    uint64_t w;          // stream bits [32*qi, 32*qi + 64)
-    int qi, rr;          // rr = x - 32*qi, position of the next unread bit inside the window (kept in [32, 64] before a read)
-    int x_zero;          // smem bit position of stream bit 0
-    __device__ __forceinline__ void init(const uint32_t* words, int x, int xz) {
-        sw = words; x_zero = xz;
-        qi = (x >> 5) - 1;
-        rr = x - (qi << 5);
-        w = ((uint64_t)sw[qi + 1] << 32) | sw[qi];
-    }
-    __device__ __forceinline__ uint32_t read(int k) {
-        if (rr < k) { w = (w << 32) | sw[--qi]; rr += 32; }
-        rr -= k;
-        return k ? (uint32_t)(w >> rr) & (k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u)) : 0u;
-    }
-    __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
-};
 
 
 // The sequence loop, written once over a reader type: shared-memory window (common) or global memory (huge sections).
