@@ -237,62 +237,47 @@ __device__ __forceinline__ uint32_t encode_off(RepSym r) {
 
 
 
-// The sequence loop, written once over a reader type: shared-memory window (common) or global memory (huge sections).
+// The tANS walk, written once over a reader type: shared-memory window (common) or global memory (huge sections).
+// PRODUCER side of k_decode_sequences: decodes `cnt` sequences into raw (offset value, match length, literal length)
+// triples in shared memory; the three states live in the caller's registers across batches.
 template <class RD>
-__device__ __forceinline__ bool seq_loop(RD& rd, const SeqCell* TLL, const SeqCell* TOF, const SeqCell* TML, const int* al, uint32_t n,
-                                         uint32_t bi, uint32_t lit_regen, uint4* rec, RepSym* rep, uint32_t& litpos, uint32_t& outpos) {
-    (void)lit_regen;
-    bool bad = false;
-    uint32_t sLL = rd.read(al[0]), sOF = rd.read(al[1]), sML = rd.read(al[2]);
-    for (uint32_t i = 0; i < n; i++) {
+__device__ __forceinline__ void seq_produce(RD& rd, const SeqCell* TLL, const SeqCell* TOF, const SeqCell* TML, uint32_t& sLL, uint32_t& sOF,
+                                            uint32_t& sML, uint32_t cnt, bool last_batch, uint32_t* r_ov, uint32_t* r_ml, uint32_t* r_ll) {
+    for (uint32_t j = 0; j < cnt; j++) {
         const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];
-        const uint32_t ov = cOF.base_value + rd.read(cOF.add_bits);
+        r_ov[j] = cOF.base_value + rd.read(cOF.add_bits);
         const uint32_t xb = rd.read(cML.add_bits + cLL.add_bits);        // ML then LL extra bits, one read
-        const uint32_t ml = cML.base_value + (xb >> cLL.add_bits);
-        const uint32_t ll = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));
-        RepSym off;
-        if (ov > 3) {
-            off.src = -1; off.val = ov - 3;
-            rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-        } else {
-            const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
-            if (idx == 0) { off = rep[0]; }
-            else if (idx == 1) { off = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-            else if (idx == 2) { off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-            else {
-                off = rep[0];
-                if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; } else off.val += 1;
-                rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-            }
-        }
-        if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
-        if (i + 1 < n) {                                     // LL, ML, OF state bits (<= 27) in one read
+        r_ml[j] = cML.base_value + (xb >> cLL.add_bits);
+        r_ll[j] = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));
+        if (!(last_batch && j + 1 == cnt)) {                             // LL, ML, OF state bits (<= 27) in one read
             const uint32_t sb = rd.read(cLL.nb + cML.nb + cOF.nb);
             sOF = cOF.next_base + (sb & ((1u << cOF.nb) - 1u));
             sML = cML.next_base + ((sb >> cOF.nb) & ((1u << cML.nb) - 1u));
             sLL = cLL.next_base + (sb >> (cOF.nb + cML.nb));
         }
-        rec[0] = make_uint4(ll, ml, encode_off(off), litpos);
-        rec[1] = make_uint4(outpos, bi, 0u, 0u);
-        rec += 2;
-        litpos += ll;
-        outpos += ll + ml;
-        if (outpos > BLOCK_MAX) { bad = true; break; }
     }
-    return bad;
 }
 
-__global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
+// k_decode_sequences: one CTA of two warps per block.  Warp 0, lane 0 is the PRODUCER: the serial chain of the three
+// interleaved tANS states and nothing else (every instruction on it costs ~6 cycles of a lone dependent warp: ncu shows
+// `wait` as the top stall, profiles/r1_fse_stage_k_decode_sequences.txt).  Warp 1 is the CONSUMER, one batch of 32
+// sequences behind through a double buffer in shared memory: repeat-offset bookkeeping (symbolic, so blocks decode
+// independently), literal / output positions by a shuffle scan, and the 32-byte sequence records with coalesced stores.
+constexpr uint32_t SEQ_BATCH = 32;
+
+__global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
     NAF_DYN_SMEM(uint32_t, sbits);                       // staged bitstream: J.seq_stage_bytes (job maximum, capped)
     __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
+    __shared__ uint32_t r_ov[2][SEQ_BATCH], r_ml[2][SEQ_BATCH], r_ll[2][SEQ_BATCH];
+    __shared__ int s_left;
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
     if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
     if (J.frame_bad[B.frame]) return;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     BlockState& S = J.bstate[bi];
     const uint8_t* src = J.comp + B.src_off;
-    if (S.seq_bits_off >= B.src_size) { if (lane == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    if (S.seq_bits_off >= B.src_size) { if (tid == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
     const uint32_t nbytes = B.src_size - S.seq_bits_off;
     const uint8_t* g = src + S.seq_bits_off;
     const bool staged = nbytes + 48 <= J.seq_stage_bytes;
@@ -302,42 +287,96 @@ __global__ void __launch_bounds__(32) k_decode_sequences(JobDev J) {
     for (int k = 0; k < 3; k++) {
         al[k] = J.table_al[B.tbl[k]];
         const uint2* T = (const uint2*)(J.tables + (size_t)B.tbl[k] * FSE_SLOT_CELLS);
-        for (int i = lane; i < (1 << al[k]); i += 32) ((uint2*)stab[k])[i] = T[i];
+        for (int i = tid; i < (1 << al[k]); i += 64) ((uint2*)stab[k])[i] = T[i];
     }
     if (staged) {
         const uint4* gbase = (const uint4*)(g - a);
         const uint32_t nchunks = (a + nbytes + 15) >> 4;
-        for (uint32_t c = lane; c < nchunks; c += 32) ((uint4*)sbits)[1 + c] = gbase[c];
-        __syncwarp();
-        if ((uint32_t)lane < 16 + a) ((uint8_t*)sbits)[lane] = 0;
+        for (uint32_t c = tid; c < nchunks; c += 64) ((uint4*)sbits)[1 + c] = gbase[c];
     }
-    __syncwarp();
-    if (lane != 0) return;
     const uint8_t last = g[nbytes - 1];
-    if (last == 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }     // (uniform)
+    __syncthreads();
+    if (staged && (uint32_t)tid < 16 + a) ((uint8_t*)sbits)[tid] = 0;
+    if (tid == 0) s_left = 0;
+    __syncthreads();
     const int P0 = 8 * (int)(nbytes - 1) + zc::highbit32(last);
-    const SeqCell* TLL = stab[0];
-    const SeqCell* TOF = stab[1];
-    const SeqCell* TML = stab[2];
-    RepSym rep[3] = {{0, 0}, {1, 0}, {2, 0}};
-    uint32_t litpos = 0, outpos = 0;
     const uint32_t n = B.n_seq, base = B.seq_base;
-    uint4* rec = (uint4*)(J.seq + base);
-    bool bad = false;
-    int left;
-    if (staged) {
-        SmemBits rd;
-        const int xz = (int)(16 + a) * 8;
-        rd.init(sbits, xz + P0, xz);
-        bad = seq_loop(rd, TLL, TOF, TML, al, n, bi, B.lit_regen, rec, rep, litpos, outpos);
-        left = rd.remaining();
-    } else {
-        BackBits rd;
-        rd.init(g, nbytes);
-        bad = seq_loop(rd, TLL, TOF, TML, al, n, bi, B.lit_regen, rec, rep, litpos, outpos);
-        left = (int)rd.P;
+    const uint32_t nbatch = (n + SEQ_BATCH - 1) / SEQ_BATCH;
+    if (warp == 0) {
+        // ---- producer ---------------------------------------------------------------------------------------------
+        SmemBits rs{};
+        BackBits rg{};
+        uint32_t sLL = 0, sOF = 0, sML = 0;
+        if (lane == 0) {
+            if (staged) { const int xz = (int)(16 + a) * 8; rs.init(sbits, xz + P0, xz); sLL = rs.read(al[0]); sOF = rs.read(al[1]); sML = rs.read(al[2]); }
+            else { rg.init(g, nbytes); sLL = rg.read(al[0]); sOF = rg.read(al[1]); sML = rg.read(al[2]); }
+        }
+        for (uint32_t k = 0; k < nbatch; k++) {
+            const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
+            if (lane == 0) {
+                if (staged) seq_produce(rs, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
+                else seq_produce(rg, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
+                if (k + 1 == nbatch) s_left = staged ? rs.remaining() : (int)rg.P;
+            }
+            __syncthreads();                             // batch k is ready; the consumer has finished batch k - 1
+        }
+        return;
     }
-    if (bad || left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    // ---- consumer -------------------------------------------------------------------------------------------------
+    RepSym rep[3] = {{0, 0}, {1, 0}, {2, 0}};              // (meaningful in lane 0 only)
+    uint32_t litpos = 0, outpos = 0;                        // running totals, uniform over the warp
+    bool bad = false;
+    uint4* rec = (uint4*)(J.seq + base);
+    for (uint32_t k = 0; k < nbatch; k++) {
+        __syncthreads();
+        const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
+        uint32_t* b_ov = r_ov[k & 1];
+        const uint32_t ll = (uint32_t)lane < cnt ? r_ll[k & 1][lane] : 0u, ml = (uint32_t)lane < cnt ? r_ml[k & 1][lane] : 0u;
+        if (lane == 0) {
+            // repeat offsets: a chain over the sequences, but a short one; the encoded offset replaces the raw value
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t ov = b_ov[j];
+                RepSym off;
+                if (ov > 3) {
+                    off.src = -1; off.val = ov - 3;
+                    rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+                } else {
+                    const uint32_t idx = ov - 1 + (r_ll[k & 1][j] == 0 ? 1u : 0u);
+                    if (idx == 0) { off = rep[0]; }
+                    else if (idx == 1) { off = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+                    else if (idx == 2) { off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+                    else {
+                        off = rep[0];
+                        if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; } else off.val += 1;
+                        rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
+                    }
+                }
+                if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
+                b_ov[j] = encode_off(off);
+            }
+        }
+        __syncwarp();
+        // positions: exclusive scans of ll and ll + ml over the batch, on top of the running totals
+        uint32_t il = ll, io = ll + ml;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d), to = __shfl_up_sync(0xFFFFFFFFu, io, d);
+            if (lane >= d) { il += tl; io += to; }
+        }
+        if ((uint32_t)lane < cnt) {
+            const uint32_t lp = litpos + il - ll, op = outpos + io - (ll + ml);
+            rec[2 * (k * SEQ_BATCH + lane)] = make_uint4(ll, ml, b_ov[lane], lp);
+            rec[2 * (k * SEQ_BATCH + lane) + 1] = make_uint4(op, bi, 0u, 0u);
+        }
+        litpos += __shfl_sync(0xFFFFFFFFu, il, 31);
+        const uint32_t otot = __shfl_sync(0xFFFFFFFFu, io, 31);
+        if (otot > BLOCK_MAX || outpos + otot > BLOCK_MAX) bad = true;      // (match lengths are < 2^17 each: no wrap within a batch)
+        outpos += otot;
+    }
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane != 0) return;
+    if (bad || s_left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
     if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
     uint32_t regen = outpos + (B.lit_regen - litpos);
     if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
@@ -1528,7 +1567,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) cudaEventRecord(join, st2);
     else ev->mark();                                  // serial (profiled) order: the Huffman branch first
     NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
-    NAF_LAUNCH(k_decode_sequences, J.n_blocks, 32, J.seq_stage_bytes, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_decode_sequences, J.n_blocks, 64, J.seq_stage_bytes, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++; ev->mark();
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
