@@ -365,7 +365,8 @@ def main():
         ctx.time_runs(3, True)
         ms1 = ctx.time_runs(20, True) / 20
         s1 = ctx.stats()
-        single = {"device_us": ms1 * 1e3, "ascii_GBps": s1.ascii_bytes / (ms1 * 1e-3) / 1e9, "kernel_launches": s1.kernel_launches,
+        st1 = {nm: round(ms, 4) for nm, ms in ctx.profile_stages()}       # serial: the two branches do not overlap here
+        single = {"device_us": ms1 * 1e3, "ascii_GBps": s1.ascii_bytes / (ms1 * 1e-3) / 1e9, "kernel_launches": s1.kernel_launches, "stage_ms_serial": st1,
                   "algorithmic_bytes": s1.algorithmic_bytes, "frac_of_hbm_peak": s1.algorithmic_bytes / (ms1 * 1e-3) / 1e9 / peak}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample, 1 thread ------------------------------------------------------
