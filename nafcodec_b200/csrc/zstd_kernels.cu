@@ -46,6 +46,66 @@ struct SmemBits {
     __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
 };
 
+// FSE decode table by a whole warp (RFC 8878 4.1.1; the serial restatement is zc::fse_build in zstd_core.cuh).
+//   A  low-probability symbols (-1) take the top cells in symbol order; counts and cumulative counts of the others
+//   B  the serial "spread" visits positions (j * step) & mask, j = 0, 1, ..., skipping those >= high: the t-th placement
+//      is the t-th position of that sequence below `high` (ballot ranks), and it belongs to the symbol whose cumulative
+//      count range holds t (binary search)
+//   C  cell i continues its symbol's state counter: start count + the number of lower cells with the same symbol
+//      (__match_any_sync ranks inside 32 consecutive cells, running per-symbol counters across them)
+template <class Emit>
+__device__ __forceinline__ bool fse_build_warp(const int16_t* norm, int max_symbol, int al, uint8_t* cell_sym, uint16_t* cnt, uint16_t* cum,
+                                               int lane, Emit emit) {
+    const int size = 1 << al, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    const uint32_t lt = (1u << lane) - 1u;
+    int n_low = 0, reg_total = 0;
+    for (int s0 = 0; s0 <= max_symbol; s0 += 32) {
+        const int s = s0 + lane;
+        const int nv = s <= max_symbol ? (int)norm[s] : 0;
+        const bool low = nv == -1;
+        const uint32_t lb = __ballot_sync(0xFFFFFFFFu, low);
+        if (low) cell_sym[size - 1 - (n_low + __popc(lb & lt))] = (uint8_t)s;
+        const int c = nv > 0 ? nv : 0;
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+        if (s <= max_symbol) { cnt[s] = (uint16_t)(low ? 1 : c); cum[s] = (uint16_t)(reg_total + inc - c); }
+        reg_total += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        n_low += __popc(lb);
+    }
+    if (lane == 0) cum[max_symbol + 1] = (uint16_t)reg_total;
+    __syncwarp();
+    if (reg_total + n_low != size) return false;           // (the serial spread would not come back to position 0)
+    const int high = size - n_low;
+    int placed = 0;
+    for (int j0 = 0; j0 < size; j0 += 32) {
+        const int p = ((j0 + lane) * step) & mask;
+        const bool valid = p < high;
+        const uint32_t vb = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid) {
+            const int t = placed + __popc(vb & lt);
+            int lo = 0, hi = max_symbol + 1;                 // cum[lo] <= t < cum[hi]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)cum[mid] <= t) lo = mid; else hi = mid; }
+            cell_sym[p] = (uint8_t)lo;
+        }
+        placed += __popc(vb);
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < size; i0 += 32) {
+        const int i = i0 + lane;
+        const int s = cell_sym[i];
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, s);
+        const int r = __popc(same & lt);
+        const uint32_t nx = (uint32_t)cnt[s] + (uint32_t)r;
+        __syncwarp();
+        if (r == 0) cnt[s] = (uint16_t)(cnt[s] + __popc(same));
+        __syncwarp();
+        const int nb = al - zc::highbit32(nx);
+        emit(i, s, nb, (int)((nx << nb) - (uint32_t)size));
+    }
+    return true;
+}
+
 // k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
 // part 0: FSE tables (32 threads, grid n_blocks + 1); part 1: Huffman weights (32 threads, grid n_blocks).  Two launches so
 // that the Huffman branch and the FSE branch of the zstd stage can run on different streams.
@@ -210,18 +270,18 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
         if (lane == 0) flag_error(J, frame, zc::E_FSE_TABLE);
         return;
     }
-    if (lane < 3 && mode[lane] >= 0) {
-        int k = lane;
+    __shared__ uint16_t cum[60];
+    for (int k = 0; k < 3; k++) {                          // (mode, al, norm are uniform: shared memory)
+        if (mode[k] < 0) continue;
         SeqCell* T = J.tables + (size_t)slot[k] * FSE_SLOT_CELLS;
         if (mode[k] == SM_RLE) {
-            T[0] = zc::make_seq_cell(k, rle_sym[k], 0, 0);
-            J.table_al[slot[k]] = 0;
+            if (lane == 0) { T[0] = zc::make_seq_cell(k, rle_sym[k], 0, 0); J.table_al[slot[k]] = 0; }
         } else {
-            bool good = zc::fse_build(norm[k], zc::kind_max_symbol(k), al[k], cell_sym[k], cnt[k],
-                                      [&](int i, int s, int nb, int base) { T[i] = zc::make_seq_cell(k, s, nb, base); });
-            J.table_al[slot[k]] = (uint8_t)al[k];
-            if (!good) flag_error(J, frame, zc::E_FSE_TABLE);
+            const bool good = fse_build_warp(norm[k], zc::kind_max_symbol(k), al[k], cell_sym[k], cnt[k], cum, lane,
+                                             [&](int i, int s, int nb, int base) { T[i] = zc::make_seq_cell(k, s, nb, base); });
+            if (lane == 0) { J.table_al[slot[k]] = (uint8_t)al[k]; if (!good) flag_error(J, frame, zc::E_FSE_TABLE); }
         }
+        __syncwarp();
     }
 }
 

@@ -74,6 +74,11 @@ template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d,
 }
 template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int x, int = 32) { return __shfl_sync(m, v, emul_lane() ^ x); }
 static inline unsigned __ballot_sync(unsigned, int p) { return emul::warp_ballot(p); }
+template <class T> static inline unsigned __match_any_sync(unsigned m, T v) {       // lanes holding the same value (all 32 lanes must call)
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++) { T x = __shfl_sync(m, v, l); if (x == v) r |= 1u << l; }
+    return r;
+}
 static inline int __any_sync(unsigned, int p) { return emul::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned m, int p) { return emul::warp_ballot(!p) == 0; (void)m; }
 static inline unsigned __activemask() { return emul::warp_ballot(1); }
