@@ -72,6 +72,21 @@ pub struct nafgpu_result {
     pub _pad: i32,
 }
 
+/// `nafgpu_text` (include/nafgpu.h): FASTA / FASTQ text of one archive in pinned host memory owned by the context.
+#[repr(C)]
+pub struct nafgpu_text {
+    pub data: *const u8,
+    pub size: u64,
+    pub format: i32,
+    pub status: i32,
+    pub first_bad_record: u64,
+}
+
+pub const NAFGPU_TEXT_AUTO: c_int = 0;
+pub const NAFGPU_TEXT_FASTA: c_int = 1;
+pub const NAFGPU_TEXT_FASTQ: c_int = 2;
+pub const NAFGPU_LINE_LENGTH_FROM_HEADER: u64 = u64::MAX;
+
 #[repr(C)]
 pub struct nafgpu_ctx {
     _private: [u8; 0],
@@ -96,5 +111,15 @@ extern "C" {
         n: u32,
         want: u32,
         out: *mut nafgpu_result,
+    ) -> c_int;
+    /// prepare + run + FASTA/FASTQ formatting on the device (what a `Decoder::to_fasta` helper would call)
+    pub fn nafgpu_format_batch(
+        ctx: *mut nafgpu_ctx,
+        archives: *const nafgpu_archive,
+        n: u32,
+        want: u32,
+        format: c_int,
+        line_length: u64,
+        out: *mut nafgpu_text,
     ) -> c_int;
 }
