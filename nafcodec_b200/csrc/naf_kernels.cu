@@ -267,7 +267,7 @@ __device__ __forceinline__ uint32_t spread4_x20(uint32_t q) {        // 4 mask b
     return ((q * 0x00204081u) & 0x01010101u) << 5;
 }
 
-__global__ void __launch_bounds__(1024) k_unpack(uint8_t* arena, const NafDev* archives) {
+__global__ void __launch_bounds__(CHUNK_WORDS) k_unpack(uint8_t* arena, const NafDev* archives) {
     const NafDev& A = archives[blockIdx.y];
     if (!(A.has & HAS_SEQUENCE) || A.seq_type > 1 || blockIdx.x >= A.n_chunks) return;
     __shared__ uint32_t wp[32], wp2[32];
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(1024) k_unpack(uint8_t* arena, const NafDev* a
         uint32_t b = __ballot_sync(FULL, __popc(w) & 1);
         if (lane == 0) wp[warp] = __popc(b) & 1;
         __syncthreads();
-        if (warp == 0) { uint32_t bb = __ballot_sync(FULL, wp[lane]); if (lane == 0) wball = bb; }
+        if (warp == 0) { uint32_t bb = __ballot_sync(FULL, lane < (int)(CHUNK_WORDS / 32) ? wp[lane] : 0u); if (lane == 0) wball = bb; }
         __syncthreads();
         // carry into this chunk = parity of all toggles in the chunks before it
         const uint32_t* cpar = (const uint32_t*)(arena + A.chunk_par_off);
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(1024) k_unpack(uint8_t* arena, const NafDev* a
         const uint32_t cb = __ballot_sync(FULL, cp & 1);
         if (lane == 0) wp2[warp] = __popc(cb) & 1;
         __syncthreads();
-        if (warp == 0) { uint32_t bb = __ballot_sync(FULL, wp2[lane]); if (lane == 0) cball = bb; }
+        if (warp == 0) { uint32_t bb = __ballot_sync(FULL, lane < (int)(CHUNK_WORDS / 32) ? wp2[lane] : 0u); if (lane == 0) cball = bb; }
         __syncthreads();
         uint32_t carry = (__popc(cball) & 1) ^ (__popc(wball & ((1u << warp) - 1u)) & 1) ^ (__popc(b & ((1u << lane) - 1u)) & 1);
         mask = carry ? ~m : m;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(1024) k_unpack(uint8_t* arena, const NafDev* a
 
 // k_text_mask: protein / text archives with a mask section: mask_sequence lower-cases A-Z in place (no type check
 // in the reference).  Thread = 32 bytes.
-__global__ void __launch_bounds__(1024) k_text_mask(uint8_t* arena, const NafDev* archives) {
+__global__ void __launch_bounds__(CHUNK_WORDS) k_text_mask(uint8_t* arena, const NafDev* archives) {
     const NafDev& A = archives[blockIdx.y];
     if (!(A.has & HAS_SEQUENCE) || !(A.has & HAS_MASK) || A.seq_type <= 1 || blockIdx.x >= A.n_chunks) return;
     const NafCounts* counts = (const NafCounts*)(arena + A.counts_off);
@@ -436,8 +436,8 @@ int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives
         ev->mark();
     } else { ev->mark(); ev->mark(); }
     if (max_chunks > 0) {
-        NAF_LAUNCH(k_unpack, dim3(max_chunks, n_archives), 1024, 0, st, arena, archives); launches++;
-        if (any_text_mask) { NAF_LAUNCH(k_text_mask, dim3(max_chunks, n_archives), 1024, 0, st, arena, archives); launches++; }
+        NAF_LAUNCH(k_unpack, dim3(max_chunks, n_archives), CHUNK_WORDS, 0, st, arena, archives); launches++;
+        if (any_text_mask) { NAF_LAUNCH(k_text_mask, dim3(max_chunks, n_archives), CHUNK_WORDS, 0, st, arena, archives); launches++; }
     }
     ev->mark();
     if (max_text_bytes > 0) {
