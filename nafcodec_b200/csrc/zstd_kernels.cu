@@ -1131,19 +1131,27 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     // one literal run (a few hundred bytes) per group of LZLIT_G lanes
     const int grp = tid / LZLIT_G, lane = tid % LZLIT_G, ng = nt / LZLIT_G;
     const uint32_t n = B.n_seq, base = B.seq_base;
+    // the record of the NEXT run is loaded before the copy of this one: a run costs two dependent latencies (record, then
+    // literals), and the copy hides the first of them
+    auto fetch = [&](uint32_t i, uint32_t& lp, uint32_t& op, uint32_t& ll, uint32_t& ml) {
+        if (i > n) return;
+        const uint32_t j = i < n ? i : n - 1;
+        const uint4 r = *(const uint4*)&J.seq[base + j];                 // ll, ml, off, litpos
+        ll = r.x; ml = r.y; lp = r.w; op = J.seq[base + j].outpos;
+    };
+    uint32_t lp = 0, op = 0, ll = 0, ml = 0;
+    fetch((uint32_t)grp, lp, op, ll, ml);
     for (uint32_t i = grp; i <= n; i += ng) {
-        uint32_t lp, op, ll;
+        uint32_t nlp = 0, nop = 0, nll = 0, nml = 0;
+        fetch(i + ng, nlp, nop, nll, nml);
         if (i < n) {
-            lp = J.seq[base + i].litpos; op = J.seq[base + i].outpos; ll = J.seq[base + i].ll;
             if (lane == 0) J.seq[base + i].match_pos = S.out_off + op + ll;     // absolute destination of the match
-        } else {                                       // literals after the last sequence
-            uint32_t j = base + n - 1;
-            lp = J.seq[j].litpos + J.seq[j].ll;
-            op = J.seq[j].outpos + J.seq[j].ll + J.seq[j].ml;
-            ll = B.lit_regen - lp;
+        } else {                                       // literals after the last sequence (the record is that of sequence n - 1)
+            lp += ll; op += ll + ml; ll = B.lit_regen - lp;
         }
         if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += LZLIT_G) out[op + k] = rle;
         else copy_g2g(out + op, lsrc + lp, ll, lane, LZLIT_G);
+        lp = nlp; op = nop; ll = nll; ml = nml;
     }
 }
 
