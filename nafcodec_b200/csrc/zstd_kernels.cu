@@ -1071,10 +1071,6 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
 // --------------------------------------------------------------------------------------------------------------
 // k_lz_literals: one CTA per block.  Raw / RLE blocks and literal-only blocks are plain copies or fills; for
 // blocks with sequences every literal run goes to its final position and match destinations are published.
-__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, int tid, int nthreads) {
-    for (uint32_t i = tid; i < n; i += nthreads) d[i] = s[i];
-}
-
 // Cooperative global -> global copy of n bytes with arbitrary alignments by `nlanes` threads (a warp or a CTA):
 // destination-aligned 16-byte stores; each is assembled from the two aligned 16-byte source words that span it.
 // The source must be readable up to 31 bytes past its end (staging buffers are padded).
@@ -1102,8 +1098,10 @@ __device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_
 
 constexpr int LZLIT_G = 32;                        // lanes per literal run (8-lane groups, four runs in flight per warp, measured no faster)
 constexpr int LZLIT_SPLIT = 4;                     // CTAs that share the runs of one block
+constexpr uint32_t LZLIT_LONG = 4096;              // longer runs are copied by the whole CTA (at most 32 per block)
 
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
+    __shared__ uint32_t lq_n, lq_lp[40], lq_op[40], lq_ll[40];
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
     if (J.frame_bad[B.frame]) return;
@@ -1112,7 +1110,7 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     // gridDim.y CTAs share a block: the time of this kernel is the time of the block with the most sequences (one literal
     // run per warp and step, two dependent latencies each), so the runs of a block are dealt out to several CTAs
     const int tid = threadIdx.x + blockIdx.y * blockDim.x, nt = blockDim.x * gridDim.y;
-    if (B.btype == BT_RAW) { copy_bytes(out, J.comp + B.src_off, B.src_size, tid, nt); return; }
+    if (B.btype == BT_RAW) { copy_g2g(out, J.comp + B.src_off, B.src_size, tid, nt); return; }   // (COMP_PAD covers the over-read)
     if (B.btype == BT_RLE) {
         uint8_t v = J.comp[B.src_off];
         for (uint32_t i = tid; i < B.src_size; i += nt) out[i] = v;
@@ -1131,6 +1129,8 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     // one literal run (a few hundred bytes) per group of LZLIT_G lanes
     const int grp = tid / LZLIT_G, lane = tid % LZLIT_G, ng = nt / LZLIT_G;
     const uint32_t n = B.n_seq, base = B.seq_base;
+    if (threadIdx.x == 0) lq_n = 0;
+    __syncthreads();
     // the record of the NEXT run is loaded before the copy of this one: a run costs two dependent latencies (record, then
     // literals), and the copy hides the first of them
     auto fetch = [&](uint32_t i, uint32_t& lp, uint32_t& op, uint32_t& ll, uint32_t& ml) {
@@ -1149,10 +1149,14 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         } else {                                       // literals after the last sequence (the record is that of sequence n - 1)
             lp += ll; op += ll + ml; ll = B.lit_regen - lp;
         }
-        if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += LZLIT_G) out[op + k] = rle;
+        if (ll > LZLIT_LONG && B.lit_type != LT_RLE) {                    // a long run (often the literals after the last sequence of a block
+            if (lane == 0) { const uint32_t q = atomicAdd(&lq_n, 1u); lq_lp[q] = lp; lq_op[q] = op; lq_ll[q] = ll; }   // with few sequences): whole CTA
+        } else if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += LZLIT_G) out[op + k] = rle;
         else copy_g2g(out + op, lsrc + lp, ll, lane, LZLIT_G);
         lp = nlp; op = nop; ll = nll; ml = nml;
     }
+    __syncthreads();
+    for (uint32_t q = 0; q < lq_n; q++) copy_g2g(out + lq_op[q], lsrc + lq_lp[q], lq_ll[q], (int)threadIdx.x, (int)blockDim.x);
 }
 
 // --------------------------------------------------------------------------------------------------------------
