@@ -2,15 +2,19 @@
 // nafcodec decode path (the reference reaches it through zstd::stream::read::Decoder,
 // nafcodec/src/decoder/mod.rs:32,221-223).  No library decompressor, no CPU fallback.
 //
-// Stage order for one job (any number of frames = NAF sections, possibly of many archives):
-//   k_build_tables      per block: parse FSE table descriptions, build LL/OF/ML decode tables
-//   k_decode_sequences  per block: serial tANS decode of (ll, ml, offset) with a symbolic repeat-offset state
-//   k_frame_scan        per frame: block output offsets (prefix sum) + repeat-offset carry across blocks
-//   k_huf_decode        per block: Huffman literals (1/4 streams), straight into the output when n_seq == 0
-//   k_lz_literals       per block: raw/RLE blocks, literal runs -> output positions
-//   k_lz_first          per match: round 1 of the dependency-resolving match execution (+ redirect through copies)
-//   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, grid barrier between rounds
-//   k_lz_finish         per frame: ordered finisher when the rounds stop making progress (text-like sections)
+// One job = any number of frames (NAF sections, possibly of many archives).  Two branches run on two streams and join
+// before the LZ stage:
+//   FSE branch      k_build_tables<0>   per block: parse the FSE table descriptions, build LL/OF/ML decode tables (whole warp)
+//                   k_decode_sequences  per block: tANS decode of (ll, ml, offset), producer / consumer warps, symbolic repeat offsets
+//                   k_frame_scan        per frame: block output offsets (prefix sum) + repeat-offset carry across blocks
+//   Huffman branch  k_build_tables<1>   per block: Huffman tree description -> 256 weights, once per tree
+//                   k_huf_tables        per tree used by long streams: decode / boundary / 3-symbol tables, once
+//                   k_huf_decode<512|128> per bitstream: intra-stream parallel decode into the literal staging buffer
+//   LZ stage        k_lz_literals       per block: raw / RLE blocks, literal runs -> their output positions
+//                   k_lz_first          per match: round 1 of the dependency-resolving match execution (+ redirect through copies)
+//                   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, one grid barrier per round
+//                   k_lz_finish, k_lz_finish2  after a hand-over (text-like sections): byte-level pointer jumping inside 64 KB
+//                                       chunks on all SMs, then across chunks
 #include "zstd_kernels.cuh"
 
 namespace zk {
