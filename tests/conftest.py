@@ -23,3 +23,16 @@ def golden_dir():
 def read_golden(name):
     with open(os.path.join(GOLDEN, name), "rb") as f:
         return f.read()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _product_library_is_built():
+    """The CPU tier checks that the C-ABI library loads and exports every declared symbol; from a fresh checkout it has to
+    be cross-compiled first (nvcc, sm_100a, no GPU needed).  On the GPU box the built .so travels with the snapshot, and
+    a missing one must stay an error there: there is no fallback to build around."""
+    import shutil
+    import subprocess
+    csrc = os.path.join(ROOT, "nafcodec_b200", "csrc")
+    if not os.path.exists(os.path.join(csrc, "libnafgpu.so")) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        subprocess.run(["make", "-s", "-j8", "-C", csrc], check=True)
+    yield
