@@ -72,7 +72,7 @@ struct nafgpu_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g;
-    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0, o_chunks = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
+    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0, o_chunks = 0, o_gbase = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -187,10 +187,13 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         chunk_first[f + 1] = chunk_first[f] + (uint32_t)nchunks;
     }
     const uint32_t total_chunks = chunk_first[nf];
-    const size_t stage_bytes = c->o_chunks + align_up((nf + 1) * 4, 16);
+    std::vector<uint64_t> g_base(nf + 1, 0);             // fin_g: one entry per byte of every frame, frames packed (16-entry aligned)
+    for (size_t f = 0; f < nf; f++) g_base[f + 1] = g_base[f] + ((pl.frames[f].dst_size + 15) & ~(uint64_t)15);
+    c->o_gbase = c->o_chunks + align_up((nf + 1) * 4, 16);
+    const size_t stage_bytes = c->o_gbase + align_up((nf + 1) * 8, 16);
     c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
-              c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)total_chunks * 65536 * 4 + 64) &&
+              c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) && c->huftabs.ensure(pl.big_tree_slots.size() * 28672 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
@@ -206,6 +209,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
     if (nbt) memcpy(sp + c->o_bt, pl.big_tree_slots.data(), nbt * 4);
     memcpy(sp + c->o_chunks, chunk_first.data(), (nf + 1) * 4);
+    memcpy(sp + c->o_gbase, g_base.data(), (nf + 1) * 8);
     if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
@@ -226,6 +230,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf;
     J.fin_chunk_first = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_chunks); J.fin_total_chunks = total_chunks;
     J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p;
+    J.fin_g_base = (const uint64_t*)((const uint8_t*)c->desc.p + c->o_gbase);
     J.coop_ctas = c->coop_ctas;
     {   // the finisher handles a 64 KB chunk in ~90 us on one SM, all SMs at once, then a few barrier rounds (profiles/r1_summary.md)
         uint64_t biggest = 0;

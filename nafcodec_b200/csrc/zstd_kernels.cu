@@ -1423,7 +1423,7 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
         const uint64_t c1 = (c0 + FIN_C < fend) ? c0 + FIN_C : fend;
         const uint32_t cn = (uint32_t)(c1 - c0);
         uint8_t* out_c0 = J.out + c0;
-        uint32_t* g = J.fin_g + (size_t)c * FIN_C;
+        uint32_t* g = J.fin_g + J.fin_g_base[f] + (size_t)(c - J.fin_chunk_first[f]) * FIN_C;
         // any pending match in this chunk?  (most chunks of a job have none)
         bool mine = false;
         for (uint32_t base = mi;; base += FIN_T) {
@@ -1440,12 +1440,14 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
         // chunk bytes as they stand (literals and finished matches are final, pending bytes are garbage), self pointers,
         // no external roots, all distances zero
         for (uint32_t e = tid * 16; e < FIN_C; e += FIN_T * 16) {
-            if (e < cn) *(uint4*)(val + e) = __ldcg((const uint4*)(out_c0 + e));   // the arena is padded past the last frame
             uint32_t* p2 = (uint32_t*)(ptr + e);
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++) p2[k] = (e + 2 * k) | ((e + 2 * k + 1) << 16);
+            if (e < cn) {                                                    // (frames are 16-entry aligned in fin_g; the arena is padded)
+                *(uint4*)(val + e) = __ldcg((const uint4*)(out_c0 + e));
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) ((uint4*)(g + e))[k] = make_uint4(0, 0, 0, 0);
+                for (uint32_t k = 0; k < 4; k++) ((uint4*)(g + e))[k] = make_uint4(0, 0, 0, 0);
+            }
         }
         for (uint32_t e = tid; e < FIN_C / 32; e += FIN_T) extbit[e] = 0;
         __syncthreads();
@@ -1548,29 +1550,30 @@ __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
             __syncthreads();
             const uint32_t f = fin_frame_of(J, c);
             const uint32_t cf = J.fin_chunk_first[f];
+            const size_t gb = (size_t)J.fin_g_base[f];                       // the frame's entries in fin_g
             const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
             const uint64_t crel = (uint64_t)(c - cf) * FIN_C;               // chunk start relative to the frame
             const uint32_t cn = (uint32_t)((crel + FIN_C < fend - f0) ? FIN_C : fend - f0 - crel);
             uint32_t left = 0;
             for (uint32_t e = tid; e < cn; e += FIN2_T) {
-                const uint32_t dist = G[(size_t)c * FIN_C + e];
+                const uint32_t dist = G[gb + crel + e];
                 if (dist == 0) continue;
                 const uint64_t prel = crel + e;                             // my position and my source, relative to the frame
-                if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[(size_t)c * FIN_C + e] = 0; continue; }
+                if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[gb + crel + e] = 0; continue; }
                 const uint64_t srel = prel - dist;
                 const uint32_t sc = cf + (uint32_t)(srel >> 16);
                 uint32_t gs = 0;
-                if (flag[sc] != 0) gs = G[(size_t)sc * FIN_C + (uint32_t)(srel & (FIN_C - 1))];
+                if (flag[sc] != 0) gs = G[gb + srel];
                 if (gs == 0) {                                              // the source is final: take its value
                     __threadfence();
                     const uint8_t v = *(volatile const uint8_t*)(J.out + f0 + srel);
                     J.out[f0 + prel] = v;
                     __threadfence();
-                    G[(size_t)c * FIN_C + e] = 0;
+                    G[gb + crel + e] = 0;
                 } else {                                                    // adopt the source's source
                     const uint64_t nd = (uint64_t)dist + gs;
-                    if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[(size_t)c * FIN_C + e] = 0; continue; }
-                    G[(size_t)c * FIN_C + e] = (uint32_t)nd;
+                    if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[gb + crel + e] = 0; continue; }
+                    G[gb + crel + e] = (uint32_t)nd;
                     left++;
                 }
             }

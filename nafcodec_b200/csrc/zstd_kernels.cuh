@@ -38,7 +38,8 @@ struct JobDev {
     const uint32_t* fin_chunk_first;  // [n_frames + 1] first chunk of every frame (host-filled)
     uint32_t fin_total_chunks;
     uint32_t fin_ctas, fin2_ctas;     // grid sizes (one CTA per SM; co-resident CTAs of the cooperative level 2)
-    uint32_t* fin_g;                  // [fin_total_chunks * 65536] distance of an unresolved byte to its source, 0 = final
+    uint32_t* fin_g;                  // one u32 per byte of every frame: distance of an unresolved byte to its source, 0 = final
+    const uint64_t* fin_g_base;       // [n_frames] first entry of every frame in fin_g (host-filled; frames are packed, 16-entry aligned)
     uint32_t* fin_chunk_flag;         // [fin_total_chunks] chunk has unresolved bytes (zeroed every run)
     uint32_t* fin_unresolved;         // unresolved bytes after level 1
     uint32_t* fin_count;              // [3] rotating per-round counters of level 2
