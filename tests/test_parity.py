@@ -269,6 +269,7 @@ def test_pipeline_lanes(backend):
     """Several contexts driven from host threads (the e2e path of bench.py) give the same results as one context."""
     lib = library(backend)
     arcs = [K.genome(300 + i, 25_000 + 999 * i, level=3) for i in range(5)] + [read_golden("phix.naf")]
+    arcs += [K.fastq_reads(9 + i, 1200 if backend == "emul" else 20000) for i in range(2)]      # lanes that take the finisher path at the same time
     parsed = [N.parse_archive(a, lib) for a in arcs]
     pipe = N.Pipeline(0, 3, lib)
     from _harness import assert_same_as_oracle
@@ -285,6 +286,6 @@ def test_pipeline_lanes(backend):
     want = [O.decode(a) for a in arcs]
     for i, r in enumerate(res):
         assert_same_as_oracle(r, want[i], f"archive {i}")
-    assert n == 16 and len(got) == 16
+    assert n == 20 and len(got) == 20
     for (bi, i), r in got.items():
         assert_same_as_oracle(r, want[i], f"stream batch {bi} archive {i}")
