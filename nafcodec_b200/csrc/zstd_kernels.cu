@@ -643,23 +643,38 @@ __device__ __forceinline__ void win_consume(Win& w, int len) {
 
 // Follows one track from q (bits below the top of the stream) to the FIRST codeword boundary >= lim, counting symbols.
 // bm: boundary-mask table, index = next 12 bits, bit j set <=> j+1 bits is a cumulative length of whole codewords.
+__device__ __forceinline__ int msb_index(uint32_t m) {            // position of the highest set bit (m != 0): one BFIND
+#if defined(__CUDA_ARCH__)
+    int r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m)); return r;
+#else
+    return 31 - __clz((int)m);
+#endif
+}
+
 __device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop, int& q, int& cnt, int lim) {
     int rem = lim - q;
     if (rem <= 0) return;
     Win w;
     win_init(w, comp, xtop - q);
-    for (;;) {
+    // steady state: whole windows, no test against the limit (every window holds >= 1 whole codeword: max_bits <= 11)
+    while (rem > HUF_W) {
         const uint32_t m = lds16(bm + 2 * win_peek(w));
-        if (rem <= HUF_W) {
-            const uint32_t t = m >> (rem - 1);                 // boundaries at or past the limit
-            if (t) {
-                const int j = __ffs((int)t) - 1 + rem - 1;
-                cnt += __popc(m & ((2u << j) - 1u));
-                rem -= j + 1;
-                break;
-            }
+        const int used = msb_index(m) + 1;
+        cnt += __popc(m);
+        rem -= used;
+        win_consume(w, used);
+    }
+    // the last windows: stop at the first boundary at or past the limit
+    while (rem > 0) {
+        const uint32_t m = lds16(bm + 2 * win_peek(w));
+        const uint32_t t = m >> (rem - 1);
+        if (t) {
+            const int j = __ffs((int)t) - 1 + rem - 1;
+            cnt += __popc(m & ((2u << j) - 1u));
+            rem -= j + 1;
+            break;
         }
-        const int used = 32 - __clz((int)m);                   // every window holds >= 1 whole codeword (max_bits <= 11)
+        const int used = msb_index(m) + 1;
         cnt += __popc(m);
         rem -= used;
         win_consume(w, used);
