@@ -20,8 +20,12 @@ _libs = {}
 
 def emul_library():
     if "emul" not in _libs:
-        subprocess.run(["make", "-s", "-j8", "-C", EMUL_DIR], check=True)
-        _libs["emul"] = _ffi.Library(EMUL_LIB)
+        override = os.environ.get("NAFGPU_EMUL_LIB")       # e.g. an AddressSanitizer build of the emulator library (tests/emul/README)
+        if override:
+            _libs["emul"] = _ffi.Library(override)
+        else:
+            subprocess.run(["make", "-s", "-j8", "-C", EMUL_DIR], check=True)
+            _libs["emul"] = _ffi.Library(EMUL_LIB)
     return _libs["emul"]
 
 
