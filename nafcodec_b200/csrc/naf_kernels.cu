@@ -274,19 +274,25 @@ __global__ void __launch_bounds__(UNPACK_T) k_unpack(uint8_t* arena, const NafDe
     __shared__ uint32_t wball, cball;
     const NafCounts* counts = (const NafCounts*)(arena + A.counts_off);
     const uint64_t total = counts->total_residues;
-    const uint64_t wi = (uint64_t)blockIdx.x * CHUNK_WORDS + 2 * threadIdx.x;     // two adjacent toggle words = 64 residues per thread
+    const uint64_t wi = (uint64_t)blockIdx.x * CHUNK_WORDS + UNPACK_W * threadIdx.x;   // UNPACK_W adjacent toggle words per thread
     const uint64_t r0 = wi * 32;
-    uint32_t mask0 = 0, mask1 = 0;
+    uint32_t mask[UNPACK_W];
+#pragma unroll
+    for (uint32_t k = 0; k < UNPACK_W; k++) mask[k] = 0;
     if (A.has & HAS_MASK) {                                           // uniform per CTA
         const uint32_t* bits = (const uint32_t*)(arena + A.mask_bits_off);
         const uint64_t n_words = (A.seq_residues + 32) / 32;
-        const uint32_t w0 = wi < n_words ? bits[wi] : 0, w1 = wi + 1 < n_words ? bits[wi + 1] : 0;
-        uint32_t m0 = w0, m1 = w1;
-        m0 ^= m0 << 1; m0 ^= m0 << 2; m0 ^= m0 << 4; m0 ^= m0 << 8; m0 ^= m0 << 16;   // in-word prefix XOR
-        m1 ^= m1 << 1; m1 ^= m1 << 2; m1 ^= m1 << 4; m1 ^= m1 << 8; m1 ^= m1 << 16;
-        if (__popc(w0) & 1) m1 = ~m1;
+        uint32_t par = 0;                                             // parity of the toggles of the words before word k of this thread
+#pragma unroll
+        for (uint32_t k = 0; k < UNPACK_W; k++) {
+            const uint32_t w = wi + k < n_words ? bits[wi + k] : 0;
+            uint32_t m = w;
+            m ^= m << 1; m ^= m << 2; m ^= m << 4; m ^= m << 8; m ^= m << 16;   // in-word prefix XOR
+            mask[k] = par ? ~m : m;
+            par ^= __popc(w) & 1;
+        }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        uint32_t b = __ballot_sync(FULL, (__popc(w0) ^ __popc(w1)) & 1);
+        uint32_t b = __ballot_sync(FULL, par);
         if (lane == 0) wp[warp] = __popc(b) & 1;
         __syncthreads();
         if (warp == 0) { uint32_t bb = __ballot_sync(FULL, lane < (int)(UNPACK_T / 32) ? wp[lane] : 0u); if (lane == 0) wball = bb; }
@@ -300,32 +306,34 @@ __global__ void __launch_bounds__(UNPACK_T) k_unpack(uint8_t* arena, const NafDe
         __syncthreads();
         if (warp == 0) { uint32_t bb = __ballot_sync(FULL, lane < (int)(UNPACK_T / 32) ? wp2[lane] : 0u); if (lane == 0) cball = bb; }
         __syncthreads();
-        uint32_t carry = (__popc(cball) & 1) ^ (__popc(wball & ((1u << warp) - 1u)) & 1) ^ (__popc(b & ((1u << lane) - 1u)) & 1);
-        mask0 = carry ? ~m0 : m0;
-        mask1 = carry ? ~m1 : m1;
+        const uint32_t carry = (__popc(cball) & 1) ^ (__popc(wball & ((1u << warp) - 1u)) & 1) ^ (__popc(b & ((1u << lane) - 1u)) & 1);
+        if (carry) {
+#pragma unroll
+            for (uint32_t k = 0; k < UNPACK_W; k++) mask[k] = ~mask[k];
+        }
     }
     if (r0 >= total) return;
     const uint32_t l0 = A.seq_type == 1 ? 0x4B47552Du : 0x4B47542Du;       // RNA: 'U' at code 1
     const uint4* src = (const uint4*)(arena + A.seq_off + r0 / 2);
-    const bool second = r0 + 32 < total;
-    const uint4 pk0 = src[0];
-    uint4 pk1 = make_uint4(0, 0, 0, 0);
-    if (second) pk1 = src[1];                                              // both loads are issued before either is used
+    uint4 pk[UNPACK_W];
+#pragma unroll
+    for (uint32_t k = 0; k < UNPACK_W; k++) {                              // every load is issued before the first is used
+        pk[k] = make_uint4(0, 0, 0, 0);
+        if (r0 + 32 * k < total) pk[k] = src[k];
+    }
     uint4* dst = (uint4*)(arena + A.ascii_off + r0);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        if (h == 1 && !second) break;
-        const uint4 pk = h ? pk1 : pk0;
-        const uint32_t mask = h ? mask1 : mask0;
-        const uint32_t x[4] = {pk.x, pk.y, pk.z, pk.w};
+    for (uint32_t k = 0; k < UNPACK_W; k++) {
+        if (r0 + 32 * k >= total) break;
+        const uint32_t x[4] = {pk[k].x, pk[k].y, pk[k].z, pk[k].w};
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            o[2 * j] = iupac4(x[j] & 0xFFFFu, l0) | spread4_x20((mask >> (8 * j)) & 0xFu);
-            o[2 * j + 1] = iupac4(x[j] >> 16, l0) | spread4_x20((mask >> (8 * j + 4)) & 0xFu);
+            o[2 * j] = iupac4(x[j] & 0xFFFFu, l0) | spread4_x20((mask[k] >> (8 * j)) & 0xFu);
+            o[2 * j + 1] = iupac4(x[j] >> 16, l0) | spread4_x20((mask[k] >> (8 * j + 4)) & 0xFu);
         }
-        dst[2 * h] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[2 * h + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        dst[2 * k] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[2 * k + 1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
 }
 

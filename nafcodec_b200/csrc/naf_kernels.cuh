@@ -8,8 +8,9 @@ namespace nk {
 
 enum : uint32_t { HAS_IDS = 1, HAS_COMMENTS = 2, HAS_LENGTHS = 4, HAS_MASK = 8, HAS_SEQUENCE = 16, HAS_QUALITY = 32 };
 
-constexpr uint32_t UNPACK_T = 256;                     // threads of an unpack CTA, two mask words (64 residues) each
-constexpr uint32_t CHUNK_WORDS = 2 * UNPACK_T;         // mask words (of 32 residues) per unpack CTA
+constexpr uint32_t UNPACK_T = 256;                     // threads of an unpack CTA
+constexpr uint32_t UNPACK_W = 2;                       // adjacent mask words (of 32 residues) per thread
+constexpr uint32_t CHUNK_WORDS = UNPACK_W * UNPACK_T;  // mask words per unpack CTA
 constexpr uint32_t CHUNK_RESIDUES = CHUNK_WORDS * 32;
 constexpr uint64_t NO_RECORD = ~0ull;
 constexpr uint32_t MASK_SLICE = 32768;                 // mask bytes per CTA of k_naf_scan's mask task
