@@ -372,16 +372,21 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
         SmemBits rs{};
         BackBits rg{};
         uint32_t sLL = 0, sOF = 0, sML = 0;
+        bool dead = false;
         if (lane == 0) {
             if (staged) { const int xz = (int)(16 + a) * 8; rs.init(sbits, xz + P0, xz); sLL = rs.read(al[0]); sOF = rs.read(al[1]); sML = rs.read(al[2]); }
             else { rg.init(g, nbytes); sLL = rg.read(al[0]); sOF = rg.read(al[1]); sML = rg.read(al[2]); }
         }
         for (uint32_t k = 0; k < nbatch; k++) {
             const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
-            if (lane == 0) {
+            if (lane == 0 && !dead) {
                 if (staged) seq_produce(rs, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
                 else seq_produce(rg, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
-                if (k + 1 == nbatch) s_left = staged ? rs.remaining() : (int)rg.P;
+                const int left = staged ? rs.remaining() : (int)rg.P;
+                // a corrupt stream over-reads: stop before the reader walks out of shared memory (one batch can go at most
+                // 32 x 90 bits below the image, which is still inside the CTA's static shared memory); the block is flagged
+                if (left < 0) { dead = true; s_left = left; }
+                else if (k + 1 == nbatch) s_left = left;
             }
             __syncthreads();                             // batch k is ready; the consumer has finished batch k - 1
         }
