@@ -126,10 +126,12 @@ const char* nafgpu_version(void);
 typedef struct nafgpu_ctx nafgpu_ctx;
 
 /* One context per Decoder (or per worker thread); owns a CUDA stream, device arenas and pinned result buffers.
+ * Replaces the construction / drop of the six `BufReader<zstd::Decoder<BufReader<IoSlice<R>>>>` section readers that
+ * `setup_block!` builds in DecoderBuilder::with_reader (nafcodec/src/decoder/mod.rs:32,199-242).
  * Not thread-safe; distinct contexts may be used concurrently from distinct threads (cudaSetDevice at every entry). */
 int nafgpu_ctx_create(int device, nafgpu_ctx** out);
 void nafgpu_ctx_destroy(nafgpu_ctx* ctx);
-const char* nafgpu_last_error(const nafgpu_ctx* ctx);
+const char* nafgpu_last_error(const nafgpu_ctx* ctx);   /* the message of the last failure (the io::Error text of error.rs:4-11) */
 
 /* Pinned host memory for callers that want zero staging copies (optional). */
 void* nafgpu_host_alloc(size_t bytes);
@@ -137,7 +139,10 @@ void nafgpu_host_free(void* p);
 
 /* ---- decode ------------------------------------------------------------------------------------------------ */
 
-/* Whole path, host buffers in, host buffers out: walk frames, H2D, kernels, D2H, synchronise. */
+/* Whole path, host buffers in, host buffers out: walk frames, H2D, kernels, D2H, synchronise.  Replaces, for ALL records of
+ * the archive at once, what Decoder::next_record (decoder/mod.rs:356-399) pulls from the readers: CStringReader::next
+ * (reader.rs:20-31), LengthReader::next (46-68), SequenceReader::next / read_nucleotide / read_text (88-172),
+ * MaskReader::next (196-231), Decoder::mask_sequence (mod.rs:402-441), and the zstd inflate underneath (mod.rs:221-223). */
 int nafgpu_decode(nafgpu_ctx* ctx, const nafgpu_archive* archive, uint32_t want, nafgpu_result* out);
 /* Same for n independent archives in ONE set of kernel launches (the batch / RefSeq-collection shape); n <= 65535 per
  * call (larger collections: several calls, e.g. Pipeline.decode_stream). */
