@@ -1681,9 +1681,9 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
         ev->mark();
-        NAF_SET_MAX_SMEM(k_lz_finish, FIN_SMEM);
         const uint32_t fin_grid = J.fin_total_chunks < J.fin_ctas ? J.fin_total_chunks : J.fin_ctas;
-        if (fin_grid) {
+        if (fin_grid && J.n_seq > LZ_MIN_PENDING) {       // (k_lz_resolve never hands over fewer than LZ_MIN_PENDING matches)
+            NAF_SET_MAX_SMEM(k_lz_finish, FIN_SMEM);
             NAF_LAUNCH(k_lz_finish, fin_grid, FIN_T, FIN_SMEM, st, J); launches++;
             const uint32_t cg2 = J.fin2_ctas ? J.fin2_ctas : 1u;
             (void)cg2;
