@@ -74,23 +74,26 @@ enum { NAFGPU_WANT_ID = 1, NAFGPU_WANT_COMMENT = 2, NAFGPU_WANT_SEQUENCE = 4, NA
  *   length   = i < n_lengths  ? lengths[i] : None
  *   sequence = (i < n_lengths && sequence) ? sequence[record_offsets[i] .. record_offsets[i+1]) : None
  *   quality  = (i < n_lengths && quality)  ? quality [record_offsets[i] .. record_offsets[i+1]) : None
- * A NULL blob pointer means the field is absent from the archive or was not requested. */
+ * A NULL blob pointer means the field is absent from the archive or was not requested.
+ * n_records is the header's number_of_sequences, which a file may overstate at will: the offset tables hold n_ids + 1,
+ * n_comments + 1 and n_lengths + 1 entries (a stream of b bytes cannot hold more than b strings or b / 4 lengths). */
 typedef struct nafgpu_result {
     uint64_t n_records;
     uint64_t n_ids, n_comments, n_lengths;
     uint64_t total_residues;            /* == record_offsets[n_lengths] */
     const uint8_t* ids;
-    const uint64_t* id_offsets;         /* n_records + 1 entries */
+    const uint64_t* id_offsets;         /* n_ids + 1 entries */
     const uint8_t* comments;
-    const uint64_t* comment_offsets;    /* n_records + 1 entries */
-    const uint64_t* lengths;            /* n_records entries */
-    const uint64_t* record_offsets;     /* n_records + 1 entries (exclusive prefix sum of lengths) */
+    const uint64_t* comment_offsets;    /* n_comments + 1 entries */
+    const uint64_t* lengths;            /* n_lengths entries */
+    const uint64_t* record_offsets;     /* n_lengths + 1 entries (exclusive prefix sum of lengths) */
     const uint8_t* sequence;            /* ASCII, soft-masked; total_residues bytes */
     const uint8_t* quality;             /* total_residues bytes */
     uint64_t first_bad_record;          /* UINT64_MAX, or the first record whose text is not UTF-8: records before it are valid,
                                            the reference yields an error AT that record (reader.rs:108-109) */
     int32_t record_status;              /* status to raise at first_bad_record (NAFGPU_ERR_UTF8) or 0 */
-    int32_t _pad;
+    int32_t status;                     /* 0, or why THIS archive could not be decoded (corrupt / truncated data): its pointers are
+                                           NULL then.  Archives of a batch fail independently, like separate reference Decoders */
 } nafgpu_result;
 
 /* Sizes of the last prepared job, for throughput arithmetic (B_alg). */
@@ -145,7 +148,9 @@ void nafgpu_host_free(void* p);
  * MaskReader::next (196-231), Decoder::mask_sequence (mod.rs:402-441), and the zstd inflate underneath (mod.rs:221-223). */
 int nafgpu_decode(nafgpu_ctx* ctx, const nafgpu_archive* archive, uint32_t want, nafgpu_result* out);
 /* Same for n independent archives in ONE set of kernel launches (the batch / RefSeq-collection shape); n <= 65535 per
- * call (larger collections: several calls, e.g. Pipeline.decode_stream). */
+ * call (larger collections: several calls, or the pipeline below).  The return value reports failures of the CALL (bad
+ * arguments, CUDA, memory); a corrupt or truncated archive only sets its own out[i].status (for n == 1 that status is
+ * also the return value) and nafgpu_last_error names the first such archive. */
 int nafgpu_decode_batch(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want, nafgpu_result* out);
 
 /* One magicless zstd frame -> exactly regen_size bytes at dst (host memory).  The pure-zstd boundary: what
@@ -186,7 +191,8 @@ typedef struct nafgpu_text {
     const uint8_t* data;                /* HOST pointer into pinned memory owned by the context (valid until its next call) */
     uint64_t size;
     int32_t format;                     /* NAFGPU_TEXT_FASTA | NAFGPU_TEXT_FASTQ, as written */
-    int32_t status;                     /* 0, or NAFGPU_ERR_UTF8: the reference fails AT first_bad_record (reader.rs:108-109) */
+    int32_t status;                     /* 0; NAFGPU_ERR_UTF8: the reference fails AT first_bad_record (reader.rs:108-109); any other
+                                           code: this archive could not be decoded (data NULL), the rest of the batch is unaffected */
     uint64_t first_bad_record;
 } nafgpu_text;
 

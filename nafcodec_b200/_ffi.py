@@ -40,7 +40,7 @@ class Result(C.Structure):
                 ("total_residues", C.c_uint64),
                 ("ids", C.c_void_p), ("id_offsets", C.c_void_p), ("comments", C.c_void_p), ("comment_offsets", C.c_void_p),
                 ("lengths", C.c_void_p), ("record_offsets", C.c_void_p), ("sequence", C.c_void_p), ("quality", C.c_void_p),
-                ("first_bad_record", C.c_uint64), ("record_status", C.c_int32), ("_pad", C.c_int32)]
+                ("first_bad_record", C.c_uint64), ("record_status", C.c_int32), ("status", C.c_int32)]
 
 
 class Text(C.Structure):

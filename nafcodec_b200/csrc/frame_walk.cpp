@@ -29,6 +29,9 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
         uint64_t base = 1ull << (10 + (wd >> 3));
         window = base + (base >> 3) * (wd & 7);
     }
+    // match offsets travel through the kernels in 29 bits beside the symbolic repeat-offset encoding (zstd_format.h,
+    // OFF_SYMBOLIC): a frame that may use longer ones (zstd --long=30/31) is refused, not mis-decoded
+    if (window > (1ull << 29)) FAIL(ERR_UNSUPPORTED, "zstd frame: window of %llu bytes exceeds the supported 512 MiB", (unsigned long long)window);
     static const int dict_sz[4] = {0, 1, 2, 4};
     uint32_t dict_id = 0;
     if (p + dict_sz[dict_flag] > n) FAIL(ERR_EOF, "zstd frame: truncated header");
@@ -176,7 +179,12 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
         p += content;
         if (last) break;
     }
-    if (checksum) { if (p + 4 > n) FAIL(ERR_EOF, "zstd frame: truncated checksum"); p += 4; }
+    if (checksum) {
+        if (p + 4 > n) FAIL(ERR_EOF, "zstd frame: truncated checksum");
+        fd.has_checksum = 1; fd.checksum = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+        p += 4;
+        plan.n_checksums++;
+    }
     fd.n_blocks = (uint32_t)plan.blocks.size() - fd.first_block;
     fd.n_seq = (uint32_t)plan.seq_total - fd.first_seq;
     if (fd.n_seq == 0 && known_total != dst_size)

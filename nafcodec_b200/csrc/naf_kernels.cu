@@ -15,6 +15,12 @@ namespace nk {
 
 #define FULL 0xFFFFFFFFu
 
+// An error of one archive: its own status word (archives of a batch fail independently) and the job-wide OR.
+__device__ __forceinline__ void flag_archive(NafCounts* counts, uint32_t* status, uint32_t bits) {
+    atomicOr((unsigned long long*)&counts->status, (unsigned long long)bits);
+    atomicOr(status, bits);
+}
+
 struct CS { uint32_t c; uint64_t s; };
 
 // Exclusive scan of (count, sum) over a 1024-thread CTA; *total gets the CTA totals.  All threads must call.
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
         if (__any_sync(FULL, hi & 0x80)) { if ((tid & 31) == 0) atomicOr((unsigned long long*)&counts->nonascii, 1ull << task); }
         if (tid == 0) {
             if (task == 0) counts->n_ids = carry; else counts->n_comments = carry;
-            if (carry < A.n_records && size > 0 && src[size - 1] != 0) atomicOr(status, zc::E_NUL);
+            if (carry < A.n_records && size > 0 && src[size - 1] != 0) flag_archive(counts, status, zc::E_NUL);
         }
     } else if (task == 2) {
         // ---- lengths: rec_offsets[k+1] = sum of all words up to and including the k-th terminating word -----
@@ -138,8 +144,8 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
             counts->n_lengths = n_len;
             counts->total_residues = total;
             counts->first_bad_record = NO_RECORD;
-            if ((A.has & HAS_SEQUENCE) && total > A.seq_residues) atomicOr(status, zc::E_LENGTHS);
-            if ((A.has & HAS_QUALITY) && total > A.qual_size) atomicOr(status, zc::E_LENGTHS);
+            if ((A.has & HAS_SEQUENCE) && total > A.seq_residues) flag_archive(counts, status, zc::E_LENGTHS);
+            if ((A.has & HAS_QUALITY) && total > A.qual_size) flag_archive(counts, status, zc::E_LENGTHS);
         }
         for (uint64_t k = tid; k < n_len; k += blockDim.x) lens[k] = rec[k + 1] - rec[k];
     } else {
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
 __global__ void __launch_bounds__(256) k_mask_fix(uint8_t* arena, const NafDev* archives, uint32_t* status) {
     const NafDev& A = archives[blockIdx.y];
     if (!(A.has & HAS_MASK) || !(A.has & HAS_SEQUENCE)) return;
-    const NafCounts* counts = (const NafCounts*)(arena + A.counts_off);
+    NafCounts* counts = (NafCounts*)(arena + A.counts_off);
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= counts->n_lengths) return;
     const uint64_t* rec = (const uint64_t*)(arena + A.rec_offsets_off);
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(256) k_mask_fix(uint8_t* arena, const NafDev* 
         uint64_t mid = (lo + hi) >> 1;
         if (bounds[mid] > pos) hi = mid; else lo = mid + 1;
     }
-    if (lo == n_runs) { atomicOr(status, zc::E_MASK); return; }      // "failed to get mask unit" (mod.rs:429-434)
+    if (lo == n_runs) { flag_archive(counts, status, zc::E_MASK); return; }      // "failed to get mask unit" (mod.rs:429-434)
     if (lo & 1) {
         uint64_t a = lo ? bounds[lo - 1] : 0;
         uint32_t* cpar = (uint32_t*)(arena + A.chunk_par_off);
@@ -273,7 +279,8 @@ __global__ void __launch_bounds__(UNPACK_T) k_unpack(uint8_t* arena, const NafDe
     __shared__ uint32_t wp[32], wp2[32];
     __shared__ uint32_t wball, cball;
     const NafCounts* counts = (const NafCounts*)(arena + A.counts_off);
-    const uint64_t total = counts->total_residues;
+    // lengths that sum to more than the section holds are an error of the archive (E_LENGTHS): never unpack past the section
+    const uint64_t total = counts->total_residues < A.seq_residues ? counts->total_residues : A.seq_residues;
     const uint64_t wi = (uint64_t)blockIdx.x * CHUNK_WORDS + UNPACK_W * threadIdx.x;   // UNPACK_W adjacent toggle words per thread
     const uint64_t r0 = wi * 32;
     uint32_t mask[UNPACK_W];
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(CHUNK_WORDS) k_text_mask(uint8_t* arena, const
     const NafDev& A = archives[blockIdx.y];
     if (!(A.has & HAS_SEQUENCE) || !(A.has & HAS_MASK) || A.seq_type <= 1 || blockIdx.x >= A.n_chunks) return;
     const NafCounts* counts = (const NafCounts*)(arena + A.counts_off);
-    const uint64_t total = counts->total_residues;
+    const uint64_t total = counts->total_residues < A.seq_residues ? counts->total_residues : A.seq_residues;
     const uint64_t wi = (uint64_t)blockIdx.x * CHUNK_WORDS + threadIdx.x;
     const uint32_t* bits = (const uint32_t*)(arena + A.mask_bits_off);
     const uint32_t* par = (const uint32_t*)(arena + A.chunk_par_off);
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(256) k_utf8_validate(uint8_t* arena, const Naf
         if (e > (field == 2 ? A.seq_size : A.qual_size)) return;
     }
     if (!utf8_ok(s + b, e - b)) {
-        atomicOr(status, zc::E_UTF8);
+        flag_archive(counts, status, zc::E_UTF8);
         atomicMin((unsigned long long*)&counts->first_bad_record, (unsigned long long)r);
     }
 }

@@ -15,7 +15,7 @@ constexpr uint32_t CHUNK_RESIDUES = CHUNK_WORDS * 32;
 constexpr uint64_t NO_RECORD = ~0ull;
 constexpr uint32_t MASK_SLICE = 32768;                 // mask bytes per CTA of k_naf_scan's mask task
 
-// Per-archive counters, device-written, copied back with the results (64 bytes).
+// Per-archive counters, device-written, copied back with the results (80 bytes).
 struct NafCounts {
     uint64_t n_ids;            // NUL-terminated strings found in the ids stream
     uint64_t n_comments;
@@ -25,6 +25,8 @@ struct NafCounts {
     uint64_t mask_sum;
     uint64_t first_bad_record; // first record whose text failed UTF-8 validation (NO_RECORD if none)
     uint64_t nonascii;         // bit f set: field f (0 ids, 1 comments, 2 text sequence, 3 quality) has bytes >= 0x80
+    uint64_t status;           // zc::E_* bits raised by the NAF kernels for THIS archive (the job-wide word keeps their OR)
+    uint64_t _pad;
 };
 
 // One per archive of the job.  All *_off fields are byte offsets into the job arena (16 B aligned at least).

@@ -46,7 +46,7 @@ struct RecView {
 struct ArchView {
     const uint8_t *ids, *com, *seq, *qual;
     const uint64_t *id_offs, *com_offs, *rec_offs;
-    uint64_t n, n_ids, n_com, n_len, W;
+    uint64_t n, n_ids, n_com, n_len, W, cap;
     uint32_t fastq, sep;
 };
 
@@ -62,6 +62,9 @@ __device__ __forceinline__ ArchView arch_view(const uint8_t* arena, const NafDev
     V.n_com = (A.has & HAS_COMMENTS) ? (C->n_comments < V.n ? C->n_comments : V.n) : 0;
     V.n_len = (A.has & HAS_SEQUENCE) ? C->n_lengths : 0;
     V.W = T.line_length; V.fastq = T.fastq; V.sep = T.sep;
+    // lengths that overrun their streams flag the archive (E_LENGTHS); the formatter must still stay inside the buffers
+    V.cap = A.seq_residues;
+    if (T.fastq && A.qual_size < V.cap) V.cap = A.qual_size;
     return V;
 }
 
@@ -70,7 +73,10 @@ __device__ __forceinline__ RecView rec_view(const ArchView& V, uint64_t r) {
     R.id0 = 0; R.idlen = 0; R.com0 = 0; R.comlen = 0; R.seq0 = 0; R.L = 0;
     if (r < V.n_ids) { R.id0 = V.id_offs[r]; R.idlen = V.id_offs[r + 1] - R.id0 - 1; }
     if (r < V.n_com) { R.com0 = V.com_offs[r]; R.comlen = V.com_offs[r + 1] - R.com0 - 1; }
-    if (r < V.n_len) { R.seq0 = V.rec_offs[r]; R.L = V.rec_offs[r + 1] - R.seq0; }
+    if (r < V.n_len) {
+        R.seq0 = V.rec_offs[r]; R.L = V.rec_offs[r + 1] - R.seq0;
+        if (R.seq0 > V.cap) { R.seq0 = V.cap; R.L = 0; } else if (R.L > V.cap - R.seq0) R.L = V.cap - R.seq0;
+    }
     R.hdr = 1 + R.idlen + (R.comlen ? 1 + R.comlen : 0) + 1;
     return R;
 }
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(1024) k_text_layout(const uint8_t* arena, cons
     }
     if (threadIdx.x == 0) {
         offs[V.n] = carry;
-        if (carry > T.cap) { atomicOr(status, zc::E_SIZE); carry = 0; }      // (the host's bound is exact arithmetic: cannot happen)
+        if (carry > T.cap) { atomicOr(status, zc::E_INTERNAL); carry = 0; }      // (the host's bound is exact arithmetic: cannot happen)
         ((uint64_t*)text)[blockIdx.x] = carry;
     }
 }

@@ -38,6 +38,7 @@ struct DevBuf {
         return true;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DevBuf() { release(); }
 };
 struct PinBuf {
     void* p = nullptr;
@@ -52,6 +53,7 @@ struct PinBuf {
         return true;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    ~PinBuf() { release(); }
 };
 
 struct ArchPlan {
@@ -62,6 +64,9 @@ struct ArchPlan {
     bool nucleotide = true;
     uint64_t line_length = 0;                    // Header::line_length / name_separator (data.rs:198-236): for the text formatter
     uint32_t sep = ' ';
+    uint32_t first_frame = 0, n_frames = 0;      // the archive's frames in the job plan (per-archive status)
+    int host_status = 0;                         // failure found on the host (frame walk, validation): the archive is not decoded
+    std::string host_msg;
 };
 
 }  // namespace
@@ -136,6 +141,7 @@ int status_to_code(uint32_t s, std::string& msg) {
     if (s & (E_FSE_TABLE | E_HUF_TREE | E_HUF_STREAM | E_SEQ_STREAM | E_LITERALS | E_OFFSET | E_NO_TABLE | E_INTERNAL)) {
         msg = std::string("corrupt zstd stream") + b; return NAFGPU_ERR_INVALID_DATA;
     }
+    if (s & E_CHECKSUM) { msg = std::string("zstd frame checksum mismatch") + b; return NAFGPU_ERR_INVALID_DATA; }
     if (s & E_SIZE) { msg = std::string("section does not regenerate the size its header states") + b; return NAFGPU_ERR_INVALID_DATA; }
     if (s & E_LENGTHS) { msg = std::string("record lengths exceed the sequence/quality stream") + b; return NAFGPU_ERR_UNEXPECTED_EOF; }
     if (s & E_MASK) { msg = std::string("failed to get mask unit") + b; return NAFGPU_ERR_UNEXPECTED_EOF; }
@@ -248,13 +254,26 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         cudaMemsetAsync(c->debug.p, 0, nh * 64, c->st);
         J.debug = (unsigned long long*)c->debug.p;
     }
-    J.n_frames = (uint32_t)nf; J.n_blocks = (uint32_t)nb; J.n_slots = pl.n_slots; J.n_seq = nseq;
+    J.n_frames = (uint32_t)nf; J.n_blocks = (uint32_t)nb; J.n_slots = pl.n_slots; J.n_seq = nseq; J.n_checksums = pl.n_checksums;
 
     c->stats.n_archives = n; c->stats.n_frames = nf; c->stats.n_blocks = nb; c->stats.n_sequences = nseq;
     c->stats.h2d_bytes = h2d; c->stats.d2h_bytes = c->z1_size + c->misc_words * 4;
     c->stats.n_stages = N_STAGES + 1;
     c->prepared = true;
     return NAFGPU_OK;
+}
+
+// Status of archive a after a run: what the host found (validation, frame walk), else the OR of the device status of its
+// frames (misc_host: frame_bad[]) and of its NAF-level checks (NafCounts::status).  UTF-8 is reported per record, not here.
+int archive_status(nafgpu_ctx* c, uint32_t a, std::string& msg) {
+    const ArchPlan& P = c->aplan[a];
+    if (P.host_status) { msg = P.host_msg; return P.host_status; }
+    const uint32_t* frame_bad = (const uint32_t*)c->misc_host.p + 10;
+    uint32_t s = 0;
+    for (uint32_t f = P.first_frame; f < P.first_frame + P.n_frames; f++) s |= frame_bad[f];
+    const nk::NafCounts* C = (const nk::NafCounts*)((const uint8_t*)c->result.p + c->arch[a].counts_off);
+    s |= (uint32_t)C->status;
+    return status_to_code(s & ~zc::E_UTF8, msg);
 }
 
 }  // namespace
@@ -290,7 +309,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     drop_graph(c);
     DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g};
     for (DevBuf* b : d) b->release();
-    c->stage.release(); c->result.release(); c->misc_host.release();
+    c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -329,6 +348,25 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     off = c->counts_size;
     uint64_t comp_off = 16;          // gathers may read up to 15 bytes below a literal run: keep them inside the allocation
     c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
+    // Everything below is sized from header fields an archive may lie about: sizes are validated first (a zstd frame
+    // regenerates at most 128 KB per 3-byte block header), record counts are clamped by what the sections can hold, and a
+    // job whose arena would not fit any device is refused before anything is laid out.
+    constexpr uint64_t MAX_SECTION = 1ull << 38;                    // 256 GB: more than a B200 holds
+    auto validate = [&](const nafgpu_archive& A, std::string& why) -> int {
+        if (A.header.sequence_type < 0 || A.header.sequence_type > 3) { why = "bad sequence type"; return NAFGPU_ERR_ARGUMENT; }
+        for (int s = 0; s < 6; s++) {
+            const nafgpu_section& S = A.sections[s];
+            if (!S.present) continue;
+            if (!S.data) { why = "present section without data"; return NAFGPU_ERR_ARGUMENT; }
+            const uint64_t regen = (s == NAFGPU_SEC_SEQUENCE && A.header.sequence_type <= 1) ? S.original_size / 2 + (S.original_size & 1) : S.original_size;
+            if (S.compressed_size > MAX_SECTION || regen > MAX_SECTION || regen > (S.compressed_size / 3 + 1) * (uint64_t)zf::BLOCK_MAX) {
+                static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
+                why = std::string(names[s]) + " section: the header states a size its zstd frame cannot regenerate";
+                return NAFGPU_ERR_INVALID_DATA;
+            }
+        }
+        return 0;
+    };
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
@@ -338,30 +376,40 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         P.n_records = nrec;
         P.nucleotide = A.header.sequence_type <= 1;
         P.line_length = A.header.line_length; P.sep = (uint32_t)(A.header.name_separator & 0xFF);
-        if (A.header.sequence_type < 0 || A.header.sequence_type > 3) return fail(c, NAFGPU_ERR_ARGUMENT, "bad sequence type");
-        for (int s = 0; s < 6; s++) if (A.sections[s].present && !A.sections[s].data) return fail(c, NAFGPU_ERR_ARGUMENT, "present section without data");
-        const bool has_len = A.sections[NAFGPU_SEC_LENGTH].present;
-        P.dec[NAFGPU_SEC_ID] = A.sections[NAFGPU_SEC_ID].present && (want & NAFGPU_WANT_ID);
-        P.dec[NAFGPU_SEC_COMMENT] = A.sections[NAFGPU_SEC_COMMENT].present && (want & NAFGPU_WANT_COMMENT);
+        {
+            std::string why;
+            const int rc = validate(A, why);
+            if (rc == NAFGPU_ERR_ARGUMENT || (rc && n == 1)) return fail(c, rc, why);
+            if (rc) { P.host_status = rc; P.host_msg = why; }       // one bad archive does not fail the batch: it is skipped and reported
+        }
+        const uint64_t nrec_dev = P.host_status ? 0 : nrec;
+        const bool live = P.host_status == 0;
+        const bool has_len = live && A.sections[NAFGPU_SEC_LENGTH].present;
+        P.dec[NAFGPU_SEC_ID] = live && A.sections[NAFGPU_SEC_ID].present && (want & NAFGPU_WANT_ID);
+        P.dec[NAFGPU_SEC_COMMENT] = live && A.sections[NAFGPU_SEC_COMMENT].present && (want & NAFGPU_WANT_COMMENT);
         P.dec[NAFGPU_SEC_LENGTH] = has_len;                                                  // mod.rs:239: always
         P.dec[NAFGPU_SEC_SEQUENCE] = has_len && A.sections[NAFGPU_SEC_SEQUENCE].present && (want & NAFGPU_WANT_SEQUENCE);
         P.dec[NAFGPU_SEC_QUALITY] = has_len && A.sections[NAFGPU_SEC_QUALITY].present && (want & NAFGPU_WANT_QUALITY);
         P.dec[NAFGPU_SEC_MASK] = P.dec[NAFGPU_SEC_SEQUENCE] && A.sections[NAFGPU_SEC_MASK].present && (want & NAFGPU_WANT_MASK);
         for (int s = 0; s < 6; s++) {
             uint64_t o = A.sections[s].original_size;
-            P.blob_size[s] = !P.dec[s] ? 0 : ((s == NAFGPU_SEC_SEQUENCE && P.nucleotide) ? (o + 1) / 2 : o);
+            P.blob_size[s] = !P.dec[s] ? 0 : ((s == NAFGPU_SEC_SEQUENCE && P.nucleotide) ? o / 2 + (o & 1) : o);
         }
         const uint64_t residues = P.dec[NAFGPU_SEC_SEQUENCE] ? A.sections[NAFGPU_SEC_SEQUENCE].original_size : 0;
-        D.n_records = nrec;
+        // number_of_sequences is whatever the header says (2^61 is a valid varint); a stream of b bytes holds at most b
+        // NUL-terminated strings / b/4 length words, so the offset tables are sized by that, not by the header
+        const uint64_t nrec_ids = std::min<uint64_t>(nrec, P.blob_size[0]), nrec_com = std::min<uint64_t>(nrec, P.blob_size[1]);
+        const uint64_t nrec_len = std::min<uint64_t>(nrec, P.blob_size[2] / 4);
+        D.n_records = nrec_dev;
         D.seq_type = (uint32_t)A.header.sequence_type;
         D.has = (P.dec[0] ? nk::HAS_IDS : 0) | (P.dec[1] ? nk::HAS_COMMENTS : 0) | (P.dec[2] ? nk::HAS_LENGTHS : 0) |
                 (P.dec[3] ? nk::HAS_MASK : 0) | (P.dec[4] ? nk::HAS_SEQUENCE : 0) | (P.dec[5] ? nk::HAS_QUALITY : 0);
         D.seq_residues = residues;
         D.counts_off = (uint64_t)a * sizeof(nk::NafCounts);
-        D.lengths_off = off; off = align_up(off + 8 * (nrec + 1));
-        D.rec_offsets_off = off; off = align_up(off + 8 * (nrec + 1));
-        D.id_offsets_off = off; if (P.dec[0]) off = align_up(off + 8 * (nrec + 1));
-        D.com_offsets_off = off; if (P.dec[1]) off = align_up(off + 8 * (nrec + 1));
+        D.lengths_off = off; off = align_up(off + 8 * (nrec_len + 1));
+        D.rec_offsets_off = off; off = align_up(off + 8 * (nrec_len + 1));
+        D.id_offsets_off = off; if (P.dec[0]) off = align_up(off + 8 * (nrec_ids + 1));
+        D.com_offsets_off = off; if (P.dec[1]) off = align_up(off + 8 * (nrec_com + 1));
         auto place = [&](int s) { P.blob_off[s] = off; off = align_up(off + P.blob_size[s] + 32); };
         if (P.dec[0]) place(0);
         if (P.dec[1]) place(1);
@@ -370,7 +418,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
             if (P.nucleotide) { D.ascii_off = off; off = align_up(off + align_up(residues, 32) + 32); }
             else { place(4); D.ascii_off = P.blob_off[4]; }
         }
-        c->max_records = std::max(c->max_records, nrec);
+        c->max_records = std::max(c->max_records, std::max(nrec_len, std::max(nrec_ids, nrec_com)));
         if (P.dec[4]) {
             D.n_chunks = (uint32_t)((residues + 1 + nk::CHUNK_RESIDUES - 1) / nk::CHUNK_RESIDUES);
             c->max_chunks = std::max(c->max_chunks, D.n_chunks);
@@ -382,7 +430,8 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         c->stats.quality_bytes += P.blob_size[5];
         c->stats.id_bytes += P.blob_size[0];
         c->stats.comment_bytes += P.blob_size[1];
-        c->stats.algorithmic_bytes += residues + P.blob_size[5] + P.blob_size[0] + P.blob_size[1] + 8 * (nrec + 1);
+        c->stats.algorithmic_bytes += residues + P.blob_size[5] + P.blob_size[0] + P.blob_size[1] + 8 * (nrec_len + 1);
+        if (off > (1ull << 40)) return fail(c, NAFGPU_ERR_NOMEM, "job does not fit the device: split the batch");
     }
     c->z1_size = off;
     c->z2_off = off;
@@ -417,6 +466,11 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
+        P.first_frame = (uint32_t)c->plan.frames.size();
+        const fw::JobPlan::Mark mark = c->plan.mark();
+        const size_t copies_mark = copies.size();
+        const Copy last_copy = copies.empty() ? Copy{nullptr, 0, 0} : copies.back();
+        const uint64_t comp_mark = comp_off, cbytes_mark = c->stats.compressed_bytes, sbytes_mark = c->stats.section_bytes;
         for (int s = 0; s < 6; s++) {
             if (!P.dec[s]) continue;
             const nafgpu_section& S = A.sections[s];
@@ -440,13 +494,23 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
             int rc = fw::walk_frame(S.data, comp_off, S.compressed_size, P.blob_off[s], P.blob_size[s], c->plan, e);
             if (rc) {
                 static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
-                return fail(c, rc, std::string(names[s]) + " section: " + e);
+                const std::string msg = std::string(names[s]) + " section: " + e;
+                if (n == 1) return fail(c, rc, msg);
+                // a batch goes on without this archive: nothing of it is uploaded or decoded, its result carries the status
+                P.host_status = rc; P.host_msg = msg;
+                c->plan.rollback(mark);
+                copies.resize(copies_mark);
+                if (copies_mark) copies.back() = last_copy;
+                comp_off = comp_mark; c->stats.compressed_bytes = cbytes_mark; c->stats.section_bytes = sbytes_mark;
+                c->arch[a].has = 0; c->arch[a].n_records = 0;
+                for (int k = 0; k < 6; k++) P.dec[k] = false;
+                break;
             }
             c->stats.compressed_bytes += S.compressed_size;
             c->stats.section_bytes += P.blob_size[s];
         }
+        P.n_frames = (uint32_t)c->plan.frames.size() - P.first_frame;
     }
-    c->stats.algorithmic_bytes += c->stats.compressed_bytes;
     c->stats.algorithmic_bytes += c->stats.compressed_bytes;
     if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
     return finish_prepare(c, copies, comp_off, n);
@@ -522,21 +586,26 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
         if (cnt) fprintf(stderr, "[huf debug] big CTAs %zu: cycles stage+weights %.0f, table %.0f, sync %.0f (iters avg %.2f max %.0f), scan %.0f, write %.0f, flush %.0f\n",
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }
-    const uint32_t status = *(const uint32_t*)c->misc_host.p;
     c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
     const uint8_t* R = (const uint8_t*)c->result.p;
-    std::string msg;
-    int code = status_to_code(status & ~zc::E_UTF8, msg);
-    if (code) return fail(c, code, msg);
+    int first_code = 0;
     for (uint32_t a = 0; a < n; a++) {
         const nk::NafDev& D = c->arch[a];
         const ArchPlan& P = c->aplan[a];
         const nk::NafCounts* C = (const nk::NafCounts*)(R + D.counts_off);
         nafgpu_result& r = out[a];
         memset(&r, 0, sizeof r);
-        r.n_records = D.n_records;
-        r.n_ids = std::min<uint64_t>(C->n_ids, D.n_records);
-        r.n_comments = std::min<uint64_t>(C->n_comments, D.n_records);
+        r.n_records = P.n_records;
+        r.first_bad_record = nk::NO_RECORD;
+        std::string msg;
+        const int code = archive_status(c, a, msg);
+        if (code) {
+            r.status = code;
+            if (!first_code) { first_code = code; char b[48]; snprintf(b, sizeof b, "archive %u: ", a); c->err = b + msg; }
+            continue;
+        }
+        r.n_ids = std::min<uint64_t>(C->n_ids, P.n_records);
+        r.n_comments = std::min<uint64_t>(C->n_comments, P.n_records);
         r.n_lengths = C->n_lengths;
         r.total_residues = C->total_residues;
         if (P.dec[0]) { r.ids = R + D.ids_off; r.id_offsets = (const uint64_t*)(R + D.id_offsets_off); }
@@ -547,7 +616,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
         r.first_bad_record = C->first_bad_record;
         r.record_status = (C->first_bad_record != nk::NO_RECORD) ? NAFGPU_ERR_UTF8 : 0;
     }
-    return NAFGPU_OK;
+    return (n == 1) ? first_code : NAFGPU_OK;
 }
 
 // FASTA / FASTQ text of the job that was just run, formatted on the device (naf_text.cu); only the text crosses PCIe.
@@ -563,9 +632,11 @@ int nafgpu_job_format(nafgpu_ctx* c, int format, uint64_t line_length, nafgpu_te
     for (uint32_t a = 0; a < n; a++) {
         const ArchPlan& P = c->aplan[a];
         const nk::NafDev& D = c->arch[a];
-        if (!P.dec[NAFGPU_SEC_SEQUENCE]) return fail(c, NAFGPU_ERR_ARGUMENT, "text output needs the sequence (and lengths) decoded");
+        const bool skipped = P.host_status != 0;          // (not decoded: no text, its status is reported; D.n_records is 0)
+        if (!skipped && !P.dec[NAFGPU_SEC_SEQUENCE]) return fail(c, NAFGPU_ERR_ARGUMENT, "text output needs the sequence (and lengths) decoded");
         const bool fastq = format == NAFGPU_TEXT_FASTQ || (format == NAFGPU_TEXT_AUTO && P.dec[NAFGPU_SEC_QUALITY]);
-        if (fastq && !P.dec[NAFGPU_SEC_QUALITY]) return fail(c, NAFGPU_ERR_ARGUMENT, "FASTQ output needs the quality section decoded");
+        if (!skipped && fastq && !P.dec[NAFGPU_SEC_QUALITY]) return fail(c, NAFGPU_ERR_ARGUMENT, "FASTQ output needs the quality section decoded");
+        if (D.n_records > (1ull << 36)) return fail(c, NAFGPU_ERR_NOMEM, "text of an archive with more than 2^36 records does not fit the device");
         nk::TextDev& T = td[a];
         T.fastq = fastq ? 1u : 0u;
         T.sep = P.sep;
@@ -601,26 +672,32 @@ int nafgpu_job_format(nafgpu_ctx* c, int format, uint64_t line_length, nafgpu_te
         CUDA_TRY(c, cudaMemcpyAsync(c->text_host.p, c->text.p, copy_size, cudaMemcpyDeviceToHost, c->st));
         CUDA_TRY(c, cudaStreamSynchronize(c->st));
     }
-    const uint32_t status = *(const uint32_t*)c->misc_host.p;
     c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
-    std::string msg;
-    int code = status_to_code(status & ~zc::E_UTF8, msg);
-    if (code) return fail(c, code, msg);
+    if (*(const uint32_t*)c->misc_host.p & zc::E_INTERNAL) return fail(c, NAFGPU_ERR_INVALID_DATA, "text layout exceeded its bound");
     const uint8_t* H = (const uint8_t*)c->text_host.p;
     c->stats.text_kernel_ms = 0; c->stats.text_bytes = 0;
     cudaEventElapsedTime(&c->stats.text_kernel_ms, c->ev[0], c->ev[1]);
-    for (uint32_t a = 0; a < n; a++) c->stats.text_bytes += ((const uint64_t*)H)[a];
+    int first_code = 0;
     for (uint32_t a = 0; a < n; a++) {
         const nk::NafCounts* C = (const nk::NafCounts*)((const uint8_t*)c->result.p + c->arch[a].counts_off);
         nafgpu_text& t = out[a];
         memset(&t, 0, sizeof t);
+        t.format = td[a].fastq ? NAFGPU_TEXT_FASTQ : NAFGPU_TEXT_FASTA;
+        t.first_bad_record = nk::NO_RECORD;
+        std::string msg;
+        const int code = archive_status(c, a, msg);
+        if (code) {
+            t.status = code;
+            if (!first_code) { first_code = code; char b[48]; snprintf(b, sizeof b, "archive %u: ", a); c->err = b + msg; }
+            continue;
+        }
         t.data = H + td[a].text_off;
         t.size = ((const uint64_t*)H)[a];
-        t.format = td[a].fastq ? NAFGPU_TEXT_FASTQ : NAFGPU_TEXT_FASTA;
+        c->stats.text_bytes += t.size;
         t.first_bad_record = C->first_bad_record;
         t.status = (C->first_bad_record != nk::NO_RECORD) ? NAFGPU_ERR_UTF8 : 0;
     }
-    return NAFGPU_OK;
+    return (n == 1) ? first_code : NAFGPU_OK;
 }
 
 int nafgpu_format_batch(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n, uint32_t want, int format, uint64_t line_length, nafgpu_text* out) {

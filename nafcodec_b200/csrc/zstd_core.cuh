@@ -31,6 +31,7 @@ enum : uint32_t {
     E_MASK = 1u << 9,            // NAF: mask runs end before the sequences do
     E_UTF8 = 1u << 10,           // NAF: text field is not valid UTF-8
     E_NUL = 1u << 11,            // NAF: id/comment stream does not end with NUL
+    E_CHECKSUM = 1u << 12,       // frame content checksum (XXH64) does not match
     E_INTERNAL = 1u << 30
 };
 

@@ -25,7 +25,7 @@ using zc::SeqCell;
 
 __device__ __forceinline__ void flag_error(const JobDev& J, uint32_t frame, uint32_t bits) {
     atomicOr(J.status, bits);
-    atomicOr(&J.frame_bad[frame], 1u);
+    atomicOr(&J.frame_bad[frame], bits);              // per frame (= per section of one archive): archives of a batch fail independently
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -1610,6 +1610,54 @@ __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
     }
 }
 
+// --------------------------------------------------------------------------------------------------------------
+// k_frame_checksum: frames whose header sets Content_Checksum_flag end with the low 32 bits of XXH64(content, 0), which
+// libzstd -- reached from decoder/mod.rs:221 -- verifies.  NAF writers never set the flag, third-party zstd frames may.
+// XXH64 is four multiplicative chains over 32-byte stripes: one warp per frame, lanes 0..3 own one accumulator each
+// (a serial chain by construction: ~10 ns per stripe; it runs only for frames that ask for it).
+__device__ __forceinline__ uint64_t xxh_rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+constexpr uint64_t XXP1 = 0x9E3779B185EBCA87ull, XXP2 = 0xC2B2AE3D27D4EB4Full, XXP3 = 0x165667B19E3779F9ull, XXP4 = 0x85EBCA77C2B2AE63ull,
+                   XXP5 = 0x27D4EB2F165667C5ull;
+__device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t in) { return xxh_rotl(acc + in * XXP2, 31) * XXP1; }
+__device__ __forceinline__ uint64_t xxh_merge(uint64_t h, uint64_t v) { return (h ^ xxh_round(0, v)) * XXP1 + XXP4; }
+
+__global__ void __launch_bounds__(32) k_frame_checksum(JobDev J) {
+    const uint32_t f = blockIdx.x;
+    const FrameDesc& F = J.frames[f];
+    if (!F.has_checksum || J.frame_bad[f]) return;
+    const int lane = threadIdx.x;
+    const uint8_t* p = J.out + F.dst_off;                       // (frames regenerate at 16 B-aligned arena offsets)
+    const uint64_t len = F.dst_size, stripes = len >> 5;
+    uint64_t h;
+    if (stripes) {
+        uint64_t v = lane == 0 ? XXP1 + XXP2 : (lane == 1 ? XXP2 : (lane == 2 ? 0ull : 0ull - XXP1));
+        if (lane < 4) {
+            const uint64_t* q = (const uint64_t*)p + lane;
+            uint64_t s = 0;
+            for (; s + 8 <= stripes; s += 8) {                  // eight independent loads in flight per chain step
+                uint64_t in[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) in[k] = q[4 * (s + k)];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v = xxh_round(v, in[k]);
+            }
+            for (; s < stripes; s++) v = xxh_round(v, q[4 * s]);
+        }
+        const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, v, 0), v2 = __shfl_sync(0xFFFFFFFFu, v, 1), v3 = __shfl_sync(0xFFFFFFFFu, v, 2),
+                       v4 = __shfl_sync(0xFFFFFFFFu, v, 3);
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    } else h = XXP5;
+    if (lane != 0) return;
+    h += len;
+    uint64_t i = stripes << 5;
+    for (; i + 8 <= len; i += 8) { h ^= xxh_round(0, *(const uint64_t*)(p + i)); h = xxh_rotl(h, 27) * XXP1 + XXP4; }
+    if (i + 4 <= len) { h ^= (uint64_t)(*(const uint32_t*)(p + i)) * XXP1; h = xxh_rotl(h, 23) * XXP2 + XXP3; i += 4; }
+    for (; i < len; i++) { h ^= (uint64_t)p[i] * XXP5; h = xxh_rotl(h, 11) * XXP1; }
+    h ^= h >> 33; h *= XXP2; h ^= h >> 29; h *= XXP3; h ^= h >> 32;
+    if ((uint32_t)h != F.checksum) flag_error(J, f, zc::E_CHECKSUM);
+}
+
 uint32_t lz_resolve_max_ctas(int device) {
 #if defined(NAFGPU_EMULATE)
     (void)device;
@@ -1691,6 +1739,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         }
         ev->mark();
     } else { ev->mark(); ev->mark(); ev->mark(); }
+    if (J.n_checksums) { NAF_LAUNCH(k_frame_checksum, J.n_frames, 32, 0, st, J); launches++; }      // (profiled runs count it with the next stage)
     return launches;
 }
 

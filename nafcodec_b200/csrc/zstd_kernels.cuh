@@ -50,6 +50,7 @@ struct JobDev {
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
     uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
     uint32_t n_frames, n_blocks, n_slots;
+    uint32_t n_checksums;             // frames with a content checksum (k_frame_checksum runs only if any)
     uint64_t n_seq;
 };
 

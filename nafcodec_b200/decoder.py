@@ -51,13 +51,20 @@ class Context:
         return parse_archive(buf, self.lib)
 
     # -- decode --------------------------------------------------------------------------------------------------
-    def decode(self, archives: List["_ffi.Archive"], want: int = _ffi.WANT_ALL) -> List["ArchiveResult"]:
+    def decode(self, archives: List["_ffi.Archive"], want: int = _ffi.WANT_ALL, strict: bool = True) -> List["ArchiveResult"]:
+        """Decodes a batch in one set of kernel launches.  Archives fail independently (like separate reference Decoders):
+        with strict=True the first corrupt archive raises; with strict=False its ArchiveResult carries `.status` /
+        `.error` and the others are returned normally."""
         n = len(archives)
         arr = (_ffi.Archive * n)(*archives)
         res = (_ffi.Result * n)()
         with self._lock:
             rc = self.lib.dll.nafgpu_decode_batch(self._ctx, arr, n, want, res)
             raise_for_status(self.lib, rc, self._ctx)
+            if strict:
+                for i in range(n):
+                    if res[i].status:
+                        raise_for_status(self.lib, res[i].status, self._ctx, f"archive {i} of {n}" if n > 1 else "")
             return [ArchiveResult._copy_from(archives[i].header, res[i]) for i in range(n)]
 
     def format(self, archives: List["_ffi.Archive"], want: int = _ffi.WANT_ALL, format: int = _ffi.TEXT_AUTO,
@@ -73,7 +80,8 @@ class Context:
             raise_for_status(self.lib, rc, self._ctx)
             out = []
             for i in range(n):
-                raise_for_status(self.lib, res[i].status, None, f"record {res[i].first_bad_record}")
+                raise_for_status(self.lib, res[i].status, self._ctx if res[i].status != _ffi.ERR_UTF8 else None,
+                                 f"record {res[i].first_bad_record}" if res[i].status == _ffi.ERR_UTF8 else f"archive {i}")
                 out.append(C.string_at(res[i].data, int(res[i].size)) if res[i].size else b"")
             return out
 
@@ -157,18 +165,20 @@ class ArchiveResult:
     @classmethod
     def _copy_from(cls, hdr, r):
         self = cls()
-        n = r.n_records
-        self.n_records = n
+        self.n_records = r.n_records
+        self.status = r.status                       # 0, or why this archive of the batch could not be decoded
         self.n_ids, self.n_comments, self.n_lengths = r.n_ids, r.n_comments, r.n_lengths
         self.total_residues = r.total_residues
         self.first_bad_record = None if r.first_bad_record == _ffi.NO_RECORD else r.first_bad_record
         self.record_status = r.record_status
-        self.id_offsets = _np_copy(r.id_offsets, n + 1, np.uint64) if r.ids else None
+        # the offset tables hold n_ids + 1 / n_comments + 1 / n_lengths + 1 entries (include/nafgpu.h): number_of_sequences
+        # is whatever the header claims
+        self.id_offsets = _np_copy(r.id_offsets, self.n_ids + 1, np.uint64) if r.ids else None
         self.ids = C.string_at(r.ids, int(self.id_offsets[self.n_ids])) if r.ids and self.n_ids else (b"" if r.ids else None)
-        self.comment_offsets = _np_copy(r.comment_offsets, n + 1, np.uint64) if r.comments else None
+        self.comment_offsets = _np_copy(r.comment_offsets, self.n_comments + 1, np.uint64) if r.comments else None
         self.comments = C.string_at(r.comments, int(self.comment_offsets[self.n_comments])) if r.comments and self.n_comments else (b"" if r.comments else None)
-        self.lengths = _np_copy(r.lengths, n, np.uint64) if r.lengths else None
-        self.record_offsets = _np_copy(r.record_offsets, n + 1, np.uint64) if r.record_offsets else None
+        self.lengths = _np_copy(r.lengths, self.n_lengths, np.uint64) if r.lengths else None
+        self.record_offsets = _np_copy(r.record_offsets, self.n_lengths + 1, np.uint64) if r.record_offsets else None
         self.sequence = C.string_at(r.sequence, r.total_residues) if r.sequence else None
         self.quality = C.string_at(r.quality, r.total_residues) if r.quality else None
         return self

@@ -113,6 +113,42 @@ int nafo_zstd_decompress(const uint8_t* src, size_t src_len, uint8_t** dst, size
     return 0;
 }
 
+/* One magicless frame of `src` in a single ZSTD_endStream sequence, with optional content checksum
+ * (ZSTD_c_checksumFlag = 201) and window log (ZSTD_c_windowLog = 101; 0 = the level's default).
+ * Test generator only: NAF writers never set these; third-party zstd frames may. */
+int nafo_zstd_compress(const uint8_t* src, size_t src_len, int level, int checksum, int window_log, uint8_t** dst, size_t* dst_len) {
+    int rc = zload();
+    if (rc) return rc;
+    void* c = Z.createCCtx();
+    if (!c) return NAFO_ERR_NOMEM;
+    Z.cctxSetParameter(c, ZSTD_c_compressionLevel, level);
+    Z.cctxSetParameter(c, ZSTD_c_format, ZSTD_f_magicless);
+    if (checksum) Z.cctxSetParameter(c, 201, 1);
+    if (window_log) Z.cctxSetParameter(c, 101, window_log);
+    vec_t out = {0, 0, 0};
+    zin_t in = {src, src_len, 0};
+    rc = 0;
+    while (in.pos < in.size) {
+        if (vec_reserve(&out, 1u << 17)) { rc = NAFO_ERR_NOMEM; break; }
+        zout_t o = {out.p + out.n, out.cap - out.n, 0};
+        size_t r = Z.compressStream(c, &o, &in);
+        if (Z.isError(r)) { set_err("zstd: %s", Z.getErrorName(r)); rc = NAFO_ERR_IO_INVALID; break; }
+        out.n += o.pos;
+    }
+    size_t r = 1;
+    while (!rc && r != 0) {
+        if (vec_reserve(&out, 1u << 17)) { rc = NAFO_ERR_NOMEM; break; }
+        zout_t o = {out.p + out.n, out.cap - out.n, 0};
+        r = Z.endStream(c, &o);
+        if (Z.isError(r)) { set_err("zstd: %s", Z.getErrorName(r)); rc = NAFO_ERR_IO_INVALID; break; }
+        out.n += o.pos;
+    }
+    Z.freeCCtx(c);
+    if (rc) { free(out.p); return rc; }
+    *dst = out.p; *dst_len = out.n;
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* parser.rs                                                                                   */
 

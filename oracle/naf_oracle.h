@@ -107,6 +107,8 @@ void nafo_free_records(nafo_records* r);
 /* Decompress one magicless zstd frame with libzstd (the L0 layer of the reference). */
 int nafo_zstd_decompress(const uint8_t* src, size_t src_len, uint8_t** dst, size_t* dst_len);
 void nafo_free(void* p);
+/* Test generator: one magicless frame, optional content checksum / explicit window log (never written by NAF tools). */
+int nafo_zstd_compress(const uint8_t* src, size_t src_len, int level, int checksum, int window_log, uint8_t** dst, size_t* dst_len);
 
 /* MaskReader (reader.rs:196-231): decode run lengths from mask bytes. Returns number of runs
  * written to runs[] (cap entries), stopping once sum >= total like the reference. */

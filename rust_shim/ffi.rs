@@ -69,7 +69,7 @@ pub struct nafgpu_result {
     pub quality: *const u8,
     pub first_bad_record: u64,
     pub record_status: i32,
-    pub _pad: i32,
+    pub status: i32, // 0, or why this archive of the batch could not be decoded
 }
 
 /// `nafgpu_text` (include/nafgpu.h): FASTA / FASTQ text of one archive in pinned host memory owned by the context.

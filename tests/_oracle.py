@@ -113,6 +113,17 @@ def zstd_decompress(data: bytes) -> bytes:
     return out
 
 
+def zstd_compress(data: bytes, level=3, checksum=False, window_log=0) -> bytes:
+    """One magicless zstd frame (optionally with a content checksum): shapes NAF writers never emit, third parties may."""
+    dst = C.c_void_p()
+    n = C.c_size_t()
+    _check(lib().nafo_zstd_compress(_buf(data), C.c_size_t(len(data)), C.c_int(level), C.c_int(int(checksum)), C.c_int(window_log),
+                                    C.byref(dst), C.byref(n)))
+    out = C.string_at(dst, n.value)
+    lib().nafo_free(dst)
+    return out
+
+
 def section_bytes(data: bytes, name: str) -> Optional[bytes]:
     L = parse(data)
     s = L.sec[SEC_NAMES.index(name)]
