@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
     import _oracle as O
     cores = os.cpu_count() or 1
     uniq = make_workload(args.unique, args.residues, args.level, 0)
-    sample_n = min(args.batch, max(cores, 8))
+    sample_n = args.batch                     # the same batch as the device arm (256 cfg2 archives: ~3 s of CPU work per step on 16 cores)
     archives = [uniq[i % len(uniq)] for i in range(sample_n)]
     for _ in range(args.warmup):
         cpu_decode_all(archives[:cores], cores)
@@ -171,6 +171,161 @@ def workload_config(args, batch):
             "l2": "batch working set (compressed + packed + ASCII) exceeds the 126 MB L2; device-resident timing also overwrites a 256 MB buffer before every timed iteration"}
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs at their stated sizes, each: parity gate vs the oracle, host prepare, device time, roofline, e2e
+BENCH_CACHE = os.path.join(ROOT, "bench_cache")          # in-tree, git-ignored: travels to the GPU box with the snapshot
+
+
+def cached(name, make):
+    """Archives that take minutes to generate (250 Mbp at zstd level 19: ~3 min on one core) are kept in bench_cache/."""
+    for d in (BENCH_CACHE, CACHE):
+        path = os.path.join(d, name)
+        if os.path.exists(path):
+            return open(path, "rb").read(), f"cached ({os.path.relpath(path, ROOT) if d == BENCH_CACHE else path})"
+    t0 = time.perf_counter()
+    data = make()
+    os.makedirs(CACHE, exist_ok=True)
+    tmp = os.path.join(CACHE, name + f".{os.getpid()}.tmp")
+    with open(tmp, "wb") as f:
+        f.write(data)
+    os.replace(tmp, os.path.join(CACHE, name))
+    return data, f"generated in {time.perf_counter() - t0:.0f} s"
+
+
+def pin(lib, blobs):
+    """Pinned host copies + parsed archive structs (the e2e legs copy from pinned memory)."""
+    from nafcodec_b200 import _ffi
+    out, keep = [], []
+    for a in blobs:
+        p = lib.dll.nafgpu_host_alloc(len(a))
+        C.memmove(p, a, len(a))
+        keep.append(p)
+        arc = _ffi.Archive()
+        rc = lib.dll.nafgpu_parse_archive(p, len(a), C.byref(arc))
+        assert rc == 0, rc
+        out.append(arc)
+    return out, keep
+
+
+def measure_config(ctx, lib, name, blobs, want, peak, fields, note, iters=10, parity_sample=None):
+    """One job = all `blobs` decoded together.  Returns the dict that goes under configs[name] in the bench line."""
+    import _oracle as O
+    from _harness import assert_same_as_oracle
+    from nafcodec_b200 import _ffi
+    archives, keep = pin(lib, blobs)
+    n = len(archives)
+    arr = (_ffi.Archive * n)(*archives)
+    res = (_ffi.Result * n)()
+    # parity gate: device == oracle, every field, on every archive (or on a stated sample of a big collection)
+    idx = list(range(n)) if parity_sample is None else parity_sample
+    t0 = time.perf_counter()
+    got = ctx.decode(archives, want)
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(len(idx), os.cpu_count() or 1)) as ex:
+        wants = list(ex.map(lambda i: O.decode(blobs[i], **fields), idx))
+    t_cpu = time.perf_counter() - t0
+    for i, w in zip(idx, wants):
+        assert_same_as_oracle(got[i], w, f"{name} archive {i}")
+    del got, wants
+    # host prepare: frame/block header walk + descriptor build + H2D enqueue (buffers exist after the first call)
+    preps = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.prepare(archives, want)
+        preps.append(time.perf_counter() - t0)
+        ctx.sync()
+    st = ctx.stats()
+    ctx.time_runs(2, True)
+    ms = ctx.time_runs(iters, True) / iters
+    stages = {nm: round(v, 4) for nm, v in ctx.profile_stages() if v >= 0.0005}
+    ctx.fetch_raw()
+    st2 = ctx.stats()
+    # end to end through the C ABI: pinned host buffers in, pinned host buffers out, one synchronous call
+    e2es = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rc = lib.dll.nafgpu_decode_batch(ctx._ctx, arr, n, want, res)
+        e2es.append(time.perf_counter() - t0)
+        assert rc == 0, rc
+    out_bytes = int(st.ascii_bytes + st.quality_bytes + st.id_bytes + st.comment_bytes)
+    e2e_s = sorted(e2es)[1]
+    prep_ms = sorted(preps)[1] * 1e3
+    for p in keep:
+        lib.dll.nafgpu_host_free(p)
+    return {"workload": note, "archives": n, "parity": f"bit-exact vs oracle on {len(idx)} archive(s), all requested fields",
+            "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences), "kernel_launches": int(st2.kernel_launches),
+            "compressed_bytes": int(st.compressed_bytes), "ascii_bytes": int(st.ascii_bytes), "output_bytes": out_bytes,
+            "algorithmic_bytes": int(st.algorithmic_bytes),
+            "device_ms": ms, "host_prepare_ms": prep_ms, "device_plus_prepare_ms": ms + prep_ms,
+            "ascii_GBps": int(st.ascii_bytes) / (ms * 1e-3) / 1e9, "output_GBps": out_bytes / (ms * 1e-3) / 1e9,
+            "path_algorithmic_GBps": int(st.algorithmic_bytes) / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": int(st.algorithmic_bytes) / (ms * 1e-3) / 1e9 / peak,
+            "e2e": {"ms": e2e_s * 1e3, "output_GBps": out_bytes / e2e_s / 1e9, "h2d_bytes": int(st.h2d_bytes), "d2h_bytes": int(st.d2h_bytes),
+                    "first_call_ms": t_first * 1e3},
+            "lz_rounds": int(st2.lz_rounds), "lz_handover_round": int(st2.lz_handover), "stage_ms_serial": stages,
+            "cpu_oracle": {"ms": t_cpu * 1e3, "threads": min(len(idx), os.cpu_count() or 1), "archives": len(idx)}}
+
+
+def run_configs(args, ctx, lib, peak, uniq_cfg2):
+    """configs[0..4] of BASELINE.json at their stated sizes (cfg2 x 256 is the headline workload itself)."""
+    import _cases as K
+    import _oracle as O
+    from nafcodec_b200 import _ffi
+    out = {}
+    ALL = dict(id=True, comment=True, sequence=True, quality=True, mask=True)
+    want = _ffi.WANT_ALL
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+            out[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+            log(f"[configs] {name}: device {out[name]['device_ms']:.3f} ms, prepare {out[name]['host_prepare_ms']:.2f} ms, "
+                f"{out[name]['ascii_GBps']:.1f} GB/s ASCII, {100 * out[name]['frac_of_hbm_peak']:.2f} % of HBM peak, e2e {out[name]['e2e']['ms']:.2f} ms")
+        except AssertionError:
+            raise                                        # a parity failure must fail the bench
+        except Exception as e:                           # (generation / memory trouble: say so instead of dropping the line)
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+
+    golden = os.path.join(ROOT, "tests", "golden", "NZ_AAEN01000029.naf")
+    guarded("cfg1_fixture", lambda: measure_config(ctx, lib, "cfg1", [open(golden, "rb").read()], want, peak, ALL,
+                                                   "cfg1: data/NZ_AAEN01000029.naf (30 records, 5.49 Mbp), all fields", iters=20))
+    guarded("cfg2_single", lambda: measure_config(ctx, lib, "cfg2", [uniq_cfg2[0]], want, peak, ALL,
+                                                  f"cfg2: ONE synthetic {args.residues / 1e6:g} Mbp genome archive alone (latency-bound: the working set sits in L2)", iters=20))
+    if args.cfg3_residues > 0:
+        def cfg3():
+            nm = f"cfg3_n{args.cfg3_residues}_s3_l19.naf"
+            data, how = cached(nm, lambda: K.cfg3_chromosome(args.cfg3_residues, workers=0))
+            r = measure_config(ctx, lib, "cfg3", [data], want, peak, ALL,
+                               f"cfg3: synthetic {args.cfg3_residues / 1e6:g} Mbp chromosome, ONE record / one zstd frame per section, level 19 (8 MiB window), "
+                               f"N telomeres + centromere + 20 gaps, ~50 % soft-masked (mean run 300); archive {how}", iters=5)
+            return r
+        guarded("cfg3_250Mbp" if args.cfg3_residues == 250_000_000 else f"cfg3_{args.cfg3_residues // 1_000_000}Mbp", cfg3)
+    if args.cfg4_reads > 0:
+        nm = f"cfg4_{args.cfg4_reads // 1000}k" if args.cfg4_reads < 1_000_000 else f"cfg4_{args.cfg4_reads // 1_000_000}M"
+        data4 = K.cfg4_fastq(args.cfg4_reads)
+        note4 = (f"cfg4: {args.cfg4_reads} x 150 bp FASTQ reads, ids + quality + mask, reference encoder framing (zstd flush per record: one tiny block "
+                 f"per read and stream), level 0 = the reference default (level 19 with 2e7 flushes is impractical to generate)")
+        guarded(nm + "_all_fields", lambda: measure_config(ctx, lib, "cfg4", [data4], want, peak, ALL, note4 + "; all fields", iters=3))
+        guarded(nm + "_no_quality", lambda: measure_config(ctx, lib, "cfg4-q", [data4], want & ~_ffi.WANT_QUALITY, peak,
+                                                           dict(ALL, quality=False), note4 + "; .quality(false)", iters=3))
+        del data4
+    if args.cfg5_archives > 0:
+        def cfg5():
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+                blobs = list(ex.map(lambda i: cached(f"cfg5_i{i}_l19.naf", lambda: K.cfg5_member(i))[0], range(args.cfg5_archives)))
+            gen_s = time.perf_counter() - t0
+            r = measure_config(ctx, lib, "cfg5", blobs, want, peak, ALL,
+                               f"cfg5: RefSeq-collection shape, {args.cfg5_archives} UNIQUE archives in one job (of the 20 000 / 8 GPUs = 2500 per GPU), N uniform 2-6 Mbp, "
+                               f"1 chromosome + 0-3 plasmid records, level 19; generated in {gen_s:.0f} s on {os.cpu_count()} host threads", iters=5)
+            return r
+        guarded(f"cfg5_mix_{args.cfg5_archives}", cfg5)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -183,6 +338,10 @@ def main():
     ap.add_argument("--residues", type=int, default=5_000_000)
     ap.add_argument("--level", type=int, default=19)
     ap.add_argument("--lanes", type=int, default=4, help="contexts (streams) used by the end-to-end leg")
+    ap.add_argument("--cfg3-residues", type=int, default=250_000_000, help="configs[2]: one chromosome-scale archive (0 = skip)")
+    ap.add_argument("--cfg4-reads", type=int, default=1_000_000, help="configs[3]: FASTQ reads (BASELINE says 10 M: 450 MB archive, ~2 min to generate; 0 = skip)")
+    ap.add_argument("--cfg5-archives", type=int, default=512, help="configs[4]: unique 2-6 Mbp archives in one job (0 = skip)")
+    ap.add_argument("--no-configs", action="store_true", help="only the headline workload (cfg2 x batch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -369,6 +528,11 @@ def main():
         single = {"device_us": ms1 * 1e3, "ascii_GBps": s1.ascii_bytes / (ms1 * 1e-3) / 1e9, "kernel_launches": s1.kernel_launches, "stage_ms_serial": st1,
                   "algorithmic_bytes": s1.algorithmic_bytes, "frac_of_hbm_peak": s1.algorithmic_bytes / (ms1 * 1e-3) / 1e9 / peak}
 
+    # ---- every BASELINE.json config at its stated size (N=1 only: each is a single-GPU job) -------------------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = run_configs(args, ctx, lib, peak, uniq)
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample, 1 thread ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -396,7 +560,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": kernel_of.get(dom_name, dom_name), "stage": dom_name, "traffic_source": traffic_src, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": int(dom_bytes),
                              "stage_ms": {nm: round(ms, 4) for nm, ms in zip(stage_names, stage_ms)}},
-                "cpu_baseline": cpu, "clocks": clocks, "single_archive": single, "text_formatter": text,
+                "cpu_baseline": cpu, "clocks": clocks, "single_archive": single, "text_formatter": text, "configs": configs,
                 "job": {"archives": int(st.n_archives), "frames": int(st.n_frames), "zstd_blocks": int(st.n_blocks), "sequences": int(st.n_sequences), "lz_rounds": lz_rounds,
                         "compressed_bytes": int(st.compressed_bytes), "ascii_bytes": int(st.ascii_bytes), "algorithmic_bytes": int(st.algorithmic_bytes)}}
         emit(line)

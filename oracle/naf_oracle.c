@@ -532,6 +532,12 @@ double nafo_time_decode(const uint8_t* buf, size_t len, int want_quality, int wa
 
 typedef struct { void* c; vec_t out; int err; } zenc_t;
 
+/* Generator-only knob (never used by the reference): ZSTD_c_nbWorkers = 400 lets libzstd compress the jobs of ONE frame
+ * on several threads, so that the 250 Mbp level-19 bench archive is generated in seconds instead of minutes.  The frame
+ * is an ordinary single zstd frame either way; 0 (default) is the reference's call pattern. */
+static int g_encoder_workers = 0;
+void nafo_set_encoder_workers(int n) { g_encoder_workers = n < 0 ? 0 : n; }
+
 /* EncoderBuilder::new_buffer (encoder/mod.rs:147-154): zstd::Encoder::new(.., level) + include_magicbytes(false) */
 static int zenc_init(zenc_t* e, int level) {
     memset(e, 0, sizeof *e);
@@ -539,6 +545,7 @@ static int zenc_init(zenc_t* e, int level) {
     if (!e->c) return NAFO_ERR_NOMEM;
     Z.cctxSetParameter(e->c, ZSTD_c_compressionLevel, level);
     Z.cctxSetParameter(e->c, ZSTD_c_format, ZSTD_f_magicless);
+    if (g_encoder_workers > 0) Z.cctxSetParameter(e->c, 400, g_encoder_workers);      /* (an error -- no MT support -- is ignored) */
     return 0;
 }
 /* Write::write_all -> ZSTD_compressStream until the input is consumed */
@@ -779,6 +786,44 @@ void nafo_synth_dna(uint64_t seed, uint64_t n, double gc, int n_repeat_families,
         memset(dst + at, 'N', n_gap_len);
     }
     if (telomere_len > 0 && 2 * telomere_len < n) { memset(dst, 'N', telomere_len); memset(dst + n - telomere_len, 'N', telomere_len); }
+}
+
+/* cfg3: a human-chromosome-shaped record: GC 0.41, 10 kb N telomeres, one N centromere (1.2 % of the
+ * length: 3 Mbp at 250 Mbp), 20 N gaps of 50 kb, a 300 bp repeat family at 10 % divergence with one copy per 2.5 kb. */
+void nafo_synth_chromosome(uint64_t seed, uint64_t n, uint8_t* dst) {
+    uint64_t gap = n >= 5000000 ? 50000 : n / 100;
+    nafo_synth_dna(seed, n, 0.41, 2, n > 3000 ? 300 : 0, (int)(n / 5000), 1e-5, 20, gap, n >= 1000000 ? 10000 : n / 100, dst);
+    uint64_t cen = n / 83, at = n * 2 / 5;
+    if (cen && at + cen < n) memset(dst + at, 'N', cen);
+}
+
+/* cfg4: n reads of exactly read_len bp sampled from a fixed 5386 bp genome with 1 % substitutions and N at
+ * 1e-3; quality from a 4-symbol Markov chain over "F:,#"; ids "SRR0000001.<i>".  Fills the three blobs; ids_off gets
+ * n + 1 entries (sequence / quality offsets are i * read_len).  ids must hold 24 bytes per read. */
+void nafo_synth_fastq(uint64_t seed, uint64_t n_reads, uint64_t read_len, uint8_t* ids, uint64_t* ids_off, uint8_t* seq, uint8_t* qual) {
+    rng_t r; rng_seed(&r, seed * 0x9E3779B97F4A7C15ull + 17);
+    enum { G = 5386 };
+    static const char Q[] = "F:,#";
+    uint8_t genome[G];
+    for (int i = 0; i < G; i++) genome[i] = (uint8_t)"ACGT"[rng_next(&r) & 3];
+    uint64_t io = 0;
+    for (uint64_t k = 0; k < n_reads; k++) {
+        ids_off[k] = io;
+        io += (uint64_t)sprintf((char*)ids + io, "SRR0000001.%llu", (unsigned long long)(k + 1));
+        uint64_t p = rng_below(&r, G - read_len);
+        uint8_t* s = seq + k * read_len; uint8_t* q = qual + k * read_len;
+        int state = (int)(rng_next(&r) & 3);
+        for (uint64_t i = 0; i < read_len; i++) {
+            uint64_t x = rng_next(&r);
+            uint8_t b = genome[p + i];
+            if ((x & 0x7F) == 0 && ((x >> 7) & 1)) b = (uint8_t)"ACGT"[(x >> 8) & 3];      /* ~1 % (incl. silent) substitutions */
+            if (((x >> 16) & 0x3FF) == 0) b = 'N';                                            /* ~1e-3 */
+            s[i] = b;
+            if (((x >> 32) & 0xF) == 0) state = (int)((x >> 40) & 3);                         /* quality runs of mean length 16 */
+            q[i] = (uint8_t)Q[state];
+        }
+    }
+    ids_off[n_reads] = io;
 }
 
 uint64_t nafo_synth_mask(uint64_t seed, uint64_t total, double mean_unmasked, double mean_masked,

@@ -134,6 +134,9 @@ int nafo_encode(int sequence_type, int level, int flush_per_record, uint64_t lin
 void nafo_synth_dna(uint64_t seed, uint64_t n, double gc, int n_repeat_families, uint64_t repeat_len,
                     int repeat_copies, double iupac_rate, uint64_t n_gap_count, uint64_t n_gap_len,
                     uint64_t telomere_len, uint8_t* dst);
+void nafo_synth_chromosome(uint64_t seed, uint64_t n, uint8_t* dst);                      /* cfg3 shape */
+void nafo_synth_fastq(uint64_t seed, uint64_t n_reads, uint64_t read_len, uint8_t* ids, uint64_t* ids_off, uint8_t* seq, uint8_t* qual);   /* cfg4 shape */
+void nafo_set_encoder_workers(int n);    /* generator-only: ZSTD_c_nbWorkers for the encoders created afterwards (0 = reference pattern) */
 /* Alternating U/M run lengths with geometric lengths; returns number of runs (sum == total). */
 uint64_t nafo_synth_mask(uint64_t seed, uint64_t total, double mean_unmasked, double mean_masked,
                          int leading_zero_run, uint64_t* runs, uint64_t cap);

@@ -115,3 +115,45 @@ def zstd_frame(payload: bytes, level=3, flush_every=0):
     L = O.parse(arc)
     s = L.sec[4]
     return arc[s.offset:s.offset + s.compressed_size]
+
+
+# ---- BASELINE.json configs at their stated sizes; shared by bench.py and the slow -m gpu parity tests ------
+def cfg3_chromosome(n=250_000_000, seed=3, level=19, workers=None):
+    """One record of n residues: N telomeres / centromere / gaps, a diverged 300 bp repeat family, ~50 % soft-masked with mean
+    run 300; every section one zstd frame at `level`.  `workers` > 0 lets libzstd compress that one frame on several threads
+    (generator convenience: the 125 MB packed stream takes minutes on one core); the reference's call pattern is workers=0."""
+    import os
+    seq = O.synth_chromosome(seed, n)
+    runs = O.synth_mask(seed, n, 300.0, 300.0, True)
+    off = np.array([0, n], dtype=np.uint64)
+    O.set_encoder_workers(min(os.cpu_count() or 1, 16) if workers is None else workers)
+    try:
+        return O.encode_blobs(1, ids=(np.frombuffer(b"synth_chr", np.uint8), np.array([0, 9], np.uint64)),
+                              comments=(np.frombuffer(b"synthetic", np.uint8), np.array([0, 9], np.uint64)),
+                              sequences=(seq, off), mask_runs_=runs, level=level, flush_per_record=True)
+    finally:
+        O.set_encoder_workers(0)
+
+
+def cfg4_fastq(n_reads=1_000_000, seed=4, read_len=150, level=0, with_mask=True):
+    """n_reads x read_len FASTQ in the reference encoder's framing (a zstd flush after every record: one tiny block per read
+    and stream, encoder/mod.rs:271,298,319), flags Id|Length|Sequence|Quality (+ Mask), level = the reference default."""
+    ids, ids_off, seq, qual = O.synth_fastq(seed, n_reads, read_len)
+    off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+    runs = O.synth_mask(seed, n_reads * read_len, 700.0, 40.0, False) if with_mask else None
+    return O.encode_blobs(n_reads, ids=(ids, ids_off), sequences=(seq, off), qualities=(qual, off), mask_runs_=runs, level=level,
+                          flush_per_record=True)
+
+
+def cfg5_member(i, base_seed=5000, level=19):
+    """Archive i of the RefSeq-collection shape: the cfg2 generator with seed base + i, N uniform in [2, 6] Mbp, one
+    chromosome + 0-3 plasmid records."""
+    rng = _rng(base_seed + i)
+    n = int(rng.integers(2_000_000, 6_000_001))
+    plasmids = int(rng.integers(0, 4))
+    seq = O.synth_dna(base_seed + i, n, gc=0.5, families=2, repeat_len=5000, copies=7, iupac_rate=1e-5)
+    runs = O.synth_mask(base_seed + i, n, 2000.0, 300.0, True)
+    cuts = [0] + sorted(n - int(x) for x in rng.integers(3_000, 200_000, size=plasmids).cumsum()) + [n] if plasmids else [0, n]
+    seqs = [seq[cuts[k]:cuts[k + 1]] for k in range(len(cuts) - 1)]
+    ids = [b"synth_%d_%d" % (base_seed + i, k) for k in range(len(seqs))]
+    return O.encode(ids=ids, comments=[b"synthetic"] * len(seqs), sequences=seqs, mask_runs_=runs, level=level, flush_per_record=True)

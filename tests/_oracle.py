@@ -242,6 +242,53 @@ def encode(ids=None, comments=None, sequences=None, qualities=None, mask_runs_=N
     return res
 
 
+def set_encoder_workers(n: int):
+    """Generator-only: libzstd worker threads for encoders created afterwards (0 = the reference's single-threaded pattern)."""
+    lib().nafo_set_encoder_workers(C.c_int(n))
+
+
+def encode_blobs(n, ids=None, comments=None, sequences=None, qualities=None, mask_runs_=None, sequence_type=DNA, level=0,
+                 flush_per_record=True, line_length=60, name_separator=" ") -> bytes:
+    """encode() for fields that already are (uint8 blob, uint64 offsets[n + 1]) numpy pairs (millions of records)."""
+    args, keep = [], []
+    for f in (ids, comments, sequences, qualities):
+        if f is None:
+            args += [None, None]
+        else:
+            blob, off = np.ascontiguousarray(f[0], dtype=np.uint8), np.ascontiguousarray(f[1], dtype=np.uint64)
+            keep.append((blob, off))
+            args += [blob.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64))]
+    if mask_runs_ is not None:
+        mr = np.asarray(mask_runs_, dtype=np.uint64)
+        mptr, mn = mr.ctypes.data_as(C.POINTER(C.c_uint64)), len(mr)
+    else:
+        mr, mptr, mn = None, None, 0
+    out = C.c_void_p()
+    out_len = C.c_size_t()
+    _check(lib().nafo_encode(C.c_int(sequence_type), C.c_int(level), C.c_int(int(flush_per_record)), C.c_uint64(line_length),
+                             C.c_int(ord(name_separator)), C.c_uint64(n), *args, mptr, C.c_uint64(mn), C.byref(out), C.byref(out_len)))
+    res = C.string_at(out, out_len.value)
+    lib().nafo_free(out)
+    return res
+
+
+def synth_chromosome(seed, n) -> np.ndarray:
+    dst = np.empty(n, dtype=np.uint8)
+    lib().nafo_synth_chromosome(C.c_uint64(seed), C.c_uint64(n), dst.ctypes.data_as(C.c_void_p))
+    return dst
+
+
+def synth_fastq(seed, n_reads, read_len=150):
+    """(ids blob, ids offsets, sequence blob, quality blob) of the cfg4 shape, generated in C."""
+    ids = np.empty(24 * n_reads + 32, dtype=np.uint8)
+    ids_off = np.empty(n_reads + 1, dtype=np.uint64)
+    seq = np.empty(n_reads * read_len, dtype=np.uint8)
+    qual = np.empty(n_reads * read_len, dtype=np.uint8)
+    lib().nafo_synth_fastq(C.c_uint64(seed), C.c_uint64(n_reads), C.c_uint64(read_len), ids.ctypes.data_as(C.c_void_p),
+                           ids_off.ctypes.data_as(C.c_void_p), seq.ctypes.data_as(C.c_void_p), qual.ctypes.data_as(C.c_void_p))
+    return ids[:int(ids_off[-1])], ids_off, seq, qual
+
+
 def synth_dna(seed, n, gc=0.5, families=2, repeat_len=5000, copies=7, iupac_rate=1e-5,
               gap_count=0, gap_len=0, telomere=0) -> bytes:
     dst = np.empty(n, dtype=np.uint8)

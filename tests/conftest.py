@@ -13,6 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: BASELINE.json configs at their stated sizes (250 Mbp, 10^6 reads): minutes, not seconds")
 
 
 @pytest.fixture(scope="session")
