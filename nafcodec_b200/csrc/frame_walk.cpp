@@ -132,6 +132,9 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                 }
                 for (int k = 0; k < streams; k++) {
                     if (ss[k] == 0) FAIL(ERR_INVALID, "zstd literals: empty Huffman stream");
+                    // codes are at most 11 bits: a longer stream cannot be consumed exactly (libzstd: corruption_detected); it also
+                    // bounds the shared memory a stream is staged in
+                    if ((uint64_t)ss[k] * 8 > (uint64_t)dn[k] * 11 + 16) FAIL(ERR_INVALID, "zstd literals: Huffman stream longer than its symbols allow");
                     zf::HufItem it{self, so[k], ss[k], dof[k], dn[k], 0u};
                     plan.huf_items.push_back(it);
                 }
@@ -195,20 +198,15 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
 }
 
 void JobPlan::finalize(uint32_t small_max_symbols) {
-    auto mid = std::stable_partition(huf_items.begin(), huf_items.end(), [&](const zf::HufItem& it) { return it.n_sym > small_max_symbols; });
+    // big = the streams of a 4-stream block whose streams regenerate more than small_max symbols: classified per BLOCK, so the
+    // four streams of a block stay together and in order (k_huf_decode_big runs them as one thread-block cluster)
+    auto is_big = [&](const zf::HufItem& it) { const zf::BlockDesc& b = blocks[it.block]; return b.n_streams == 4 && (b.lit_regen + 3) / 4 > small_max_symbols; };
+    auto mid = std::stable_partition(huf_items.begin(), huf_items.end(), is_big);
     n_huf_big = (uint32_t)(mid - huf_items.begin());
     max_huf_stream = max_huf_small = 0;
     for (size_t i = 0; i < huf_items.size(); i++) {
         uint32_t& m = i < n_huf_big ? max_huf_stream : max_huf_small;
         m = std::max(m, huf_items[i].src_size);
-    }
-    // trees whose tables the big streams need: built once each by k_huf_tables
-    big_tree_slots.clear();
-    std::vector<uint32_t> index_of(n_huf_slots, 0xFFFFFFFFu);
-    for (uint32_t i = 0; i < n_huf_big; i++) {
-        const uint32_t slot = blocks[huf_items[i].block].huf_slot;
-        if (index_of[slot] == 0xFFFFFFFFu) { index_of[slot] = (uint32_t)big_tree_slots.size(); big_tree_slots.push_back(slot); }
-        huf_items[i].tab = index_of[slot];
     }
 }
 

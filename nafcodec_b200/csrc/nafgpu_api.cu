@@ -76,8 +76,8 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, desc, bstate, hufw, huftabs, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g;
-    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_bt = 0, o_chunks = 0, o_gbase = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
+    DevBuf comp, arena, lit, desc, bstate, hufw, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g;
+    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -177,14 +177,13 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
     c->misc_words = 0;                                 // set below, once the number of finisher chunks is known
-    const size_t nh = pl.huf_items.size(), nbt = pl.big_tree_slots.size();
+    const size_t nh = pl.huf_items.size();
     // descriptors: [blocks | frames | NafDev | HufItem | big-tree slots], the same layout in pinned staging and on the device,
     // so that they go up in ONE copy (a burst of small H2D copies is time-sliced against other contexts' result copies)
     c->o_frames = align_up(nb * sizeof(zf::BlockDesc), 16);
     c->o_naf = c->o_frames + align_up(nf * sizeof(zf::FrameDesc), 16);
     c->o_huf = c->o_naf + align_up((size_t)n * sizeof(nk::NafDev), 16);
-    c->o_bt = c->o_huf + align_up(nh * sizeof(zf::HufItem), 16);
-    c->o_chunks = c->o_bt + align_up(nbt * 4, 16);
+    c->o_chunks = c->o_huf + align_up(nh * sizeof(zf::HufItem), 16);
     // finisher chunk table: first 64 KB chunk of every frame (zstd_kernels.cu, k_lz_finish)
     std::vector<uint32_t> chunk_first(nf + 1, 0);
     for (size_t f = 0; f < nf; f++) {
@@ -200,7 +199,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) && c->huftabs.ensure(pl.big_tree_slots.size() * 28672 + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
@@ -213,7 +212,6 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (nf) memcpy(sp + c->o_frames, pl.frames.data(), nf * sizeof(zf::FrameDesc));
     if (n) memcpy(sp + c->o_naf, c->arch.data(), (size_t)n * sizeof(nk::NafDev));
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
-    if (nbt) memcpy(sp + c->o_bt, pl.big_tree_slots.data(), nbt * 4);
     memcpy(sp + c->o_chunks, chunk_first.data(), (nf + 1) * 4);
     memcpy(sp + c->o_gbase, g_base.data(), (nf + 1) * 8);
     if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
@@ -246,7 +244,6 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         J.fin_cost_us = (uint32_t)std::min<uint64_t>(150 + waves * 90, 0x7FFFFFFFu);
     }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
-    J.huf_tabs = (uint8_t*)c->huftabs.p; J.big_tree_slots = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_bt); J.n_big_trees = (uint32_t)nbt;
     J.huf_items = (const zf::HufItem*)((const uint8_t*)c->desc.p + c->o_huf); J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
     J.debug = nullptr;
     if (getenv("NAFGPU_DEBUG_HUF") && nh) {
@@ -307,7 +304,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->huftabs, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);

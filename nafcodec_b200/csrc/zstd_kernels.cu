@@ -617,12 +617,14 @@ __device__ __forceinline__ saddr_t to_saddr(const void* p) { return (saddr_t)__c
 __device__ __forceinline__ uint32_t lds32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds16(saddr_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ void sts32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
 #else
 typedef uintptr_t saddr_t;
 static inline saddr_t to_saddr(const void* p) { return (saddr_t)p; }
 static inline uint32_t lds32(saddr_t a) { return *(const uint32_t*)a; }
 static inline uint32_t lds16(saddr_t a) { return *(const uint16_t*)a; }
 static inline void sts8(saddr_t a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
+static inline void sts32(saddr_t a, uint32_t v) { *(uint32_t*)a = v; }
 #endif
 
 constexpr int HUF_W = 12;                          // index width of the multi-symbol tables
@@ -641,9 +643,17 @@ __device__ __forceinline__ void win_init(Win& w, saddr_t comp, int x) {
     w.rr = x - (qi << 5);
 }
 __device__ __forceinline__ uint32_t win_peek(const Win& w) { return __funnelshift_r(w.lo, w.hi, w.rr - HUF_W) & 0xFFFu; }
+// The refill is PREDICATED, not branched: per lookup a lane needs it with p = 0.3, so some lane of a warp always does, and
+// a branch costs the whole warp the body plus the divergence bookkeeping (ncu, round 1: 14 % of the kernel's instructions
+// at 0.64 thread efficiency on this line).
 __device__ __forceinline__ void win_consume(Win& w, int len) {
     w.rr -= len;
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, 12;\n\t@p mov.b32 %1, %0;\n\t@p sub.u32 %2, %2, 4;\n\t@p ld.shared.u32 %0, [%2];\n\t@p add.s32 %3, %3, 32;\n\t}"
+                 : "+r"(w.lo), "+r"(w.hi), "+r"(w.waddr), "+r"(w.rr));
+#else
     if (w.rr < HUF_W) { w.hi = w.lo; w.waddr -= 4; w.lo = lds32(w.waddr); w.rr += 32; }
+#endif
 }
 
 // Follows one track from q (bits below the top of the stream) to the FIRST codeword boundary >= lim, counting symbols.
@@ -754,14 +764,33 @@ __device__ __forceinline__ uint64_t map_compose(uint64_t g, uint64_t f) {
 }
 constexpr uint64_t MAP_IDENTITY = 0xFEDCBA9876543210ull;
 
+// Entries [lo, hi) of the two tables over 12-bit windows, from the finished base table: decode the window while whole
+// codewords fit (no barrier inside; the caller separates it from the base-table build and from the first use).
+template <int HUF_T, bool MULTI>
+__device__ __forceinline__ void huf_build_wide(const uint16_t* table, int maxbits, uint16_t* bm, uint32_t* t3, uint32_t lo, uint32_t hi) {
+    const int sh1 = HUF_W - maxbits;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += HUF_T) {
+        uint32_t used = 0, n = 0, syms = 0, used3 = 0, mask = 0;
+        for (;;) {
+            const uint32_t e = table[((i << used) & 0xFFFu) >> sh1];
+            const uint32_t len = e & 0xFFu;
+            if (used + len > (uint32_t)HUF_W) break;
+            if (n < 3) { syms |= (e >> 8) << (8 * n); used3 = used + len; n++; }
+            used += len;
+            mask |= 1u << (used - 1);
+            if (used == (uint32_t)HUF_W) break;
+        }
+        bm[i] = (uint16_t)mask;
+        if (MULTI) t3[i] = syms | (used3 << 24) | (n << 28);
+    }
+}
+
 // Builds the three decode tables of one Huffman tree in shared memory (all HUF_T threads of the CTA must call):
 //   table: base table, index = next max_bits bits -> symbol << 8 | length (RFC 8878 4.2.1: ascending weight, then symbol)
 //   bm   : boundary masks of 12-bit windows;  t3 (WITH_T3): 3-symbol write table of 12-bit windows
-template <int HUF_T, bool WITH_T3>
-__device__ __forceinline__ void huf_build_tables(const uint8_t* weights, int nsym, int maxbits, uint16_t* table, uint16_t* bm, uint32_t* t3,
-                                                 uint16_t* wcnt) {
+template <int HUF_T>
+__device__ __forceinline__ void huf_build_t1(const uint8_t* weights, int nsym, int maxbits, uint16_t* table, uint16_t* wcnt) {
     const int tid = threadIdx.x, lane = tid & 31;
-    constexpr bool MULTI = WITH_T3;
     // symbols are handled in 8 groups of 32 (group g = symbols 32g..32g+31); wcnt[g][w] = symbols of weight w in group g
     constexpr int GROUPS_PER_PASS = HUF_T >= 256 ? 8 : HUF_T / 32;
     int wreg[8 / GROUPS_PER_PASS], rankreg[8 / GROUPS_PER_PASS];
@@ -805,48 +834,14 @@ __device__ __forceinline__ void huf_build_tables(const uint8_t* weights, int nsy
         }
     }
     __syncthreads();
-    {
-        // tables over 12-bit windows: decode the window with the base table while whole codewords fit
-        const int sh1 = HUF_W - maxbits;
-        for (uint32_t i = tid; i < (1u << HUF_W); i += HUF_T) {
-            uint32_t used = 0, n = 0, syms = 0, used3 = 0, mask = 0;
-            for (;;) {
-                const uint32_t e = table[((i << used) & 0xFFFu) >> sh1];
-                const uint32_t len = e & 0xFFu;
-                if (used + len > (uint32_t)HUF_W) break;
-                if (n < 3) { syms |= (e >> 8) << (8 * n); used3 = used + len; n++; }
-                used += len;
-                mask |= 1u << (used - 1);
-                if (used == (uint32_t)HUF_W) break;
-            }
-            bm[i] = (uint16_t)mask;
-            if (MULTI) t3[i] = syms | (used3 << 24) | (n << 28);
-        }
-        __syncthreads();
-    }
 }
 
-constexpr uint32_t HUF_TAB_BYTES = 4096u + 8192u + 16384u;        // t1 | bm | t3 of one tree in global memory
-
-// k_huf_tables: one CTA per Huffman tree that big streams use: the tables are built ONCE per tree (a 4-stream block, and
-// every treeless block after it, share them) and the stream CTAs just copy 28 KB in.
-__global__ void __launch_bounds__(512) k_huf_tables(JobDev J) {
-    __shared__ __align__(16) uint16_t table[2048];
-    __shared__ __align__(16) uint16_t bm[4096];
-    __shared__ __align__(16) uint32_t t3[4096];
-    __shared__ __align__(16) uint8_t weights[256];
-    __shared__ uint16_t wcnt[128];
-    const int tid = threadIdx.x;
-    const uint32_t slot = J.big_tree_slots[blockIdx.x];
-    for (int i = tid; i < 64; i += 512) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)slot * 256))[i];
-    const int nsym = (int)J.huf_meta[(size_t)slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)slot * 2 + 1];
-    if (maxbits == 0) return;                                           // bad tree: flagged by k_build_tables<1>
+template <int HUF_T, bool WITH_T3>
+__device__ __forceinline__ void huf_build_tables(const uint8_t* weights, int nsym, int maxbits, uint16_t* table, uint16_t* bm, uint32_t* t3,
+                                                 uint16_t* wcnt) {
+    huf_build_t1<HUF_T>(weights, nsym, maxbits, table, wcnt);
+    huf_build_wide<HUF_T, WITH_T3>(table, maxbits, bm, t3, 0u, 1u << HUF_W);
     __syncthreads();
-    huf_build_tables<512, true>(weights, nsym, maxbits, table, bm, t3, wcnt);
-    uint4* g = (uint4*)(J.huf_tabs + (size_t)blockIdx.x * HUF_TAB_BYTES);
-    for (int i = tid; i < 256; i += 512) g[i] = ((const uint4*)table)[i];
-    for (int i = tid; i < 512; i += 512) g[256 + i] = ((const uint4*)bm)[i];
-    for (int i = tid; i < 1024; i += 512) g[768 + i] = ((const uint4*)t3)[i];
 }
 
 template <int HUF_T>
@@ -887,16 +882,7 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
     __syncthreads();
     HUF_TICK(1);
     if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;              // bits below the stream start read as zero
-    if (MULTI) {
-        // the tree's tables were built once by k_huf_tables: copy 28 KB (t1 | bm | t3) from global memory
-        const uint4* g = (const uint4*)(J.huf_tabs + (size_t)it.tab * HUF_TAB_BYTES);
-        for (int i = tid; i < 256; i += HUF_T) ((uint4*)table)[i] = g[i];
-        for (int i = tid; i < 512; i += HUF_T) ((uint4*)bm)[i] = g[256 + i];
-        for (int i = tid; i < 1024; i += HUF_T) ((uint4*)t3)[i] = g[768 + i];
-        __syncthreads();
-    } else {
-        huf_build_tables<HUF_T, false>(weights, nsym, maxbits, table, bm, t3, wcnt);
-    }
+    huf_build_tables<HUF_T, MULTI>(weights, nsym, maxbits, table, bm, t3, wcnt);
     HUF_TICK(2);
 
     // ---- phase 1: transition map of every range -------------------------------------------------------------------------
@@ -1090,6 +1076,320 @@ __global__ void __launch_bounds__(HUF_T, HUF_T == 512 ? 3 : 4) k_huf_decode(JobD
             for (uint32_t k = (last_full << 4) + tid; k < endb; k += HUF_T) dal[k] = sout[k];
     }
     HUF_TICK(6);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_huf_decode_big: the streams of 4-stream blocks (up to 32 Ki symbols each), one CTA of 256 threads per stream, the four
+// CTAs of a block launched as ONE THREAD-BLOCK CLUSTER.
+//
+//   * The compressed stream is staged with ONE bulk asynchronous copy (cp.async.bulk global -> shared, completion on an
+//     mbarrier) issued by a single thread; the other threads build the decode tables meanwhile.
+//   * The four streams of a block share a Huffman tree: every CTA builds the small base table itself and ONE QUARTER of the
+//     two tables over 12-bit windows (boundary masks, 3-symbol write table), then fetches the other three quarters from its
+//     cluster peers through distributed shared memory.  Round 1 built them once per tree in a separate kernel and every stream
+//     CTA copied 28 KB back from global memory (+ 175 MB of DRAM reads per 256-archive step, + one launch).
+//   * Intra-stream parallelism as in k_huf_decode (candidate tracks, transition maps, composition), restructured around what
+//     ncu showed (profiles/r1_huf_decode512_batch256.txt: 40 thread-instructions per table lookup, most of them bookkeeping):
+//       - 256 ranges per stream instead of 512: the price of not knowing where a range starts is ~1000 bit-steps of
+//         speculation PER RANGE whatever its length (measured on cfg2: 3.7 tracks alive 12 bits into a range, 2.0 at 108,
+//         1.4 at 256, 1.2 at 512), and every per-range fixed cost halves;
+//       - the live tracks of a range at a checkpoint are a BITMASK of landing offsets (a track lands on the first codeword
+//         boundary at or past the checkpoint, at most max_bits - 1 further): merging tracks is an OR, not 55 compares;
+//       - what a track did on a leg (landing offset, symbols) goes to a small shared-memory table indexed by (leg, range,
+//         offset); the per-candidate results are recovered by walking three entries, only for what is needed;
+//       - all tracks of all ranges on a leg are work items dealt out evenly over the CTA (as before);
+//       - composing the transition maps: a map that sends every candidate to the same offset (all tracks merged: nearly every
+//         range) absorbs whatever comes before it, so the shuffle scan skips the 11-nibble gather when no lane needs it;
+//       - the window refill is predicated; the write pass assembles 4-byte words in registers (one store per four symbols
+//         instead of four byte stores: the pass was bound by shared-memory bank conflicts, not by issue slots).
+constexpr int HB_T = 256;
+constexpr int HB_NW = HB_T / 32;
+#if defined(NAFGPU_EMULATE)
+constexpr int HB_CL = 1;                            // the emulator runs one CTA at a time: every CTA builds whole tables
+#define HB_CLUSTER_ATTR
+#else
+constexpr int HB_CL = 4;
+#define HB_CLUSTER_ATTR __cluster_dims__(4, 1, 1)
+#endif
+constexpr int HB_NLEG = 3;
+constexpr int HB_CK0 = 12, HB_CK1 = 108, HB_CK2 = 320;      // checkpoints (bits below the top of a range) where tracks are compared
+constexpr uint32_t HB_SOUT = 32768u + 64u;                  // output image (phase 2); phase 1: boundary masks | leg tables | work queue
+constexpr uint32_t HB_BM_BYTES = 8192u, HB_LEG_BYTES = HB_NLEG * HB_T * MAXC * 2u, HB_Q_BYTES = HB_T * MAXC * 2u;
+static_assert(HB_BM_BYTES + HB_LEG_BYTES + HB_Q_BYTES <= HB_SOUT, "phase-1 scratch must fit the output image");
+constexpr uint32_t HB_FIXED = 4096u + 768u + 16384u + HB_SOUT;      // t1 | weights, wcnt, misc | t3 | output image
+__host__ __device__ constexpr uint32_t hb_smem_bytes(uint32_t max_stream) { return HB_FIXED + ((max_stream + 15u + 16u + 16u + 15u) & ~15u); }
+
+// Exclusive prefix sum of one small value per thread over the CTA (HB_T threads); *total gets the sum.  One barrier; `buf`
+// (HB_NW words) must not be reused before another barrier.
+__device__ __forceinline__ uint32_t hb_scan(uint32_t v, uint32_t* buf, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) buf[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < HB_NW; w++) { const uint32_t x = buf[w]; all += x; if (w < warp) before += x; }
+    *total = all;
+    return before + inc - v;
+}
+
+__device__ __forceinline__ bool map_is_const(uint64_t m, int maxbits) {        // every candidate < maxbits goes to the same offset
+    const uint64_t lowmask = maxbits >= 16 ? ~0ull : ((1ull << (4 * maxbits)) - 1ull);
+    const uint64_t rep = (m & 15ull) * 0x1111111111111111ull;
+    return ((m ^ rep) & lowmask) == 0;
+}
+
+__global__ void HB_CLUSTER_ATTR __launch_bounds__(HB_T, 3) k_huf_decode_big(JobDev J) {
+    NAF_DYN_SMEM(unsigned char, smem);
+    uint16_t* t1 = (uint16_t*)smem;
+    uint8_t* weights = smem + 4096;
+    uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);
+    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..15] two scan buffers, [16..23] warp start candidates, [56..57] mbarrier
+    uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [HB_NW] composed map of each warp (reuses wcnt after the table build)
+    uint32_t* t3 = (uint32_t*)(smem + 4864);
+    uint8_t* sout = smem + 4864 + 16384;
+    uint16_t* bm = (uint16_t*)sout;
+    uint16_t* legtab = (uint16_t*)(sout + HB_BM_BYTES);                 // [leg][range][offset] = landing offset | symbols << 4
+    uint16_t* qitems = (uint16_t*)(sout + HB_BM_BYTES + HB_LEG_BYTES);  // range | offset << 8
+    uint32_t* scomp = (uint32_t*)(smem + HB_FIXED);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const HufItem it = J.huf_items[blockIdx.x];
+    const BlockDesc& B = J.blocks[it.block];
+    // ---- stage the stream: the 16 B-aligned image of global memory, behind 16 bytes that stay zero --------------------------
+    const uint8_t* g = J.comp + B.src_off + it.src_off;
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    const uint32_t image_bytes = ((a + it.src_size + 15u) >> 4) << 4;
+#if defined(__CUDA_ARCH__)
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&misc[56]);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(image_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(scomp + 4)), "l"(g - a), "r"(image_bytes), "r"(mbar) : "memory");
+    }
+#else
+    for (uint32_t c = tid; c < (image_bytes >> 4); c += HB_T) ((uint4*)scomp)[1 + c] = ((const uint4*)(g - a))[c];
+#endif
+    for (int i = tid; i < 64; i += HB_T) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)B.huf_slot * 256))[i];
+    const int nsym = (int)J.huf_meta[(size_t)B.huf_slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)B.huf_slot * 2 + 1];
+    __syncthreads();
+    // a bad tree (flagged by k_build_tables) is the same for the whole cluster: nobody builds, nobody waits for a peer
+    if (maxbits != 0) {
+        huf_build_t1<HB_T>(weights, nsym, maxbits, t1, wcnt);
+#if defined(__CUDA_ARCH__)
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        const uint32_t rank = cluster.block_rank();
+        constexpr uint32_t QUARTER = (1u << HUF_W) / HB_CL;
+        huf_build_wide<HB_T, true>(t1, maxbits, bm, t3, rank * QUARTER, (rank + 1) * QUARTER);
+        cluster.sync();
+        // the other quarters, from the peers' shared memory (DSMEM): 2 KB of boundary masks + 4 KB of write table each
+        constexpr uint32_t BM16 = QUARTER * 2 / 16, T316 = QUARTER * 4 / 16;
+        for (uint32_t i = tid; i < (HB_CL - 1) * (BM16 + T316); i += HB_T) {
+            const uint32_t r = (rank + 1 + i / (BM16 + T316)) % HB_CL, j = i % (BM16 + T316);
+            if (j < BM16) ((uint4*)bm)[r * BM16 + j] = ((const uint4*)cluster.map_shared_rank(bm, r))[r * BM16 + j];
+            else ((uint4*)t3)[r * T316 + (j - BM16)] = ((const uint4*)cluster.map_shared_rank(t3, r))[r * T316 + (j - BM16)];
+        }
+        cluster.sync();                                                 // (nobody overwrites its boundary masks or exits while a peer still reads)
+#else
+        huf_build_wide<HB_T, true>(t1, maxbits, bm, t3, 0u, 1u << HUF_W);
+        __syncthreads();
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    {   // the bulk copy has landed (also before an early exit: the shared memory must not be handed to another CTA under it)
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar), "r"(0) : "memory");
+        } while (!done);
+    }
+#endif
+    // (one thread reads the flag: another stream's kernel may set it at any moment, and the decision must be the CTA's)
+    if (__syncthreads_or(maxbits == 0 || (tid == 0 && J.frame_bad[B.frame] != 0))) return;
+    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;              // bits below the stream start read as zero
+    // a tree whose codes all have the same length (e.g. 16 equiprobable byte values) never lets tracks merge -- and does not
+    // need to: the codeword boundaries are the multiples of that length
+    const bool fixed_len = !__syncthreads_or(tid < 128 && (tid & 15) >= 2 && (tid & 15) <= zc::HUF_MAX_BITS && wcnt[tid] != 0);
+
+    // ---- phase 1: transition map of every range -------------------------------------------------------------------------
+    // q = distance (in bits) from the top of the stream; smem bit position x = XTOP - q.
+    const int Z = (int)(16 + a) * 8;
+    const uint8_t last = ((const uint8_t*)scomp)[16 + a + it.src_size - 1];
+    if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+    const int P0 = 8 * (int)(it.src_size - 1) + zc::highbit32(last);
+    const int XTOP = Z + P0;
+    int S = (P0 + HB_T - 1) / HB_T;
+    if (S < 2 * MAXC) S = 2 * MAXC;
+    const int ck[HB_NLEG + 1] = {S < HB_CK0 ? S : HB_CK0, S < HB_CK1 ? S : HB_CK1, S < HB_CK2 ? S : HB_CK2, S};
+    const int q0 = tid * S;
+    const int qe = (q0 + S < P0) ? q0 + S : P0;
+    const bool active = q0 < P0;
+    const saddr_t s_comp = to_saddr(scomp), s_bm = to_saddr(bm);
+    auto cp_at = [&](int rq0, int rqe, int j) { const int x = rq0 + ck[j]; return x < rqe ? x : rqe; };      // checkpoint j of a range
+
+    // (1) first stop: every candidate lands on its first codeword boundary at or past checkpoint 0 (one lookup each, out of one
+    //     64-bit window); candidates of the same codeword chain land together.
+    uint64_t first = ~0ull, fcnt = 0;                                   // candidate -> landing offset / symbols so far (4 bits each)
+    uint32_t live = 0;                                                  // landing offsets in use at the current checkpoint
+    if (active) {
+        const int l0 = cp_at(q0, qe, 0);
+        first = 0;
+        if (fixed_len) {
+            int q = q0 + (maxbits - q0 % maxbits) % maxbits, c = 0;     // the one candidate that is a boundary; the others follow it
+            track_advance(s_comp, s_bm, XTOP, q, c, l0);
+            first = (uint64_t)(uint32_t)(q - l0) * 0x1111111111111111ull;
+            fcnt = (uint64_t)(uint32_t)c * 0x1111111111111111ull;
+            live = 1u << (q - l0);
+        } else {
+            for (int k = 0; k < maxbits; k++) {
+                int q = q0 + k, c = 0;
+                track_advance(s_comp, s_bm, XTOP, q, c, l0);
+                const uint32_t o = (uint32_t)(q - l0);
+                first |= (uint64_t)o << (4 * k);
+                fcnt |= (uint64_t)c << (4 * k);
+                live |= 1u << o;
+            }
+        }
+        if (maxbits < 16) first |= ~0ull << (4 * maxbits);              // candidates that cannot occur: dead (15)
+    }
+    // (2) legs between checkpoints: the live tracks of ALL ranges are work items dealt out evenly over the CTA
+    uint32_t leg_done = 0;
+    for (int leg = 0; leg < HB_NLEG; leg++) {
+        if (ck[leg + 1] == ck[leg]) continue;                           // (uniform) short ranges: nothing between these checkpoints
+        leg_done |= 1u << leg;
+        const uint32_t n_mine = (uint32_t)__popc(live);
+        uint32_t qtotal;
+        uint32_t idx = hb_scan(n_mine, misc + 8 * (leg & 1), &qtotal);
+        for (uint32_t m = live; m; m &= m - 1) qitems[idx++] = (uint16_t)((uint32_t)tid | ((uint32_t)(__ffs((int)m) - 1) << 8));
+        __syncthreads();
+        for (uint32_t i = tid; i < qtotal; i += HB_T) {
+            const uint32_t item = qitems[i];
+            const int owner = (int)(item & 0xFFu), o = (int)(item >> 8);
+            const int oq0 = owner * S, oqe = (oq0 + S < P0) ? oq0 + S : P0;
+            const int lim = cp_at(oq0, oqe, leg + 1);
+            int q = cp_at(oq0, oqe, leg) + o, c = 0;
+            track_advance(s_comp, s_bm, XTOP, q, c, lim);
+            legtab[(leg * HB_T + owner) * MAXC + o] = (uint16_t)((uint32_t)(q - lim) | ((uint32_t)c << 4));
+        }
+        __syncthreads();
+        uint32_t nl = 0;
+        for (uint32_t m = live; m; m &= m - 1) nl |= 1u << (legtab[(leg * HB_T + tid) * MAXC + (__ffs((int)m) - 1)] & 15u);
+        live = nl;
+    }
+    // (3) the map candidate -> candidate of the next range: exit offset of every landing offset in use after the first stop
+    uint64_t fmap = MAP_IDENTITY;
+    if (active) {
+        uint64_t exit_of = 0;
+        uint32_t starts = 0;
+        for (int k = 0; k < maxbits; k++) starts |= 1u << ((uint32_t)(first >> (4 * k)) & 15u);
+        for (uint32_t m = starts; m; m &= m - 1) {
+            const int o0 = __ffs((int)m) - 1;
+            uint32_t o = (uint32_t)o0;
+#pragma unroll
+            for (int leg = 0; leg < HB_NLEG; leg++) if (leg_done & (1u << leg)) o = legtab[(leg * HB_T + tid) * MAXC + o] & 15u;
+            exit_of |= (uint64_t)o << (4 * o0);
+        }
+        fmap = 0;
+        for (int k = 0; k < maxbits; k++) fmap |= ((exit_of >> (4 * ((uint32_t)(first >> (4 * k)) & 15u))) & 15ull) << (4 * k);
+        if (maxbits < 16) fmap |= ~0ull << (4 * maxbits);
+    }
+    // ---- compose the maps along the stream: inclusive scan in the warp, then warp totals serially ------------------------------
+    // inc_map(lane) = f_lane o ... o f_(lane - 2^d + 1); a constant map absorbs everything before it, and after the first
+    // step nearly every lane holds one: the gather runs only when some lane of the warp still needs it.
+    uint64_t inc_map = fmap;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, inc_map, d);
+        const bool need = lane >= d && !map_is_const(inc_map, maxbits);
+        if (__any_sync(0xFFFFFFFFu, need)) { if (need) inc_map = map_compose(inc_map, o); }
+    }
+    uint64_t exc_map = __shfl_up_sync(0xFFFFFFFFu, inc_map, 1);
+    if (lane == 0) exc_map = MAP_IDENTITY;
+    if (lane == 31) wmap[warp] = inc_map;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t k = 0;
+        for (int w = 0; w < HB_NW; w++) { misc[16 + w] = k; k = (uint32_t)(wmap[w] >> (4 * k)) & 15u; }
+    }
+    __syncthreads();
+    const uint32_t kw = misc[16 + warp];
+    const uint32_t ktrue = (uint32_t)(exc_map >> (4 * kw)) & 15u;      // this thread's true candidate
+    // symbols of the true track, and where it lands
+    uint32_t mycnt = 0;
+    int myland = -1;
+    if (active && ktrue < (uint32_t)maxbits) {
+        uint32_t o = (uint32_t)(first >> (4 * ktrue)) & 15u;
+        mycnt = (uint32_t)(fcnt >> (4 * ktrue)) & 15u;
+#pragma unroll
+        for (int leg = 0; leg < HB_NLEG; leg++) {
+            if (leg_done & (1u << leg)) { const uint32_t e = legtab[(leg * HB_T + tid) * MAXC + o]; o = e & 15u; mycnt += e >> 4; }
+        }
+        myland = qe + (int)o;
+    }
+    // the stream must end exactly on its first bit: the last active range's true track lands on P0
+    const bool bad_end = active && qe == P0 && myland != P0;
+    // ---- count, scan, write ------------------------------------------------------------------------------------------
+    const int any_bad = __syncthreads_or(bad_end);                      // (also: every read of the leg tables is done before phase 2 overwrites them)
+    uint32_t total;
+    const uint32_t off = hb_scan(mycnt, misc, &total);
+    if (any_bad || total != it.n_sym) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); return; }
+    uint8_t* dst = J.lit + B.lit_base + it.dst_off;
+    const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
+    if (mycnt) {
+        // write pass: from the true start to the first boundary at or past the end of the range.  Bytes go out as aligned 4-byte
+        // words assembled in a register pair; the ragged head and tail (words shared with the neighbouring ranges) as bytes.
+        const saddr_t s_t3 = to_saddr(t3), s_t1 = to_saddr(t1);
+        saddr_t out = to_saddr(sout) + a2 + off;
+        int q = q0 + (int)ktrue;
+        int rem = qe - q;
+        Win w;
+        win_init(w, s_comp, XTOP - q);
+        const int sh1 = HUF_W - maxbits;
+        while ((out & 3u) && rem > 0) {                                 // head: single symbols up to a word boundary
+            const uint32_t e = lds16(s_t1 + 2 * (win_peek(w) >> sh1));
+            sts8(out, e >> 8); out++;
+            rem -= (int)(e & 0xFFu);
+            win_consume(w, (int)(e & 0xFFu));
+        }
+        uint32_t acc_lo = 0, acc_hi = 0;
+        int pc = 0;                                                     // bytes waiting in acc
+        while (rem > HUF_W) {
+            const uint32_t e = lds32(s_t3 + 4 * win_peek(w));
+            const int n = (int)(e >> 28), len = (int)(e >> 24) & 15;
+            const uint32_t sy = e & 0xFFFFFFu;
+            acc_lo |= sy << (8 * pc);
+            acc_hi |= __funnelshift_l(sy, 0u, 8 * pc);                  // the bits that fall off the top of acc_lo
+            pc += n;
+            if (pc >= 4) { sts32(out, acc_lo); out += 4; acc_lo = acc_hi; acc_hi = 0; pc -= 4; }
+            rem -= len;
+            win_consume(w, len);
+        }
+        while (rem > 0) {                                               // the last symbols, one at a time
+            const uint32_t e = lds16(s_t1 + 2 * (win_peek(w) >> sh1));
+            acc_lo |= (e >> 8) << (8 * pc);
+            pc++;
+            if (pc == 4) { sts32(out, acc_lo); out += 4; acc_lo = 0; pc = 0; }
+            rem -= (int)(e & 0xFFu);
+            win_consume(w, (int)(e & 0xFFu));
+        }
+        for (int k = 0; k < pc; k++) sts8(out + k, acc_lo >> (8 * k));
+    }
+    __syncthreads();
+    {
+        // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends ----------------
+        const uint32_t n = it.n_sym, endb = a2 + n;
+        uint8_t* dal = dst - a2;
+        const uint32_t first_full = a2 ? 1u : 0u, last_full = endb >> 4;     // chunks [first_full, last_full) are complete
+        for (uint32_t c = first_full + tid; c < last_full; c += HB_T) ((uint4*)dal)[c] = ((const uint4*)sout)[c];
+        if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HB_T) dal[k] = sout[k]; }
+        if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
+            for (uint32_t k = (last_full << 4) + tid; k < endb; k += HB_T) dal[k] = sout[k];
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -1698,12 +1998,11 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) { cudaEventRecord(fork, st); cudaStreamWaitEvent(st2, fork, 0); }
     if (J.n_huf_items) {
         NAF_LAUNCH(k_build_tables<1>, J.n_blocks, 32, 0, sb, J); launches++;
-        if (J.n_big_trees) { NAF_LAUNCH(k_huf_tables, J.n_big_trees, 512, 0, sb, J); launches++; }
-        if (J.n_huf_big) {   // items [0, n_huf_big): streams of 4-stream blocks; the rest: short streams
-            const uint32_t smem = huf_fixed_smem(HUF_T_BIG) + ((J.max_huf_stream + 15 + 16 + 16 + 15) & ~15u);
-            NAF_SET_MAX_SMEM(k_huf_decode<HUF_T_BIG>, smem);
+        if (J.n_huf_big) {   // items [0, n_huf_big): the streams of 4-stream blocks, four consecutive items (= one cluster) per block
+            const uint32_t smem = hb_smem_bytes(J.max_huf_stream);
+            NAF_SET_MAX_SMEM(k_huf_decode_big, smem);
             if (!st2) ev->kernel_begin();
-            NAF_LAUNCH((k_huf_decode<HUF_T_BIG>), J.n_huf_big, HUF_T_BIG, smem, sb, J, J.huf_items); launches++;
+            NAF_LAUNCH(k_huf_decode_big, J.n_huf_big, HB_T, smem, sb, J); launches++;
             if (!st2) ev->kernel_end();
         }
         if (J.n_huf_items > J.n_huf_big) {

@@ -8,7 +8,7 @@
 
 namespace zk {
 
-constexpr uint32_t HUF_SMALL_SYMBOLS = 2048;   // streams regenerating <= this many symbols are decoded by one warp          // dependency-resolving passes before the ordered fallback
+constexpr uint32_t HUF_SMALL_SYMBOLS = 2048;   // blocks whose streams regenerate <= this many symbols each go to the four-warp kernel
 
 // Everything the zstd kernels need, by value.  All pointers are device pointers.
 struct JobDev {
@@ -43,11 +43,8 @@ struct JobDev {
     uint32_t* fin_chunk_flag;         // [fin_total_chunks] chunk has unresolved bytes (zeroed every run)
     uint32_t* fin_unresolved;         // unresolved bytes after level 1
     uint32_t* fin_count;              // [3] rotating per-round counters of level 2
-    uint8_t* huf_tabs;                // n_big_trees x 28 KB prebuilt decode tables (t1 | bm | t3) of trees used by big streams
-    const uint32_t* big_tree_slots;   // weight-record slot of each of them
-    uint32_t n_big_trees;
     const zf::HufItem* huf_items;     // one per Huffman bitstream
-    uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big) use the 512-thread kernel, the rest one warp each
+    uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big): streams of 4-stream blocks, four per block (k_huf_decode_big, one cluster per block); the rest: k_huf_decode<128>
     uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
     uint32_t n_frames, n_blocks, n_slots;
     uint32_t n_checksums;             // frames with a content checksum (k_frame_checksum runs only if any)
