@@ -112,6 +112,7 @@ typedef struct nafgpu_job_stats {
     uint32_t lz_unresolved;             /* bytes the finisher's first level left to its cross-chunk level (0 without a hand-over) */
     float text_kernel_ms;               /* device time of the last nafgpu_job_format's kernels (CUDA events on the context's stream) */
     uint64_t text_bytes;                /* bytes of text the last nafgpu_job_format produced */
+    uint32_t lz_pending[24];            /* matches still waiting after dependency round 1, 2, ... of the last fetched run (0 past the last round) */
 } nafgpu_job_stats;
 
 /* ---- host-only helpers -------------------------------------------------------------------------------- */
@@ -201,6 +202,39 @@ int nafgpu_job_format(nafgpu_ctx* ctx, int format, uint64_t line_length, nafgpu_
 /* prepare + run + format in one call. */
 int nafgpu_format_batch(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want, int format,
                         uint64_t line_length, nafgpu_text* out);
+
+/* ---- encode side -----------------------------------------------------------------------------------
+ * What the reference's writers compute per record before the bytes reach the zstd compressors, for all records of an
+ * archive at once:
+ *   SequenceWriter::encode / write / into_inner (nafcodec/src/encoder/writer.rs:21-90): IUPAC -> 4 bit, first residue in the
+ *     LOW nibble, the odd-length `cache` carried into the next record, the last nibble padded with 0;
+ *   write_length (nafcodec/src/encoder/mod.rs:37-44): u32 LE words, 0xFFFFFFFF continues a length;
+ *   and the soft-mask extraction the reference never wrote (its mask writer is commented out, encoder/mod.rs:240, and
+ *   SequenceWriter rejects lower case): with extract_mask the lower-case runs come back as the bytes of a Mask section in
+ *   the format MaskReader decodes (decoder/reader.rs:196-231), and the residues are packed as their upper-case codes.
+ * zstd compression of these streams stays with the caller (the CPU, as in the reference: encoder/mod.rs:147-154,365). */
+typedef struct nafgpu_pack_input {
+    const uint8_t* sequence;            /* HOST: the residues of all records, concatenated (ASCII) */
+    const uint64_t* lengths;            /* HOST: n_records lengths; their sum must be n_residues (else Error::InvalidLength) */
+    uint64_t n_records;
+    uint64_t n_residues;
+    int32_t sequence_type;              /* 0 dna ('T'), 1 rna ('U'); protein / text are written verbatim by the reference: not packed */
+    int32_t extract_mask;               /* 0: lower case is "unexpected sequence character" like the reference; 1: see above */
+} nafgpu_pack_input;
+
+typedef struct nafgpu_pack_result {
+    const uint8_t* packed;              /* HOST (pinned, owned by the context): (n_residues + 1) / 2 bytes of the Sequence stream */
+    uint64_t packed_size;
+    const uint8_t* length_words;        /* the Length stream: length_size bytes (4 per word) */
+    uint64_t length_size;
+    const uint8_t* mask;                /* the Mask stream (NULL without extract_mask): mask_size bytes, n_mask_runs runs */
+    uint64_t mask_size;
+    uint64_t n_mask_runs;
+    uint64_t first_invalid;             /* UINT64_MAX, or the index (in the concatenation) of the first character SequenceWriter::encode
+                                           rejects: Error::InvalidSequence (encoder/mod.rs:283-286); the call returns NAFGPU_ERR_INVALID_DATA */
+} nafgpu_pack_result;
+
+int nafgpu_pack(nafgpu_ctx* ctx, const nafgpu_pack_input* in, nafgpu_pack_result* out);
 
 /* Device pointers of the last run's outputs, for callers that keep results in HBM (device-resident variant). */
 int nafgpu_job_device_result(nafgpu_ctx* ctx, uint32_t archive, const uint8_t** sequence_dev, uint64_t* capacity_bytes);

@@ -7,17 +7,10 @@ The compute runs in hand-written sm_100a kernels behind the C ABI of include/naf
 from .data import Flag, Flags, FormatVersion, Header, Record, SequenceType
 from .decoder import (ArchiveResult, Context, Decoder, DecoderBuilder, Pipeline, decode_batch, parse_archive, shared_context,
                       to_fasta, to_fastq, to_text)
+from .encoder import Encoder, pack_sequences
 from .errors import NafDeviceError, NafError, NafIoError, NafParseError, NafUnicodeError
 
 __version__ = "0.1.0"
-
-
-class Encoder:
-    """Writing archives is outside the accelerated path: zstd *compression* stays on the CPU in the
-    reference crate.  The name is kept so `open(..., "w")` fails with a clear message instead of an AttributeError."""
-
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("nafcodec_b200 accelerates decoding only; use the reference nafcodec.Encoder to write archives")
 
 
 def open(file, mode="r", **options):
@@ -30,5 +23,5 @@ def open(file, mode="r", **options):
 
 
 __all__ = ["Decoder", "DecoderBuilder", "Record", "Header", "Flag", "Flags", "SequenceType", "FormatVersion", "Encoder", "open",
-           "Context", "Pipeline", "ArchiveResult", "decode_batch", "to_text", "to_fasta", "to_fastq", "parse_archive", "shared_context",
+           "pack_sequences", "Context", "Pipeline", "ArchiveResult", "decode_batch", "to_text", "to_fasta", "to_fastq", "parse_archive", "shared_context",
            "NafError", "NafIoError", "NafParseError", "NafUnicodeError", "NafDeviceError"]

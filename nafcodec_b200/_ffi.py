@@ -48,6 +48,16 @@ class Text(C.Structure):
                 ("first_bad_record", C.c_uint64)]
 
 
+class PackInput(C.Structure):
+    _fields_ = [("sequence", C.c_void_p), ("lengths", C.c_void_p), ("n_records", C.c_uint64), ("n_residues", C.c_uint64),
+                ("sequence_type", C.c_int32), ("extract_mask", C.c_int32)]
+
+
+class PackResult(C.Structure):
+    _fields_ = [("packed", C.c_void_p), ("packed_size", C.c_uint64), ("length_words", C.c_void_p), ("length_size", C.c_uint64),
+                ("mask", C.c_void_p), ("mask_size", C.c_uint64), ("n_mask_runs", C.c_uint64), ("first_invalid", C.c_uint64)]
+
+
 class JobStats(C.Structure):
     _fields_ = [("n_archives", C.c_uint64), ("n_frames", C.c_uint64), ("n_blocks", C.c_uint64), ("n_sequences", C.c_uint64),
                 ("compressed_bytes", C.c_uint64), ("section_bytes", C.c_uint64), ("ascii_bytes", C.c_uint64),
@@ -55,7 +65,7 @@ class JobStats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("n_stages", C.c_uint32), ("lz_handover", C.c_uint32),
                 ("lz_rounds", C.c_uint32), ("lz_unresolved", C.c_uint32),
-                ("text_kernel_ms", C.c_float), ("text_bytes", C.c_uint64)]
+                ("text_kernel_ms", C.c_float), ("text_bytes", C.c_uint64), ("lz_pending", C.c_uint32 * 24)]
 
 
 # every symbol include/nafgpu.h declares (tests check the library exports all of them)
@@ -63,7 +73,7 @@ SYMBOLS = ["nafgpu_parse_archive", "nafgpu_variable_u64", "nafgpu_strerror", "na
            "nafgpu_ctx_destroy", "nafgpu_last_error", "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_decode",
            "nafgpu_decode_batch", "nafgpu_job_prepare", "nafgpu_job_run", "nafgpu_job_fetch", "nafgpu_job_sync",
            "nafgpu_job_get_stats", "nafgpu_job_time", "nafgpu_job_run_profiled", "nafgpu_stage_name",
-           "nafgpu_job_device_result", "nafgpu_zstd_decompress", "nafgpu_job_format", "nafgpu_format_batch"]
+           "nafgpu_job_device_result", "nafgpu_zstd_decompress", "nafgpu_job_format", "nafgpu_format_batch", "nafgpu_pack"]
 
 
 class Library:
@@ -103,6 +113,7 @@ class Library:
         L.nafgpu_zstd_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.nafgpu_job_format.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(Text), C.c_uint32]
         L.nafgpu_format_batch.argtypes = [C.c_void_p, C.POINTER(Archive), C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(Text)]
+        L.nafgpu_pack.argtypes = [C.c_void_p, C.POINTER(PackInput), C.POINTER(PackResult)]
         L.nafgpu_job_device_result.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
 
     def strerror(self, code):

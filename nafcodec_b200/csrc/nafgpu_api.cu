@@ -15,6 +15,7 @@
 #include "cuda_compat.h"
 #include "frame_walk.h"
 #include "naf_kernels.cuh"
+#include "naf_pack.cuh"
 #include "naf_text.cuh"
 #include "zstd_kernels.cuh"
 
@@ -76,9 +77,9 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, desc, bstate, hufw, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g;
+    DevBuf comp, arena, lit, desc, bstate, hufw, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
-    PinBuf stage, result, misc_host, text_host, text_stage;
+    PinBuf stage, result, misc_host, text_host, text_stage, pack_host;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
     std::vector<ArchPlan> aplan;
@@ -121,6 +122,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     cudaStream_t st = c->st;
     CUDA_TRY(c, cudaMemsetAsync(c->misc.p, 0, c->misc_words * 4, st));
     if (c->J.n_seq) CUDA_TRY(c, cudaMemsetAsync(c->J.seq_done, 0, c->J.n_seq * 4, st));
+    if (c->J.n_seq) CUDA_TRY(c, cudaMemsetAsync(c->J.lz_blocker, 0xFF, c->J.n_seq * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(c->arena.p, 0, c->counts_size, st));
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     // profiled runs (ev != null) are serial so that every stage has its own interval
@@ -131,6 +133,12 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     CUDA_TRY(c, cudaGetLastError());
     c->ran = true;
     return NAFGPU_OK;
+}
+
+void read_lz_stats(nafgpu_ctx* c) {
+    const uint32_t* m = (const uint32_t*)c->misc_host.p;
+    c->stats.lz_handover = m[4]; c->stats.lz_rounds = m[5]; c->stats.lz_unresolved = m[6];
+    if (c->misc_words >= 24) memcpy(c->stats.lz_pending, m + c->misc_words - 24, 24 * 4);
 }
 
 int status_to_code(uint32_t s, std::string& msg) {
@@ -196,12 +204,12 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     for (size_t f = 0; f < nf; f++) g_base[f + 1] = g_base[f] + ((pl.frames[f].dst_size + 15) & ~(uint64_t)15);
     c->o_gbase = c->o_chunks + align_up((nf + 1) * 4, 16);
     const size_t stage_bytes = c->o_gbase + align_up((nf + 1) * 8, 16);
-    c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8;
+    c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8 + 24;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
-              c->seq32.ensure(nseq * 4 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
+              c->seq32.ensure(nseq * 5 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
         return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
@@ -226,22 +234,24 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.frames = (const zf::FrameDesc*)((const uint8_t*)c->desc.p + c->o_frames); J.blocks = (const zf::BlockDesc*)c->desc.p;
     J.bstate = (zf::BlockState*)c->bstate.p; J.tables = (zc::SeqCell*)c->tables.p; J.table_al = (uint8_t*)c->table_al.p;
     J.seq_done = (uint32_t*)c->seq32.p;
-    J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq; J.lz_list[2] = J.seq_done + 3 * nseq;
+    J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq; J.lz_list[2] = J.seq_done + 3 * nseq; J.lz_blocker = J.seq_done + 4 * nseq;
     J.seq = (zf::SeqRec*)c->seq64.p;
     J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.fin_unresolved = misc + 6; J.fin_count = misc + 7;
-    J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf;
+    J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf; J.lz_pending = misc + 10 + nf + total_chunks + 8;
     J.fin_chunk_first = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_chunks); J.fin_total_chunks = total_chunks;
     J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p;
     J.fin_g_base = (const uint64_t*)((const uint8_t*)c->desc.p + c->o_gbase);
     J.coop_ctas = c->coop_ctas;
-    {   // the finisher handles a 64 KB chunk in ~90 us on one SM, all SMs at once, then a few barrier rounds (profiles/r1_summary.md)
+    {   // the finisher's first level handles a 64 KB chunk in ~90 us on one SM, all SMs at once; its second level (barrier rounds over the
+        // unresolved bytes) costs about twice that again when the chains cross many chunks (cfg3: 13 M bytes)
         uint64_t biggest = 0;
         for (const auto& F : c->plan.frames) biggest = std::max<uint64_t>(biggest, F.dst_size);
         (void)biggest;
         const uint64_t waves = ((uint64_t)total_chunks + c->fin_ctas - 1) / std::max<uint32_t>(c->fin_ctas, 1u);
-        J.fin_cost_us = (uint32_t)std::min<uint64_t>(150 + waves * 90, 0x7FFFFFFFu);
+        J.fin_cost_us = (uint32_t)std::min<uint64_t>(300 + waves * 270, 0x7FFFFFFFu);     // (both levels: 3.6 ms for the 1907 chunks of a 250 Mbp frame)
+        if (const char* e = getenv("NAFGPU_FIN_COST_US")) J.fin_cost_us = (uint32_t)atoi(e);     // (probing: e.g. 100000000 never hands over)
     }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)((const uint8_t*)c->desc.p + c->o_huf); J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
@@ -304,9 +314,9 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g, &c->pack_in, &c->pack_out};
     for (DevBuf* b : d) b->release();
-    c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release();
+    c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release(); c->pack_host.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -475,7 +485,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
             // Sections that follow one another in the caller's buffer (the sections of a NAF file do, a few header bytes
             // apart) keep their relative positions on the device and travel in one copy, gap bytes included.
             bool merged = false;
-            if (!copies.empty()) {
+            if (copies.size() > copies_mark) {                  // (only within ONE archive: two archives may sit in adjacent allocations)
                 Copy& L = copies.back();
                 const uint8_t* lend = L.src + L.size;
                 if (S.data >= lend && (uint64_t)(S.data - lend) <= 64) {
@@ -541,7 +551,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     { int rc_d2h = d2h_results(c); if (rc_d2h) return rc_d2h; }
     std::string msg;
     int code = status_to_code(*(const uint32_t*)c->misc_host.p, msg);
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
+    read_lz_stats(c);
     if (code) return fail(c, code, msg);
     if (regen_size) memcpy(dst, (const uint8_t*)c->result.p + ALIGN, regen_size);
     return NAFGPU_OK;
@@ -583,7 +593,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
         if (cnt) fprintf(stderr, "[huf debug] big CTAs %zu: cycles stage+weights %.0f, table %.0f, sync %.0f (iters avg %.2f max %.0f), scan %.0f, write %.0f, flush %.0f\n",
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
+    read_lz_stats(c);
     const uint8_t* R = (const uint8_t*)c->result.p;
     int first_code = 0;
     for (uint32_t a = 0; a < n; a++) {
@@ -669,7 +679,7 @@ int nafgpu_job_format(nafgpu_ctx* c, int format, uint64_t line_length, nafgpu_te
         CUDA_TRY(c, cudaMemcpyAsync(c->text_host.p, c->text.p, copy_size, cudaMemcpyDeviceToHost, c->st));
         CUDA_TRY(c, cudaStreamSynchronize(c->st));
     }
-    c->stats.lz_handover = ((const uint32_t*)c->misc_host.p)[4]; c->stats.lz_rounds = ((const uint32_t*)c->misc_host.p)[5]; c->stats.lz_unresolved = ((const uint32_t*)c->misc_host.p)[6];
+    read_lz_stats(c);
     if (*(const uint32_t*)c->misc_host.p & zc::E_INTERNAL) return fail(c, NAFGPU_ERR_INVALID_DATA, "text layout exceeded its bound");
     const uint8_t* H = (const uint8_t*)c->text_host.p;
     c->stats.text_kernel_ms = 0; c->stats.text_bytes = 0;
@@ -792,6 +802,70 @@ const char* nafgpu_stage_name(uint32_t s) {
     static const char* names[N_STAGES] = {"memset+huf_decode", "build_tables", "decode_sequences", "frame_scan", "lz_literals", "lz_first",
                                           "lz_resolve", "lz_finish", "naf_scan", "mask_fix", "-", "unpack", "utf8_check"};
     return s < (uint32_t)N_STAGES ? names[s] : (s == (uint32_t)N_STAGES ? "k_huf_decode<512>" : "?");
+}
+
+// Encode side: pack + length words + mask runs of one archive's records (include/nafgpu.h).
+int nafgpu_pack(nafgpu_ctx* c, const nafgpu_pack_input* in, nafgpu_pack_result* out) {
+    if (!c || !in || !out) return NAFGPU_ERR_ARGUMENT;
+    if ((in->n_residues && !in->sequence) || (in->n_records && !in->lengths)) return fail(c, NAFGPU_ERR_ARGUMENT, "null input");
+    if (in->sequence_type < 0 || in->sequence_type > 1) return fail(c, NAFGPU_ERR_ARGUMENT, "only nucleotide sequences are packed (protein / text go to the compressor verbatim)");
+    if (in->n_residues > (1ull << 38) || in->n_records > (1ull << 36)) return fail(c, NAFGPU_ERR_NOMEM, "archive does not fit the device");
+    memset(out, 0, sizeof *out);
+    out->first_invalid = ~0ull;
+    uint64_t total = 0, n_words = 0;
+    for (uint64_t i = 0; i < in->n_records; i++) {
+        if (in->lengths[i] > in->n_residues - total) return fail(c, NAFGPU_ERR_ARGUMENT, "record lengths exceed the sequence (Error::InvalidLength)");
+        total += in->lengths[i];
+        n_words += in->lengths[i] / 0xFFFFFFFFull + 1;
+    }
+    if (total != in->n_residues) return fail(c, NAFGPU_ERR_ARGUMENT, "record lengths do not add up to the sequence (Error::InvalidLength)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    const uint64_t nres = in->n_residues, npacked = (nres + 1) / 2;
+    // device input: [sequence (padded to 32) | lengths]; device output: [counters 4 x u64 | length words | packed | mask | flag words]
+    const uint64_t i_len = align_up(nres + 32), in_bytes = i_len + 8 * in->n_records + 64;
+    const uint64_t o_words = 64, o_packed = align_up(o_words + 4 * n_words), o_mask = align_up(o_packed + npacked + 16);
+    const uint64_t mask_cap = in->extract_mask ? nres / 255 + nres + 16 : 0;     // every residue its own run, at worst
+    const uint64_t o_low = align_up(o_mask + mask_cap), out_bytes = o_low + (in->extract_mask ? 4 * ((nres + 31) / 32) : 0) + 64;
+    if (!c->pack_in.ensure(in_bytes) || !c->pack_out.ensure(out_bytes)) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
+    uint8_t* di = (uint8_t*)c->pack_in.p;
+    uint8_t* dout = (uint8_t*)c->pack_out.p;
+    if (nres) CUDA_TRY(c, cudaMemcpyAsync(di, in->sequence, nres, cudaMemcpyHostToDevice, c->st));
+    if (in->n_records) CUDA_TRY(c, cudaMemcpyAsync(di + i_len, in->lengths, 8 * in->n_records, cudaMemcpyHostToDevice, c->st));
+    CUDA_TRY(c, cudaMemsetAsync(dout, 0xFF, 8, c->st));                          // first invalid residue: none
+    CUDA_TRY(c, cudaMemsetAsync(dout + 8, 0, 24, c->st));
+    nk::launch_pack_stage(di, nres, (uint32_t)in->sequence_type, in->extract_mask != 0, dout + o_packed, (uint32_t*)(dout + o_low),
+                          (const uint64_t*)(di + i_len), in->n_records, (uint32_t*)(dout + o_words), dout + o_mask,
+                          (unsigned long long*)dout, c->st);
+    CUDA_TRY(c, cudaGetLastError());
+    // the counters first (the mask size is only known now), then the streams themselves
+    if (!c->pack_host.ensure(64)) return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+    CUDA_TRY(c, cudaMemcpyAsync(c->pack_host.p, dout, 32, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    uint64_t cnt[4];
+    memcpy(cnt, c->pack_host.p, 32);
+    if (cnt[1] != n_words || cnt[2] > mask_cap) return fail(c, NAFGPU_ERR_CUDA, "pack stage produced inconsistent sizes");
+    const uint64_t mask_size = in->extract_mask ? cnt[2] : 0;
+    const uint64_t h_words = 64, h_packed = align_up(h_words + 4 * n_words), h_mask = align_up(h_packed + npacked + 16);
+    if (!c->pack_host.ensure(h_mask + mask_size + 64)) return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+    uint8_t* H = (uint8_t*)c->pack_host.p;
+    {
+        std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
+        if (n_words) CUDA_TRY(c, cudaMemcpyAsync(H + h_words, dout + o_words, 4 * n_words, cudaMemcpyDeviceToHost, c->st));
+        if (npacked) CUDA_TRY(c, cudaMemcpyAsync(H + h_packed, dout + o_packed, npacked, cudaMemcpyDeviceToHost, c->st));
+        if (mask_size) CUDA_TRY(c, cudaMemcpyAsync(H + h_mask, dout + o_mask, mask_size, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    }
+    out->packed = H + h_packed; out->packed_size = npacked;
+    out->length_words = H + h_words; out->length_size = 4 * n_words;
+    if (in->extract_mask) { out->mask = H + h_mask; out->mask_size = mask_size; out->n_mask_runs = cnt[3]; }
+    out->first_invalid = cnt[0];
+    if (cnt[0] != ~0ull) {
+        char b[96];
+        snprintf(b, sizeof b, "unexpected sequence character at residue %llu", (unsigned long long)cnt[0]);
+        return fail(c, NAFGPU_ERR_INVALID_DATA, b);
+    }
+    return NAFGPU_OK;
 }
 
 int nafgpu_job_device_result(nafgpu_ctx* c, uint32_t archive, const uint8_t** sequence_dev, uint64_t* capacity_bytes) {

@@ -1557,6 +1557,11 @@ constexpr uint32_t LZ_MIN_ROUNDS = 3, LZ_MIN_PENDING = 192;        // no hand-ov
 
 // Returns 1 when match i may be copied now (d/off/ml filled), 0 when it has to wait, 2 when it was rejected.
 __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t round, uint64_t& d, uint32_t& off, uint32_t& ml) {
+    // What blocked this match last time is remembered: while that match is still unfinished there is nothing to look for
+    // (one load instead of a binary search and a dozen dependent probes).  Sections whose matches descend from one another
+    // through tens of generations -- a diverged repeat family, cfg3: 78 rounds with ~2 % of the pending matches becoming ready
+    // in each -- spent their time re-examining matches that could not have become ready.
+    // (lz_round does that check before calling here)
     SeqRec& R = J.seq[i];
     const uint32_t bi = R.block;
     const BlockDesc& B = J.blocks[bi];
@@ -1587,7 +1592,7 @@ __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t roun
         }
         if (blocker == 0xFFFFFFFFu) { verdict = 1; break; }
         const SeqRec& Q = J.seq[blocker];
-        if (hop == LZ_HOPS || off < ml || Q.match_pos > s || e > Q.match_pos + Q.ml) break;      // cannot redirect: wait
+        if (hop == LZ_HOPS || off < ml || Q.match_pos > s || e > Q.match_pos + Q.ml) { J.lz_blocker[i] = blocker; break; }      // cannot redirect: wait
         off += resolve_offset(J, Q.off, Q.block);
     }
     if (off != off0) R.off = off;                                      // keep the shortcut for later rounds (and for others)
@@ -1596,35 +1601,64 @@ __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t roun
 
 // One round over a list of matches: items [0, n) of `list` (or the identity when list == nullptr).  Matches that still
 // have to wait are appended to `next` (count in *next_n).
+constexpr int LZ_U = 4;                             // list entries per thread and step: their "still blocked?" loads are in flight together
+
 __device__ __forceinline__ void lz_round(const JobDev& J, const uint32_t* list, uint32_t n, uint32_t round, uint32_t* next, uint32_t* next_n,
                                          uint32_t first, uint32_t stride,
                                          uint32_t* q_n, uint64_t* q_d, uint32_t* q_off, uint32_t* q_ml, uint32_t* q_i) {
     const int tid = threadIdx.x, lane = tid & 31;
-    for (uint32_t base = first; base < n; base += stride) {          // `base` is CTA-uniform
+    for (uint32_t base = first; base < n; base += stride * LZ_U) {   // `base` is CTA-uniform
         if (tid == 0) *q_n = 0;
         __syncthreads();
-        const uint32_t k = base + tid;
-        bool pending = false;
-        uint32_t i = 0;
-        if (k < n) {
-            i = list ? list[k] : k;
-            if (J.seq_done[i] == 0) {
-                uint64_t d; uint32_t off, ml;
-                const int v = lz_try(J, i, round, d, off, ml);
-                if (v == 0) pending = true;
-                else if (v == 1) {
-                    if (ml <= LZ_SHORT) { copy_match(J.out, d, off, ml, 0, 1); J.seq_done[i] = round; }
-                    else { const uint32_t slot = atomicAdd(q_n, 1u); q_d[slot] = d; q_off[slot] = off; q_ml[slot] = ml; q_i[slot] = i; }
+        // (a) which of this thread's entries are worth a look: not executed yet, and not waiting for a match that is still
+        //     unfinished.  LZ_U independent chains of two loads; in deep rounds ~98 % of the entries stop here.
+        uint32_t idx[LZ_U];
+        bool look[LZ_U], pend[LZ_U];
+#pragma unroll
+        for (int u = 0; u < LZ_U; u++) {
+            const uint32_t k = base + (uint32_t)u * stride + (uint32_t)tid;
+            look[u] = false; pend[u] = false; idx[u] = 0;
+            if (k < n) {
+                const uint32_t i = list ? list[k] : k;
+                idx[u] = i;
+                if (J.seq_done[i] == 0) {
+                    look[u] = true;
+                    if (round > 1) {
+                        const uint32_t b = J.lz_blocker[i];
+                        if (b != 0xFFFFFFFFu) { const uint32_t dn = J.seq_done[b]; if (dn == 0 || dn >= round) { look[u] = false; pend[u] = true; } }
+                    }
                 }
             }
         }
-        const uint32_t pb = __ballot_sync(0xFFFFFFFFu, pending);
-        uint32_t wbase = 0;
-        if (lane == 0 && pb) wbase = atomicAdd(next_n, (uint32_t)__popc(pb));
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        if (pending) next[wbase + __popc(pb & ((1u << lane) - 1u))] = i;
+        // (b) the full readiness probe, and the copy if the match may run
+#pragma unroll
+        for (int u = 0; u < LZ_U; u++) {
+            if (look[u]) {
+                uint64_t d; uint32_t off, ml;
+                const int v = lz_try(J, idx[u], round, d, off, ml);
+                if (v == 0) pend[u] = true;
+                else if (v == 1) {
+                    if (ml <= LZ_SHORT) { copy_match(J.out, d, off, ml, 0, 1); J.seq_done[idx[u]] = round; }
+                    else {
+                        const uint32_t slot = atomicAdd(q_n, 1u);
+                        if (slot < (uint32_t)LZ_CTA) { q_d[slot] = d; q_off[slot] = off; q_ml[slot] = ml; q_i[slot] = idx[u]; }
+                        else pend[u] = true;                         // (queue full: next round)
+                    }
+                }
+            }
+        }
+        // (c) entries that stay pending go to the next round's list
+#pragma unroll
+        for (int u = 0; u < LZ_U; u++) {
+            const uint32_t pb = __ballot_sync(0xFFFFFFFFu, pend[u]);
+            uint32_t wbase = 0;
+            if (lane == 0 && pb) wbase = atomicAdd(next_n, (uint32_t)__popc(pb));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (pend[u]) next[wbase + __popc(pb & ((1u << lane) - 1u))] = idx[u];
+        }
         __syncthreads();
-        const uint32_t nq = *q_n;
+        uint32_t nq = *q_n;
+        if (nq > (uint32_t)LZ_CTA) nq = LZ_CTA;
         // long matches: one warp each; the very long ones (N stretches: offset 1, ~100 KB) by the whole CTA
         for (uint32_t t = (uint32_t)tid >> 5; t < nq; t += LZ_CTA / 32)
             if (q_ml[t] <= LZ_WARP_MAX) copy_long_match(J.out, q_d[t], q_off[t], q_ml[t], lane, 32);
@@ -1653,7 +1687,7 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
     for (uint32_t round = 2;; round++) {
         const uint32_t nxt = cur == 2 ? 0 : cur + 1, clr = nxt == 2 ? 0 : nxt + 1;
         const uint32_t n = J.lz_count[cur];                          // stable: written before the last grid barrier
-        if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_rounds = round - 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { *J.lz_rounds = round - 1; if (round - 2 < 24) J.lz_pending[round - 2] = n; }
         if (n == 0) break;
         if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[clr] = 0; // append target of the NEXT round; idle in this one
         lz_round(J, J.lz_list[cur], n, round, J.lz_list[nxt], &J.lz_count[nxt], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
@@ -1665,7 +1699,7 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         // the rest would take n_next / progress more rounds; when that costs more than k_lz_finish (whose cost depends on
         // the bytes of the frame, not on the depth of the chain), the section is text-like: hand it over.
         const uint32_t progress = n - n_next;
-        const uint64_t round_ns = 3000 + n_next / 5;                       // measured: ~250 us per round at 1.4 M entries
+        const uint64_t round_ns = 5000 + n_next / 25;                      // measured: ~30 us per round at 600 K entries (most of them one load: still blocked)
         if (round >= LZ_MIN_ROUNDS && n_next > LZ_MIN_PENDING &&
             (uint64_t)n_next * round_ns > (uint64_t)(progress ? progress : 1u) * J.fin_cost_us * 1000u) {
             if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = round;
@@ -1966,7 +2000,7 @@ uint32_t lz_resolve_max_ctas(int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz_resolve, LZ_CTA, 0);
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > 4) per_sm = 4;
     return (uint32_t)(sms > 0 && per_sm > 0 ? sms * per_sm : 1);
 #endif
 }
@@ -2019,7 +2053,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
     NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
-        uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
+        uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA * LZ_U - 1) / (LZ_CTA * LZ_U));
         if (grid > 148u * 64u) grid = 148u * 64u;
         NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();

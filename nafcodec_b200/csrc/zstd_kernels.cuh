@@ -25,6 +25,7 @@ struct JobDev {
     zf::SeqRec* seq;                  // one 32-byte record per sequence (written by k_decode_sequences / k_lz_literals)
     uint32_t seq_stage_bytes;         // shared-memory staging size of k_decode_sequences (largest sequence bitstream, capped)
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
+    uint32_t* lz_blocker;             // per match: the unfinished match it was last found waiting for (0xFFFFFFFF: none yet)
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
     unsigned long long* debug;        // optional per-CTA phase clocks of k_huf_decode (NAFGPU_DEBUG_HUF=1), else null
@@ -32,6 +33,7 @@ struct JobDev {
     uint32_t* lz_count;               // [3] their lengths
     uint32_t* lz_rounds;              // rounds k_lz_first + k_lz_resolve ran (statistics)
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
+    uint32_t* lz_pending;             // [24] matches still pending after round 1, 2, ... (statistics)
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
     uint32_t fin_cost_us;             // estimated cost of the finisher kernels on this job (hand-over decision)
     // finisher (k_lz_finish, k_lz_finish2): the frames cut into 64 KB chunks

@@ -66,7 +66,7 @@ def test_cfg4_million_reads(quality):
     assert res.n_lengths == 1_000_000 and int(res.lengths.min()) == 150 and int(res.lengths.max()) == 150
     assert (res.quality is None) == (not quality)
     st = N.shared_context(0, lib).stats()
-    assert st.n_blocks > 2_000_000                               # one tiny zstd block per read and flushed stream
+    assert st.n_blocks > (2_000_000 if quality else 1_000_000)    # one tiny zstd block per read and flushed stream
 
 
 def test_cfg5_collection_mix():
