@@ -77,8 +77,8 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, desc, bstate, hufw, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
-    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
+    DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
+    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage, pack_host;
     fw::JobPlan plan;
     std::vector<nk::NafDev> arch;
@@ -203,11 +203,24 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     std::vector<uint64_t> g_base(nf + 1, 0);             // fin_g: one entry per byte of every frame, frames packed (16-entry aligned)
     for (size_t f = 0; f < nf; f++) g_base[f + 1] = g_base[f] + ((pl.frames[f].dst_size + 15) & ~(uint64_t)15);
     c->o_gbase = c->o_chunks + align_up((nf + 1) * 4, 16);
-    const size_t stage_bytes = c->o_gbase + align_up((nf + 1) * 8, 16);
+    // tiles of the frames that are too long for one scanning CTA
+    std::vector<zf::FsTile> tiles;
+    std::vector<zf::FsBigFrame> bigs;
+    uint32_t fs_big = zf::FS_BIG_FRAME, fs_tile = zf::FS_TILE;
+    if (const char* e = getenv("NAFGPU_FS_TILE")) { fs_tile = (uint32_t)std::max(1, atoi(e)); fs_big = 2 * fs_tile; }      // (test hook: small tiles)
+    for (size_t f = 0; f < nf; f++) {
+        const zf::FrameDesc& F = pl.frames[f];
+        if (F.n_blocks <= fs_big) continue;
+        bigs.push_back({(uint32_t)f, (uint32_t)tiles.size(), (F.n_blocks + fs_tile - 1) / fs_tile, 0u});
+        for (uint32_t b = 0; b < F.n_blocks; b += fs_tile) tiles.push_back({(uint32_t)f, F.first_block + b, std::min(fs_tile, F.n_blocks - b), 0u});
+    }
+    c->o_tiles = c->o_gbase + align_up((nf + 1) * 8, 16);
+    c->o_big = c->o_tiles + align_up(tiles.size() * sizeof(zf::FsTile), 16);
+    const size_t stage_bytes = c->o_big + align_up(bigs.size() * sizeof(zf::FsBigFrame), 16);
     c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8 + 24;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->fsstate.ensure(tiles.size() * sizeof(zf::FsTileState) + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 5 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
@@ -222,6 +235,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
     memcpy(sp + c->o_chunks, chunk_first.data(), (nf + 1) * 4);
     memcpy(sp + c->o_gbase, g_base.data(), (nf + 1) * 8);
+    if (!tiles.empty()) { memcpy(sp + c->o_tiles, tiles.data(), tiles.size() * sizeof(zf::FsTile)); memcpy(sp + c->o_big, bigs.data(), bigs.size() * sizeof(zf::FsBigFrame)); }
     if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
@@ -261,6 +275,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         cudaMemsetAsync(c->debug.p, 0, nh * 64, c->st);
         J.debug = (unsigned long long*)c->debug.p;
     }
+    J.fs_tiles = (const zf::FsTile*)((const uint8_t*)c->desc.p + c->o_tiles); J.fs_big = (const zf::FsBigFrame*)((const uint8_t*)c->desc.p + c->o_big);
+    J.fs_state = (zf::FsTileState*)c->fsstate.p; J.n_fs_tiles = (uint32_t)tiles.size(); J.n_fs_big = (uint32_t)bigs.size(); J.fs_big_frame = fs_big;
     J.n_frames = (uint32_t)nf; J.n_blocks = (uint32_t)nb; J.n_slots = pl.n_slots; J.n_seq = nseq; J.n_checksums = pl.n_checksums;
 
     c->stats.n_archives = n; c->stats.n_frames = nf; c->stats.n_blocks = nb; c->stats.n_sequences = nseq;
@@ -314,7 +330,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g, &c->pack_in, &c->pack_out};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->fsstate, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g, &c->pack_in, &c->pack_out};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release(); c->pack_host.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);

@@ -511,21 +511,18 @@ __device__ __forceinline__ void rep_shfl(RepMap& out, const RepMap& m, int src) 
     for (int k = 0; k < 3; k++) { out.s[k] = __shfl_sync(0xFFFFFFFFu, m.s[k], src); out.v[k] = __shfl_sync(0xFFFFFFFFu, m.v[k], src); }
 }
 
-__global__ void __launch_bounds__(FSCAN_T) k_frame_scan(JobDev J) {
+// Blocks [b_begin, b_end) of frame f, FSCAN_T per step.  REDUCE: only what the range does as a whole (regenerated bytes, the
+// composed repeat-offset map) -- the first pass over a tile of a long frame.  Otherwise: from the state at b_begin (`off`,
+// `rep`), write every block's output offset and incoming repeat offsets; the state after b_end is left in `off` / `rep`.
+template <bool REDUCE>
+__device__ __forceinline__ void fs_range(const JobDev& J, uint32_t b_begin, uint32_t b_end, uint64_t& off, uint32_t rep[3], RepMap& total, bool& bad) {
     __shared__ RepMap agg_map[2][FSCAN_W];
     __shared__ uint32_t agg_regen[2][FSCAN_W];
-    const uint32_t f = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (J.frame_bad[f]) return;
-    const FrameDesc& F = J.frames[f];
-    const uint32_t nb = F.n_blocks, fb = F.first_block;
-    uint64_t off = F.dst_off;
-    uint32_t rep[3] = {1, 4, 8};
-    bool bad = false;
     int buf = 0;
-    for (uint32_t b0 = 0; b0 < nb; b0 += FSCAN_T, buf ^= 1) {
-        const uint32_t b = fb + b0 + threadIdx.x;
-        const bool valid = b0 + threadIdx.x < nb;
+    for (uint32_t b0 = b_begin; b0 < b_end; b0 += FSCAN_T, buf ^= 1) {
+        const uint32_t b = b0 + threadIdx.x;
+        const bool valid = b < b_end;
         uint32_t regen = 0;
         bool has_seq = false;
         RepMap m; rep_identity(m);
@@ -553,32 +550,104 @@ __global__ void __launch_bounds__(FSCAN_T) k_frame_scan(JobDev J) {
 #pragma unroll
         for (int d = 1; d < FSCAN_W; d <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ainc, d); if (lane >= d) ainc += t; }
         rep_warp_scan(a, lane, bad);
-        // everything before this thread's block: the warps before mine, then the lanes before mine
-        RepMap wp, x;
-        rep_shfl(wp, a, w ? w - 1 : 0);
-        uint32_t wregen = __shfl_sync(0xFFFFFFFFu, ainc, w ? w - 1 : 0);
-        if (w == 0) { rep_identity(wp); wregen = 0; }
-        rep_shfl(x, m, lane ? lane - 1 : 0);
-        if (lane == 0) rep_identity(x);
-        bool xbad = false;
-        rep_compose(x, wp, xbad);
-        uint32_t in[3];
-        const bool ok = rep_apply(x, rep, in);
-        if (valid) {
-            BlockState& S = J.bstate[b];
-            S.regen = regen; S.out_off = off + wregen + (inc - regen);
-            if (has_seq) { S.rep_in[0] = in[0]; S.rep_in[1] = in[1]; S.rep_in[2] = in[2]; if (!ok || xbad) bad = true; }
-        }
-        // what leaves this group of blocks
         RepMap tot;
         rep_shfl(tot, a, FSCAN_W - 1);
-        uint32_t out[3];
-        if (!rep_apply(tot, rep, out)) bad = true;
-        rep[0] = out[0]; rep[1] = out[1]; rep[2] = out[2];
+        if (REDUCE) {
+            rep_compose(tot, total, bad);                  // tot <- (tot after everything so far)
+            total = tot;
+        } else {
+            // everything before this thread's block: the warps before mine, then the lanes before mine
+            RepMap wp, x;
+            rep_shfl(wp, a, w ? w - 1 : 0);
+            uint32_t wregen = __shfl_sync(0xFFFFFFFFu, ainc, w ? w - 1 : 0);
+            if (w == 0) { rep_identity(wp); wregen = 0; }
+            rep_shfl(x, m, lane ? lane - 1 : 0);
+            if (lane == 0) rep_identity(x);
+            bool xbad = false;
+            rep_compose(x, wp, xbad);
+            uint32_t in[3];
+            const bool ok = rep_apply(x, rep, in);
+            if (valid) {
+                BlockState& S = J.bstate[b];
+                S.regen = regen; S.out_off = off + wregen + (inc - regen);
+                if (has_seq) { S.rep_in[0] = in[0]; S.rep_in[1] = in[1]; S.rep_in[2] = in[2]; if (!ok || xbad) bad = true; }
+            }
+            // what leaves this group of blocks
+            uint32_t out[3];
+            if (!rep_apply(tot, rep, out)) bad = true;
+            rep[0] = out[0]; rep[1] = out[1]; rep[2] = out[2];
+        }
         off += __shfl_sync(0xFFFFFFFFu, ainc, FSCAN_W - 1);
     }
+}
+
+__global__ void __launch_bounds__(FSCAN_T) k_frame_scan(JobDev J) {
+    const uint32_t f = blockIdx.x;
+    if (J.frame_bad[f]) return;
+    const FrameDesc& F = J.frames[f];
+    if (F.n_blocks > J.fs_big_frame) return;               // long frames: k_fs_reduce / k_fs_prefix / k_fs_apply, a CTA per tile
+    uint64_t off = F.dst_off;
+    uint32_t rep[3] = {1, 4, 8};
+    bool bad = false;
+    RepMap unused; rep_identity(unused);
+    fs_range<false>(J, F.first_block, F.first_block + F.n_blocks, off, rep, unused, bad);
     if (off - F.dst_off != F.dst_size) bad = true;
     if (__syncthreads_or(bad) && threadIdx.x == 0) flag_error(J, f, zc::E_SIZE);
+}
+
+// Frames of more than FS_BIG_FRAME blocks (a FASTQ section flushed per record has 10^6 of them: one CTA took 10 ms for it)
+// are cut into tiles of FS_TILE blocks: (1) every tile's aggregate, (2) one thread per frame walks its tiles' aggregates
+// -- a few hundred -- and leaves every tile its starting state, (3) every tile scans its blocks from there.
+__global__ void __launch_bounds__(FSCAN_T) k_fs_reduce(JobDev J) {
+    const FsTile T = J.fs_tiles[blockIdx.x];
+    if (J.frame_bad[T.frame]) return;
+    uint64_t sum = 0;
+    uint32_t rep[3] = {0, 0, 0};
+    bool bad = false;
+    RepMap total; rep_identity(total);
+    fs_range<true>(J, T.first_block, T.first_block + T.n_blocks, sum, rep, total, bad);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        FsTileState& S = J.fs_state[blockIdx.x];
+        S.regen = sum; S.bad = bad ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { S.ms[k] = total.s[k]; S.mv[k] = total.v[k]; }
+    }
+}
+
+__global__ void __launch_bounds__(32) k_fs_prefix(JobDev J) {
+    if (threadIdx.x != 0) return;
+    const FsBigFrame G = J.fs_big[blockIdx.x];
+    if (J.frame_bad[G.frame]) return;
+    const FrameDesc& F = J.frames[G.frame];
+    uint64_t off = F.dst_off;
+    uint32_t rep[3] = {1, 4, 8};
+    bool bad = false;
+    for (uint32_t t = G.first_tile; t < G.first_tile + G.n_tiles; t++) {
+        FsTileState& S = J.fs_state[t];
+        S.off_in = off; S.rep_in[0] = rep[0]; S.rep_in[1] = rep[1]; S.rep_in[2] = rep[2];
+        RepMap m;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { m.s[k] = S.ms[k]; m.v[k] = S.mv[k]; }
+        uint32_t out[3];
+        if (!rep_apply(m, rep, out) || S.bad) bad = true;
+        rep[0] = out[0]; rep[1] = out[1]; rep[2] = out[2];
+        off += S.regen;
+    }
+    if (off - F.dst_off != F.dst_size) bad = true;
+    if (bad) flag_error(J, G.frame, zc::E_SIZE);
+}
+
+__global__ void __launch_bounds__(FSCAN_T) k_fs_apply(JobDev J) {
+    const FsTile T = J.fs_tiles[blockIdx.x];
+    if (J.frame_bad[T.frame]) return;
+    const FsTileState& S = J.fs_state[blockIdx.x];
+    uint64_t off = S.off_in;
+    uint32_t rep[3] = {S.rep_in[0], S.rep_in[1], S.rep_in[2]};
+    bool bad = false;
+    RepMap unused; rep_identity(unused);
+    fs_range<false>(J, T.first_block, T.first_block + T.n_blocks, off, rep, unused, bad);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) flag_error(J, T.frame, zc::E_SIZE);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -2048,7 +2117,14 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     else ev->mark();                                  // serial (profiled) order: the Huffman branch first
     NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 64, J.seq_stage_bytes, st, J); launches++; ev->mark();
-    NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++;
+    if (J.n_fs_tiles) {
+        NAF_LAUNCH(k_fs_reduce, J.n_fs_tiles, FSCAN_T, 0, st, J);
+        NAF_LAUNCH(k_fs_prefix, J.n_fs_big, 32, 0, st, J);
+        NAF_LAUNCH(k_fs_apply, J.n_fs_tiles, FSCAN_T, 0, st, J);
+        launches += 3;
+    }
+    ev->mark();
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
     NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();

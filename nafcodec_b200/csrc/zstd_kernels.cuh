@@ -48,6 +48,11 @@ struct JobDev {
     const zf::HufItem* huf_items;     // one per Huffman bitstream
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big): streams of 4-stream blocks, four per block (k_huf_decode_big, one cluster per block); the rest: k_huf_decode<128>
     uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
+    const zf::FsTile* fs_tiles;       // tiles of the frames with more than FS_BIG_FRAME blocks (host-filled)
+    const zf::FsBigFrame* fs_big;
+    zf::FsTileState* fs_state;
+    uint32_t n_fs_tiles, n_fs_big;
+    uint32_t fs_big_frame;            // frames with more blocks than this are scanned by tiles
     uint32_t n_frames, n_blocks, n_slots;
     uint32_t n_checksums;             // frames with a content checksum (k_frame_checksum runs only if any)
     uint64_t n_seq;

@@ -303,3 +303,15 @@ def test_pipeline_lanes(backend):
     assert n == 20 and len(got) == 20
     for (bi, i), r in got.items():
         assert_same_as_oracle(r, want[i], f"stream batch {bi} archive {i}")
+
+
+def test_long_frames_are_scanned_by_tiles(backend, monkeypatch):
+    """Frames with very many blocks (a FASTQ section flushed per record) get their block offsets and repeat-offset carries from
+    a tiled scan (k_fs_reduce / k_fs_prefix / k_fs_apply); small tiles here so that the path runs on a modest archive."""
+    monkeypatch.setenv("NAFGPU_FS_TILE", "37")
+    lib = library(backend)
+    arc = K.fastq_reads(21, 700 if backend == "emul" else 30000, with_mask=True)
+    res, d = check_parity(backend, arc, "tiled frame scan")
+    assert N.shared_context(0, lib).stats().n_blocks > 1400
+    monkeypatch.delenv("NAFGPU_FS_TILE")
+    check_parity(backend, arc, "default tiles")
