@@ -269,11 +269,12 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)((const uint8_t*)c->desc.p + c->o_huf); J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
-    J.debug = nullptr;
+    J.debug = nullptr; J.debug_seq = nullptr;
     if (getenv("NAFGPU_DEBUG_HUF") && nh) {
-        if (!c->debug.ensure(nh * 64)) return fail(c, NAFGPU_ERR_NOMEM, "debug buffer");
-        cudaMemsetAsync(c->debug.p, 0, nh * 64, c->st);
+        if (!c->debug.ensure(nh * 64 + 64)) return fail(c, NAFGPU_ERR_NOMEM, "debug buffer");
+        cudaMemsetAsync(c->debug.p, 0, nh * 64 + 64, c->st);
         J.debug = (unsigned long long*)c->debug.p;
+        J.debug_seq = J.debug + nh * 8;
     }
     J.fs_tiles = (const zf::FsTile*)((const uint8_t*)c->desc.p + c->o_tiles); J.fs_big = (const zf::FsBigFrame*)((const uint8_t*)c->desc.p + c->o_big);
     J.fs_state = (zf::FsTileState*)c->fsstate.p; J.n_fs_tiles = (uint32_t)tiles.size(); J.n_fs_big = (uint32_t)bigs.size(); J.fs_big_frame = fs_big;
@@ -596,8 +597,9 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
     CUDA_TRY(c, cudaGetLastError());
     if (c->J.debug) {
         size_t nh = c->J.n_huf_items;
-        std::vector<unsigned long long> d(nh * 8);
-        cudaMemcpy(d.data(), c->J.debug, nh * 64, cudaMemcpyDeviceToHost);
+        std::vector<unsigned long long> d(nh * 8 + 8);
+        cudaMemcpy(d.data(), c->J.debug, nh * 64 + 64, cudaMemcpyDeviceToHost);
+        const unsigned long long* q = d.data() + nh * 8;
         double ph[6] = {0, 0, 0, 0, 0, 0}, iters = 0, maxit = 0;
         size_t cnt = 0;
         for (size_t i = 0; i < c->J.n_huf_big; i++) {
@@ -606,6 +608,8 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
             iters += (double)d[i * 8 + 7]; if ((double)d[i * 8 + 7] > maxit) maxit = (double)d[i * 8 + 7];
             cnt++;
         }
+        if (q[4]) fprintf(stderr, "[seq debug] %llu sequences: producer %.0f cycles work + %.0f waiting, consumer %.0f work + %.0f waiting (per sequence)\n", q[4],
+                          (double)q[0] / q[4], (double)q[1] / q[4], (double)q[2] / q[4], (double)q[3] / q[4]);
         if (cnt) fprintf(stderr, "[huf debug] big CTAs %zu: cycles stage+weights %.0f, table %.0f, sync %.0f (iters avg %.2f max %.0f), scan %.0f, write %.0f, flush %.0f\n",
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }

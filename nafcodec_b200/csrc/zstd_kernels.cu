@@ -17,6 +17,8 @@
 //                                       chunks on all SMs, then across chunks
 #include "zstd_kernels.cuh"
 
+#include <algorithm>
+
 namespace zk {
 
 using namespace zf;
@@ -301,168 +303,8 @@ __device__ __forceinline__ uint32_t encode_off(RepSym r) {
 
 
 
-// The tANS walk, written once over a reader type: shared-memory window (common) or global memory (huge sections).
-// PRODUCER side of k_decode_sequences: decodes `cnt` sequences into raw (offset value, match length, literal length)
-// triples in shared memory; the three states live in the caller's registers across batches.
-template <class RD>
-__device__ __forceinline__ void seq_produce(RD& rd, const SeqCell* TLL, const SeqCell* TOF, const SeqCell* TML, uint32_t& sLL, uint32_t& sOF,
-                                            uint32_t& sML, uint32_t cnt, bool last_batch, uint32_t* r_ov, uint32_t* r_ml, uint32_t* r_ll) {
-    for (uint32_t j = 0; j < cnt; j++) {
-        const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];
-        r_ov[j] = cOF.base_value + rd.read(cOF.add_bits);
-        const uint32_t xb = rd.read(cML.add_bits + cLL.add_bits);        // ML then LL extra bits, one read
-        r_ml[j] = cML.base_value + (xb >> cLL.add_bits);
-        r_ll[j] = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));
-        if (!(last_batch && j + 1 == cnt)) {                             // LL, ML, OF state bits (<= 27) in one read
-            const uint32_t sb = rd.read(cLL.nb + cML.nb + cOF.nb);
-            sOF = cOF.next_base + (sb & ((1u << cOF.nb) - 1u));
-            sML = cML.next_base + ((sb >> cOF.nb) & ((1u << cML.nb) - 1u));
-            sLL = cLL.next_base + (sb >> (cOF.nb + cML.nb));
-        }
-    }
-}
-
-// k_decode_sequences: one CTA of two warps per block.  Warp 0, lane 0 is the PRODUCER: the serial chain of the three
-// interleaved tANS states and nothing else (every instruction on it costs ~6 cycles of a lone dependent warp: ncu shows
-// `wait` as the top stall, profiles/r1_fse_stage_k_decode_sequences.txt).  Warp 1 is the CONSUMER, one batch of 32
-// sequences behind through a double buffer in shared memory: repeat-offset bookkeeping (symbolic, so blocks decode
-// independently), literal / output positions by a shuffle scan, and the 32-byte sequence records with coalesced stores.
-constexpr uint32_t SEQ_BATCH = 32;
-
-__global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
-    NAF_DYN_SMEM(uint32_t, sbits);                       // staged bitstream: J.seq_stage_bytes (job maximum, capped)
-    __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
-    __shared__ uint32_t r_ov[2][SEQ_BATCH], r_ml[2][SEQ_BATCH], r_ll[2][SEQ_BATCH];
-    __shared__ int s_left;
-    const uint32_t bi = blockIdx.x;
-    const BlockDesc& B = J.blocks[bi];
-    if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
-    if (J.frame_bad[B.frame]) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    BlockState& S = J.bstate[bi];
-    const uint8_t* src = J.comp + B.src_off;
-    if (S.seq_bits_off >= B.src_size) { if (tid == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
-    const uint32_t nbytes = B.src_size - S.seq_bits_off;
-    const uint8_t* g = src + S.seq_bits_off;
-    const bool staged = nbytes + 48 <= J.seq_stage_bytes;
-    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
-    int al[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        al[k] = J.table_al[B.tbl[k]];
-        const uint2* T = (const uint2*)(J.tables + (size_t)B.tbl[k] * FSE_SLOT_CELLS);
-        for (int i = tid; i < (1 << al[k]); i += 64) ((uint2*)stab[k])[i] = T[i];
-    }
-    if (staged) {
-        const uint4* gbase = (const uint4*)(g - a);
-        const uint32_t nchunks = (a + nbytes + 15) >> 4;
-        for (uint32_t c = tid; c < nchunks; c += 64) ((uint4*)sbits)[1 + c] = gbase[c];
-    }
-    const uint8_t last = g[nbytes - 1];
-    if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }     // (uniform)
-    __syncthreads();
-    if (staged && (uint32_t)tid < 16 + a) ((uint8_t*)sbits)[tid] = 0;
-    if (tid == 0) s_left = 0;
-    __syncthreads();
-    const int P0 = 8 * (int)(nbytes - 1) + zc::highbit32(last);
-    const uint32_t n = B.n_seq, base = B.seq_base;
-    const uint32_t nbatch = (n + SEQ_BATCH - 1) / SEQ_BATCH;
-    if (warp == 0) {
-        // ---- producer ---------------------------------------------------------------------------------------------
-        SmemBits rs{};
-        BackBits rg{};
-        uint32_t sLL = 0, sOF = 0, sML = 0;
-        bool dead = false;
-        if (lane == 0) {
-            if (staged) { const int xz = (int)(16 + a) * 8; rs.init(sbits, xz + P0, xz); sLL = rs.read(al[0]); sOF = rs.read(al[1]); sML = rs.read(al[2]); }
-            else { rg.init(g, nbytes); sLL = rg.read(al[0]); sOF = rg.read(al[1]); sML = rg.read(al[2]); }
-        }
-        for (uint32_t k = 0; k < nbatch; k++) {
-            const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
-            if (lane == 0 && !dead) {
-                if (staged) seq_produce(rs, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
-                else seq_produce(rg, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
-                const int left = staged ? rs.remaining() : (int)rg.P;
-                // a corrupt stream over-reads: stop before the reader walks out of shared memory (one batch can go at most
-                // 32 x 90 bits below the image, which is still inside the CTA's static shared memory); the block is flagged
-                if (left < 0) { dead = true; s_left = left; }
-                else if (k + 1 == nbatch) s_left = left;
-            }
-            __syncthreads();                             // batch k is ready; the consumer has finished batch k - 1
-        }
-        return;
-    }
-    // ---- consumer -------------------------------------------------------------------------------------------------
-    RepSym rep[3] = {{0, 0}, {1, 0}, {2, 0}};              // (meaningful in lane 0 only)
-    uint32_t litpos = 0, outpos = 0;                        // running totals, uniform over the warp
-    bool bad = false;
-    uint4* rec = (uint4*)(J.seq + base);
-    for (uint32_t k = 0; k < nbatch; k++) {
-        __syncthreads();
-        const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
-        uint32_t* b_ov = r_ov[k & 1];
-        const uint32_t ll = (uint32_t)lane < cnt ? r_ll[k & 1][lane] : 0u, ml = (uint32_t)lane < cnt ? r_ml[k & 1][lane] : 0u;
-        if (lane == 0) {
-            // repeat offsets: a chain over the sequences, but a short one; the encoded offset replaces the raw value
-            for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t ov = b_ov[j];
-                RepSym off;
-                if (ov > 3) {
-                    off.src = -1; off.val = ov - 3;
-                    rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-                } else {
-                    const uint32_t idx = ov - 1 + (r_ll[k & 1][j] == 0 ? 1u : 0u);
-                    if (idx == 0) { off = rep[0]; }
-                    else if (idx == 1) { off = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-                    else if (idx == 2) { off = rep[2]; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-                    else {
-                        off = rep[0];
-                        if (off.src < 0) { if (off.val <= 1) bad = true; off.val -= 1; } else off.val += 1;
-                        rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off;
-                    }
-                }
-                if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
-                b_ov[j] = encode_off(off);
-            }
-        }
-        __syncwarp();
-        // positions: exclusive scans of ll and ll + ml over the batch, on top of the running totals
-        uint32_t il = ll, io = ll + ml;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d), to = __shfl_up_sync(0xFFFFFFFFu, io, d);
-            if (lane >= d) { il += tl; io += to; }
-        }
-        if ((uint32_t)lane < cnt) {
-            const uint32_t lp = litpos + il - ll, op = outpos + io - (ll + ml);
-            rec[2 * (k * SEQ_BATCH + lane)] = make_uint4(ll, ml, b_ov[lane], lp);
-            rec[2 * (k * SEQ_BATCH + lane) + 1] = make_uint4(op, bi, 0u, 0u);
-        }
-        litpos += __shfl_sync(0xFFFFFFFFu, il, 31);
-        const uint32_t otot = __shfl_sync(0xFFFFFFFFu, io, 31);
-        if (otot > BLOCK_MAX || outpos + otot > BLOCK_MAX) bad = true;      // (match lengths are < 2^17 each: no wrap within a batch)
-        outpos += otot;
-    }
-    bad = __any_sync(0xFFFFFFFFu, bad);
-    if (lane != 0) return;
-    if (bad || s_left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
-    if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
-    uint32_t regen = outpos + (B.lit_regen - litpos);
-    if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
-    S.regen = regen;
-    for (int k = 0; k < 3; k++) { S.rep_src[k] = rep[k].src; S.rep_val[k] = rep[k].val; }
-}
-
-// --------------------------------------------------------------------------------------------------------------
-// k_frame_scan: one CTA per frame.  Exclusive prefix sum of regenerated block sizes -> out_off; composes the
-// repeat-offset transfer functions -> rep_in per block; checks the total against the size the container states.
-//
-// A block's effect on the three repeat offsets is a map: slot k = constant v, or incoming slot s minus v (blocks
-// without sequences are the identity).  Maps compose associatively, so the chain across the blocks of a frame is a
-// scan: shuffles inside a warp, the warps' aggregates scanned once more by every warp; FSCAN_T blocks per step.
-// A genome frame has a handful of blocks; a FASTQ section flushed per record has 10^5 of them.
-constexpr int FSCAN_T = 512, FSCAN_W = FSCAN_T / 32;
-
+// A transfer function of the three repeat offsets: slot k = constant v[k] (s[k] < 0), or incoming slot s[k] minus v[k].  One
+// sequence is such a map, so is a block, so is any run of either: they compose associatively (scans below and in k_frame_scan).
 struct RepMap { int32_t s[3]; uint32_t v[3]; };
 
 __device__ __forceinline__ void rep_identity(RepMap& m) { m.s[0] = 0; m.s[1] = 1; m.s[2] = 2; m.v[0] = m.v[1] = m.v[2] = 0; }
@@ -510,6 +352,241 @@ __device__ __forceinline__ void rep_shfl(RepMap& out, const RepMap& m, int src) 
 #pragma unroll
     for (int k = 0; k < 3; k++) { out.s[k] = __shfl_sync(0xFFFFFFFFu, m.s[k], src); out.v[k] = __shfl_sync(0xFFFFFFFFu, m.v[k], src); }
 }
+
+// The tANS walk, written once over a reader type: shared-memory window (common) or global memory (huge sections).
+// PRODUCER side of k_decode_sequences: decodes `cnt` sequences into raw (offset value, match length, literal length)
+// triples in shared memory; the three states live in the caller's registers across batches.
+template <class RD>
+__device__ __forceinline__ void seq_produce(RD& rd, const SeqCell* TLL, const SeqCell* TOF, const SeqCell* TML, uint32_t& sLL, uint32_t& sOF,
+                                            uint32_t& sML, uint32_t cnt, bool last_batch, uint32_t* r_ov, uint32_t* r_ml, uint32_t* r_ll) {
+    for (uint32_t j = 0; j < cnt; j++) {
+        const SeqCell cOF = TOF[sOF], cML = TML[sML], cLL = TLL[sLL];
+        r_ov[j] = cOF.base_value + rd.read(cOF.add_bits);
+        const uint32_t xb = rd.read(cML.add_bits + cLL.add_bits);        // ML then LL extra bits, one read
+        r_ml[j] = cML.base_value + (xb >> cLL.add_bits);
+        r_ll[j] = cLL.base_value + (xb & ((1u << cLL.add_bits) - 1u));
+        if (!(last_batch && j + 1 == cnt)) {                             // LL, ML, OF state bits (<= 27) in one read
+            const uint32_t sb = rd.read(cLL.nb + cML.nb + cOF.nb);
+            sOF = cOF.next_base + (sb & ((1u << cOF.nb) - 1u));
+            sML = cML.next_base + ((sb >> cOF.nb) & ((1u << cML.nb) - 1u));
+            sLL = cLL.next_base + (sb >> (cOF.nb + cML.nb));
+        }
+    }
+}
+
+// The same walk over the shared-memory image by THREE LANES, one per state (lane 0: offset, 1: match length, 2: literal
+// length).  Measured (ncu, round 1; and two rewrites of the one-lane reader this round): a lone lane retires one instruction
+// per ~5 cycles whether or not the instructions depend on each other, so what counts is the NUMBER of warp instructions
+// per sequence -- 133 in the one-lane walk.  Here every lane loads its own cell, the field widths of the three cells are
+// exchanged with three shuffles (packed: extra bits | state bits << 8), and every lane cuts its own two fields (extra bits,
+// next-state bits) straight out of the shared-memory image at the bit address that the prefix sums of those widths give:
+//   extra bits, consumed OF, ML, LL from position P down:   field k = [P - pre_a(k) - a_k, P - pre_a(k))
+//   state bits, consumed LL, ML, OF after them:             field k = [Pend + pre_n(k), Pend + pre_n(k) + n_k),  Pend = P - sum a - sum n
+// ~40 warp instructions per sequence, no reader state but P.
+__device__ __forceinline__ uint32_t smem_bits(const uint32_t* sw, int o, uint32_t k) {         // bits [o, o + k) of the image, k <= 32
+    const uint32_t lo = sw[o >> 5], hi = sw[(o >> 5) + 1];
+    const uint32_t v = __funnelshift_r(lo, hi, (uint32_t)o);          // (shift taken modulo 32)
+    return k >= 32 ? v : (v & ((1u << k) - 1u));
+}
+
+// All 32 lanes of the producer warp call this; lanes 0..2 work.  Decodes `cnt` sequences from smem bit position P (counting
+// down); returns false once the stream is over-read (P below x_zero: corrupt) -- uniform, P is the same in every lane.
+__device__ __forceinline__ bool seq_produce3(const uint32_t* sw, int& P, int x_zero, const SeqCell* T, uint32_t& state, int lane, uint32_t cnt,
+                                             bool last_batch, uint32_t* r_mine) {
+    for (uint32_t j = 0; j < cnt; j++) {
+        if (P < x_zero) return false;
+        const uint2 q = *(const uint2*)&T[state];                       // base_value | next_base (16) | nb (8) | add_bits (8)
+        const uint32_t a = q.y >> 24;
+        const uint32_t n = (last_batch && j + 1 == cnt) ? 0u : ((q.y >> 16) & 0xFFu);       // no state update after the last sequence
+        const uint32_t pk = lane < 3 ? (a | (n << 8)) : 0u;
+        const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, pk, 0), p1 = __shfl_sync(0xFFFFFFFFu, pk, 1), p2 = __shfl_sync(0xFFFFFFFFu, pk, 2);
+        const uint32_t tot = p0 + p1 + p2;                              // sums stay inside their bytes (3 x 31, 3 x 9)
+        const uint32_t pre = (lane > 0 ? p0 : 0u) + (lane > 1 ? p1 : 0u);
+        const int Pend = P - (int)(tot & 0xFFu) - (int)(tot >> 8);
+        if (lane < 3) {
+            r_mine[j] = q.x + smem_bits(sw, P - (int)(pre & 0xFFu) - (int)a, a);
+            state = (q.y & 0xFFFFu) + smem_bits(sw, Pend + (int)(pre >> 8), n);
+        }
+        P = Pend;
+    }
+    return true;
+}
+
+// k_decode_sequences: one CTA of two warps per block.  Warp 0, lane 0 is the PRODUCER: the serial chain of the three
+// interleaved tANS states and nothing else (every instruction on it costs ~6 cycles of a lone dependent warp: ncu shows
+// `wait` as the top stall, profiles/r1_fse_stage_k_decode_sequences.txt).  Warp 1 is the CONSUMER, one batch of 32
+// sequences behind through a double buffer in shared memory: repeat-offset bookkeeping (symbolic, so blocks decode
+// independently), literal / output positions by a shuffle scan, and the 32-byte sequence records with coalesced stores.
+constexpr uint32_t SEQ_BATCH = 32;
+
+// optional cycle accounting of the two sides (NAFGPU_DEBUG_HUF=1): work vs waiting at the hand-over barrier
+#if defined(__CUDA_ARCH__)
+#define SEQ_CLK(t) do { if (J.debug_seq) t = clock64(); } while (0)
+#define SEQ_LAP(acc, t) do { if (J.debug_seq) { const long long _n = clock64(); acc += _n - t; t = _n; } } while (0)
+#define SEQ_REPORT(slot, a, b, nseq) do { if (J.debug_seq && lane == 0) { atomicAdd(&J.debug_seq[slot], (unsigned long long)(a)); atomicAdd(&J.debug_seq[(slot) + 1], (unsigned long long)(b)); \
+                                         if (nseq) atomicAdd(&J.debug_seq[4], (unsigned long long)(nseq)); } } while (0)
+#else
+#define SEQ_CLK(t) ((void)t)
+#define SEQ_LAP(acc, t) ((void)acc)
+#define SEQ_REPORT(slot, a, b, nseq) ((void)0)
+#endif
+
+__global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
+    NAF_DYN_SMEM(uint32_t, sbits);                       // staged bitstream: J.seq_stage_bytes (job maximum, capped)
+    __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
+    __shared__ uint32_t r_ov[2][SEQ_BATCH], r_ml[2][SEQ_BATCH], r_ll[2][SEQ_BATCH];
+    __shared__ int s_left;
+    const uint32_t bi = blockIdx.x;
+    const BlockDesc& B = J.blocks[bi];
+    if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
+    if (J.frame_bad[B.frame]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    BlockState& S = J.bstate[bi];
+    const uint8_t* src = J.comp + B.src_off;
+    if (S.seq_bits_off >= B.src_size) { if (tid == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    const uint32_t nbytes = B.src_size - S.seq_bits_off;
+    const uint8_t* g = src + S.seq_bits_off;
+    const bool staged = nbytes + 48 <= J.seq_stage_bytes;
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    int al[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        al[k] = J.table_al[B.tbl[k]];
+        const uint2* T = (const uint2*)(J.tables + (size_t)B.tbl[k] * FSE_SLOT_CELLS);
+        for (int i = tid; i < (1 << al[k]); i += 64) ((uint2*)stab[k])[i] = T[i];
+    }
+    if (staged) {
+        const uint4* gbase = (const uint4*)(g - a);
+        const uint32_t nchunks = (a + nbytes + 15) >> 4;
+        for (uint32_t c = tid; c < nchunks; c += 64) ((uint4*)sbits)[1 + c] = gbase[c];
+    }
+    const uint8_t last = g[nbytes - 1];
+    if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }     // (uniform)
+    __syncthreads();
+    if (staged && (uint32_t)tid < 16 + a) ((uint8_t*)sbits)[tid] = 0;
+    if (tid == 0) s_left = 0;
+    __syncthreads();
+    const int P0 = 8 * (int)(nbytes - 1) + zc::highbit32(last);
+    const uint32_t n = B.n_seq, base = B.seq_base;
+    const uint32_t nbatch = (n + SEQ_BATCH - 1) / SEQ_BATCH;
+    if (warp == 0) {
+        // ---- producer ---------------------------------------------------------------------------------------------
+        BackBits rg{};
+        const int xz = (int)(16 + a) * 8;                // smem bit position of stream bit 0
+        int P = xz + P0;                                 // staged: the smem bit position of the next unread bit (the same in every lane)
+        uint32_t sLL = 0, sOF = 0, sML = 0;              // global-memory reader (lane 0)
+        uint32_t state = 0;                              // staged reader: this lane's state (lane 0: OF, 1: ML, 2: LL)
+        const int kind = lane == 0 ? 1 : (lane == 1 ? 2 : 0);                               // stab / al / r_* index of the lane's state
+        uint32_t* const r_base = lane == 0 ? &r_ov[0][0] : (lane == 1 ? &r_ml[0][0] : &r_ll[0][0]);
+        bool dead = false;
+        if (staged) {
+            // the three initial states: AL_ll, AL_of, AL_ml bits from the top, in that order
+            const int before = lane == 2 ? 0 : (lane == 0 ? al[0] : al[0] + al[1]);
+            if (lane < 3) state = smem_bits(sbits, P - before - al[kind], (uint32_t)al[kind]);
+            P -= al[0] + al[1] + al[2];
+        } else if (lane == 0) { rg.init(g, nbytes); sLL = rg.read(al[0]); sOF = rg.read(al[1]); sML = rg.read(al[2]); }
+        long long t_work = 0, t_wait = 0, t0 = 0;
+        for (uint32_t k = 0; k < nbatch; k++) {
+            const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
+            SEQ_CLK(t0);
+            if (staged) {
+                if (!dead) {
+                    const bool ok = seq_produce3(sbits, P, xz, stab[kind], state, lane, cnt, k + 1 == nbatch, r_base + (k & 1) * SEQ_BATCH);
+                    // a corrupt stream over-reads: the reader stops at the first sequence that starts below bit 0 (it has read at
+                    // most 90 bits of the zero padding by then); the block is flagged
+                    const int left = ok ? P - xz : -1;
+                    if (left < 0) { dead = true; if (lane == 0) s_left = left; }
+                    else if (k + 1 == nbatch && lane == 0) s_left = left;
+                }
+            } else if (lane == 0 && !dead) {
+                seq_produce(rg, stab[0], stab[1], stab[2], sLL, sOF, sML, cnt, k + 1 == nbatch, r_ov[k & 1], r_ml[k & 1], r_ll[k & 1]);
+                const int left = (int)rg.P;
+                if (left < 0) { dead = true; s_left = left; }
+                else if (k + 1 == nbatch) s_left = left;
+            }
+            SEQ_LAP(t_work, t0);
+            __syncthreads();                             // batch k is ready; the consumer has finished batch k - 1
+            SEQ_LAP(t_wait, t0);
+        }
+        SEQ_REPORT(0, t_work, t_wait, n);
+        return;
+    }
+    // ---- consumer -------------------------------------------------------------------------------------------------
+    RepMap carry; rep_identity(carry);                      // the block's repeat-offset map up to the current batch (uniform over the warp)
+    uint32_t litpos = 0, outpos = 0;                        // running totals, uniform over the warp
+    bool bad = false;
+    uint4* rec = (uint4*)(J.seq + base);
+    long long c_work = 0, c_wait = 0, c0 = 0;
+    SEQ_CLK(c0);
+    for (uint32_t k = 0; k < nbatch; k++) {
+        SEQ_LAP(c_work, c0);
+        __syncthreads();
+        SEQ_LAP(c_wait, c0);
+        const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
+        uint32_t* b_ov = r_ov[k & 1];
+        const uint32_t ll = (uint32_t)lane < cnt ? r_ll[k & 1][lane] : 0u, ml = (uint32_t)lane < cnt ? r_ml[k & 1][lane] : 0u;
+        {
+            // repeat offsets (RFC 8878 3.1.1.5): what a sequence does to the three slots is a map; the offset it uses is slot 0
+            // AFTER its own map.  An inclusive scan over the batch (on top of the carry) gives every sequence its offset,
+            // symbolically in the block's incoming slots -- 5 shuffle steps instead of a 32-step chain in one lane (which had
+            // become as slow as the tANS walk: 319 cycles per sequence, measured).
+            RepMap m; rep_identity(m);
+            if ((uint32_t)lane < cnt) {
+                const uint32_t ov = b_ov[lane];
+                if (ov > 3) { m.s[0] = -1; m.v[0] = ov - 3; m.s[1] = 0; m.s[2] = 1; }
+                else {
+                    const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+                    if (idx == 1) { m.s[0] = 1; m.s[1] = 0; }
+                    else if (idx == 2) { m.s[0] = 2; m.s[1] = 0; m.s[2] = 1; }
+                    else if (idx == 3) { m.v[0] = 1; m.s[1] = 0; m.s[2] = 1; }
+                }
+            }
+            if (lane == 0) rep_compose(m, carry, bad);
+            rep_warp_scan(m, lane, bad);
+            RepSym off; off.src = m.s[0]; off.val = m.v[0];
+            if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
+            if ((uint32_t)lane < cnt) b_ov[lane] = encode_off(off);
+            rep_shfl(carry, m, 31);                          // (lanes past the batch hold the identity: lane 31 has the batch's total)
+        }
+        __syncwarp();
+        // positions: exclusive scans of ll and ll + ml over the batch, on top of the running totals
+        uint32_t il = ll, io = ll + ml;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d), to = __shfl_up_sync(0xFFFFFFFFu, io, d);
+            if (lane >= d) { il += tl; io += to; }
+        }
+        if ((uint32_t)lane < cnt) {
+            const uint32_t lp = litpos + il - ll, op = outpos + io - (ll + ml);
+            rec[2 * (k * SEQ_BATCH + lane)] = make_uint4(ll, ml, b_ov[lane], lp);
+            rec[2 * (k * SEQ_BATCH + lane) + 1] = make_uint4(op, bi, 0u, 0u);
+        }
+        litpos += __shfl_sync(0xFFFFFFFFu, il, 31);
+        const uint32_t otot = __shfl_sync(0xFFFFFFFFu, io, 31);
+        if (otot > BLOCK_MAX || outpos + otot > BLOCK_MAX) bad = true;      // (match lengths are < 2^17 each: no wrap within a batch)
+        outpos += otot;
+    }
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane != 0) return;
+    SEQ_LAP(c_work, c0);
+    SEQ_REPORT(2, c_work, c_wait, 0);
+    if (bad || s_left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
+    uint32_t regen = outpos + (B.lit_regen - litpos);
+    if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
+    S.regen = regen;
+    for (int k = 0; k < 3; k++) { S.rep_src[k] = carry.s[k]; S.rep_val[k] = carry.v[k]; }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// k_frame_scan: one CTA per frame.  Exclusive prefix sum of regenerated block sizes -> out_off; composes the
+// repeat-offset transfer functions -> rep_in per block; checks the total against the size the container states.
+//
+// A block's effect on the three repeat offsets is a map: slot k = constant v, or incoming slot s minus v (blocks
+// without sequences are the identity).  Maps compose associatively, so the chain across the blocks of a frame is a
+// scan: shuffles inside a warp, the warps' aggregates scanned once more by every warp; FSCAN_T blocks per step.
+// A genome frame has a handful of blocks; a FASTQ section flushed per record has 10^5 of them.
+constexpr int FSCAN_T = 512, FSCAN_W = FSCAN_T / 32;
 
 // Blocks [b_begin, b_end) of frame f, FSCAN_T per step.  REDUCE: only what the range does as a whole (regenerated bytes, the
 // composed repeat-offset map) -- the first pass over a tile of a long frame.  Otherwise: from the state at b_begin (`off`,
@@ -2129,7 +2206,9 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
     NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
-        uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA * LZ_U - 1) / (LZ_CTA * LZ_U));
+        // (small jobs: one entry per thread, as many CTAs as entries need -- latency; big jobs: LZ_U entries per thread)
+        uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
+        if (grid > 148u * 8u) grid = std::max<uint32_t>(148u * 8u, (uint32_t)((J.n_seq + LZ_CTA * LZ_U - 1) / (LZ_CTA * LZ_U)));
         if (grid > 148u * 64u) grid = 148u * 64u;
         NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();

@@ -29,6 +29,7 @@ struct JobDev {
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
     unsigned long long* debug;        // optional per-CTA phase clocks of k_huf_decode (NAFGPU_DEBUG_HUF=1), else null
+    unsigned long long* debug_seq;    // optional cycle accounting of k_decode_sequences (8 counters), else null
     uint32_t* lz_list[3];             // rotating worklists of matches still pending (n_seq entries each)
     uint32_t* lz_count;               // [3] their lengths
     uint32_t* lz_rounds;              // rounds k_lz_first + k_lz_resolve ran (statistics)

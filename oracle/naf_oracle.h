@@ -147,6 +147,10 @@ void nafo_apply_mask(uint8_t* seq, uint64_t n, const uint64_t* runs, uint64_t n_
 double nafo_time_decode(const uint8_t* buf, size_t len, int want_quality, int want_mask, int iters,
                         uint64_t* ascii_bytes_out);
 
+/* The same for a collection on `threads` native threads, one archive per core at a time; seconds for the whole list. */
+double nafo_time_decode_many(const uint8_t* const* bufs, const size_t* lens, size_t n, int threads, int want_quality, int want_mask,
+                             uint64_t* ascii_bytes_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ def lib():
         L.nafo_zstd_version.restype = C.c_char_p
         L.nafo_last_error.restype = C.c_char_p
         L.nafo_time_decode.restype = C.c_double
+        L.nafo_time_decode_many.restype = C.c_double
         L.nafo_mask_runs.restype = C.c_int64
         L.nafo_synth_mask.restype = C.c_uint64
         L.nafo_free.argtypes = [C.c_void_p]
@@ -317,6 +318,20 @@ def time_decode(data: bytes, quality=True, mask=True, iters=1):
     """Seconds for `iters` full CPU decodes (1 thread) and the ASCII sequence bytes of one decode."""
     nb = C.c_uint64()
     t = lib().nafo_time_decode(_buf(data), C.c_size_t(len(data)), int(quality), int(mask), int(iters), C.byref(nb))
+    if t < 0:
+        raise OracleError(-1, lib().nafo_last_error().decode())
+    return t, nb.value
+
+
+def time_decode_many(archives, threads: int, quality=True, mask=True):
+    """Seconds for one CPU decode of every archive on `threads` native threads (one archive per core at a time), and the
+    ASCII sequence bytes decoded."""
+    n = len(archives)
+    keep = [_buf(a) for a in archives]
+    ptrs = (C.c_void_p * n)(*[C.cast(k, C.c_void_p) for k in keep])
+    lens = (C.c_size_t * n)(*[len(a) for a in archives])
+    nb = C.c_uint64()
+    t = lib().nafo_time_decode_many(ptrs, lens, C.c_size_t(n), C.c_int(threads), int(quality), int(mask), C.byref(nb))
     if t < 0:
         raise OracleError(-1, lib().nafo_last_error().decode())
     return t, nb.value
