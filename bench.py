@@ -491,6 +491,32 @@ def main():
     e2e_val = world * ascii_bytes * args.steps / e2e_s / 1e9
     clocks = sampler.summary()
 
+    # ---- what the host <-> device link gives for the SAME bytes with the same concurrency (every rank at the same time): the
+    # ceiling of the end-to-end number.  Pure copies, no kernels: `lanes` streams, each H2D then D2H of its share per step.
+    ceil_bufs = []
+    for _ in range(args.lanes):
+        hi = torch.empty(max(h2d_step // args.lanes, 1), dtype=torch.uint8, pin_memory=True)
+        ho = torch.empty(max(d2h_step // args.lanes, 1), dtype=torch.uint8, pin_memory=True)
+        ceil_bufs.append((hi, ho, torch.empty_like(hi, device="cuda"), torch.empty_like(ho, device="cuda"), torch.cuda.Stream()))
+
+    def copy_steps(k):
+        for _ in range(k):
+            for hi, ho, di, do, stream in ceil_bufs:
+                with torch.cuda.stream(stream):
+                    di.copy_(hi, non_blocking=True)
+                    ho.copy_(do, non_blocking=True)
+        torch.cuda.synchronize()
+
+    copy_steps(args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    copy_steps(args.steps)
+    ceil_s = time.perf_counter() - t0
+    barrier()
+    ceil_s = max_over_ranks(ceil_s)
+    ceil_val = world * ascii_bytes * args.steps / ceil_s / 1e9
+    del ceil_bufs
+
     # ---- FASTA text of the same batch, formatted on the device (reported beside the metric, not part of it) ----
     text = None
     if rank == 0:
@@ -549,7 +575,11 @@ def main():
                 "path_algorithmic_GBps": path_gbs, "path_frac_of_hbm_peak": path_gbs / peak,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "lanes": args.lanes, "mode": "K steps streamed through Pipeline.decode_stream (no barrier between steps)",
                         "per_step_sync": {"value": world * ascii_bytes * args.steps / sync_s / 1e9, "ms_per_step": sync_s / args.steps * 1e3},
-                        "ms_per_step": e2e_s / args.steps * 1e3},
+                        "ms_per_step": e2e_s / args.steps * 1e3,
+                        "ceiling": {"value": ceil_val, "unit": UNIT, "ms_per_step": ceil_s / args.steps * 1e3,
+                                    "what": f"pure copies of the same {h2d_step} B H2D + {d2h_step} B D2H per step and GPU over {args.lanes} streams from pinned memory, "
+                                            f"all {world} rank(s) at once, expressed in the metric's unit (ASCII bytes / time)"},
+                        "frac_of_ceiling": e2e_val / ceil_val},
                 "gpu_launches": int(st.kernel_launches) * args.steps,
                 "roofline": {"bound": "hbm", "kernel": kernel_of.get(dom_name, dom_name), "stage": dom_name, "traffic_source": traffic_src, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": int(dom_bytes),

@@ -203,6 +203,25 @@ int nafgpu_job_format(nafgpu_ctx* ctx, int format, uint64_t line_length, nafgpu_
 int nafgpu_format_batch(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t n, uint32_t want, int format,
                         uint64_t line_length, nafgpu_text* out);
 
+/* ---- pipeline ----------------------------------------------------------------------------------------------------------
+ * The reference seam is an iterator a consumer drives (Decoder::next, nafcodec/src/decoder/mod.rs:444-457); a device backend
+ * called synchronously leaves the copy engines idle while kernels run.  A pipeline owns `lanes` contexts and host threads:
+ * batches are submitted without waiting, and the H2D copy of one batch, the kernels of another and the D2H copy of a third
+ * overlap.  Typical use (a collection of archives, cfg5): submit every sub-batch, then wait / consume / release in order.
+ *   submit   returns a ticket (>= 0) at once; `archives` and the compressed bytes they point to are borrowed until wait returns
+ *   wait     blocks until the ticket is decoded; `out` gets n results whose pointers stay valid until release
+ *   release  hands the lane's pinned buffers back (a lane takes no new batch before its last ticket is released)
+ * At most `lanes` tickets can be decoded-but-unreleased at a time; thread-safe. */
+typedef struct nafgpu_pipeline nafgpu_pipeline;
+int nafgpu_pipeline_create(int device, uint32_t lanes, nafgpu_pipeline** out);
+void nafgpu_pipeline_destroy(nafgpu_pipeline* p);
+int64_t nafgpu_pipeline_submit(nafgpu_pipeline* p, const nafgpu_archive* archives, uint32_t n, uint32_t want);
+int nafgpu_pipeline_wait(nafgpu_pipeline* p, int64_t ticket, nafgpu_result* out, uint32_t n);
+int nafgpu_pipeline_release(nafgpu_pipeline* p, int64_t ticket);
+const char* nafgpu_pipeline_last_error(const nafgpu_pipeline* p);
+uint32_t nafgpu_pipeline_lanes(const nafgpu_pipeline* p);
+int nafgpu_pipeline_lane_stats(nafgpu_pipeline* p, uint32_t lane, nafgpu_job_stats* out);   /* sizes of the lane's last batch */
+
 /* ---- encode side -----------------------------------------------------------------------------------
  * What the reference's writers compute per record before the bytes reach the zstd compressors, for all records of an
  * archive at once:

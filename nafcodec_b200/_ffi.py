@@ -73,7 +73,8 @@ SYMBOLS = ["nafgpu_parse_archive", "nafgpu_variable_u64", "nafgpu_strerror", "na
            "nafgpu_ctx_destroy", "nafgpu_last_error", "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_decode",
            "nafgpu_decode_batch", "nafgpu_job_prepare", "nafgpu_job_run", "nafgpu_job_fetch", "nafgpu_job_sync",
            "nafgpu_job_get_stats", "nafgpu_job_time", "nafgpu_job_run_profiled", "nafgpu_stage_name",
-           "nafgpu_job_device_result", "nafgpu_zstd_decompress", "nafgpu_job_format", "nafgpu_format_batch", "nafgpu_pack"]
+           "nafgpu_job_device_result", "nafgpu_zstd_decompress", "nafgpu_job_format", "nafgpu_format_batch", "nafgpu_pack", "nafgpu_pipeline_create", "nafgpu_pipeline_destroy", "nafgpu_pipeline_submit",
+           "nafgpu_pipeline_wait", "nafgpu_pipeline_release", "nafgpu_pipeline_last_error", "nafgpu_pipeline_lanes", "nafgpu_pipeline_lane_stats"]
 
 
 class Library:
@@ -113,6 +114,18 @@ class Library:
         L.nafgpu_zstd_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.nafgpu_job_format.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(Text), C.c_uint32]
         L.nafgpu_format_batch.argtypes = [C.c_void_p, C.POINTER(Archive), C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(Text)]
+        L.nafgpu_pipeline_create.argtypes = [C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.nafgpu_pipeline_destroy.argtypes = [C.c_void_p]
+        L.nafgpu_pipeline_destroy.restype = None
+        L.nafgpu_pipeline_submit.argtypes = [C.c_void_p, C.POINTER(Archive), C.c_uint32, C.c_uint32]
+        L.nafgpu_pipeline_submit.restype = C.c_int64
+        L.nafgpu_pipeline_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Result), C.c_uint32]
+        L.nafgpu_pipeline_release.argtypes = [C.c_void_p, C.c_int64]
+        L.nafgpu_pipeline_last_error.argtypes = [C.c_void_p]
+        L.nafgpu_pipeline_last_error.restype = C.c_char_p
+        L.nafgpu_pipeline_lanes.argtypes = [C.c_void_p]
+        L.nafgpu_pipeline_lanes.restype = C.c_uint32
+        L.nafgpu_pipeline_lane_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(JobStats)]
         L.nafgpu_pack.argtypes = [C.c_void_p, C.POINTER(PackInput), C.POINTER(PackResult)]
         L.nafgpu_job_device_result.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
 

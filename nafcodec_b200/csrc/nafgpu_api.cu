@@ -75,7 +75,7 @@ struct ArchPlan {
 struct nafgpu_ctx {
     int device = 0;
     cudaStream_t st = 0, st2 = 0;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_block = nullptr;
     std::string err;
     DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
@@ -165,12 +165,22 @@ int status_to_code(uint32_t s, std::string& msg) {
 // the lanes stay staggered, so the link is always busy (tools/e2e_probe.py).
 static std::mutex g_d2h_turn[16];
 
+// Waiting for the context's stream.  A big job waits on an event created with cudaEventBlockingSync: the thread sleeps
+// instead of spinning.  With 8 GPUs x 4 lanes on a 32-vCPU host, 32 threads spinning in cudaStreamSynchronize next to the
+// header walks halved the end-to-end rate per GPU (round 1: 49.5 -> 11 GB/s per GPU at N = 8).  Small jobs keep spinning:
+// a wake-up costs tens of microseconds, which is the whole decode of a 5 Mbp archive.
+static cudaError_t wait_stream(nafgpu_ctx* c) {
+    if (c->z1_size < (8u << 20) || !c->ev_block) return cudaStreamSynchronize(c->st);
+    cudaError_t e = cudaEventRecord(c->ev_block, c->st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+}
+
 static int d2h_results(nafgpu_ctx* c) {
-    CUDA_TRY(c, cudaStreamSynchronize(c->st));                  // kernels first: do not hold the turn while they run
+    CUDA_TRY(c, wait_stream(c));                                // kernels first: do not hold the turn while they run
     std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
     CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
     CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
-    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    CUDA_TRY(c, wait_stream(c));
     return NAFGPU_OK;
 }
 
@@ -318,6 +328,7 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { c->ev_block = nullptr; cudaGetLastError(); }
     for (int i = 0; i < N_STAGES + 3; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     c->ev_ok = true;
     c->coop_ctas = zk::lz_resolve_max_ctas(device);
@@ -337,6 +348,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_block) cudaEventDestroy(c->ev_block);
     cudaStreamDestroy(c->st2);
     cudaStreamDestroy(c->st);
     delete c;

@@ -405,54 +405,70 @@ class DecoderBuilder:
 
 
 class Pipeline:
-    """Several contexts (CUDA streams) on one GPU fed from host threads: the H2D copy of one sub-batch, the kernels of
-    another and the D2H copy of a third overlap.  This is the intended way to drive a collection of archives through the
-    C ABI ("distinct contexts may be used concurrently from distinct threads", include/nafgpu.h)."""
+    """The C ABI's pipeline (nafgpu_pipeline_*, include/nafgpu.h): `lanes` contexts and host threads inside the library, so
+    that the H2D copy of one sub-batch, the kernels of another and the D2H copy of a third overlap.  This class only cuts
+    batches into sub-batches and keeps a few tickets in flight; a Rust or C++ caller uses the same three calls."""
 
     def __init__(self, device: int = 0, lanes: int = 3, library: Optional[_ffi.Library] = None):
-        from concurrent.futures import ThreadPoolExecutor
         self.lib = library or _ffi.default_library()
-        self.ctxs = [Context(device, self.lib) for _ in range(lanes)]
-        self.pool = ThreadPoolExecutor(max_workers=lanes)
+        self.lanes = lanes
+        self._p = C.c_void_p()
+        raise_for_status(self.lib, self.lib.dll.nafgpu_pipeline_create(device, lanes, C.byref(self._p)), what="nafgpu_pipeline_create")
+
+    def _raise(self, rc):
+        if rc:
+            msg = self.lib.dll.nafgpu_pipeline_last_error(self._p).decode()
+            raise_for_status(self.lib, rc, None, msg)
+
+    def _submit(self, part, want):
+        cnt = len(part)
+        arr = (_ffi.Archive * cnt)(*part)
+        t = self.lib.dll.nafgpu_pipeline_submit(self._p, arr, cnt, want)
+        if t < 0:
+            self._raise(int(t))
+        return t, arr, cnt
+
+    def _finish(self, ticket, cnt, each):
+        res = (_ffi.Result * cnt)()
+        rc = self.lib.dll.nafgpu_pipeline_wait(self._p, ticket, res, cnt)
+        try:
+            self._raise(rc)
+            for i in range(cnt):
+                if res[i].status:
+                    raise_for_status(self.lib, res[i].status, None, f"archive {i} of the sub-batch")
+                each(i, res[i])
+        finally:
+            self.lib.dll.nafgpu_pipeline_release(self._p, ticket)
 
     def decode(self, archives, want: int = _ffi.WANT_ALL, consume=None):
-        """Decodes `archives` (list of _ffi.Archive) in len(ctxs) interleaved sub-batches.  `consume(index, result_struct)`
-        is called on the worker thread for every archive while its pinned buffers are valid; without it the results are
-        copied out as ArchiveResult objects."""
-        n, lanes = len(archives), len(self.ctxs)
+        """Decodes `archives` (list of _ffi.Archive) in `lanes` sub-batches.  `consume(index, result_struct)` is called for
+        every archive while its pinned buffers are valid; without it the results are copied out as ArchiveResult objects."""
+        n, lanes = len(archives), self.lanes
         bounds = [(n * k) // lanes for k in range(lanes + 1)]
         out = [None] * n
-
-        def work(k):
-            lo, hi = bounds[k], bounds[k + 1]
-            if hi == lo:
-                return
-            ctx = self.ctxs[k]
-            cnt = hi - lo
-            arr = (_ffi.Archive * cnt)(*archives[lo:hi])
-            res = (_ffi.Result * cnt)()
-            with ctx._lock:
-                rc = self.lib.dll.nafgpu_decode_batch(ctx._ctx, arr, cnt, want, res)
-                raise_for_status(self.lib, rc, ctx._ctx)
-                for i in range(cnt):
-                    if consume is not None:
-                        consume(lo + i, res[i])
-                    else:
-                        out[lo + i] = ArchiveResult._copy_from(archives[lo + i].header, res[i])
-
-        list(self.pool.map(work, range(lanes)))
+        inflight = [(lo,) + self._submit(archives[lo:hi], want) for lo, hi in zip(bounds, bounds[1:]) if hi > lo]
+        err = None
+        for lo, t, arr, cnt in inflight:
+            def each(i, r, lo=lo):
+                if consume is not None:
+                    consume(lo + i, r)
+                else:
+                    out[lo + i] = ArchiveResult._copy_from(archives[lo + i].header, r)
+            try:
+                self._finish(t, cnt, each)
+            except Exception as e:              # every ticket is waited for and released, then the first error is raised
+                err = err or e
+        if err is not None:
+            raise err
         return out
 
     def decode_stream(self, batches, want: int = _ffi.WANT_ALL, consume=None, sub_batch: Optional[int] = None):
         """Decodes a sequence of batches (each a list of _ffi.Archive) as ONE stream of work: every batch is cut into
-        sub-batches, and the lanes pull them from a shared queue with no barrier between batches, so the header walk, H2D
-        and kernels of one sub-batch always overlap the D2H of another (a collection of archives is processed this way;
-        `decode` waits for every lane at the end of each batch).  `consume(batch_index, index, result_struct)` runs on
-        the worker thread while the pinned buffers of that sub-batch are valid.  Returns the number of archives decoded."""
-        import itertools
-        import threading
-        lanes = len(self.ctxs)
-        lock = threading.Lock()
+        sub-batches that are submitted ahead of the consumer (2 x lanes tickets in flight, no barrier between batches), so the
+        header walk, H2D and kernels of one sub-batch always overlap the D2H of another.  `consume(batch_index, index,
+        result_struct)` runs while the pinned buffers of that sub-batch are valid.  Returns the number of archives decoded."""
+        from collections import deque
+        lanes = self.lanes
 
         def pieces():
             for bi, archives in enumerate(batches):
@@ -462,38 +478,50 @@ class Pipeline:
                     yield bi, lo, archives[lo:lo + step]
 
         it = pieces()
-        done = [0]
-
-        def work(k):
-            ctx = self.ctxs[k]
-            while True:
-                with lock:
-                    nxt = next(it, None)
+        inflight = deque()
+        done = 0
+        err = None
+        while True:
+            while len(inflight) < 2 * lanes and err is None:
+                nxt = next(it, None)
                 if nxt is None:
-                    return
+                    break
                 bi, lo, part = nxt
-                cnt = len(part)
-                arr = (_ffi.Archive * cnt)(*part)
-                res = (_ffi.Result * cnt)()
-                with ctx._lock:
-                    rc = self.lib.dll.nafgpu_decode_batch(ctx._ctx, arr, cnt, want, res)
-                    raise_for_status(self.lib, rc, ctx._ctx)
-                    if consume is not None:
-                        for i in range(cnt):
-                            consume(bi, lo + i, res[i])
-                with lock:
-                    done[0] += cnt
+                inflight.append((bi, lo) + self._submit(part, want))
+            if not inflight:
+                break
+            bi, lo, t, arr, cnt = inflight.popleft()
 
-        list(self.pool.map(work, range(lanes)))
-        return done[0]
+            def each(i, r, bi=bi, lo=lo):
+                if consume is not None:
+                    consume(bi, lo + i, r)
+            try:
+                self._finish(t, cnt, each)
+                done += cnt
+            except Exception as e:
+                err = err or e
+        if err is not None:
+            raise err
+        return done
 
     def stats(self):
-        return [c.stats() for c in self.ctxs]
+        out = []
+        for k in range(self.lanes):
+            s = _ffi.JobStats()
+            self.lib.dll.nafgpu_pipeline_lane_stats(self._p, k, C.byref(s))
+            out.append(s)
+        return out
 
     def close(self):
-        self.pool.shutdown()
-        for c in self.ctxs:
-            c.close()
+        if self._p:
+            self.lib.dll.nafgpu_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def decode_batch(files: Iterable, *, id=True, comment=True, sequence=True, quality=True, mask=True, device: int = 0,

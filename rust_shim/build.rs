@@ -16,7 +16,7 @@ fn main() {
         .flag("-std=c++17")
         .include("include")
         .files(["zstd_kernels.cu", "naf_kernels.cu", "naf_text.cu", "naf_pack.cu", "nafgpu_api.cu"].iter().map(|f| format!("{src}/{f}")))
-        .files(["frame_walk.cpp", "naf_parse.cpp"].iter().map(|f| format!("{src}/{f}")))
+        .files(["frame_walk.cpp", "naf_parse.cpp", "nafgpu_pipeline.cpp"].iter().map(|f| format!("{src}/{f}")))
         .compile("nafgpu");
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=dylib=stdc++");

@@ -145,7 +145,7 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 cudaError_t cudaEventCreate(cudaEvent_t* e);
-enum { cudaEventDisableTiming = 2 };
+enum { cudaEventDisableTiming = 2, cudaEventBlockingSync = 1 };
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0);
