@@ -135,7 +135,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                     // codes are at most 11 bits: a longer stream cannot be consumed exactly (libzstd: corruption_detected); it also
                     // bounds the shared memory a stream is staged in
                     if ((uint64_t)ss[k] * 8 > (uint64_t)dn[k] * 11 + 16) FAIL(ERR_INVALID, "zstd literals: Huffman stream longer than its symbols allow");
-                    zf::HufItem it{self, so[k], ss[k], dof[k], dn[k], 0u};
+                    zf::HufItem it{self, so[k], ss[k], dof[k], dn[k], streams == 4 ? (regen + 3) / 4 : 0u};
                     plan.huf_items.push_back(it);
                 }
             }
@@ -200,7 +200,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
 void JobPlan::finalize(uint32_t small_max_symbols) {
     // big = the streams of a 4-stream block whose streams regenerate more than small_max symbols: classified per BLOCK, so the
     // four streams of a block stay together and in order (k_huf_decode_big runs them as one thread-block cluster)
-    auto is_big = [&](const zf::HufItem& it) { const zf::BlockDesc& b = blocks[it.block]; return b.n_streams == 4 && (b.lit_regen + 3) / 4 > small_max_symbols; };
+    auto is_big = [&](const zf::HufItem& it) { return it.seg_symbols > small_max_symbols; };
     auto mid = std::stable_partition(huf_items.begin(), huf_items.end(), is_big);
     n_huf_big = (uint32_t)(mid - huf_items.begin());
     max_huf_stream = max_huf_small = 0;

@@ -7,7 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -70,6 +72,37 @@ struct ArchPlan {
     std::string host_msg;
 };
 
+// One section (= one zstd frame) of one archive: walked into its own plan, so that the sections of a job can be walked by
+// several host threads (a FASTQ archive flushed per record has 10^6 block headers per section: 30 ns each on one core was
+// as long as the whole device decode); the plans are then laid end to end, block descriptors going straight into the pinned
+// staging buffer with their indices rebased.
+struct WalkTask {
+    uint32_t arch = 0;
+    int sec = 0;
+    const uint8_t* data = nullptr;
+    uint64_t comp_off = 0, comp_size = 0, dst_off = 0, dst_size = 0;
+    fw::JobPlan plan;
+    int rc = 0;
+    std::string err;
+    bool live = true;
+    size_t bo = 0;                     // first block of the task among the job's blocks
+    uint32_t so = 0, slot_off = 0, ho = 0;
+    uint64_t lo = 0;
+};
+
+// fn(i) for i in [0, n) on up to `max_threads` host threads (inline when that is one).
+template <class F>
+void parallel_for(size_t n, unsigned max_threads, F fn) {
+    if (n <= 1 || max_threads <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    const unsigned w = (unsigned)std::min<size_t>(n, max_threads);
+    std::atomic<size_t> next{0};
+    auto body = [&] { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) return; fn(i); } };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < w; t++) th.emplace_back(body);
+    body();
+    for (std::thread& t : th) t.join();
+}
+
 }  // namespace
 
 struct nafgpu_ctx {
@@ -80,7 +113,8 @@ struct nafgpu_ctx {
     DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage, pack_host;
-    fw::JobPlan plan;
+    fw::JobPlan plan;                  // frames, Huffman items and totals of the job (block descriptors live in the tasks)
+    std::vector<WalkTask> tasks;
     std::vector<nk::NafDev> arch;
     std::vector<ArchPlan> aplan;
     zk::JobDev J;
@@ -188,9 +222,27 @@ struct Copy { const uint8_t* src; uint64_t dst, size; };
 
 // Device allocation + H2D of descriptors and compressed frames for the plan in c->plan / c->arch.
 int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp_off, uint32_t n) {
+    // lay the tasks' plans end to end: frames and Huffman items into the job plan (few), block descriptors later, straight
+    // into the staging buffer
+    size_t nb = 0;
+    uint64_t walked_bytes = 0;
+    for (WalkTask& T : c->tasks) {
+        if (!T.live) continue;
+        fw::JobPlan& G = c->plan;
+        const fw::JobPlan& L = T.plan;
+        T.bo = nb; T.so = (uint32_t)G.seq_total; T.lo = G.lit_total - 16; T.slot_off = G.n_slots - 3; T.ho = G.n_huf_slots;
+        if (G.seq_total + L.seq_total > 0xFFFFFFF0ull || nb + L.blocks.size() > 0xFFFFFFF0ull) return fail(c, NAFGPU_ERR_UNSUPPORTED, "job has too many blocks or sequences: split the batch");
+        for (zf::FrameDesc F : L.frames) { F.first_block += (uint32_t)T.bo; F.first_seq += T.so; G.frames.push_back(F); }
+        for (zf::HufItem it : L.huf_items) { it.block += (uint32_t)T.bo; G.huf_items.push_back(it); }
+        G.seq_total += L.seq_total; G.lit_total += L.lit_total - 16; G.n_slots += L.n_slots - 3; G.n_huf_slots += L.n_huf_slots;
+        G.n_huf_blocks += L.n_huf_blocks; G.n_seq_blocks += L.n_seq_blocks; G.n_checksums += L.n_checksums;
+        G.max_seq_section = std::max(G.max_seq_section, L.max_seq_section);
+        nb += L.blocks.size();
+        walked_bytes += T.comp_size;
+    }
     c->plan.finalize(zk::HUF_SMALL_SYMBOLS);
     const fw::JobPlan& pl = c->plan;
-    const size_t nb = pl.blocks.size(), nf = pl.frames.size();
+    const size_t nf = pl.frames.size();
     const uint64_t nseq = pl.seq_total;
 
     // ---- device buffers ----------------------------------------------------------------------------------------------
@@ -239,7 +291,30 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
 
     // ---- H2D ---------------------------------------------------------------------------------------------------------
     uint8_t* sp = (uint8_t*)c->stage.p;
-    if (nb) memcpy(sp, pl.blocks.data(), nb * sizeof(zf::BlockDesc));
+    {
+        // block descriptors: every task's blocks to their place, indices rebased to the job (frames, sequences, literal staging,
+        // FSE table slots, Huffman weight records)
+        std::vector<uint32_t> frame_off(c->tasks.size(), 0);
+        { uint32_t fo = 0; for (size_t t = 0; t < c->tasks.size(); t++) { frame_off[t] = fo; if (c->tasks[t].live) fo += (uint32_t)c->tasks[t].plan.frames.size(); } }
+        const unsigned threads = walked_bytes > (4u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+        parallel_for(c->tasks.size(), threads, [&](size_t t) {
+            const WalkTask& T = c->tasks[t];
+            if (!T.live) return;
+            zf::BlockDesc* out = (zf::BlockDesc*)sp + T.bo;
+            const zf::BlockDesc* in = T.plan.blocks.data();
+            const size_t cnt = T.plan.blocks.size();
+            const uint32_t fo = frame_off[t];
+            for (size_t i = 0; i < cnt; i++) {
+                zf::BlockDesc b = in[i];
+                b.frame += fo;
+                if (b.n_seq) b.seq_base += T.so;
+                if (b.lit_type >= zf::LT_HUF && b.btype == zf::BT_COMPRESSED) { b.lit_base += T.lo; b.huf_slot += T.ho; }
+                if (b.huf_block != zf::NO_BLOCK) b.huf_block += (uint32_t)T.bo;
+                for (int k = 0; k < 3; k++) if (b.tbl[k] != zf::NO_SLOT && b.tbl[k] >= 3) b.tbl[k] += T.slot_off;
+                out[i] = b;
+            }
+        });
+    }
     if (nf) memcpy(sp + c->o_frames, pl.frames.data(), nf * sizeof(zf::FrameDesc));
     if (n) memcpy(sp + c->o_naf, c->arch.data(), (size_t)n * sizeof(nk::NafDev));
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
@@ -499,18 +574,15 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
 
     // ---- host frame walk (north star: "The host walks the frame and block headers") --------------------------------
     std::vector<Copy> copies;
+    c->tasks.clear();
+    uint64_t total_comp = 0;
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
-        P.first_frame = (uint32_t)c->plan.frames.size();
-        const fw::JobPlan::Mark mark = c->plan.mark();
         const size_t copies_mark = copies.size();
-        const Copy last_copy = copies.empty() ? Copy{nullptr, 0, 0} : copies.back();
-        const uint64_t comp_mark = comp_off, cbytes_mark = c->stats.compressed_bytes, sbytes_mark = c->stats.section_bytes;
         for (int s = 0; s < 6; s++) {
             if (!P.dec[s]) continue;
             const nafgpu_section& S = A.sections[s];
-            std::string e;
             // Sections that follow one another in the caller's buffer (the sections of a NAF file do, a few header bytes
             // apart) keep their relative positions on the device and travel in one copy, gap bytes included.
             bool merged = false;
@@ -527,25 +599,51 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
                 if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
                 copies.push_back({S.data, comp_off, S.compressed_size});
             }
-            int rc = fw::walk_frame(S.data, comp_off, S.compressed_size, P.blob_off[s], P.blob_size[s], c->plan, e);
-            if (rc) {
-                static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
-                const std::string msg = std::string(names[s]) + " section: " + e;
-                if (n == 1) return fail(c, rc, msg);
-                // a batch goes on without this archive: nothing of it is uploaded or decoded, its result carries the status
-                P.host_status = rc; P.host_msg = msg;
-                c->plan.rollback(mark);
-                copies.resize(copies_mark);
-                if (copies_mark) copies.back() = last_copy;
-                comp_off = comp_mark; c->stats.compressed_bytes = cbytes_mark; c->stats.section_bytes = sbytes_mark;
+            c->tasks.emplace_back();
+            WalkTask& T = c->tasks.back();
+            T.arch = a; T.sec = s; T.data = S.data; T.comp_off = comp_off; T.comp_size = S.compressed_size;
+            T.dst_off = P.blob_off[s]; T.dst_size = P.blob_size[s];
+            total_comp += S.compressed_size;
+        }
+    }
+    // the frame / block header walk, one task per section; big jobs on several host threads
+    {
+        const unsigned threads = total_comp > (4u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+        parallel_for(c->tasks.size(), threads, [&](size_t t) {
+            WalkTask& T = c->tasks[t];
+            T.rc = fw::walk_frame(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.plan, T.err);
+        });
+    }
+    {
+        static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
+        uint32_t frames_so_far = 0;
+        size_t t = 0;
+        for (uint32_t a = 0; a < n; a++) {
+            ArchPlan& P = c->aplan[a];
+            const size_t t0 = t;
+            while (t < c->tasks.size() && c->tasks[t].arch == a) t++;
+            int bad_rc = 0;
+            for (size_t k = t0; k < t && !bad_rc; k++) {
+                if (c->tasks[k].rc) { bad_rc = c->tasks[k].rc; P.host_msg = std::string(names[c->tasks[k].sec]) + " section: " + c->tasks[k].err; }
+            }
+            if (bad_rc) {
+                if (n == 1) return fail(c, bad_rc, P.host_msg);
+                // a batch goes on without this archive: none of it is decoded, its result carries the status (its bytes still travel)
+                P.host_status = bad_rc;
                 c->arch[a].has = 0; c->arch[a].n_records = 0;
                 for (int k = 0; k < 6; k++) P.dec[k] = false;
-                break;
+                for (size_t k = t0; k < t; k++) c->tasks[k].live = false;
             }
-            c->stats.compressed_bytes += S.compressed_size;
-            c->stats.section_bytes += P.blob_size[s];
+            P.first_frame = frames_so_far;
+            P.n_frames = 0;
+            for (size_t k = t0; k < t; k++) {
+                if (!c->tasks[k].live) continue;
+                P.n_frames += (uint32_t)c->tasks[k].plan.frames.size();
+                c->stats.compressed_bytes += c->tasks[k].comp_size;
+                c->stats.section_bytes += c->tasks[k].dst_size;
+            }
+            frames_so_far += P.n_frames;
         }
-        P.n_frames = (uint32_t)c->plan.frames.size() - P.first_frame;
     }
     c->stats.algorithmic_bytes += c->stats.compressed_bytes;
     if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
@@ -567,9 +665,15 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->z2_off = c->z1_size; c->z2_size = 0;
     c->arena_size = c->z1_size + 256;
     c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
-    std::string e;
-    int rc = fw::walk_frame(frame, 16, frame_size, ALIGN, regen_size, c->plan, e);
-    if (rc) return fail(c, rc, e);
+    c->tasks.clear();
+    c->tasks.emplace_back();
+    {
+        WalkTask& T = c->tasks.back();
+        T.data = frame; T.comp_off = 16; T.comp_size = frame_size; T.dst_off = ALIGN; T.dst_size = regen_size;
+        T.rc = fw::walk_frame(frame, 16, frame_size, ALIGN, regen_size, T.plan, T.err);
+        if (T.rc) return fail(c, T.rc, T.err);
+    }
+    int rc = 0;
     std::vector<Copy> copies{{frame, 16, frame_size}};
     c->stats.compressed_bytes = frame_size; c->stats.section_bytes = regen_size;
     c->stats.algorithmic_bytes = frame_size + regen_size;
