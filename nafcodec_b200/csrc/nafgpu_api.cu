@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -90,6 +91,18 @@ struct WalkTask {
     uint64_t lo = 0;
 };
 
+// NAFGPU_DEBUG_PREP=1: phase times of nafgpu_job_prepare on stderr
+struct PrepClock {
+    bool on = getenv("NAFGPU_DEBUG_PREP") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[prepare] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 // fn(i) for i in [0, n) on up to `max_threads` host threads (inline when that is one).
 template <class F>
 void parallel_for(size_t n, unsigned max_threads, F fn) {
@@ -114,7 +127,8 @@ struct nafgpu_ctx {
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage, pack_host;
     fw::JobPlan plan;                  // frames, Huffman items and totals of the job (block descriptors live in the tasks)
-    std::vector<WalkTask> tasks;
+    std::vector<WalkTask> tasks;       // [0, n_tasks) belong to the current job
+    size_t n_tasks = 0;
     std::vector<nk::NafDev> arch;
     std::vector<ArchPlan> aplan;
     zk::JobDev J;
@@ -222,11 +236,13 @@ struct Copy { const uint8_t* src; uint64_t dst, size; };
 
 // Device allocation + H2D of descriptors and compressed frames for the plan in c->plan / c->arch.
 int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp_off, uint32_t n) {
+    PrepClock clk;
     // lay the tasks' plans end to end: frames and Huffman items into the job plan (few), block descriptors later, straight
     // into the staging buffer
     size_t nb = 0;
     uint64_t walked_bytes = 0;
-    for (WalkTask& T : c->tasks) {
+    for (size_t ti = 0; ti < c->n_tasks; ti++) {
+        WalkTask& T = c->tasks[ti];
         if (!T.live) continue;
         fw::JobPlan& G = c->plan;
         const fw::JobPlan& L = T.plan;
@@ -286,6 +302,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 5 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
+    clk.lap("merge + device buffers");
     if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
         return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
 
@@ -294,17 +311,24 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     {
         // block descriptors: every task's blocks to their place, indices rebased to the job (frames, sequences, literal staging,
         // FSE table slots, Huffman weight records)
-        std::vector<uint32_t> frame_off(c->tasks.size(), 0);
-        { uint32_t fo = 0; for (size_t t = 0; t < c->tasks.size(); t++) { frame_off[t] = fo; if (c->tasks[t].live) fo += (uint32_t)c->tasks[t].plan.frames.size(); } }
-        const unsigned threads = walked_bytes > (4u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
-        parallel_for(c->tasks.size(), threads, [&](size_t t) {
-            const WalkTask& T = c->tasks[t];
-            if (!T.live) return;
+        std::vector<uint32_t> frame_off(c->n_tasks, 0);
+        { uint32_t fo = 0; for (size_t t = 0; t < c->n_tasks; t++) { frame_off[t] = fo; if (c->tasks[t].live) fo += (uint32_t)c->tasks[t].plan.frames.size(); } }
+        (void)walked_bytes;
+        const unsigned threads = nb > 200000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+        struct Chunk { size_t task, begin, end; };
+        std::vector<Chunk> chunks;
+        for (size_t t = 0; t < c->n_tasks; t++) {
+            if (!c->tasks[t].live) continue;
+            const size_t cnt = c->tasks[t].plan.blocks.size();
+            for (size_t b = 0; b < cnt; b += 65536) chunks.push_back({t, b, std::min(cnt, b + 65536)});
+        }
+        parallel_for(chunks.size(), threads, [&](size_t ci) {
+            const Chunk& K = chunks[ci];
+            const WalkTask& T = c->tasks[K.task];
             zf::BlockDesc* out = (zf::BlockDesc*)sp + T.bo;
             const zf::BlockDesc* in = T.plan.blocks.data();
-            const size_t cnt = T.plan.blocks.size();
-            const uint32_t fo = frame_off[t];
-            for (size_t i = 0; i < cnt; i++) {
+            const uint32_t fo = frame_off[K.task];
+            for (size_t i = K.begin; i < K.end; i++) {
                 zf::BlockDesc b = in[i];
                 b.frame += fo;
                 if (b.n_seq) b.seq_base += T.so;
@@ -315,6 +339,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
             }
         });
     }
+    clk.lap("pinned staging + block copy");
     if (nf) memcpy(sp + c->o_frames, pl.frames.data(), nf * sizeof(zf::FrameDesc));
     if (n) memcpy(sp + c->o_naf, c->arch.data(), (size_t)n * sizeof(nk::NafDev));
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
@@ -328,6 +353,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         h2d += cp.size;
     }
 
+    clk.lap("H2D enqueue");
     zk::JobDev& J = c->J;
     J.comp = (const uint8_t*)c->comp.p; J.out = (uint8_t*)c->arena.p; J.lit = (uint8_t*)c->lit.p;
     J.frames = (const zf::FrameDesc*)((const uint8_t*)c->desc.p + c->o_frames); J.blocks = (const zf::BlockDesc*)c->desc.p;
@@ -574,8 +600,8 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
 
     // ---- host frame walk (north star: "The host walks the frame and block headers") --------------------------------
     std::vector<Copy> copies;
-    c->tasks.clear();
-    uint64_t total_comp = 0;
+    size_t n_tasks = 0;                                         // (tasks are reused from call to call: their plans keep their capacity)
+    uint32_t big_sections = 0;
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
@@ -599,21 +625,33 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
                 if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
                 copies.push_back({S.data, comp_off, S.compressed_size});
             }
-            c->tasks.emplace_back();
-            WalkTask& T = c->tasks.back();
+            if (n_tasks == c->tasks.size()) c->tasks.emplace_back();
+            WalkTask& T = c->tasks[n_tasks++];
+            T.plan.clear(); T.rc = 0; T.err.clear(); T.live = true;
             T.arch = a; T.sec = s; T.data = S.data; T.comp_off = comp_off; T.comp_size = S.compressed_size;
             T.dst_off = P.blob_off[s]; T.dst_size = P.blob_size[s];
-            total_comp += S.compressed_size;
+            if (S.compressed_size > (8u << 20)) big_sections++;
         }
     }
+    c->n_tasks = n_tasks;
+    PrepClock clk;
     // the frame / block header walk, one task per section; big jobs on several host threads
     {
-        const unsigned threads = total_comp > (4u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
-        parallel_for(c->tasks.size(), threads, [&](size_t t) {
-            WalkTask& T = c->tasks[t];
-            T.rc = fw::walk_frame(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.plan, T.err);
-        });
+        // (threads only when at least two sections are big enough to hold 10^5+ block headers: starting threads costs more than
+        // walking the ~30 headers of a genome section)
+        const unsigned threads = big_sections >= 2 ? std::min(std::min(big_sections, 8u), std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+        if (threads > 1) {
+            std::vector<size_t> big, small;
+            for (size_t t = 0; t < n_tasks; t++) (c->tasks[t].comp_size > (8u << 20) ? big : small).push_back(t);
+            auto walk = [&](size_t t) { WalkTask& T = c->tasks[t]; T.rc = fw::walk_frame(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.plan, T.err); };
+            std::thread rest([&] { for (size_t t : small) walk(t); });
+            parallel_for(big.size(), threads, [&](size_t i) { walk(big[i]); });
+            rest.join();
+        } else {
+            for (size_t t = 0; t < n_tasks; t++) { WalkTask& T = c->tasks[t]; T.rc = fw::walk_frame(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.plan, T.err); }
+        }
     }
+    clk.lap("header walk");
     {
         static const char* names[6] = {"ids", "comments", "lengths", "mask", "sequence", "quality"};
         uint32_t frames_so_far = 0;
@@ -621,7 +659,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         for (uint32_t a = 0; a < n; a++) {
             ArchPlan& P = c->aplan[a];
             const size_t t0 = t;
-            while (t < c->tasks.size() && c->tasks[t].arch == a) t++;
+            while (t < n_tasks && c->tasks[t].arch == a) t++;
             int bad_rc = 0;
             for (size_t k = t0; k < t && !bad_rc; k++) {
                 if (c->tasks[k].rc) { bad_rc = c->tasks[k].rc; P.host_msg = std::string(names[c->tasks[k].sec]) + " section: " + c->tasks[k].err; }
@@ -665,10 +703,11 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->z2_off = c->z1_size; c->z2_size = 0;
     c->arena_size = c->z1_size + 256;
     c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
-    c->tasks.clear();
-    c->tasks.emplace_back();
+    if (c->tasks.empty()) c->tasks.emplace_back();
+    c->n_tasks = 1;
     {
-        WalkTask& T = c->tasks.back();
+        WalkTask& T = c->tasks[0];
+        T.plan.clear(); T.rc = 0; T.err.clear(); T.live = true; T.arch = 0; T.sec = 0;
         T.data = frame; T.comp_off = 16; T.comp_size = frame_size; T.dst_off = ALIGN; T.dst_size = regen_size;
         T.rc = fw::walk_frame(frame, 16, frame_size, ALIGN, regen_size, T.plan, T.err);
         if (T.rc) return fail(c, T.rc, T.err);
