@@ -1682,6 +1682,30 @@ __device__ __forceinline__ void copy_long_match(uint8_t* out, uint64_t d, uint32
     else copy_match(out, d, off, ml, lane, nlanes);
 }
 
+// k_lz_index: for every 4 KB cell of every frame's output, the first match of the frame that ends after the start of the cell
+// (the frame's match count if none does).  Matches are ordered and disjoint, so match i owns the cells whose start lies in
+// [end of match i - 1, end of match i).  One thread per match; the last match of a frame also fills the cells behind it.
+constexpr uint32_t LZ_IDX_SHIFT = 12, LZ_IDX_PER_CHUNK = 65536u >> LZ_IDX_SHIFT;          // index cells per 64 KB chunk of the chunk table
+
+__global__ void __launch_bounds__(256) k_lz_index(JobDev J) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J.n_seq) return;
+    const SeqRec& R = J.seq[i];
+    const BlockDesc& B = J.blocks[R.block];
+    const FrameDesc& F = J.frames[B.frame];
+    if (J.frame_bad[B.frame]) return;
+    uint32_t* ix = J.lz_idx + (size_t)J.fin_chunk_first[B.frame] * LZ_IDX_PER_CHUNK + B.frame;      // (one extra cell per frame: the cell past its end)
+    const uint64_t n_cells = (uint64_t)(J.fin_chunk_first[B.frame + 1] - J.fin_chunk_first[B.frame]) * LZ_IDX_PER_CHUNK + 1;     // (+1: the cell past the end)
+    const uint64_t e_prev = i == F.first_seq ? 0 : (J.seq[i - 1].match_pos + J.seq[i - 1].ml - F.dst_off);
+    const uint64_t e = R.match_pos + R.ml - F.dst_off;
+    // cells k with e_prev <= k * 4096 < e  (the first match: every cell from 0 on)
+    uint64_t k0 = i == F.first_seq ? 0 : (e_prev + (1u << LZ_IDX_SHIFT) - 1) >> LZ_IDX_SHIFT;
+    uint64_t k1 = (e + (1u << LZ_IDX_SHIFT) - 1) >> LZ_IDX_SHIFT;      // first cell that starts at or after e
+    if (k1 > n_cells) k1 = n_cells;
+    for (uint64_t k = k0; k < k1; k++) ix[k] = (uint32_t)i;
+    if (i + 1 == (uint64_t)F.first_seq + F.n_seq) for (uint64_t k = k1; k < n_cells; k++) ix[k] = (uint32_t)(i + 1);
+}
+
 // Match resolution.
 //
 // A match may run once every earlier match whose destination intersects its source range has finished in an EARLIER
@@ -1726,7 +1750,16 @@ __device__ __forceinline__ int lz_try(const JobDev& J, uint32_t i, uint32_t roun
         }
         const uint64_t s = d - off;
         const uint64_t e = (off < ml) ? d : s + ml;                   // external source range [s, e)
-        uint32_t lo = F.first_seq, hi = i;                            // first earlier match (same frame) ending after s
+        // first earlier match (same frame) ending after s: between the index entries of the 4 KB cell that holds s and of the
+        // next one (k_lz_index), so the bisection has ~5 steps instead of ~20 over a frame of 10^6 matches
+        uint32_t lo = F.first_seq, hi = i;
+        {
+            const uint32_t* ix = J.lz_idx + (size_t)J.fin_chunk_first[B.frame] * LZ_IDX_PER_CHUNK + B.frame + ((s - F.dst_off) >> LZ_IDX_SHIFT);
+            const uint32_t a = ix[0], b = ix[1];
+            if (a > lo) lo = a;
+            if (b < hi) hi = b;
+            if (lo > hi) lo = hi;
+        }
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
             if (J.seq[mid].match_pos + J.seq[mid].ml > s) hi = mid; else lo = mid + 1;
@@ -2210,6 +2243,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
         if (grid > 148u * 8u) grid = std::max<uint32_t>(148u * 8u, (uint32_t)((J.n_seq + LZ_CTA * LZ_U - 1) / (LZ_CTA * LZ_U)));
         if (grid > 148u * 64u) grid = 148u * 64u;
+        NAF_LAUNCH(k_lz_index, (uint32_t)((J.n_seq + 255) / 256), 256, 0, st, J); launches++;
         NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();
         uint32_t cg = J.coop_ctas ? J.coop_ctas : 1u;                 // co-resident CTAs for the grid barrier (queried by the API)

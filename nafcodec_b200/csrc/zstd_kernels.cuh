@@ -25,6 +25,7 @@ struct JobDev {
     zf::SeqRec* seq;                  // one 32-byte record per sequence (written by k_decode_sequences / k_lz_literals)
     uint32_t seq_stage_bytes;         // shared-memory staging size of k_decode_sequences (largest sequence bitstream, capped)
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
+    uint32_t* lz_idx;                 // per frame, per 4 KB of output: first match ending after the start of the cell (k_lz_index)
     uint32_t* lz_blocker;             // per match: the unfinished match it was last found waiting for (0xFFFFFFFF: none yet)
     uint32_t* frame_bad;              // per frame: non-zero once anything in it failed validation
     uint32_t* status;                 // OR of zc::E_* bits
