@@ -381,6 +381,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     }
     J.huf_weights = (uint8_t*)c->hufw.p; J.huf_meta = (uint8_t*)c->hufw.p + (size_t)pl.n_huf_slots * 256;
     J.huf_items = (const zf::HufItem*)((const uint8_t*)c->desc.p + c->o_huf); J.n_huf_items = (uint32_t)nh; J.n_huf_big = pl.n_huf_big; J.max_huf_stream = pl.max_huf_stream; J.max_huf_small = pl.max_huf_small;
+    J.huf_block_min = 0;
+    if (const char* e = getenv("NAFGPU_HUF_BLOCK_MIN")) J.huf_block_min = (uint32_t)std::max(1, atoi(e));     // (tests: force either kernel)
     J.debug = nullptr; J.debug_seq = nullptr;
     if (getenv("NAFGPU_DEBUG_HUF") && nh) {
         if (!c->debug.ensure(nh * 64 + 64)) return fail(c, NAFGPU_ERR_NOMEM, "debug buffer");

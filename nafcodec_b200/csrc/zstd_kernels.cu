@@ -926,7 +926,7 @@ __device__ __forceinline__ void huf_build_wide(const uint16_t* table, int maxbit
             mask |= 1u << (used - 1);
             if (used == (uint32_t)HUF_W) break;
         }
-        bm[i] = (uint16_t)mask;
+        if (bm) bm[i] = (uint16_t)mask;
         if (MULTI) t3[i] = syms | (used3 << 24) | (n << 28);
     }
 }
@@ -1535,6 +1535,286 @@ __global__ void HB_CLUSTER_ATTR __launch_bounds__(HB_T, 3) k_huf_decode_big(JobD
         if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HB_T) dal[k] = sout[k]; }
         if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
             for (uint32_t k = (last_full << 4) + tid; k < endb; k += HB_T) dal[k] = sout[k];
+    }
+}
+
+// The counting legs of k_huf_decode_block: like track_advance, but the steady state reads the 3-symbol table (bits used and
+// symbol count are in its top byte) and the exact stop at `lim` walks single symbols with the base table.
+__device__ __forceinline__ void track_advance3(saddr_t comp, saddr_t t3, saddr_t t1, int maxbits, int xtop, int& q, int& cnt, int lim) {
+    int rem = lim - q;
+    if (rem <= 0) return;
+    Win w;
+    win_init(w, comp, xtop - q);
+    while (rem > HUF_W) {
+        const uint32_t e = lds32(t3 + 4 * win_peek(w));
+        const int used = (int)(e >> 24) & 15;
+        cnt += (int)(e >> 28);
+        rem -= used;
+        win_consume(w, used);
+    }
+    const int sh1 = HUF_W - maxbits;
+    while (rem > 0) {
+        const uint32_t e = lds16(t1 + 2 * (win_peek(w) >> sh1));
+        cnt++;
+        rem -= (int)(e & 0xFFu);
+        win_consume(w, (int)(e & 0xFFu));
+    }
+    q = lim - rem;
+}
+
+// k_huf_decode_block: the same decode, ONE CTA PER BLOCK working through the block's four streams one after the other.  The
+// tables (base table, 3-symbol table) are built once per block by the CTA itself -- no cluster, no exchange -- and stay in
+// shared memory for all four streams; the counting legs read the 3-symbol table too (bits used, symbols), so the boundary-mask
+// table is gone, and with it the two XU-pipe instructions per lookup that decoded it; the exact stop at a checkpoint walks
+// single symbols with the base table.  The next stream's bytes are fetched (bulk asynchronous copy) while the current
+// stream's output is flushed.  Measured against the cluster version on the 256-archive job: see profiles/r2_summary.md.
+__global__ void __launch_bounds__(HB_T, 3) k_huf_decode_block(JobDev J) {
+    NAF_DYN_SMEM(unsigned char, smem);
+    uint16_t* t1 = (uint16_t*)smem;
+    uint8_t* weights = smem + 4096;
+    uint16_t* wcnt = (uint16_t*)(smem + 4096 + 256);
+    uint32_t* misc = (uint32_t*)(smem + 4096 + 512);                    // [0..15] two scan buffers, [16..23] warp start candidates, [56..57] mbarrier
+    uint64_t* wmap = (uint64_t*)(smem + 4096 + 256);                    // [HB_NW] composed map of each warp (reuses wcnt after the table build)
+    uint32_t* t3 = (uint32_t*)(smem + 4864);
+    uint8_t* sout = smem + 4864 + 16384;
+    uint16_t* legtab = (uint16_t*)sout;                                 // [leg][range][offset] = landing offset | symbols << 4
+    uint16_t* qitems = (uint16_t*)(sout + HB_LEG_BYTES);                // range | offset << 8
+    uint32_t* scomp = (uint32_t*)(smem + HB_FIXED);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const uint32_t item0 = blockIdx.x * 4u;                              // the block's four streams are four consecutive items
+    const BlockDesc& B = J.blocks[J.huf_items[item0].block];
+#if defined(__CUDA_ARCH__)
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&misc[56]);
+#endif
+    // stages stream `sidx`: the 16 B-aligned image of global memory, behind 16 bytes that stay zero (one bulk asynchronous copy)
+    auto stage = [&](uint32_t sidx) {
+        const HufItem si = J.huf_items[item0 + sidx];
+        const uint8_t* sg = J.comp + B.src_off + si.src_off;
+        const uint32_t sa = (uint32_t)((uintptr_t)sg & 15);
+        const uint32_t bytes = ((sa + si.src_size + 15u) >> 4) << 4;
+#if defined(__CUDA_ARCH__)
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(scomp + 4)), "l"(sg - sa), "r"(bytes), "r"(mbar) : "memory");
+        }
+#else
+        for (uint32_t c = tid; c < (bytes >> 4); c += HB_T) ((uint4*)scomp)[1 + c] = ((const uint4*)(sg - sa))[c];
+#endif
+    };
+#if defined(__CUDA_ARCH__)
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+#endif
+    stage(0);
+    for (int i = tid; i < 64; i += HB_T) ((uint32_t*)weights)[i] = ((const uint32_t*)(J.huf_weights + (size_t)B.huf_slot * 256))[i];
+    const int nsym = (int)J.huf_meta[(size_t)B.huf_slot * 2] + 1, maxbits = (int)J.huf_meta[(size_t)B.huf_slot * 2 + 1];
+    __syncthreads();
+    if (maxbits != 0) {                                                 // (a bad tree was flagged by k_build_tables)
+        huf_build_t1<HB_T>(weights, nsym, maxbits, t1, wcnt);
+        huf_build_wide<HB_T, true>(t1, maxbits, nullptr, t3, 0u, 1u << HUF_W);
+    }
+    // a tree whose codes all have the same length (e.g. 16 equiprobable byte values) never lets tracks merge -- and does not
+    // need to: the codeword boundaries are the multiples of that length
+    const bool fixed_len = !__syncthreads_or(tid < 128 && (tid & 15) >= 2 && (tid & 15) <= zc::HUF_MAX_BITS && wcnt[tid] != 0);
+    // (one thread reads the flag: another stream's kernel may set it at any moment, and the decision must be the CTA's)
+    const bool skip = __syncthreads_or(maxbits == 0 || (tid == 0 && J.frame_bad[B.frame] != 0));
+    for (uint32_t sidx = 0; sidx < 4u; sidx++) {
+    const HufItem it = J.huf_items[item0 + sidx];
+    const uint8_t* g = J.comp + B.src_off + it.src_off;
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+#if defined(__CUDA_ARCH__)
+    {   // the bulk copy of this stream has landed (also before an early exit: the shared memory must not be handed on under it)
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar), "r"(sidx & 1u) : "memory");
+        } while (!done);
+    }
+#endif
+    if (skip) break;
+    if ((uint32_t)tid < 16 + a) ((uint8_t*)scomp)[tid] = 0;              // bits below the stream start read as zero
+    __syncthreads();
+
+    // ---- phase 1: transition map of every range -------------------------------------------------------------------------
+    // q = distance (in bits) from the top of the stream; smem bit position x = XTOP - q.
+    const int Z = (int)(16 + a) * 8;
+    const uint8_t last = ((const uint8_t*)scomp)[16 + a + it.src_size - 1];
+    if (last == 0) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); break; }
+    const int P0 = 8 * (int)(it.src_size - 1) + zc::highbit32(last);
+    const int XTOP = Z + P0;
+    int S = (P0 + HB_T - 1) / HB_T;
+    if (S < 2 * MAXC) S = 2 * MAXC;
+    const int ck[HB_NLEG + 1] = {S < HB_CK0 ? S : HB_CK0, S < HB_CK1 ? S : HB_CK1, S < HB_CK2 ? S : HB_CK2, S};
+    const int q0 = tid * S;
+    const int qe = (q0 + S < P0) ? q0 + S : P0;
+    const bool active = q0 < P0;
+    const saddr_t s_comp = to_saddr(scomp), s_t3 = to_saddr(t3), s_t1 = to_saddr(t1);
+    auto cp_at = [&](int rq0, int rqe, int j) { const int x = rq0 + ck[j]; return x < rqe ? x : rqe; };      // checkpoint j of a range
+
+    // (1) first stop: every candidate lands on its first codeword boundary at or past checkpoint 0 (one lookup each, out of one
+    //     64-bit window); candidates of the same codeword chain land together.
+    uint64_t first = ~0ull, fcnt = 0;                                   // candidate -> landing offset / symbols so far (4 bits each)
+    uint32_t live = 0;                                                  // landing offsets in use at the current checkpoint
+    if (active) {
+        const int l0 = cp_at(q0, qe, 0);
+        first = 0;
+        if (fixed_len) {
+            int q = q0 + (maxbits - q0 % maxbits) % maxbits, c = 0;     // the one candidate that is a boundary; the others follow it
+            track_advance3(s_comp, s_t3, s_t1, maxbits, XTOP, q, c, l0);
+            first = (uint64_t)(uint32_t)(q - l0) * 0x1111111111111111ull;
+            fcnt = (uint64_t)(uint32_t)c * 0x1111111111111111ull;
+            live = 1u << (q - l0);
+        } else {
+            for (int k = 0; k < maxbits; k++) {
+                int q = q0 + k, c = 0;
+                track_advance3(s_comp, s_t3, s_t1, maxbits, XTOP, q, c, l0);
+                const uint32_t o = (uint32_t)(q - l0);
+                first |= (uint64_t)o << (4 * k);
+                fcnt |= (uint64_t)c << (4 * k);
+                live |= 1u << o;
+            }
+        }
+        if (maxbits < 16) first |= ~0ull << (4 * maxbits);              // candidates that cannot occur: dead (15)
+    }
+    // (2) legs between checkpoints: the live tracks of ALL ranges are work items dealt out evenly over the CTA
+    uint32_t leg_done = 0;
+    for (int leg = 0; leg < HB_NLEG; leg++) {
+        if (ck[leg + 1] == ck[leg]) continue;                           // (uniform) short ranges: nothing between these checkpoints
+        leg_done |= 1u << leg;
+        const uint32_t n_mine = (uint32_t)__popc(live);
+        uint32_t qtotal;
+        uint32_t idx = hb_scan(n_mine, misc + 8 * (leg & 1), &qtotal);
+        for (uint32_t m = live; m; m &= m - 1) qitems[idx++] = (uint16_t)((uint32_t)tid | ((uint32_t)(__ffs((int)m) - 1) << 8));
+        __syncthreads();
+        for (uint32_t i = tid; i < qtotal; i += HB_T) {
+            const uint32_t item = qitems[i];
+            const int owner = (int)(item & 0xFFu), o = (int)(item >> 8);
+            const int oq0 = owner * S, oqe = (oq0 + S < P0) ? oq0 + S : P0;
+            const int lim = cp_at(oq0, oqe, leg + 1);
+            int q = cp_at(oq0, oqe, leg) + o, c = 0;
+            track_advance3(s_comp, s_t3, s_t1, maxbits, XTOP, q, c, lim);
+            legtab[(leg * HB_T + owner) * MAXC + o] = (uint16_t)((uint32_t)(q - lim) | ((uint32_t)c << 4));
+        }
+        __syncthreads();
+        uint32_t nl = 0;
+        for (uint32_t m = live; m; m &= m - 1) nl |= 1u << (legtab[(leg * HB_T + tid) * MAXC + (__ffs((int)m) - 1)] & 15u);
+        live = nl;
+    }
+    // (3) the map candidate -> candidate of the next range: exit offset of every landing offset in use after the first stop
+    uint64_t fmap = MAP_IDENTITY;
+    if (active) {
+        uint64_t exit_of = 0;
+        uint32_t starts = 0;
+        for (int k = 0; k < maxbits; k++) starts |= 1u << ((uint32_t)(first >> (4 * k)) & 15u);
+        for (uint32_t m = starts; m; m &= m - 1) {
+            const int o0 = __ffs((int)m) - 1;
+            uint32_t o = (uint32_t)o0;
+#pragma unroll
+            for (int leg = 0; leg < HB_NLEG; leg++) if (leg_done & (1u << leg)) o = legtab[(leg * HB_T + tid) * MAXC + o] & 15u;
+            exit_of |= (uint64_t)o << (4 * o0);
+        }
+        fmap = 0;
+        for (int k = 0; k < maxbits; k++) fmap |= ((exit_of >> (4 * ((uint32_t)(first >> (4 * k)) & 15u))) & 15ull) << (4 * k);
+        if (maxbits < 16) fmap |= ~0ull << (4 * maxbits);
+    }
+    // ---- compose the maps along the stream: inclusive scan in the warp, then warp totals serially ------------------------------
+    // inc_map(lane) = f_lane o ... o f_(lane - 2^d + 1); a constant map absorbs everything before it, and after the first
+    // step nearly every lane holds one: the gather runs only when some lane of the warp still needs it.
+    uint64_t inc_map = fmap;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, inc_map, d);
+        const bool need = lane >= d && !map_is_const(inc_map, maxbits);
+        if (__any_sync(0xFFFFFFFFu, need)) { if (need) inc_map = map_compose(inc_map, o); }
+    }
+    uint64_t exc_map = __shfl_up_sync(0xFFFFFFFFu, inc_map, 1);
+    if (lane == 0) exc_map = MAP_IDENTITY;
+    if (lane == 31) wmap[warp] = inc_map;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t k = 0;
+        for (int w = 0; w < HB_NW; w++) { misc[16 + w] = k; k = (uint32_t)(wmap[w] >> (4 * k)) & 15u; }
+    }
+    __syncthreads();
+    const uint32_t kw = misc[16 + warp];
+    const uint32_t ktrue = (uint32_t)(exc_map >> (4 * kw)) & 15u;      // this thread's true candidate
+    // symbols of the true track, and where it lands
+    uint32_t mycnt = 0;
+    int myland = -1;
+    if (active && ktrue < (uint32_t)maxbits) {
+        uint32_t o = (uint32_t)(first >> (4 * ktrue)) & 15u;
+        mycnt = (uint32_t)(fcnt >> (4 * ktrue)) & 15u;
+#pragma unroll
+        for (int leg = 0; leg < HB_NLEG; leg++) {
+            if (leg_done & (1u << leg)) { const uint32_t e = legtab[(leg * HB_T + tid) * MAXC + o]; o = e & 15u; mycnt += e >> 4; }
+        }
+        myland = qe + (int)o;
+    }
+    // the stream must end exactly on its first bit: the last active range's true track lands on P0
+    const bool bad_end = active && qe == P0 && myland != P0;
+    // ---- count, scan, write ------------------------------------------------------------------------------------------
+    const int any_bad = __syncthreads_or(bad_end);                      // (also: every read of the leg tables is done before phase 2 overwrites them)
+    uint32_t total;
+    const uint32_t off = hb_scan(mycnt, misc, &total);
+    if (any_bad || total != it.n_sym) { if (tid == 0) flag_error(J, B.frame, zc::E_HUF_STREAM); break; }
+    uint8_t* dst = J.lit + B.lit_base + it.dst_off;
+    const uint32_t a2 = (uint32_t)((uintptr_t)dst & 15);
+    if (mycnt) {
+        // write pass: from the true start to the first boundary at or past the end of the range.  Bytes go out as aligned 4-byte
+        // words assembled in a register pair; the ragged head and tail (words shared with the neighbouring ranges) as bytes.
+        saddr_t out = to_saddr(sout) + a2 + off;
+        int q = q0 + (int)ktrue;
+        int rem = qe - q;
+        Win w;
+        win_init(w, s_comp, XTOP - q);
+        const int sh1 = HUF_W - maxbits;
+        while ((out & 3u) && rem > 0) {                                 // head: single symbols up to a word boundary
+            const uint32_t e = lds16(s_t1 + 2 * (win_peek(w) >> sh1));
+            sts8(out, e >> 8); out++;
+            rem -= (int)(e & 0xFFu);
+            win_consume(w, (int)(e & 0xFFu));
+        }
+        uint32_t acc_lo = 0, acc_hi = 0;
+        int pc = 0;                                                     // bytes waiting in acc
+        while (rem > HUF_W) {
+            const uint32_t e = lds32(s_t3 + 4 * win_peek(w));
+            const int n = (int)(e >> 28), len = (int)(e >> 24) & 15;
+            const uint32_t sy = e & 0xFFFFFFu;
+            acc_lo |= sy << (8 * pc);
+            acc_hi |= __funnelshift_l(sy, 0u, 8 * pc);                  // the bits that fall off the top of acc_lo
+            pc += n;
+            if (pc >= 4) { sts32(out, acc_lo); out += 4; acc_lo = acc_hi; acc_hi = 0; pc -= 4; }
+            rem -= len;
+            win_consume(w, len);
+        }
+        while (rem > 0) {                                               // the last symbols, one at a time
+            const uint32_t e = lds16(s_t1 + 2 * (win_peek(w) >> sh1));
+            acc_lo |= (e >> 8) << (8 * pc);
+            pc++;
+            if (pc == 4) { sts32(out, acc_lo); out += 4; acc_lo = 0; pc = 0; }
+            rem -= (int)(e & 0xFFu);
+            win_consume(w, (int)(e & 0xFFu));
+        }
+        for (int k = 0; k < pc; k++) sts8(out + k, acc_lo >> (8 * k));
+    }
+    __syncthreads();
+    if (sidx + 1 < 4u) stage(sidx + 1);                                 // the next stream's bytes travel while this one's output is flushed
+    {
+        // ---- flush: sout[a2 + k] -> dst[k]; aligned 16 B chunks in the middle, bytes at the ragged ends ----------------
+        const uint32_t n = it.n_sym, endb = a2 + n;
+        uint8_t* dal = dst - a2;
+        const uint32_t first_full = a2 ? 1u : 0u, last_full = endb >> 4;     // chunks [first_full, last_full) are complete
+        for (uint32_t c = first_full + tid; c < last_full; c += HB_T) ((uint4*)dal)[c] = ((const uint4*)sout)[c];
+        if (a2) { uint32_t hend = endb < 16 ? endb : 16; for (uint32_t k = a2 + tid; k < hend; k += HB_T) dal[k] = sout[k]; }
+        if (last_full >= first_full && (last_full << 4) < endb && !(a2 && last_full == 0))
+            for (uint32_t k = (last_full << 4) + tid; k < endb; k += HB_T) dal[k] = sout[k];
+    }
+    __syncthreads();                                                    // the output image becomes the next stream's scratch
     }
 }
 
@@ -2213,9 +2493,20 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         NAF_LAUNCH(k_build_tables<1>, J.n_blocks, 32, 0, sb, J); launches++;
         if (J.n_huf_big) {   // items [0, n_huf_big): the streams of 4-stream blocks, four consecutive items (= one cluster) per block
             const uint32_t smem = hb_smem_bytes(J.max_huf_stream);
-            NAF_SET_MAX_SMEM(k_huf_decode_big, smem);
             if (!st2) ev->kernel_begin();
-            NAF_LAUNCH(k_huf_decode_big, J.n_huf_big, HB_T, smem, sb, J); launches++;
+            // Two shapes of the same decode.  Enough blocks to fill the device several times over (a batch, a chromosome): one CTA
+            // per BLOCK, its four streams in turn, tables built once (k_huf_decode_block: 1.31 ms against 1.63 ms on the
+            // 256-archive job).  A handful of blocks (one small archive): one CTA per STREAM, the four of a block as a
+            // thread-block cluster that shares the table construction through DSMEM -- four times the CTAs in flight, which
+            // is what latency wants (k_huf_decode_big).
+            const bool per_block = J.n_huf_big / 4 >= (J.huf_block_min ? J.huf_block_min : 296u);
+            if (per_block) {
+                NAF_SET_MAX_SMEM(k_huf_decode_block, smem);
+                NAF_LAUNCH(k_huf_decode_block, J.n_huf_big / 4, HB_T, smem, sb, J); launches++;
+            } else {
+                NAF_SET_MAX_SMEM(k_huf_decode_big, smem);
+                NAF_LAUNCH(k_huf_decode_big, J.n_huf_big, HB_T, smem, sb, J); launches++;
+            }
             if (!st2) ev->kernel_end();
         }
         if (J.n_huf_items > J.n_huf_big) {

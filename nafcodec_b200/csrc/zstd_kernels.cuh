@@ -48,6 +48,7 @@ struct JobDev {
     uint32_t* fin_unresolved;         // unresolved bytes after level 1
     uint32_t* fin_count;              // [3] rotating per-round counters of level 2
     const zf::HufItem* huf_items;     // one per Huffman bitstream
+    uint32_t huf_block_min;           // jobs with at least this many big blocks use k_huf_decode_block (0: default; NAFGPU_HUF_BLOCK_MIN overrides)
     uint32_t n_huf_items, n_huf_big;  // items [0, n_huf_big): streams of 4-stream blocks, four per block (k_huf_decode_big, one cluster per block); the rest: k_huf_decode<128>
     uint32_t max_huf_stream, max_huf_small;   // largest stream (bytes) in each class
     const zf::FsTile* fs_tiles;       // tiles of the frames with more than FS_BIG_FRAME blocks (host-filled)

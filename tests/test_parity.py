@@ -315,3 +315,16 @@ def test_long_frames_are_scanned_by_tiles(backend, monkeypatch):
     assert N.shared_context(0, lib).stats().n_blocks > 1400
     monkeypatch.delenv("NAFGPU_FS_TILE")
     check_parity(backend, arc, "default tiles")
+
+
+@pytest.mark.parametrize("block_min", ["1", "1000000"])
+def test_both_huffman_kernels(backend, monkeypatch, block_min):
+    """Big Huffman streams are decoded by one CTA per block (throughput: batches, chromosomes) or by one CTA per stream in
+    clusters of four (latency: a single small archive); the job size picks.  Both on the same archives here."""
+    monkeypatch.setenv("NAFGPU_HUF_BLOCK_MIN", block_min)
+    check_parity(backend, read_golden("NZ_AAEN01000029.naf"), "fixture, forced kernel")
+    check_parity(backend, K.genome(77, 600_000 if backend == "emul" else 3_000_000, level=19), "genome, forced kernel")
+    ctx = N.shared_context(0, library(backend))
+    p = bytes(np.random.default_rng(3).integers(0, 16, size=300_000).astype(np.uint8))        # fixed-length codes
+    frame = K.zstd_frame(p, 3)
+    assert ctx.zstd_decompress(frame, len(p)) == p
