@@ -775,30 +775,35 @@ static inline void sts32(saddr_t a, uint32_t v) { *(uint32_t*)a = v; }
 
 constexpr int HUF_W = 12;                          // index width of the multi-symbol tables
 
-// 64-bit register window over the stream image: {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q in [12, 44).
+// 64-bit register window over the stream image: {hi:lo} = stream bits [Q, Q+64), Q 32-aligned; rr = x - Q in [14, 46).
+// (14, not 12: the byte offset of a 4-byte table entry, 4 * the next 12 bits, is then ONE funnel shift by rr - 14 and a mask.)
+constexpr int WIN_MIN = HUF_W + 2;
 struct Win {
     saddr_t waddr;      // shared address of the `lo` word
     uint32_t lo, hi;
     int rr;
 };
 __device__ __forceinline__ void win_init(Win& w, saddr_t comp, int x) {
-    const int qi = (x - HUF_W) >> 5;
+    const int qi = (x - WIN_MIN) >> 5;
     w.waddr = comp + 4 * qi;
     w.lo = lds32(w.waddr);
     w.hi = lds32(w.waddr + 4);
     w.rr = x - (qi << 5);
 }
-__device__ __forceinline__ uint32_t win_peek(const Win& w) { return __funnelshift_r(w.lo, w.hi, w.rr - HUF_W) & 0xFFFu; }
+// (rr - 14 is in [0, 32): a funnel shift takes its amount modulo 32, so the 12-bit and x2 forms are derived from this one)
+__device__ __forceinline__ uint32_t win_peek_x4(const Win& w) { return __funnelshift_r(w.lo, w.hi, w.rr - WIN_MIN) & 0x3FFCu; }     // 4 * (next 12 bits)
+__device__ __forceinline__ uint32_t win_peek_x2(const Win& w) { return win_peek_x4(w) >> 1; }
+__device__ __forceinline__ uint32_t win_peek(const Win& w) { return win_peek_x4(w) >> 2; }
 // The refill is PREDICATED, not branched: per lookup a lane needs it with p = 0.3, so some lane of a warp always does, and
 // a branch costs the whole warp the body plus the divergence bookkeeping (ncu, round 1: 14 % of the kernel's instructions
 // at 0.64 thread efficiency on this line).
 __device__ __forceinline__ void win_consume(Win& w, int len) {
     w.rr -= len;
 #if defined(__CUDA_ARCH__)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, 12;\n\t@p mov.b32 %1, %0;\n\t@p sub.u32 %2, %2, 4;\n\t@p ld.shared.u32 %0, [%2];\n\t@p add.s32 %3, %3, 32;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, 14;\n\t@p mov.b32 %1, %0;\n\t@p sub.u32 %2, %2, 4;\n\t@p ld.shared.u32 %0, [%2];\n\t@p add.s32 %3, %3, 32;\n\t}"
                  : "+r"(w.lo), "+r"(w.hi), "+r"(w.waddr), "+r"(w.rr));
 #else
-    if (w.rr < HUF_W) { w.hi = w.lo; w.waddr -= 4; w.lo = lds32(w.waddr); w.rr += 32; }
+    if (w.rr < WIN_MIN) { w.hi = w.lo; w.waddr -= 4; w.lo = lds32(w.waddr); w.rr += 32; }
 #endif
 }
 
@@ -819,7 +824,7 @@ __device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop
     win_init(w, comp, xtop - q);
     // steady state: whole windows, no test against the limit (every window holds >= 1 whole codeword: max_bits <= 11)
     while (rem > HUF_W) {
-        const uint32_t m = lds16(bm + 2 * win_peek(w));
+        const uint32_t m = lds16(bm + win_peek_x2(w));
         const int used = msb_index(m) + 1;
         cnt += __popc(m);
         rem -= used;
@@ -827,7 +832,7 @@ __device__ __forceinline__ void track_advance(saddr_t comp, saddr_t bm, int xtop
     }
     // the last windows: stop at the first boundary at or past the limit
     while (rem > 0) {
-        const uint32_t m = lds16(bm + 2 * win_peek(w));
+        const uint32_t m = lds16(bm + win_peek_x2(w));
         const uint32_t t = m >> (rem - 1);
         if (t) {
             const int j = __ffs((int)t) - 1 + rem - 1;
@@ -855,7 +860,7 @@ __device__ __forceinline__ int track_write(saddr_t comp, saddr_t t3, saddr_t t1,
     int cnt = 0;
     if (MULTI) {
         while (rem > HUF_W) {
-            const uint32_t e = lds32(t3 + 4 * win_peek(w));
+            const uint32_t e = lds32(t3 + win_peek_x4(w));
             const int n = (int)(e >> 28), len = (int)(e >> 24) & 15;
             sts8(out + cnt, e);
             if (n > 1) sts8(out + cnt + 1, e >> 8);
@@ -1505,7 +1510,7 @@ __global__ void HB_CLUSTER_ATTR __launch_bounds__(HB_T, 3) k_huf_decode_big(JobD
         uint32_t acc_lo = 0, acc_hi = 0;
         int pc = 0;                                                     // bytes waiting in acc
         while (rem > HUF_W) {
-            const uint32_t e = lds32(s_t3 + 4 * win_peek(w));
+            const uint32_t e = lds32(s_t3 + win_peek_x4(w));
             const int n = (int)(e >> 28), len = (int)(e >> 24) & 15;
             const uint32_t sy = e & 0xFFFFFFu;
             acc_lo |= sy << (8 * pc);
@@ -1546,7 +1551,7 @@ __device__ __forceinline__ void track_advance3(saddr_t comp, saddr_t t3, saddr_t
     Win w;
     win_init(w, comp, xtop - q);
     while (rem > HUF_W) {
-        const uint32_t e = lds32(t3 + 4 * win_peek(w));
+        const uint32_t e = lds32(t3 + win_peek_x4(w));
         const int used = (int)(e >> 24) & 15;
         cnt += (int)(e >> 28);
         rem -= used;
@@ -1782,7 +1787,7 @@ __global__ void __launch_bounds__(HB_T, 3) k_huf_decode_block(JobDev J) {
         uint32_t acc_lo = 0, acc_hi = 0;
         int pc = 0;                                                     // bytes waiting in acc
         while (rem > HUF_W) {
-            const uint32_t e = lds32(s_t3 + 4 * win_peek(w));
+            const uint32_t e = lds32(s_t3 + win_peek_x4(w));
             const int n = (int)(e >> 28), len = (int)(e >> 24) & 15;
             const uint32_t sy = e & 0xFFFFFFu;
             acc_lo |= sy << (8 * pc);
