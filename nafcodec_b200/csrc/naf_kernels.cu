@@ -66,29 +66,87 @@ __device__ __forceinline__ void toggle_bit(uint32_t* bits, uint32_t* chunk_par, 
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// k_naf_scan: grid (3 tasks + mask slices, n_archives), 1024 threads.  One CTA streams its section (or mask slice) with a
-// running carry.
-__global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev* archives, uint32_t* status) {
+// k_naf_scan: the four streaming scans of the NAF layer -- ids and comments (k-th NUL -> string offsets), lengths (u32 words,
+// 0xFFFFFFFF continues a length -> record offsets), mask (byte RLE, 0xFF continues a run -> run bounds + toggle bitmap).
+// Every section is cut into NAF_SLICE-byte slices, one CTA of 1024 threads each: grid (4 tasks x n_slices, n_archives).
+// What a slice needs from everything before it is a pair (count of terminators, sum): with more than one slice, k_naf_agg
+// computes every slice's pair first and a slice adds up the pairs of the slices before it (a 10^6-read FASTQ archive has
+// 17 MB of ids: one CTA streaming them took 3.5 ms); with one slice per section there is nothing to add and no extra launch.
+struct SliceView { const uint8_t* src; uint64_t size, begin, end; bool present, last; };
+
+__device__ __forceinline__ SliceView slice_view(const uint8_t* arena, const NafDev& A, int task, uint32_t slice) {
+    SliceView V;
+    V.present = task == 0 ? (A.has & HAS_IDS) != 0 : task == 1 ? (A.has & HAS_COMMENTS) != 0 : task == 2 ? (A.has & HAS_LENGTHS) != 0
+                                                                                                          : (A.has & HAS_MASK) && (A.has & HAS_SEQUENCE);
+    V.src = arena + (task == 0 ? A.ids_off : task == 1 ? A.com_off : task == 2 ? A.len_off : A.mask_off);
+    V.size = !V.present ? 0 : task == 0 ? A.ids_size : task == 1 ? A.com_size : task == 2 ? (A.len_size & ~3ull) : A.mask_size;
+    V.begin = (uint64_t)slice * NAF_SLICE;
+    V.end = V.begin + NAF_SLICE < V.size ? V.begin + NAF_SLICE : V.size;
+    V.last = V.begin < V.size ? V.end == V.size : (slice == 0);          // an empty section is "finished" by its slice 0
+    return V;
+}
+
+// (terminators, sum) of 16 bytes of a section: ids / comments: NULs; lengths: words != FFFFFFFF and the sum of all words;
+// mask: bytes != FF and the sum of all bytes.  `nvalid` bytes of v count.
+__device__ __forceinline__ void pair_of16(int task, const uint4& v, uint32_t nvalid, uint32_t& c, uint64_t& s) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (task == 2) { for (uint32_t j = 0; j < nvalid / 4; j++) { c += (w[j] != FULL); s += w[j]; } return; }
+    const uint32_t term = task == 3 ? 0xFFu : 0u;
+    for (uint32_t j = 0; j < nvalid; j++) {
+        const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFF;
+        c += task == 3 ? (b != term) : (b == term);
+        if (task == 3) s += b;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_naf_agg(const uint8_t* arena, const NafDev* archives, CS* agg, uint32_t n_slices) {
     const NafDev& A = archives[blockIdx.y];
-    const int task = blockIdx.x;
+    const int task = blockIdx.x / n_slices;
+    const uint32_t slice = blockIdx.x % n_slices;
+    const SliceView V = slice_view(arena, A, task, slice);
+    uint32_t c = 0;
+    uint64_t s = 0;
+    for (uint64_t p0 = V.begin + (uint64_t)threadIdx.x * 16; p0 < V.end; p0 += 1024 * 16) {
+        const uint4 v = *(const uint4*)(V.src + p0);
+        pair_of16(task, v, V.end - p0 >= 16 ? 16u : (uint32_t)(V.end - p0), c, s);
+    }
+    CS tot;
+    block_excl_scan(c, s, &tot);
+    if (threadIdx.x == 0) agg[((size_t)blockIdx.y * 4 + task) * n_slices + slice] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev* archives, uint32_t* status, const CS* agg, uint32_t n_slices) {
+    const NafDev& A = archives[blockIdx.y];
+    const int task = blockIdx.x / n_slices;
+    const uint32_t slice = blockIdx.x % n_slices;
     const int tid = threadIdx.x;
     NafCounts* counts = (NafCounts*)(arena + A.counts_off);
+    const SliceView V = slice_view(arena, A, task, slice);
+    if (V.begin >= V.size && slice != 0) return;                          // (uniform) nothing of the section in this slice
+    // what the slices before this one hold
+    uint64_t carry_c = 0, carry_s = 0;
+    if (slice) {
+        const CS* ag = agg + ((size_t)blockIdx.y * 4 + task) * n_slices;
+        uint32_t c = 0;
+        uint64_t s = 0;
+        for (uint32_t j = tid; j < slice; j += 1024) { c += ag[j].c; s += ag[j].s; }
+        CS tot;
+        block_excl_scan(c, s, &tot);
+        carry_c = tot.c; carry_s = tot.s;
+    }
     if (task <= 1) {
         // ---- ids / comments: string k ends at the k-th NUL; offsets[k+1] = position after it -----------------
-        const uint32_t bit = task == 0 ? HAS_IDS : HAS_COMMENTS;
-        if (!(A.has & bit)) { if (tid == 0) { if (task == 0) counts->n_ids = 0; else counts->n_comments = 0; } return; }
-        const uint8_t* src = arena + (task == 0 ? A.ids_off : A.com_off);
-        const uint64_t size = task == 0 ? A.ids_size : A.com_size;
+        if (!V.present) { if (tid == 0) { if (task == 0) counts->n_ids = 0; else counts->n_comments = 0; } return; }
         uint64_t* offs = (uint64_t*)(arena + (task == 0 ? A.id_offsets_off : A.com_offsets_off));
-        if (tid == 0) offs[0] = 0;
-        uint64_t carry = 0;
+        if (tid == 0 && slice == 0) offs[0] = 0;
+        uint64_t carry = carry_c;
         uint32_t hi = 0;
-        for (uint64_t base = 0; base < size; base += 1024 * 16) {
+        for (uint64_t base = V.begin; base < V.end; base += 1024 * 16) {
             uint64_t p0 = base + (uint64_t)tid * 16;
             uint4 v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-            if (p0 < size) v = *(const uint4*)(src + p0);
+            if (p0 < V.end) v = *(const uint4*)(V.src + p0);
             uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t nvalid = p0 >= size ? 0 : (size - p0 >= 16 ? 16 : (uint32_t)(size - p0));
+            uint32_t nvalid = p0 >= V.end ? 0 : (V.end - p0 >= 16 ? 16 : (uint32_t)(V.end - p0));
             uint32_t c = 0;
             for (uint32_t j = 0; j < nvalid; j++) {
                 uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFF;
@@ -107,24 +165,22 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
             carry += tot.c;
         }
         if (__any_sync(FULL, hi & 0x80)) { if ((tid & 31) == 0) atomicOr((unsigned long long*)&counts->nonascii, 1ull << task); }
-        if (tid == 0) {
+        if (tid == 0 && V.last) {
             if (task == 0) counts->n_ids = carry; else counts->n_comments = carry;
-            if (carry < A.n_records && size > 0 && src[size - 1] != 0) flag_archive(counts, status, zc::E_NUL);
+            if (carry < A.n_records && V.size > 0 && V.src[V.size - 1] != 0) flag_archive(counts, status, zc::E_NUL);
         }
     } else if (task == 2) {
         // ---- lengths: rec_offsets[k+1] = sum of all words up to and including the k-th terminating word -----
         uint64_t* rec = (uint64_t*)(arena + A.rec_offsets_off);
         uint64_t* lens = (uint64_t*)(arena + A.lengths_off);
-        if (tid == 0) rec[0] = 0;
-        uint64_t n_words = (A.has & HAS_LENGTHS) ? A.len_size / 4 : 0;
-        const uint8_t* src = arena + A.len_off;
-        uint64_t carry_c = 0, carry_s = 0;
-        for (uint64_t base = 0; base < n_words; base += 1024 * 4) {
+        if (tid == 0 && slice == 0) rec[0] = 0;
+        const uint64_t w_begin = V.begin / 4, w_end = V.end / 4;
+        for (uint64_t base = w_begin; base < w_end; base += 1024 * 4) {
             uint64_t i0 = base + (uint64_t)tid * 4;
             uint4 v = make_uint4(FULL, FULL, FULL, FULL);
-            if (i0 < n_words) v = *(const uint4*)(src + i0 * 4);
+            if (i0 < w_end) v = *(const uint4*)(V.src + i0 * 4);
             uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t nvalid = i0 >= n_words ? 0 : (n_words - i0 >= 4 ? 4 : (uint32_t)(n_words - i0));
+            uint32_t nvalid = i0 >= w_end ? 0 : (w_end - i0 >= 4 ? 4 : (uint32_t)(w_end - i0));
             uint32_t c = 0;
             uint64_t s = 0;
             for (uint32_t j = 0; j < nvalid; j++) { c += (w[j] != FULL); s += w[j]; }
@@ -136,6 +192,10 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
                 if (w[j] != FULL) { k++; if (k <= A.n_records) rec[k] = S; }
             }
             carry_c += tot.c; carry_s += tot.s;
+        }
+        if (n_slices > 1) {                                  // other slices are still writing rec[]: k_naf_lengths finishes the job
+            if (tid == 0 && V.last) counts->n_lengths = carry_c;
+            return;
         }
         __syncthreads();
         uint64_t n_len = carry_c < A.n_records ? carry_c : A.n_records;
@@ -150,47 +210,16 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
         for (uint64_t k = tid; k < n_len; k += blockDim.x) lens[k] = rec[k + 1] - rec[k];
     } else {
         // ---- mask: run k ends at the inclusive byte sum at the k-th byte != 0xFF; toggle the bitmap there --------
-        // The section is cut into MASK_SLICE-byte slices, one CTA each (a dense mask is ~1 byte per run, and every run
-        // costs atomics: one CTA for a 250 Mbp chromosome took 1.3 ms).  A run boundary is the plain sum of all bytes up to
-        // its terminator, so a slice's carry-in is the byte sum (and terminator count) of everything before it, which
-        // every CTA adds up for itself with wide loads (cheap next to its own atomics).
-        const uint32_t slice = (uint32_t)(task - 3);
-        if (!(A.has & HAS_MASK) || !(A.has & HAS_SEQUENCE)) { if (tid == 0 && slice == 0) { counts->n_mask_runs = 0; counts->mask_sum = 0; } return; }
-        const uint8_t* src = arena + A.mask_off;
-        const uint64_t size = A.mask_size;
-        const uint64_t s_begin = (uint64_t)slice * MASK_SLICE;
-        if (s_begin >= size && !(slice == 0 && size == 0)) return;
-        const uint64_t s_end = s_begin + MASK_SLICE < size ? s_begin + MASK_SLICE : size;
-        const bool last = s_end == size;
+        if (!V.present) { if (tid == 0 && slice == 0) { counts->n_mask_runs = 0; counts->mask_sum = 0; } return; }
         uint64_t* bounds = (uint64_t*)(arena + A.mask_bounds_off);
         uint32_t* bits = (uint32_t*)(arena + A.mask_bits_off);
         uint32_t* cpar = (uint32_t*)(arena + A.chunk_par_off);
-        uint64_t carry_c = 0, carry_s = 0;
-        if (s_begin) {
-            uint32_t c = 0;
-            uint64_t sm = 0;
-            for (uint64_t p = (uint64_t)tid * 16; p < s_begin; p += 1024 * 16) {       // s_begin is a multiple of 16
-                const uint4 v = *(const uint4*)(src + p);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t h = (w[j] & 0x00FF00FFu) + ((w[j] >> 8) & 0x00FF00FFu);
-                    sm += (h & 0xFFFFu) + (h >> 16);
-                    const uint32_t z = ~w[j];                                          // zero byte <=> 0xFF byte of the mask
-                    const uint32_t y = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);
-                    c += 4u - (uint32_t)__popc(y);
-                }
-            }
-            CS tot;
-            block_excl_scan(c, sm, &tot);
-            carry_c = tot.c; carry_s = tot.s;
-        }
-        for (uint64_t base = s_begin; base < s_end; base += 1024 * 16) {
+        for (uint64_t base = V.begin; base < V.end; base += 1024 * 16) {
             uint64_t p0 = base + (uint64_t)tid * 16;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (p0 < s_end) v = *(const uint4*)(src + p0);
+            if (p0 < V.end) v = *(const uint4*)(V.src + p0);
             uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t nvalid = p0 >= s_end ? 0 : (s_end - p0 >= 16 ? 16 : (uint32_t)(s_end - p0));
+            uint32_t nvalid = p0 >= V.end ? 0 : (V.end - p0 >= 16 ? 16 : (uint32_t)(V.end - p0));
             uint32_t c = 0;
             uint64_t s = 0;
             for (uint32_t j = 0; j < nvalid; j++) {
@@ -207,14 +236,35 @@ __global__ void __launch_bounds__(1024) k_naf_scan(uint8_t* arena, const NafDev*
             }
             carry_c += tot.c; carry_s += tot.s;
         }
-        if (tid == 0 && last) {
-            if (size > 0 && src[size - 1] == 0xFF) {        // trailing 0xFF bytes at EOF still form a unit (reader.rs:206-209)
+        if (tid == 0 && V.last) {
+            if (V.size > 0 && V.src[V.size - 1] == 0xFF) {        // trailing 0xFF bytes at EOF still form a unit (reader.rs:206-209)
                 bounds[carry_c++] = carry_s;
                 if (carry_s <= A.seq_residues) toggle_bit(bits, cpar, carry_s);
             }
             counts->n_mask_runs = carry_c;
             counts->mask_sum = carry_s;
         }
+    }
+}
+
+// k_naf_lengths: after a SLICED lengths scan (every slice has written its part of rec_offsets): the record count, the total,
+// the checks, and lengths[k] = rec_offsets[k + 1] - rec_offsets[k].  Thread per record.
+__global__ void __launch_bounds__(256) k_naf_lengths(uint8_t* arena, const NafDev* archives, uint32_t* status) {
+    const NafDev& A = archives[blockIdx.y];
+    NafCounts* counts = (NafCounts*)(arena + A.counts_off);
+    const uint64_t* rec = (const uint64_t*)(arena + A.rec_offsets_off);
+    uint64_t* lens = (uint64_t*)(arena + A.lengths_off);
+    const uint64_t raw = (A.has & HAS_LENGTHS) ? counts->n_lengths : 0;   // (written by the last slice; clamping it below is idempotent)
+    const uint64_t n_len = raw < A.n_records ? raw : A.n_records;
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_len) lens[r] = rec[r + 1] - rec[r];
+    if (r == 0) {
+        const uint64_t total = rec[n_len];
+        counts->n_lengths = n_len;
+        counts->total_residues = total;
+        counts->first_bad_record = NO_RECORD;
+        if ((A.has & HAS_SEQUENCE) && total > A.seq_residues) flag_archive(counts, status, zc::E_LENGTHS);
+        if ((A.has & HAS_QUALITY) && total > A.qual_size) flag_archive(counts, status, zc::E_LENGTHS);
     }
 }
 
@@ -448,16 +498,19 @@ __global__ void __launch_bounds__(256) k_utf8_validate(uint8_t* arena, const Naf
 }
 
 // --------------------------------------------------------------------------------------------------------------
-int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives, uint64_t max_records, uint64_t max_mask_bytes,
+int launch_naf_stage(uint8_t* arena, const NafDev* archives, uint32_t n_archives, uint64_t max_records, uint64_t max_scan_bytes, void* scan_agg,
                      uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, bool any_text_mask, uint32_t* status, cudaStream_t st,
                      StageEvents* ev) {
     StageEvents none;
     if (!ev) ev = &none;
     int launches = 0;
     if (n_archives == 0) { for (int i = 0; i < NAF_STAGES; i++) ev->mark(); return 0; }
-    const uint32_t mask_slices = (uint32_t)std::max<uint64_t>(1, (max_mask_bytes + MASK_SLICE - 1) / MASK_SLICE);
-    NAF_LAUNCH(k_naf_scan, dim3(3 + mask_slices, n_archives), 1024, 0, st, arena, archives, status); launches++; ev->mark();
+    const uint32_t n_slices = (uint32_t)std::max<uint64_t>(1, (max_scan_bytes + NAF_SLICE - 1) / NAF_SLICE);
     uint32_t rec_grid = (uint32_t)((max_records + 255) / 256);
+    if (n_slices > 1) { NAF_LAUNCH(k_naf_agg, dim3(4 * n_slices, n_archives), 1024, 0, st, arena, archives, (CS*)scan_agg, n_slices); launches++; }
+    NAF_LAUNCH(k_naf_scan, dim3(4 * n_slices, n_archives), 1024, 0, st, arena, archives, status, (const CS*)scan_agg, n_slices); launches++;
+    if (n_slices > 1) { NAF_LAUNCH(k_naf_lengths, dim3(rec_grid ? rec_grid : 1, n_archives), 256, 0, st, arena, archives, status); launches++; }
+    ev->mark();
     if (max_chunks > 0 && any_mask) {
         if (rec_grid) { NAF_LAUNCH(k_mask_fix, dim3(rec_grid, n_archives), 256, 0, st, arena, archives, status); launches++; }
         ev->mark();

@@ -13,7 +13,8 @@ constexpr uint32_t UNPACK_W = 2;                       // adjacent mask words (o
 constexpr uint32_t CHUNK_WORDS = UNPACK_W * UNPACK_T;  // mask words per unpack CTA
 constexpr uint32_t CHUNK_RESIDUES = CHUNK_WORDS * 32;
 constexpr uint64_t NO_RECORD = ~0ull;
-constexpr uint32_t MASK_SLICE = 32768;                 // mask bytes per CTA of k_naf_scan's mask task
+constexpr uint32_t NAF_SLICE = 32768;                  // section bytes per CTA of k_naf_scan (ids, comments, lengths, mask alike)
+constexpr uint32_t NAF_AGG_BYTES = 16;                 // per (archive, task, slice) when a job has more than one slice: (count, sum)
 
 // Per-archive counters, device-written, copied back with the results (80 bytes).
 struct NafCounts {
@@ -44,9 +45,10 @@ struct NafDev {
 };
 
 // Enqueues the NAF stage for n_archives archives on `stream`.  max_* are maxima over the archives (grid sizing).
-// Returns the number of kernels launched; `ev` (optional) gets one mark per stage (NAF_STAGES).
+// max_scan_bytes: largest ids / comments / lengths / mask section of the job; scan_agg: n_archives x 4 x slices x NAF_AGG_BYTES of
+// scratch when that is more than one NAF_SLICE.  Returns the number of kernels launched; `ev` (optional) gets one mark per stage (NAF_STAGES).
 // any_mask: some archive decodes sequence + mask; any_text_mask: one of those is protein/text.
-int launch_naf_stage(uint8_t* arena, const NafDev* archives_dev, uint32_t n_archives, uint64_t max_records, uint64_t max_mask_bytes,
+int launch_naf_stage(uint8_t* arena, const NafDev* archives_dev, uint32_t n_archives, uint64_t max_records, uint64_t max_scan_bytes, void* scan_agg,
                      uint32_t max_chunks, uint64_t max_text_bytes, bool any_mask, bool any_text_mask, uint32_t* status, cudaStream_t stream,
                      StageEvents* ev);
 constexpr int NAF_STAGES = 5;

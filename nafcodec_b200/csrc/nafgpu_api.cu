@@ -123,7 +123,7 @@ struct nafgpu_ctx {
     cudaStream_t st = 0, st2 = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_block = nullptr;
     std::string err;
-    DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, lzidx, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
+    DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, lzidx, scanagg, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage, pack_host;
     fw::JobPlan plan;                  // frames, Huffman items and totals of the job (block descriptors live in the tasks)
@@ -133,7 +133,7 @@ struct nafgpu_ctx {
     std::vector<ArchPlan> aplan;
     zk::JobDev J;
     uint64_t z1_size = 0, z2_off = 0, z2_size = 0, arena_size = 0, counts_size = 0;
-    uint64_t max_records = 0, max_text = 0, max_mask = 0;
+    uint64_t max_records = 0, max_text = 0, max_mask = 0, max_scan = 0;
     uint32_t max_chunks = 0;
     bool any_mask = false, any_text_mask = false;
     uint32_t coop_ctas = 1, fin_ctas = 1, fin2_ctas = 1;
@@ -175,7 +175,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     // profiled runs (ev != null) are serial so that every stage has its own interval
     int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev);
-    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records, c->max_mask,
+    launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records, c->max_scan, c->scanagg.p,
                                      c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
     CUDA_TRY(c, cudaGetLastError());
@@ -298,7 +298,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8 + 24;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256) &&
-              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->fsstate.ensure(tiles.size() * sizeof(zf::FsTileState) + 64) && c->lzidx.ensure(((size_t)total_chunks * 16 + nf + 16) * 4) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
+              c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->fsstate.ensure(tiles.size() * sizeof(zf::FsTileState) + 64) && c->lzidx.ensure(((size_t)total_chunks * 16 + nf + 16) * 4) &&
+              c->scanagg.ensure((size_t)n * 4 * ((c->max_scan + nk::NAF_SLICE - 1) / nk::NAF_SLICE + 1) * nk::NAF_AGG_BYTES + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
               c->seq32.ensure(nseq * 5 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
@@ -446,7 +447,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_graph(c);
-    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->fsstate, &c->lzidx, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g, &c->pack_in, &c->pack_out};
+    DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->fsstate, &c->lzidx, &c->scanagg, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g, &c->pack_in, &c->pack_out};
     for (DevBuf* b : d) b->release();
     c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release(); c->pack_host.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
@@ -487,7 +488,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     c->counts_size = align_up((uint64_t)n * sizeof(nk::NafCounts));
     off = c->counts_size;
     uint64_t comp_off = 16;          // gathers may read up to 15 bytes below a literal run: keep them inside the allocation
-    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->max_scan = 0; c->any_mask = false; c->any_text_mask = false;
     // Everything below is sized from header fields an archive may lie about: sizes are validated first (a zstd frame
     // regenerates at most 128 KB per 3-byte block header), record counts are clamped by what the sections can hold, and a
     // job whose arena would not fit any device is refused before anything is laid out.
@@ -535,6 +536,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
             uint64_t o = A.sections[s].original_size;
             P.blob_size[s] = !P.dec[s] ? 0 : ((s == NAFGPU_SEC_SEQUENCE && P.nucleotide) ? o / 2 + (o & 1) : o);
         }
+        for (int k = 0; k < 4; k++) c->max_scan = std::max(c->max_scan, P.blob_size[k]);      // ids, comments, lengths, mask: the streaming scans
         const uint64_t residues = P.dec[NAFGPU_SEC_SEQUENCE] ? A.sections[NAFGPU_SEC_SEQUENCE].original_size : 0;
         // number_of_sequences is whatever the header says (2^61 is a valid varint); a stream of b bytes holds at most b
         // NUL-terminated strings / b/4 length words, so the offset tables are sized by that, not by the header
@@ -705,7 +707,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->z1_size = align_up(ALIGN + regen_size + 32);
     c->z2_off = c->z1_size; c->z2_size = 0;
     c->arena_size = c->z1_size + 256;
-    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->any_mask = false; c->any_text_mask = false;
+    c->max_records = 0; c->max_chunks = 0; c->max_text = 0; c->max_mask = 0; c->max_scan = 0; c->any_mask = false; c->any_text_mask = false;
     if (c->tasks.empty()) c->tasks.emplace_back();
     c->n_tasks = 1;
     {

@@ -328,3 +328,20 @@ def test_both_huffman_kernels(backend, monkeypatch, block_min):
     p = bytes(np.random.default_rng(3).integers(0, 16, size=300_000).astype(np.uint8))        # fixed-length codes
     frame = K.zstd_frame(p, 3)
     assert ctx.zstd_decompress(frame, len(p)) == p
+
+
+def test_sections_longer_than_one_scan_slice(backend):
+    """ids, comments and lengths sections of more than 32 KiB are scanned by several CTAs (k_naf_agg + sliced k_naf_scan +
+    k_naf_lengths); continuation words and empty strings fall on slice boundaries here."""
+    rng = np.random.default_rng(17)
+    n = 9000
+    lens = rng.integers(0, 12, size=n)
+    seqs = [K.random_dna(rng, int(l), b"ACGTN") for l in lens]
+    ids = [b"read/%d/%s" % (i, b"x" * int(rng.integers(0, 9))) for i in range(n)]
+    coms = [b"" if i % 5 == 0 else b"c%d" % (i * 7919) for i in range(n)]
+    arc = O.encode(ids=ids, comments=coms, sequences=seqs, mask_runs_=[3, 5, 40000, 9, int(lens.sum())], level=3, flush_per_record=False)
+    L = O.parse(arc)
+    assert L.sec[0].original_size > 2 * 32768 and L.sec[2].original_size > 32768
+    res, d = check_parity(backend, arc, "sliced scans")
+    assert res.n_ids == n and res.n_lengths == n
+    check_parity(backend, arc, "sliced scans, no ids", id=False)
