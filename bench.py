@@ -423,7 +423,7 @@ def main():
         stage_acc = [x[1] for x in s] if stage_acc is None else [a + x[1] for a, x in zip(stage_acc, s)]
     stage_names = [x[0] for x in s]
     stage_ms = [a / reps for a in stage_acc]
-    kern_ms = dict(zip(stage_names, stage_ms)).get("k_huf_decode<512>", 0.0)     # the dominant kernel alone (own event pair)
+    kern_ms = dict(zip(stage_names, stage_ms)).get("huf_big_kernel", 0.0)     # the dominant kernel alone (own event pair)
     stage_names, stage_ms = stage_names[:-1], stage_ms[:-1]
     dom = max(range(len(stage_ms)), key=lambda i: stage_ms[i])
     lits = st.section_bytes                # every regenerated section byte is produced once by the zstd stage
@@ -434,13 +434,13 @@ def main():
         "lz_literals": 2 * lits, "lz_first": 2 * lits, "lz_resolve": 2 * lits,
     }
     dom_name = stage_names[dom]
-    kernel_of = {"memset+huf_decode": "k_huf_decode<512>", "decode_sequences": "k_decode_sequences", "unpack": "k_unpack",
+    kernel_of = {"memset+huf_decode": "k_huf_decode_block", "decode_sequences": "k_decode_sequences", "unpack": "k_unpack",
                  "lz_resolve": "k_lz_resolve", "lz_first": "k_lz_first", "lz_literals": "k_lz_literals", "build_tables": "k_build_tables<0>"}
     dom_bytes = kernel_bytes.get(dom_name, st.algorithmic_bytes)
     peak, peak_src = measured_peak()
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture (profiles/r1_traffic.json)
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture (profiles/r2_traffic.json)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         ent = tj.get(kernel_of.get(dom_name, dom_name))

@@ -172,7 +172,8 @@ int nafgpu_job_get_stats(const nafgpu_ctx* ctx, nafgpu_job_stats* out);
  * with CUDA events on the context's own stream (where the kernels are launched). If flush_l2 != 0 a buffer larger
  * than L2 is overwritten before every iteration, outside the timed intervals (per-iteration events are summed). */
 int nafgpu_job_time(nafgpu_ctx* ctx, int iters, int flush_l2, float* total_ms);
-/* One serial run with an event after every stage (the last entry is the dominant kernel, k_huf_decode<512>, alone);
+/* One serial run with an event after every stage (the last entry is the dominant kernel alone: the Huffman decode of the
+ * big streams, k_huf_decode_block or k_huf_decode_big depending on the job size);
  * stage_ms must hold stats.n_stages floats. Stage names: nafgpu_stage_name. */
 int nafgpu_job_run_profiled(nafgpu_ctx* ctx, float* stage_ms, uint32_t n_stages);
 const char* nafgpu_stage_name(uint32_t stage);

@@ -973,7 +973,7 @@ int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
         if (i < se.n) CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
         stage_ms[i] = ms;
     }
-    stage_ms[N_STAGES] = 0;                       // the dominant kernel alone (k_huf_decode<512>)
+    stage_ms[N_STAGES] = 0;                       // the dominant kernel alone (the Huffman kernel of the big streams)
     if (se.k_used) CUDA_TRY(c, cudaEventElapsedTime(&stage_ms[N_STAGES], se.kb, se.ke));
     return NAFGPU_OK;
 }
@@ -981,7 +981,7 @@ int nafgpu_job_run_profiled(nafgpu_ctx* c, float* stage_ms, uint32_t n_stages) {
 const char* nafgpu_stage_name(uint32_t s) {
     static const char* names[N_STAGES] = {"memset+huf_decode", "build_tables", "decode_sequences", "frame_scan", "lz_literals", "lz_first",
                                           "lz_resolve", "lz_finish", "naf_scan", "mask_fix", "-", "unpack", "utf8_check"};
-    return s < (uint32_t)N_STAGES ? names[s] : (s == (uint32_t)N_STAGES ? "k_huf_decode<512>" : "?");
+    return s < (uint32_t)N_STAGES ? names[s] : (s == (uint32_t)N_STAGES ? "huf_big_kernel" : "?");
 }
 
 // Encode side: pack + length words + mask runs of one archive's records (include/nafgpu.h).

@@ -542,7 +542,18 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
                 }
             }
             if (lane == 0) rep_compose(m, carry, bad);
-            rep_warp_scan(m, lane, bad);
+            if (cnt <= 8) {
+                // a handful of sequences (the tiny blocks of a FASTQ section flushed per record): a short chain of shuffles is
+                // cheaper than the five-step scan
+                for (uint32_t j = 1; j < cnt; j++) {
+                    RepMap f;
+                    rep_shfl(f, m, (int)j - 1);
+                    if ((uint32_t)lane == j) rep_compose(m, f, bad);
+                }
+                RepMap last;
+                rep_shfl(last, m, (int)cnt - 1);
+                if ((uint32_t)lane >= cnt) m = last;                     // (lane 31 carries the batch's total below)
+            } else rep_warp_scan(m, lane, bad);
             RepSym off; off.src = m.s[0]; off.val = m.v[0];
             if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
             if ((uint32_t)lane < cnt) b_ov[lane] = encode_off(off);
@@ -2542,7 +2553,10 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         NAF_LAUNCH(k_lz_index, (uint32_t)((J.n_seq + 255) / 256), 256, 0, st, J); launches++;
         NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();
-        uint32_t cg = J.coop_ctas ? J.coop_ctas : 1u;                 // co-resident CTAs for the grid barrier (queried by the API)
+        // co-resident CTAs for the grid barrier (queried by the API); a small job takes no more than its matches can use: a
+        // barrier over 27 CTAs returns sooner than one over 592, and a single archive pays one per dependency round
+        uint32_t cg = J.coop_ctas ? J.coop_ctas : 1u;
+        { const uint64_t want = (J.n_seq + LZ_CTA * 2 - 1) / (LZ_CTA * 2); if (want < cg) cg = want < 8 ? 8u : (uint32_t)want; if (cg > (J.coop_ctas ? J.coop_ctas : 1u)) cg = J.coop_ctas ? J.coop_ctas : 1u; }
         (void)cg;
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
