@@ -92,6 +92,36 @@ pub struct nafgpu_ctx {
     _private: [u8; 0],
 }
 
+/// Several contexts and their host threads behind submit / wait / release (include/nafgpu.h, "pipeline").
+#[repr(C)]
+pub struct nafgpu_pipeline {
+    _private: [u8; 0],
+}
+
+/// Input of `nafgpu_pack`: what `Encoder::push` receives for every record, concatenated (encoder/mod.rs:265-300).
+#[repr(C)]
+pub struct nafgpu_pack_input {
+    pub sequence: *const u8,
+    pub lengths: *const u64,
+    pub n_records: u64,
+    pub n_residues: u64,
+    pub sequence_type: i32, // 0 dna, 1 rna
+    pub extract_mask: i32,
+}
+
+/// The Sequence, Length and Mask streams as the writers would hand them to zstd (encoder/writer.rs:21-90, mod.rs:37-44).
+#[repr(C)]
+pub struct nafgpu_pack_result {
+    pub packed: *const u8,
+    pub packed_size: u64,
+    pub length_words: *const u8,
+    pub length_size: u64,
+    pub mask: *const u8,
+    pub mask_size: u64,
+    pub n_mask_runs: u64,
+    pub first_invalid: u64,
+}
+
 extern "C" {
     pub fn nafgpu_ctx_create(device: c_int, out: *mut *mut nafgpu_ctx) -> c_int;
     pub fn nafgpu_ctx_destroy(ctx: *mut nafgpu_ctx);
@@ -122,4 +152,13 @@ extern "C" {
         line_length: u64,
         out: *mut nafgpu_text,
     ) -> c_int;
+    pub fn nafgpu_pipeline_create(device: c_int, lanes: u32, out: *mut *mut nafgpu_pipeline) -> c_int;
+    pub fn nafgpu_pipeline_destroy(p: *mut nafgpu_pipeline);
+    /// returns a ticket (>= 0) or a negative status; the archives are borrowed until `wait` returns
+    pub fn nafgpu_pipeline_submit(p: *mut nafgpu_pipeline, archives: *const nafgpu_archive, n: u32, want: u32) -> i64;
+    pub fn nafgpu_pipeline_wait(p: *mut nafgpu_pipeline, ticket: i64, out: *mut nafgpu_result, n: u32) -> c_int;
+    pub fn nafgpu_pipeline_release(p: *mut nafgpu_pipeline, ticket: i64) -> c_int;
+    pub fn nafgpu_pipeline_last_error(p: *const nafgpu_pipeline) -> *const c_char;
+    pub fn nafgpu_pipeline_lanes(p: *const nafgpu_pipeline) -> u32;
+    pub fn nafgpu_pack(ctx: *mut nafgpu_ctx, input: *const nafgpu_pack_input, out: *mut nafgpu_pack_result) -> c_int;
 }
