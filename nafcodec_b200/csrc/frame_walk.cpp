@@ -174,6 +174,8 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                 if (plan.seq_total > 0xFFFFFFF0ull) FAIL(ERR_UNSUPPORTED, "job has too many sequences");
                 plan.n_seq_blocks++;
                 if (bsize - q > plan.max_seq_section) plan.max_seq_section = bsize - q;
+                if (nseq <= 32) plan.n_tiny_seq_blocks++;
+                else if (bsize - q > plan.max_seq_section_big) plan.max_seq_section_big = bsize - q;
             }
             b.seq_src = q;
         }

@@ -253,6 +253,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         G.seq_total += L.seq_total; G.lit_total += L.lit_total - 16; G.n_slots += L.n_slots - 3; G.n_huf_slots += L.n_huf_slots;
         G.n_huf_blocks += L.n_huf_blocks; G.n_seq_blocks += L.n_seq_blocks; G.n_checksums += L.n_checksums;
         G.max_seq_section = std::max(G.max_seq_section, L.max_seq_section);
+        G.max_seq_section_big = std::max(G.max_seq_section_big, L.max_seq_section_big); G.n_tiny_seq_blocks += L.n_tiny_seq_blocks;
         nb += L.blocks.size();
         walked_bytes += T.comp_size;
     }
@@ -362,7 +363,11 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.seq_done = (uint32_t*)c->seq32.p;
     J.lz_list[0] = J.seq_done + nseq; J.lz_list[1] = J.seq_done + 2 * nseq; J.lz_list[2] = J.seq_done + 3 * nseq; J.lz_blocker = J.seq_done + 4 * nseq;
     J.seq = (zf::SeqRec*)c->seq64.p;
-    J.seq_stage_bytes = std::min<uint32_t>(((pl.max_seq_section + 15u) & ~15u) + 64u, 16u * 1024u);
+    // thousands of tiny blocks (a FASTQ section flushed per record): warp-per-block kernels for them, and the two-warp CTAs of
+    // the others do not carry the shared memory of ... the others
+    J.tiny_blocks = pl.n_tiny_seq_blocks >= 4096u ? 1u : 0u;
+    if (const char* e = getenv("NAFGPU_TINY_BLOCKS")) J.tiny_blocks = (uint32_t)atoi(e);      // (tests: both paths on small inputs)
+    J.seq_stage_bytes = std::min<uint32_t>((((J.tiny_blocks ? pl.max_seq_section_big : pl.max_seq_section) + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.fin_unresolved = misc + 6; J.fin_count = misc + 7;
     J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf; J.lz_pending = misc + 10 + nf + total_chunks + 8;

@@ -412,6 +412,80 @@ __device__ __forceinline__ bool seq_produce3(const uint32_t* sw, int& P, int x_z
     return true;
 }
 
+// CONSUMER side, one batch of at most 32 sequences held by a warp (lane j: sequence j): repeat offsets, positions, records.
+struct SeqTotals {
+    RepMap carry;                    // the block's repeat-offset map up to the current batch (uniform over the warp)
+    uint32_t litpos, outpos;         // running totals, uniform over the warp
+    bool bad;
+    __device__ __forceinline__ void init() { rep_identity(carry); litpos = outpos = 0; bad = false; }
+};
+
+__device__ __forceinline__ void seq_consume_batch(uint32_t* b_ov, const uint32_t* b_ml, const uint32_t* b_ll, uint32_t cnt, int lane, uint4* rec,
+                                                  uint32_t bi, SeqTotals& t) {
+    const uint32_t ll = (uint32_t)lane < cnt ? b_ll[lane] : 0u, ml = (uint32_t)lane < cnt ? b_ml[lane] : 0u;
+    {
+        // repeat offsets (RFC 8878 3.1.1.5): what a sequence does to the three slots is a map; the offset it uses is slot 0
+        // AFTER its own map.  An inclusive scan over the batch (on top of the carry) gives every sequence its offset,
+        // symbolically in the block's incoming slots -- 5 shuffle steps instead of a 32-step chain in one lane (which had
+        // become as slow as the tANS walk: 319 cycles per sequence, measured).
+        RepMap m; rep_identity(m);
+        if ((uint32_t)lane < cnt) {
+            const uint32_t ov = b_ov[lane];
+            if (ov > 3) { m.s[0] = -1; m.v[0] = ov - 3; m.s[1] = 0; m.s[2] = 1; }
+            else {
+                const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+                if (idx == 1) { m.s[0] = 1; m.s[1] = 0; }
+                else if (idx == 2) { m.s[0] = 2; m.s[1] = 0; m.s[2] = 1; }
+                else if (idx == 3) { m.v[0] = 1; m.s[1] = 0; m.s[2] = 1; }
+            }
+        }
+        if (lane == 0) rep_compose(m, t.carry, t.bad);
+        if (cnt <= 8) {
+            // a handful of sequences (the tiny blocks of a FASTQ section flushed per record): a short chain of shuffles is
+            // cheaper than the five-step scan
+            for (uint32_t j = 1; j < cnt; j++) {
+                RepMap f;
+                rep_shfl(f, m, (int)j - 1);
+                if ((uint32_t)lane == j) rep_compose(m, f, t.bad);
+            }
+            RepMap last;
+            rep_shfl(last, m, (int)cnt - 1);
+            if ((uint32_t)lane >= cnt) m = last;                     // (lane 31 carries the batch's total below)
+        } else rep_warp_scan(m, lane, t.bad);
+        RepSym off; off.src = m.s[0]; off.val = m.v[0];
+        if (off.src >= 0 && off.val > 0x1FFFFFFFu) t.bad = true;
+        if ((uint32_t)lane < cnt) b_ov[lane] = encode_off(off);
+        rep_shfl(t.carry, m, 31);                        // (lanes past the batch hold the identity: lane 31 has the batch's total)
+    }
+    __syncwarp();
+    // positions: exclusive scans of ll and ll + ml over the batch, on top of the running totals
+    uint32_t il = ll, io = ll + ml;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d), to = __shfl_up_sync(0xFFFFFFFFu, io, d);
+        if (lane >= d) { il += tl; io += to; }
+    }
+    if ((uint32_t)lane < cnt) {
+        const uint32_t lp = t.litpos + il - ll, op = t.outpos + io - (ll + ml);
+        rec[2 * lane] = make_uint4(ll, ml, b_ov[lane], lp);
+        rec[2 * lane + 1] = make_uint4(op, bi, 0u, 0u);
+    }
+    t.litpos += __shfl_sync(0xFFFFFFFFu, il, 31);
+    const uint32_t otot = __shfl_sync(0xFFFFFFFFu, io, 31);
+    if (otot > BLOCK_MAX || t.outpos + otot > BLOCK_MAX) t.bad = true;      // (match lengths are < 2^17 each: no wrap within a batch)
+    t.outpos += otot;
+}
+
+// what a block's sequences leave behind (one lane): regenerated size, the block's repeat-offset map
+__device__ __forceinline__ void seq_finish_block(const JobDev& J, const BlockDesc& B, BlockState& S, const SeqTotals& t, int left) {
+    if (t.bad || left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    if (t.litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
+    const uint32_t regen = t.outpos + (B.lit_regen - t.litpos);
+    if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
+    S.regen = regen;
+    for (int k = 0; k < 3; k++) { S.rep_src[k] = t.carry.s[k]; S.rep_val[k] = t.carry.v[k]; }
+}
+
 // k_decode_sequences: one CTA of two warps per block.  Warp 0, lane 0 is the PRODUCER: the serial chain of the three
 // interleaved tANS states and nothing else (every instruction on it costs ~6 cycles of a lone dependent warp: ncu shows
 // `wait` as the top stall, profiles/r1_fse_stage_k_decode_sequences.txt).  Warp 1 is the CONSUMER, one batch of 32
@@ -439,6 +513,7 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
     if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
+    if (J.tiny_blocks && B.n_seq <= SEQ_BATCH) return;      // k_decode_sequences_tiny's
     if (J.frame_bad[B.frame]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     BlockState& S = J.bstate[bi];
@@ -512,9 +587,7 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
         return;
     }
     // ---- consumer -------------------------------------------------------------------------------------------------
-    RepMap carry; rep_identity(carry);                      // the block's repeat-offset map up to the current batch (uniform over the warp)
-    uint32_t litpos = 0, outpos = 0;                        // running totals, uniform over the warp
-    bool bad = false;
+    SeqTotals tot; tot.init();
     uint4* rec = (uint4*)(J.seq + base);
     long long c_work = 0, c_wait = 0, c0 = 0;
     SEQ_CLK(c0);
@@ -523,70 +596,70 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
         __syncthreads();
         SEQ_LAP(c_wait, c0);
         const uint32_t cnt = (k + 1 < nbatch) ? SEQ_BATCH : n - k * SEQ_BATCH;
-        uint32_t* b_ov = r_ov[k & 1];
-        const uint32_t ll = (uint32_t)lane < cnt ? r_ll[k & 1][lane] : 0u, ml = (uint32_t)lane < cnt ? r_ml[k & 1][lane] : 0u;
-        {
-            // repeat offsets (RFC 8878 3.1.1.5): what a sequence does to the three slots is a map; the offset it uses is slot 0
-            // AFTER its own map.  An inclusive scan over the batch (on top of the carry) gives every sequence its offset,
-            // symbolically in the block's incoming slots -- 5 shuffle steps instead of a 32-step chain in one lane (which had
-            // become as slow as the tANS walk: 319 cycles per sequence, measured).
-            RepMap m; rep_identity(m);
-            if ((uint32_t)lane < cnt) {
-                const uint32_t ov = b_ov[lane];
-                if (ov > 3) { m.s[0] = -1; m.v[0] = ov - 3; m.s[1] = 0; m.s[2] = 1; }
-                else {
-                    const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
-                    if (idx == 1) { m.s[0] = 1; m.s[1] = 0; }
-                    else if (idx == 2) { m.s[0] = 2; m.s[1] = 0; m.s[2] = 1; }
-                    else if (idx == 3) { m.v[0] = 1; m.s[1] = 0; m.s[2] = 1; }
-                }
-            }
-            if (lane == 0) rep_compose(m, carry, bad);
-            if (cnt <= 8) {
-                // a handful of sequences (the tiny blocks of a FASTQ section flushed per record): a short chain of shuffles is
-                // cheaper than the five-step scan
-                for (uint32_t j = 1; j < cnt; j++) {
-                    RepMap f;
-                    rep_shfl(f, m, (int)j - 1);
-                    if ((uint32_t)lane == j) rep_compose(m, f, bad);
-                }
-                RepMap last;
-                rep_shfl(last, m, (int)cnt - 1);
-                if ((uint32_t)lane >= cnt) m = last;                     // (lane 31 carries the batch's total below)
-            } else rep_warp_scan(m, lane, bad);
-            RepSym off; off.src = m.s[0]; off.val = m.v[0];
-            if (off.src >= 0 && off.val > 0x1FFFFFFFu) bad = true;
-            if ((uint32_t)lane < cnt) b_ov[lane] = encode_off(off);
-            rep_shfl(carry, m, 31);                          // (lanes past the batch hold the identity: lane 31 has the batch's total)
-        }
-        __syncwarp();
-        // positions: exclusive scans of ll and ll + ml over the batch, on top of the running totals
-        uint32_t il = ll, io = ll + ml;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d), to = __shfl_up_sync(0xFFFFFFFFu, io, d);
-            if (lane >= d) { il += tl; io += to; }
-        }
-        if ((uint32_t)lane < cnt) {
-            const uint32_t lp = litpos + il - ll, op = outpos + io - (ll + ml);
-            rec[2 * (k * SEQ_BATCH + lane)] = make_uint4(ll, ml, b_ov[lane], lp);
-            rec[2 * (k * SEQ_BATCH + lane) + 1] = make_uint4(op, bi, 0u, 0u);
-        }
-        litpos += __shfl_sync(0xFFFFFFFFu, il, 31);
-        const uint32_t otot = __shfl_sync(0xFFFFFFFFu, io, 31);
-        if (otot > BLOCK_MAX || outpos + otot > BLOCK_MAX) bad = true;      // (match lengths are < 2^17 each: no wrap within a batch)
-        outpos += otot;
+        seq_consume_batch(r_ov[k & 1], r_ml[k & 1], r_ll[k & 1], cnt, lane, rec + 2 * (size_t)k * SEQ_BATCH, bi, tot);
     }
-    bad = __any_sync(0xFFFFFFFFu, bad);
+    tot.bad = __any_sync(0xFFFFFFFFu, tot.bad);
     if (lane != 0) return;
     SEQ_LAP(c_work, c0);
     SEQ_REPORT(2, c_work, c_wait, 0);
-    if (bad || s_left != 0) { flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
-    if (litpos > B.lit_regen) { flag_error(J, B.frame, zc::E_LITERALS); return; }
-    uint32_t regen = outpos + (B.lit_regen - litpos);
-    if (regen > BLOCK_MAX) { flag_error(J, B.frame, zc::E_SIZE); return; }
-    S.regen = regen;
-    for (int k = 0; k < 3; k++) { S.rep_src[k] = carry.s[k]; S.rep_val[k] = carry.v[k]; }
+    seq_finish_block(J, B, S, tot, s_left);
+}
+
+// The same decode for TINY blocks (at most one batch of sequences): one WARP per block, eight blocks per CTA.  A FASTQ
+// archive in the reference encoder's framing (one flush per record) is 2 x 10^6 blocks of 3-20 sequences per 10^6 reads; a
+// two-warp CTA each, with the shared memory of the job's largest block, kept an SM at 5-7 blocks in flight (11 ms for 10^6
+// reads).  Here the bitstream (at most 361 bytes: 32 sequences of at most 89 bits, 26 bits of initial states, the end mark)
+// is staged per warp, the table cells are read where k_build_tables left them (a tiny block uses predefined or repeated
+// tables: hot in L1), lanes 0..2 walk the three states, and the same warp then does the consumer's batch.
+constexpr int SEQ_TINY_WARPS = 8;
+constexpr uint32_t SEQ_TINY_BYTES = 368;
+constexpr uint32_t SEQ_TINY_WORDS = (16 + 16 + SEQ_TINY_BYTES + 16 + 16) / 4;
+
+__global__ void __launch_bounds__(SEQ_TINY_WARPS * 32) k_decode_sequences_tiny(JobDev J) {
+    __shared__ __align__(16) uint32_t sb_all[SEQ_TINY_WARPS][SEQ_TINY_WORDS];
+    __shared__ uint32_t r_all[SEQ_TINY_WARPS][3][SEQ_BATCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bi = blockIdx.x * SEQ_TINY_WARPS + warp;
+    if (bi >= J.n_blocks) return;
+    const BlockDesc& B = J.blocks[bi];
+    if (B.btype != BT_COMPRESSED || B.n_seq == 0 || B.n_seq > SEQ_BATCH) return;
+    if (J.frame_bad[B.frame]) return;
+    BlockState& S = J.bstate[bi];
+    if (S.seq_bits_off >= B.src_size) { if (lane == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    const uint32_t nbytes = B.src_size - S.seq_bits_off;
+    const uint8_t* g = J.comp + B.src_off + S.seq_bits_off;
+    // (more bytes than 32 sequences can consume: the stream cannot end exactly at bit 0)
+    if (nbytes > SEQ_TINY_BYTES || g[nbytes - 1] == 0) { if (lane == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
+    uint32_t* sbits = sb_all[warp];
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    const uint32_t nchunks = (a + nbytes + 15) >> 4;                       // <= 25
+    if ((uint32_t)lane < nchunks) ((uint4*)sbits)[1 + lane] = ((const uint4*)(g - a))[lane];
+    const uint8_t last = g[nbytes - 1];
+    __syncwarp();
+    if ((uint32_t)lane < 16 + a) ((uint8_t*)sbits)[lane] = 0;
+    __syncwarp();
+    const int kind = lane == 0 ? 1 : (lane == 1 ? 2 : 0);                  // lane 0: OF, 1: ML, 2: LL (as in k_decode_sequences)
+    const int al0 = J.table_al[B.tbl[0]], al1 = J.table_al[B.tbl[1]], al2 = J.table_al[B.tbl[2]];
+    const int alk = kind == 0 ? al0 : (kind == 1 ? al1 : al2);
+    const SeqCell* T = (const SeqCell*)(J.tables + (size_t)B.tbl[kind] * FSE_SLOT_CELLS);
+    const int xz = (int)(16 + a) * 8;
+    int P = xz + 8 * (int)(nbytes - 1) + zc::highbit32(last);
+    uint32_t state = 0;
+    {
+        const int before = lane == 2 ? 0 : (lane == 0 ? al0 : al0 + al1);
+        if (lane < 3) state = smem_bits(sbits, P - before - alk, (uint32_t)alk);
+        P -= al0 + al1 + al2;
+    }
+    const uint32_t n = B.n_seq;
+    uint32_t* r_mine = r_all[warp][kind];
+    const bool ok = P >= xz && seq_produce3(sbits, P, xz, T, state, lane, n, true, r_mine);
+    const int left = ok ? P - xz : -1;
+    __syncwarp();
+    SeqTotals tot; tot.init();
+    if (left == 0) seq_consume_batch(r_all[warp][1], r_all[warp][2], r_all[warp][0], n, lane, (uint4*)(J.seq + B.seq_base), bi, tot);
+    tot.bad = __any_sync(0xFFFFFFFFu, tot.bad);
+    if (lane != 0) return;
+    seq_finish_block(J, B, S, tot, left);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -1866,10 +1939,18 @@ constexpr int LZLIT_G = 32;                        // lanes per literal run (8-l
 constexpr int LZLIT_SPLIT = 4;                     // CTAs that share the runs of one block
 constexpr uint32_t LZLIT_LONG = 4096;              // longer runs are copied by the whole CTA (at most 32 per block)
 
+// tiny blocks (a FASTQ section flushed per record: 2 x 10^6 blocks of ~100 bytes): one warp each, see k_lz_literals_tiny
+constexpr uint32_t LZLIT_TINY = 2048;
+__device__ __forceinline__ bool lz_lit_tiny(const BlockDesc& B) {
+    if (B.btype != BT_COMPRESSED) return B.src_size <= LZLIT_TINY;
+    return B.n_seq <= 32 && B.lit_regen <= LZLIT_TINY;
+}
+
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     __shared__ uint32_t lq_n, lq_lp[40], lq_op[40], lq_ll[40];
     const uint32_t bi = blockIdx.x;
     const BlockDesc& B = J.blocks[bi];
+    if (J.tiny_blocks && lz_lit_tiny(B)) return;             // k_lz_literals_tiny's
     if (J.frame_bad[B.frame]) return;
     const BlockState& S = J.bstate[bi];
     uint8_t* out = J.out + S.out_off;
@@ -1923,6 +2004,53 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     }
     __syncthreads();
     for (uint32_t q = 0; q < lq_n; q++) copy_g2g(out + lq_op[q], lsrc + lq_lp[q], lq_ll[q], (int)threadIdx.x, (int)blockDim.x);
+}
+
+// One warp per tiny block, eight blocks per CTA: a CTA per block spent its time being launched (5.5 ms for the 2 x 10^6
+// blocks of a 10^6-read archive).  Lane j holds the record of sequence j; the runs are copied one after the other by the
+// whole warp (they are a few dozen bytes each).
+__global__ void __launch_bounds__(256) k_lz_literals_tiny(JobDev J) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t bi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (bi >= J.n_blocks) return;
+    const BlockDesc& B = J.blocks[bi];
+    if (!lz_lit_tiny(B)) return;
+    if (J.frame_bad[B.frame]) return;
+    const BlockState& S = J.bstate[bi];
+    uint8_t* out = J.out + S.out_off;
+    if (B.btype == BT_RAW) { copy_g2g(out, J.comp + B.src_off, B.src_size, lane, 32); return; }
+    if (B.btype == BT_RLE) {
+        const uint8_t v = J.comp[B.src_off];
+        for (uint32_t i = lane; i < B.src_size; i += 32) out[i] = v;
+        return;
+    }
+    const uint8_t* lsrc = nullptr;
+    uint8_t rle = 0;
+    if (B.lit_type == LT_RAW) lsrc = J.comp + B.src_off + B.lit_src;
+    else if (B.lit_type == LT_RLE) rle = J.comp[B.src_off + B.lit_src];
+    else lsrc = J.lit + B.lit_base;
+    const uint32_t n = B.n_seq, base = B.seq_base;
+    uint32_t lp = 0, op = 0, ll = 0, ml = 0;
+    if ((uint32_t)lane < n) {
+        const uint4 r = *(const uint4*)&J.seq[base + lane];                  // ll, ml, off, litpos
+        ll = r.x; ml = r.y; lp = r.w; op = J.seq[base + lane].outpos;
+        J.seq[base + lane].match_pos = S.out_off + op + ll;                  // absolute destination of the match
+    }
+    // the literals after the last sequence: lane n (n <= 32; lane 32 does not exist, so lane 31's record is extended in place)
+    uint32_t t_lp = 0, t_op = 0;
+    if (n) {
+        const uint32_t e_lp = __shfl_sync(0xFFFFFFFFu, lp + ll, (int)n - 1), e_op = __shfl_sync(0xFFFFFFFFu, op + ll + ml, (int)n - 1);
+        t_lp = e_lp; t_op = e_op;
+    }
+    for (uint32_t i = 0; i <= n; i++) {
+        uint32_t rl, rp, ro;
+        if (i < n) { rl = __shfl_sync(0xFFFFFFFFu, ll, (int)i); rp = __shfl_sync(0xFFFFFFFFu, lp, (int)i); ro = __shfl_sync(0xFFFFFFFFu, op, (int)i); }
+        else { rp = t_lp; ro = t_op; rl = B.lit_regen > t_lp ? B.lit_regen - t_lp : 0u; }
+        if (rl == 0) continue;
+        if (rp + rl > B.lit_regen) break;                // (inconsistent records: the block was flagged by the sequence decode)
+        if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < rl; k += 32) out[ro + k] = rle;
+        else copy_g2g(out + ro, lsrc + rp, rl, lane, 32);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -2533,6 +2661,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) cudaEventRecord(join, st2);
     else ev->mark();                                  // serial (profiled) order: the Huffman branch first
     NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
+    if (J.tiny_blocks) { NAF_LAUNCH(k_decode_sequences_tiny, (J.n_blocks + SEQ_TINY_WARPS - 1) / SEQ_TINY_WARPS, SEQ_TINY_WARPS * 32, 0, st, J); launches++; }
     NAF_LAUNCH(k_decode_sequences, J.n_blocks, 64, J.seq_stage_bytes, st, J); launches++; ev->mark();
     NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++;
     if (J.n_fs_tiles) {
@@ -2544,6 +2673,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     ev->mark();
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
+    if (J.tiny_blocks) { NAF_LAUNCH(k_lz_literals_tiny, (J.n_blocks + 7) / 8, 256, 0, st, J); launches++; }
     NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
     if (J.n_seq > 0) {
         // (small jobs: one entry per thread, as many CTAs as entries need -- latency; big jobs: LZ_U entries per thread)

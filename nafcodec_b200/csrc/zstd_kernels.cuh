@@ -23,6 +23,7 @@ struct JobDev {
     uint8_t* huf_weights;             // n_huf_slots x 256 weights (k_build_tables decodes every tree description once)
     uint8_t* huf_meta;                // n_huf_slots x {n_symbols - 1, max_bits}; max_bits == 0: bad tree
     zf::SeqRec* seq;                  // one 32-byte record per sequence (written by k_decode_sequences / k_lz_literals)
+    uint32_t tiny_blocks;             // nonzero: blocks of at most 32 sequences / 2 KiB of literals go through the warp-per-block kernels
     uint32_t seq_stage_bytes;         // shared-memory staging size of k_decode_sequences (largest sequence bitstream, capped)
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
     uint32_t* lz_idx;                 // per frame, per 4 KB of output: first match ending after the start of the cell (k_lz_index)

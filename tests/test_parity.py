@@ -330,6 +330,31 @@ def test_both_huffman_kernels(backend, monkeypatch, block_min):
     assert ctx.zstd_decompress(frame, len(p)) == p
 
 
+@pytest.mark.parametrize("tiny", ["0", "1"])
+def test_tiny_blocks_take_the_warp_per_block_kernels(backend, monkeypatch, tiny):
+    """Blocks of at most 32 sequences / 2 KiB of literals (a FASTQ archive in the reference encoder's framing: one flush per
+    record) are decoded by one warp each (k_decode_sequences_tiny, k_lz_literals_tiny) once a job has thousands of them; both
+    paths on the same archives here, mixed with ordinary blocks, raw and RLE blocks."""
+    monkeypatch.setenv("NAFGPU_TINY_BLOCKS", tiny)
+    rng = np.random.default_rng(23)
+    n = 150 if backend == "emul" else 3000
+    motifs = [K.random_dna(rng, 40, b"ACGT") for _ in range(6)]
+    seqs, quals = [], []
+    for i in range(n):
+        parts = [motifs[int(rng.integers(0, 6))] if rng.random() < 0.6 else K.random_dna(rng, int(rng.integers(1, 60)), b"ACGTN") for _ in range(int(rng.integers(1, 6)))]
+        s = b"".join(parts)
+        if i % 17 == 0: s = b"A" * int(rng.integers(1, 400))                 # RLE blocks
+        if i % 29 == 0: s = K.random_dna(rng, 5000, b"ACGT") + s + s        # a block with more than 32 sequences among the tiny ones
+        seqs.append(s)
+        quals.append(bytes(rng.choice(np.frombuffer(b"FFFF:,#", dtype=np.uint8), size=len(s))))
+    ids = [b"r%d" % i for i in range(n)]
+    arc = O.encode(ids=ids, sequences=seqs, qualities=quals, level=3, flush_per_record=True)
+    res, d = check_parity(backend, arc, "tiny blocks " + tiny)
+    assert res.n_lengths == n
+    check_parity(backend, read_golden("phix.naf"), "phix " + tiny)
+    check_parity(backend, read_golden("NZ_AAEN01000029.naf"), "fixture " + tiny)
+
+
 def test_sections_longer_than_one_scan_slice(backend):
     """ids, comments and lengths sections of more than 32 KiB are scanned by several CTAs (k_naf_agg + sliced k_naf_scan +
     k_naf_lengths); continuation words and empty strings fall on slice boundaries here."""
