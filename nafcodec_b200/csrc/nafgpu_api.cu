@@ -120,8 +120,8 @@ void parallel_for(size_t n, unsigned max_threads, F fn) {
 
 struct nafgpu_ctx {
     int device = 0;
-    cudaStream_t st = 0, st2 = 0;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_block = nullptr;
+    cudaStream_t st = 0, st2 = 0, st3 = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr, ev_block = nullptr;
     std::string err;
     DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, lzidx, scanagg, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
@@ -169,12 +169,14 @@ void drop_graph(nafgpu_ctx* c) {
 int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     cudaStream_t st = c->st;
     CUDA_TRY(c, cudaMemsetAsync(c->misc.p, 0, c->misc_words * 4, st));
-    if (c->J.n_seq) CUDA_TRY(c, cudaMemsetAsync(c->J.seq_done, 0, c->J.n_seq * 4, st));
-    if (c->J.n_seq) CUDA_TRY(c, cudaMemsetAsync(c->J.lz_blocker, 0xFF, c->J.n_seq * 4, st));
+    if (c->J.n_seq && !c->J.lz_small) {             // (k_lz_small keeps these in shared memory and writes seq_done itself)
+        CUDA_TRY(c, cudaMemsetAsync(c->J.seq_done, 0, c->J.n_seq * 4, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->J.lz_blocker, 0xFF, c->J.n_seq * 4, st));
+    }
     CUDA_TRY(c, cudaMemsetAsync(c->arena.p, 0, c->counts_size, st));
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     // profiled runs (ev != null) are serial so that every stage has its own interval
-    int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev);
+    int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev, c->st3, c->ev_fork3, c->ev_join3);
     launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records, c->max_scan, c->scanagg.p,
                                      c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
@@ -298,7 +300,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     const size_t stage_bytes = c->o_big + align_up(bigs.size() * sizeof(zf::FsBigFrame), 16);
     c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8 + 24;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
-              c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256) &&
+              c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256 + (size_t)total_chunks * 8192) &&
               c->bstate.ensure(nb * sizeof(zf::BlockState) + 64) && c->fsstate.ensure(tiles.size() * sizeof(zf::FsTileState) + 64) && c->lzidx.ensure(((size_t)total_chunks * 16 + nf + 16) * 4) &&
               c->scanagg.ensure((size_t)n * 4 * ((c->max_scan + nk::NAF_SLICE - 1) / nk::NAF_SLICE + 1) * nk::NAF_AGG_BYTES + 64) && c->hufw.ensure((size_t)pl.n_huf_slots * 258 + 64) &&
               c->tables.ensure((size_t)pl.n_slots * zf::FSE_SLOT_CELLS * sizeof(zc::SeqCell)) && c->table_al.ensure(pl.n_slots + 64) &&
@@ -367,13 +369,18 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     // the others do not carry the shared memory of ... the others
     J.tiny_blocks = pl.n_tiny_seq_blocks >= 4096u ? 1u : 0u;
     if (const char* e = getenv("NAFGPU_TINY_BLOCKS")) J.tiny_blocks = (uint32_t)atoi(e);      // (tests: both paths on small inputs)
+    {   // one CTA for the matches of a small job (k_lz_small holds up to 8192; beyond ~2000 the general rounds are faster)
+        uint64_t small_max = 2048;
+        if (const char* e = getenv("NAFGPU_LZ_SMALL")) small_max = (uint64_t)std::min(8192, std::max(0, atoi(e)));      // (tests: either path)
+        J.lz_small = (nseq <= small_max && nf <= 65535 && c->arena_size < (1ull << 32)) ? 1u : 0u;
+    }
     J.seq_stage_bytes = std::min<uint32_t>((((J.tiny_blocks ? pl.max_seq_section_big : pl.max_seq_section) + 15u) & ~15u) + 64u, 16u * 1024u);
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.fin_unresolved = misc + 6; J.fin_count = misc + 7;
     J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf; J.lz_pending = misc + 10 + nf + total_chunks + 8;
     J.fin_chunk_first = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_chunks); J.fin_total_chunks = total_chunks;
     J.lz_idx = (uint32_t*)c->lzidx.p;
-    J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p;
+    J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p; J.fin_ext = (uint32_t*)c->fin_g.p + g_base[nf] + 64;
     J.fin_g_base = (const uint64_t*)((const uint8_t*)c->desc.p + c->o_gbase);
     J.coop_ctas = c->coop_ctas;
     {   // the finisher's first level handles a 64 KB chunk in ~90 us on one SM, all SMs at once; its second level (barrier rounds over the
@@ -436,7 +443,8 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->J, 0, sizeof c->J);
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { c->ev_block = nullptr; cudaGetLastError(); }
     for (int i = 0; i < N_STAGES + 3; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
@@ -458,8 +466,11 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
+    if (c->ev_join3) cudaEventDestroy(c->ev_join3);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     cudaStreamDestroy(c->st2);
+    if (c->st3) cudaStreamDestroy(c->st3);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -775,6 +786,7 @@ int nafgpu_job_fetch(nafgpu_ctx* c, nafgpu_result* out, uint32_t n) {
         }
         if (q[4]) fprintf(stderr, "[seq debug] %llu sequences: producer %.0f cycles work + %.0f waiting, consumer %.0f work + %.0f waiting (per sequence)\n", q[4],
                           (double)q[0] / q[4], (double)q[1] / q[4], (double)q[2] / q[4], (double)q[3] / q[4]);
+        if (q[7]) fprintf(stderr, "[lz small debug] cycles: probe %llu, copy %llu, all rounds %llu\n", q[5], q[6], q[7]);
         if (cnt) fprintf(stderr, "[huf debug] big CTAs %zu: cycles stage+weights %.0f, table %.0f, sync %.0f (iters avg %.2f max %.0f), scan %.0f, write %.0f, flush %.0f\n",
                          cnt, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, iters / cnt, maxit, ph[3] / cnt, ph[4] / cnt, ph[5] / cnt);
     }

@@ -52,6 +52,13 @@ struct SmemBits {
     __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
 };
 
+// bits [o, o + k) of a shared-memory image of a bitstream (32-bit words), k <= 32: no reader state
+__device__ __forceinline__ uint32_t smem_bits(const uint32_t* sw, int o, uint32_t k) {         // bits [o, o + k) of the image, k <= 32
+    const uint32_t lo = sw[o >> 5], hi = sw[(o >> 5) + 1];
+    const uint32_t v = __funnelshift_r(lo, hi, (uint32_t)o);          // (shift taken modulo 32)
+    return k >= 32 ? v : (v & ((1u << k) - 1u));
+}
+
 // FSE decode table by a whole warp (RFC 8878 4.1.1; the serial restatement is zc::fse_build in zstd_core.cuh).
 //   A  low-probability symbols (-1) take the top cells in symbol order; counts and cumulative counts of the others
 //   B  the serial "spread" visits positions (j * step) & mask, j = 0, 1, ..., skipping those >= high: the t-th placement
@@ -133,6 +140,8 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
         __shared__ uint8_t cell_sym[64];
         __shared__ __align__(4) uint8_t w[256];
         __shared__ int s_n, s_mode, s_start, s_nbytes, s_al;
+        __shared__ int16_t hnorm[16];
+        __shared__ uint16_t hcnt[16], hcum[16];
         const int l1 = threadIdx.x;
         const uint32_t tsize = B.lit_csize < 130u ? B.lit_csize : 130u;
         for (uint32_t i = l1; i < 192; i += 32) tree[i] = i < tsize ? J.comp[B.src_off + B.lit_src + i] : 0;
@@ -144,18 +153,20 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
         if (l1 == 0 && tsize) {
             if (h >= 128) { if (1u + (h - 127u + 1u) / 2u <= tsize) { s_mode = 0; s_n = (int)h - 127; } }
             else if (h >= 2 && 1u + h <= tsize) {
-                int16_t norm[16];
-                uint16_t cnt[16];
                 int al = 0;
                 // weights are 0..11: at most 13 symbols, at most 64 cells
-                const uint32_t used = zc::fse_read_ncount(tree + 1, h, 12, zc::MAX_AL_HUF, norm, &al);
-                if (used != 0 && used < h &&
-                    zc::fse_build(norm, 12, al, cell_sym, cnt, [&](int i, int sy, int nb, int base) { cells[i] = (uint32_t)sy | ((uint32_t)nb << 8) | ((uint32_t)base << 16); })) {
-                    s_mode = 1; s_start = 1 + (int)used; s_nbytes = (int)(h - used); s_al = al;
-                }
+                const uint32_t used = zc::fse_read_ncount(tree + 1, h, 12, zc::MAX_AL_HUF, hnorm, &al);
+                if (used != 0 && used < h) { s_mode = 2; s_start = 1 + (int)used; s_nbytes = (int)(h - used); s_al = al; }
             }
         }
         __syncwarp();
+        if (s_mode == 2) {                                   // (uniform) the table of the weights' FSE code, by the whole warp
+            const bool good = fse_build_warp(hnorm, 12, s_al, cell_sym, hcnt, hcum, l1,
+                                             [&](int i, int sy, int nb, int base) { cells[i] = (uint32_t)sy | ((uint32_t)nb << 8) | ((uint32_t)base << 16); });
+            __syncwarp();
+            if (l1 == 0) s_mode = good ? 1 : -1;
+            __syncwarp();
+        }
         int n = 0;
         bool good = s_mode >= 0;
         if (s_mode == 0) {
@@ -168,22 +179,32 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
                 const uint8_t last = ((const uint8_t*)sb)[16 + s_nbytes - 1];
                 bool ok = last != 0;
                 if (ok) {
-                    SmemBits rd;
-                    rd.init(sb, 128 + 8 * (s_nbytes - 1) + zc::highbit32(last), 128);
-                    uint32_t s1 = rd.read(s_al), s2 = rd.read(s_al);
-                    ok = rd.remaining() >= 0;
+                    // Two interleaved states over one backward bitstream.  `pos` = unread bits; a field is cut straight out of
+                    // the image (16 zero bytes below bit 0: an over-read yields zeros and a negative pos, which ends the walk
+                    // exactly where the serial reader does).  Both cells of a pair are fetched before either state moves, so the
+                    // two table look-ups overlap: ~40 cycles per weight instead of ~130 with a refilling reader and a test
+                    // after every read (a single small archive waits for this chain: 25 trees x 255 weights).
+                    const int al = s_al;
+                    int pos = 8 * (s_nbytes - 1) + zc::highbit32(last);
+                    pos -= al; uint32_t s1 = smem_bits(sb, 128 + pos, (uint32_t)al);
+                    pos -= al; uint32_t s2 = smem_bits(sb, 128 + pos, (uint32_t)al);
+                    ok = pos >= 0;
                     int k = 0;
                     while (ok) {
                         if (k > 253) { ok = false; break; }
-                        const uint32_t c1 = cells[s1];
+                        const uint32_t c1 = cells[s1], c2 = cells[s2];
+                        const int n1 = (int)((c1 >> 8) & 0xFF), n2 = (int)((c2 >> 8) & 0xFF);
+                        const int p1 = pos - n1, p2 = p1 - n2;
+                        const uint32_t b1 = smem_bits(sb, 128 + p1, (uint32_t)n1);
+                        const uint32_t b2 = smem_bits(sb, 128 + (p2 < -96 ? -96 : p2), (uint32_t)n2);
                         w[k++] = (uint8_t)c1;
-                        s1 = (c1 >> 16) + rd.read((int)((c1 >> 8) & 0xFF));
-                        if (rd.remaining() < 0) { w[k++] = (uint8_t)cells[s2]; break; }
+                        s1 = (c1 >> 16) + b1;
+                        if (p1 < 0) { w[k++] = (uint8_t)c2; break; }
                         if (k > 253) { ok = false; break; }
-                        const uint32_t c2 = cells[s2];
                         w[k++] = (uint8_t)c2;
-                        s2 = (c2 >> 16) + rd.read((int)((c2 >> 8) & 0xFF));
-                        if (rd.remaining() < 0) { w[k++] = (uint8_t)cells[s1]; break; }
+                        s2 = (c2 >> 16) + b2;
+                        if (p2 < 0) { w[k++] = (uint8_t)cells[s1]; break; }
+                        pos = p2;
                     }
                     s_n = ok ? k : 0;
                 }
@@ -383,11 +404,6 @@ __device__ __forceinline__ void seq_produce(RD& rd, const SeqCell* TLL, const Se
 //   extra bits, consumed OF, ML, LL from position P down:   field k = [P - pre_a(k) - a_k, P - pre_a(k))
 //   state bits, consumed LL, ML, OF after them:             field k = [Pend + pre_n(k), Pend + pre_n(k) + n_k),  Pend = P - sum a - sum n
 // ~40 warp instructions per sequence, no reader state but P.
-__device__ __forceinline__ uint32_t smem_bits(const uint32_t* sw, int o, uint32_t k) {         // bits [o, o + k) of the image, k <= 32
-    const uint32_t lo = sw[o >> 5], hi = sw[(o >> 5) + 1];
-    const uint32_t v = __funnelshift_r(lo, hi, (uint32_t)o);          // (shift taken modulo 32)
-    return k >= 32 ? v : (v & ((1u << k) - 1u));
-}
 
 // All 32 lanes of the producer warp call this; lanes 0..2 work.  Decodes `cnt` sequences from smem bit position P (counting
 // down); returns false once the stream is over-read (P below x_zero: corrupt) -- uniform, P is the same in every lane.
@@ -1913,7 +1929,7 @@ __global__ void __launch_bounds__(HB_T, 3) k_huf_decode_block(JobDev J) {
 // Cooperative global -> global copy of n bytes with arbitrary alignments by `nlanes` threads (a warp or a CTA):
 // destination-aligned 16-byte stores; each is assembled from the two aligned 16-byte source words that span it.
 // The source must be readable up to 31 bytes past its end (staging buffers are padded).
-__device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
+__device__ __forceinline__ void copy_g2g_plain(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
     if (n < 64) { for (uint32_t k = lane; k < n; k += nlanes) dst[k] = src[k]; return; }
     const uint32_t h = (uint32_t)(-(intptr_t)dst) & 15u;
     for (uint32_t k = lane; k < h; k += nlanes) dst[k] = src[k];
@@ -1935,6 +1951,54 @@ __device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_
     for (uint32_t k = done + lane; k < n; k += nlanes) dst[k] = src[k];
 }
 
+// U: chunks per lane in flight.  1 (the loop above) for the short runs of a batch -- registers: k_lz_literals lost 40 % with 4.
+// 4 where a lone CTA or warp copies kilobytes and would otherwise pay a round trip to memory per chunk (a single small
+// archive): every load of a pass is issued before its first store -- head and tail bytes (fewer than 16 each: one per lane)
+// and up to U chunks per lane: one round trip for a match of up to U x nlanes x 16 bytes.  nlanes >= 32.
+template <int U = 1>
+__device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
+    if (U == 1) { copy_g2g_plain(dst, src, n, lane, nlanes); return; }
+    if (n < 64) {                                      // both bytes of a lane loaded before either is stored
+        const uint32_t k0 = lane, k1 = lane + nlanes;
+        uint8_t v0 = 0, v1 = 0;
+        if (k0 < n) v0 = src[k0];
+        if (k1 < n) v1 = src[k1];
+        if (k0 < n) dst[k0] = v0;
+        if (k1 < n) dst[k1] = v1;
+        return;
+    }
+    const uint32_t h = (uint32_t)(-(intptr_t)dst) & 15u;
+    const uint32_t body = (n - h) >> 4;
+    const uintptr_t sa = (uintptr_t)(src + h);
+    const uint4* sw = (const uint4*)(sa & ~(uintptr_t)15);
+    const uint32_t mis = (uint32_t)(sa & 15), q = mis >> 2, sh = (mis & 3) * 8;
+    uint4* d4 = (uint4*)(dst + h);
+    const uint32_t tk = h + (body << 4) + (uint32_t)lane;
+    uint8_t hb = 0, tb = 0;
+    if ((uint32_t)lane < h) hb = src[lane];
+    if (tk < n) tb = src[tk];
+    for (uint32_t c = lane; c < body; c += (uint32_t)U * (uint32_t)nlanes) {
+        uint4 A[U], B[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const uint32_t x = c + (uint32_t)u * nlanes; if (x < body) { A[u] = sw[x]; B[u] = sw[x + 1]; } }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t x = c + (uint32_t)u * nlanes;
+            if (x < body) {
+                const uint4 a = A[u], b = B[u];
+                uint32_t w0, w1, w2, w3, w4;
+                if (q == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
+                else if (q == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+                else if (q == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+                else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
+                d4[x] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+            }
+        }
+    }
+    if ((uint32_t)lane < h) dst[lane] = hb;
+    if (tk < n) dst[tk] = tb;
+}
+
 constexpr int LZLIT_G = 32;                        // lanes per literal run (8-lane groups, four runs in flight per warp, measured no faster)
 constexpr int LZLIT_SPLIT = 4;                     // CTAs that share the runs of one block
 constexpr uint32_t LZLIT_LONG = 4096;              // longer runs are copied by the whole CTA (at most 32 per block)
@@ -1946,6 +2010,8 @@ __device__ __forceinline__ bool lz_lit_tiny(const BlockDesc& B) {
     return B.n_seq <= 32 && B.lit_regen <= LZLIT_TINY;
 }
 
+// U: see copy_g2g (4 for a job of a few blocks, where the long runs of a block are what the kernel waits for)
+template <int U>
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     __shared__ uint32_t lq_n, lq_lp[40], lq_op[40], lq_ll[40];
     const uint32_t bi = blockIdx.x;
@@ -1974,7 +2040,11 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         return;
     }
     // one literal run (a few hundred bytes) per group of LZLIT_G lanes
-    const int grp = tid / LZLIT_G, lane = tid % LZLIT_G, ng = nt / LZLIT_G;
+    // (consecutive runs go to different CTAs: a block of a real genome has a handful of runs of tens of kilobytes, each copied
+    //  by the whole CTA that owns it)
+    //  (U == 1, a batch: the runs of a block stay with neighbouring warps -- dealt across CTAs k_lz_literals took 0.63 ms
+    //  instead of 0.52 on the 256-archive job)
+    const int lane = tid % LZLIT_G, ng = nt / LZLIT_G, grp = U > 1 ? (int)(threadIdx.x / LZLIT_G) * (int)gridDim.y + (int)blockIdx.y : tid / LZLIT_G;
     const uint32_t n = B.n_seq, base = B.seq_base;
     if (threadIdx.x == 0) lq_n = 0;
     __syncthreads();
@@ -2003,7 +2073,7 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         lp = nlp; op = nop; ll = nll; ml = nml;
     }
     __syncthreads();
-    for (uint32_t q = 0; q < lq_n; q++) copy_g2g(out + lq_op[q], lsrc + lq_lp[q], lq_ll[q], (int)threadIdx.x, (int)blockDim.x);
+    for (uint32_t q = 0; q < lq_n; q++) copy_g2g<U>(out + lq_op[q], lsrc + lq_lp[q], lq_ll[q], (int)threadIdx.x, (int)blockDim.x);
 }
 
 // One warp per tiny block, eight blocks per CTA: a CTA per block spent its time being launched (5.5 ms for the 2 x 10^6
@@ -2311,6 +2381,126 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
     }
 }
 
+// k_lz_small: the whole match stage of a SMALL job (one bacterial genome: a few hundred to a few thousand matches) in one CTA.
+// The rounds above cost a kernel launch (round 1) or a grid barrier (the others) plus a dozen dependent global loads each --
+// list entry, record, blocker's flag, index cells, bisection steps: ~8 us per round whatever the number of matches, 85 us for
+// the 107 matches and 7 rounds of the cfg1 fixture.  Here the records (position, length, resolved offset, done round, frame)
+// sit in shared memory, a round is a pass of the CTA over its pending matches and a __syncthreads, and only the copies touch
+// global memory.  Same readiness rule, same redirects, same hand-over to the finisher as lz_try / k_lz_resolve.
+constexpr uint32_t LZS_MAX = 8192;               // matches (the host sets J.lz_small when the job has no more, and an arena below 4 GB)
+constexpr int LZS_T = 1024;
+__host__ __device__ constexpr uint32_t lzs_smem_bytes(uint32_t n) { return ((n + 3u) & ~3u) * 24u; }
+
+__global__ void __launch_bounds__(LZS_T) k_lz_small(JobDev J) {
+    NAF_DYN_SMEM(uint32_t, lzs);
+    const uint32_t n = (uint32_t)J.n_seq, np = (n + 3u) & ~3u;
+    uint32_t* pos = lzs;                          // destination, relative to J.out
+    uint32_t* mlen = pos + np;
+    uint32_t* moff = mlen + np;                   // resolved offset (redirects add to it)
+    uint16_t* done = (uint16_t*)(moff + np);      // 0: pending, else the round that copied (or rejected) it
+    uint16_t* frm = done + np;
+    uint32_t* q_i = (uint32_t*)(frm + np);        // the matches a round may copy: index, then the offset to copy with
+    uint32_t* q_off = q_i + np;
+    __shared__ uint32_t q_n, q_big, s_pending[3];      // (three counters rotate: the one a round adds to is cleared two rounds earlier, while nobody reads it)
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t i = tid; i < n; i += LZS_T) {
+        const SeqRec& R = J.seq[i];
+        const BlockDesc& B = J.blocks[R.block];
+        pos[i] = (uint32_t)R.match_pos; mlen[i] = R.ml; frm[i] = (uint16_t)B.frame;
+        moff[i] = resolve_offset(J, R.off, R.block);
+        done[i] = J.frame_bad[B.frame] ? 1 : 0;
+    }
+    if (tid == 0) { s_pending[0] = s_pending[1] = s_pending[2] = 0; }
+    __shared__ uint32_t fr_first[64], fr_off[64];            // a single archive has a handful of frames: their first match and offset
+    const bool fr_cached = J.n_frames <= 64u;
+    if (fr_cached && (uint32_t)tid < J.n_frames) { fr_first[tid] = J.frames[tid].first_seq; fr_off[tid] = (uint32_t)J.frames[tid].dst_off; }
+    __syncthreads();
+    long long t_probe = 0, t_copy = 0, t0 = 0, t_begin = 0;      // (cycle accounting with NAFGPU_DEBUG_HUF=1)
+    SEQ_CLK(t_begin);
+    uint32_t prev_pending = n, handover = 0, round = 1;
+    for (;; round++) {
+        if (tid == 0) { q_n = 0; q_big = 0; s_pending[(round + 1) % 3] = 0; }
+        __syncthreads();
+        SEQ_CLK(t0);
+        uint32_t mine = 0;
+        for (uint32_t i = tid; i < n; i += LZS_T) {
+            if (done[i]) continue;
+            const uint32_t f = frm[i];
+            const uint32_t f_first = fr_cached ? fr_first[f] : J.frames[f].first_seq, f_off = fr_cached ? fr_off[f] : (uint32_t)J.frames[f].dst_off;
+            const uint32_t d = pos[i], ml = mlen[i];
+            uint32_t off = moff[i];
+            int verdict = 0;
+            for (int hop = 0; hop <= LZ_HOPS; hop++) {
+                if (off == 0 || off > d - f_off) { flag_error(J, f, zc::E_OFFSET); verdict = 2; break; }
+                const uint32_t sp = d - off, e = off < ml ? d : sp + ml;      // external source range [sp, e)
+                uint32_t lo = f_first, hi = i;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (pos[mid] + mlen[mid] > sp) hi = mid; else lo = mid + 1; }
+                uint32_t blocker = 0xFFFFFFFFu;
+                for (uint32_t j = lo; j < i && pos[j] < e; j++) {
+                    const uint32_t dn = done[j];
+                    if (dn == 0 || dn >= round) { blocker = j; break; }
+                }
+                if (blocker == 0xFFFFFFFFu) { verdict = 1; break; }
+                if (hop == LZ_HOPS || off < ml || pos[blocker] > sp || e > pos[blocker] + mlen[blocker]) break;      // cannot redirect: wait
+                off += moff[blocker];
+            }
+            moff[i] = off;                              // (only this thread writes it; others read it for their redirects: any
+                                                        //  value it ever had is a valid offset of this match)
+            if (verdict == 2) done[i] = (uint16_t)round;
+            else if (verdict == 1) {
+                // two queues in one array: matches a warp copies whole from the front, long disjoint ones (copied in pieces by all
+                // warps) from the back
+                const bool big = ml > 2048u && off >= ml;
+                const uint32_t slot = big ? np - 1u - atomicAdd(&q_big, 1u) : atomicAdd(&q_n, 1u);
+                q_i[slot] = i; q_off[slot] = off;
+            }
+            else mine++;
+        }
+        if (mine) atomicAdd(&s_pending[round % 3], mine);
+        __syncthreads();
+        SEQ_LAP(t_probe, t0);
+        // the copies of the round, a warp per match (a thread copying its own 40 bytes pays a round trip to memory per 8 of
+        // them, and the round lasts as long as its slowest copy); the long disjoint ones in 2 KB pieces dealt to all warps.
+        // No barrier in between: every piece is one round trip, all in flight together.
+        const uint32_t nq = q_n, nbig = q_big;
+        {
+            const uint32_t warp = (uint32_t)tid >> 5, NW = LZS_T / 32;
+            for (uint32_t t = warp; t < nq; t += NW) {
+                const uint32_t i = q_i[t], ml = mlen[i], off = q_off[t];
+                if (off >= ml) copy_g2g<4>(J.out + pos[i], J.out + pos[i] - off, ml, lane, 32);
+                else copy_long_match(J.out, pos[i], off, ml, lane, 32);
+            }
+            for (uint32_t t = 0; t < nbig; t++) {
+                const uint32_t i = q_i[np - 1u - t], ml = mlen[i], off = q_off[np - 1u - t], d = pos[i];
+                for (uint32_t pc = (warp + NW - (t & (NW - 1))) & (NW - 1); pc * 2048u < ml; pc += NW) {
+                    const uint32_t b = pc * 2048u, len = ml - b < 2048u ? ml - b : 2048u;
+                    copy_g2g<4>(J.out + d + b, J.out + d - off + b, len, lane, 32);
+                }
+            }
+        }
+        __syncthreads();                                // (the done flags are written after every copy of the round)
+        SEQ_LAP(t_copy, t0);
+        for (uint32_t t = tid; t < nq; t += LZS_T) done[q_i[t]] = (uint16_t)round;
+        for (uint32_t t = tid; t < nbig; t += LZS_T) done[q_i[np - 1u - t]] = (uint16_t)round;
+        __syncthreads();
+        const uint32_t pending = s_pending[round % 3];
+        if (tid == 0 && round - 1 < 24) J.lz_pending[round - 1] = pending;             // (matches still waiting after round 1, 2, ...)
+        if (pending == 0) break;
+        // the hand-over rule of k_lz_resolve, with this kernel's cost of a round
+        const uint32_t progress = prev_pending - pending;
+        if (round >= LZ_MIN_ROUNDS && pending > LZ_MIN_PENDING && round < 60000u &&
+            (uint64_t)pending * (1500u + pending / 2u) > (uint64_t)(progress ? progress : 1u) * J.fin_cost_us * 1000u) { handover = round; break; }
+        if (round >= 60000u) { handover = round; break; }             // (16-bit round numbers; unreachable with 8192 matches)
+        prev_pending = pending;
+    }
+    // what the finisher and the statistics read
+    for (uint32_t i = tid; i < n; i += LZS_T) J.seq_done[i] = done[i];
+    if (tid == 0) { *J.lz_rounds = round; if (handover) *J.lz_handover = handover; }
+    long long t_end = 0;
+    SEQ_CLK(t_end);
+    if (J.debug_seq && tid == 0) { J.debug_seq[5] = (unsigned long long)t_probe; J.debug_seq[6] = (unsigned long long)t_copy; J.debug_seq[7] = (unsigned long long)(t_end - t_begin); }
+}
+
 // k_lz_finish / k_lz_finish2: what k_lz_resolve leaves behind when its rounds stop paying (text-like sections -- quality
 // strings, ids -- where nearly every match feeds the next one: a dependency chain as long as the section has matches).
 // Walking such a chain in order costs hundreds of cycles per match on a GPU; instead the chain is cut at BYTE level, where
@@ -2365,11 +2555,15 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
         if (tid == 0) {
             const uint32_t f = fin_frame_of(J, c);
             s_f = f; s_bad = 0; s_unres = 0;
-            // first match of the frame that ends after the start of the chunk (matches are ordered by position)
-            const uint64_t cs = J.frames[f].dst_off + (uint64_t)(c - J.fin_chunk_first[f]) * FIN_C;
-            uint32_t lo = J.frames[f].first_seq, hi = lo + J.frames[f].n_seq;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (J.seq[mid].match_pos + J.seq[mid].ml > cs) hi = mid; else lo = mid + 1; }
-            s_mi = lo;
+            // first match of the frame that ends after the start of the chunk: k_lz_index's cell for the chunk's first 4 KB
+            // (a bisection over the frame's matches here cost 24 dependent loads with the CTA waiting)
+            if (!J.lz_small) s_mi = J.frames[f].n_seq ? J.lz_idx[(size_t)c * LZ_IDX_PER_CHUNK + f] : J.frames[f].first_seq;
+            else {                                   // (a small job's rounds ran in k_lz_small: no index)
+                const uint64_t cs = J.frames[f].dst_off + (uint64_t)(c - J.fin_chunk_first[f]) * FIN_C;
+                uint32_t lo = J.frames[f].first_seq, hi = lo + J.frames[f].n_seq;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (J.seq[mid].match_pos + J.seq[mid].ml > cs) hi = mid; else lo = mid + 1; }
+                s_mi = lo;
+            }
         }
         __syncthreads();
         const uint32_t f = s_f, mi = s_mi;
@@ -2477,23 +2671,33 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
             const uint32_t p = ptr[e];
             const bool ext = (extbit[p >> 5] >> (p & 31)) & 1u;
             if (p != e) {
-                if (ext) { g[e] = (e - p) + __ldcg(g + p); unres++; }       // (g[p] was written by this CTA before the barriers above)
+                if (ext) { g[e] = e - p; unres++; }                         // same value as its root p, which level 2 resolves
                 else out_c0[e] = val[p];                                    // roots are not written here: no hazard
             } else if (ext) unres++;
         }
         if (unres) atomicAdd(&s_unres, unres);
         __syncthreads();
+        if (s_unres) {                                                      // (uniform) the chunk's external roots, for level 2
+            uint32_t* xb = J.fin_ext + (size_t)c * (FIN_C / 32);
+            for (uint32_t e = tid; e < FIN_C / 32; e += FIN_T) xb[e] = extbit[e];
+        }
         if (tid == 0 && s_unres) { J.fin_chunk_flag[c] = 1; atomicAdd(J.fin_unresolved, s_unres); }
     }
 }
 
-// Level 2: see above.  Cooperative; every round scans the distances of the chunks that still have unresolved bytes.
+// Level 2: see above.  Cooperative.  Only the ROOTS take part in the rounds (the chunk's bitmap of external roots, compacted
+// per 8 KB tile): in a text-like section the offsets are a few hundred bytes, so a chunk has a few hundred roots at its
+// start and 60 000 bytes hanging off them -- jumping every byte (round 1 of this kernel's life) moved 205 M distances per
+// round for a 10^6-read archive, 15 ms; the roots are 1.5 M.  A last pass gives every other byte the value of its root.
+constexpr uint32_t FIN2_TILE = FIN2_T * 32;      // bytes of a chunk whose roots are compacted at a time (one bitmap word per thread)
+
 __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
     if (*J.lz_handover == 0 || *J.fin_unresolved == 0) return;
-    __shared__ uint32_t s_left;
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint32_t s_left, s_wsum[FIN2_T / 32];
+    __shared__ uint16_t s_root[FIN2_TILE];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     volatile uint32_t* G = J.fin_g;
-    volatile uint32_t* flag = J.fin_chunk_flag;
+    volatile uint32_t* flag = J.fin_chunk_flag;       // 1: unresolved roots; 2: roots final, the bytes under them not yet written; 0: final
     for (uint32_t round = 0;; round++) {
         // three counters rotate: this round adds to `cur` and reads it after the barrier (a slow CTA as late as during the next
         // round); the NEXT round's counter is cleared now, while nobody reads it or adds to it
@@ -2501,49 +2705,82 @@ __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
         if (blockIdx.x == 0 && tid == 0) J.fin_count[clr] = 0;
         uint32_t left_total = 0;
         for (uint32_t c = blockIdx.x; c < J.fin_total_chunks; c += gridDim.x) {
-            if (flag[c] == 0) continue;                                     // (uniform)
+            if (flag[c] != 1) continue;                                     // (uniform)
             __syncthreads();
             if (tid == 0) s_left = 0;
-            __syncthreads();
             const uint32_t f = fin_frame_of(J, c);
             const uint32_t cf = J.fin_chunk_first[f];
             const size_t gb = (size_t)J.fin_g_base[f];                       // the frame's entries in fin_g
-            const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
+            const uint64_t f0 = J.frames[f].dst_off;
             const uint64_t crel = (uint64_t)(c - cf) * FIN_C;               // chunk start relative to the frame
-            const uint32_t cn = (uint32_t)((crel + FIN_C < fend - f0) ? FIN_C : fend - f0 - crel);
+            const uint32_t* xb = J.fin_ext + (size_t)c * (FIN_C / 32);
             uint32_t left = 0;
-            for (uint32_t e = tid; e < cn; e += FIN2_T) {
-                const uint32_t dist = G[gb + crel + e];
-                if (dist == 0) continue;
-                const uint64_t prel = crel + e;                             // my position and my source, relative to the frame
-                if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[gb + crel + e] = 0; continue; }
-                const uint64_t srel = prel - dist;
-                const uint32_t sc = cf + (uint32_t)(srel >> 16);
-                uint32_t gs = 0;
-                if (flag[sc] != 0) gs = G[gb + srel];
-                if (gs == 0) {                                              // the source is final: take its value
-                    __threadfence();
-                    const uint8_t v = *(volatile const uint8_t*)(J.out + f0 + srel);
-                    J.out[f0 + prel] = v;
-                    __threadfence();
-                    G[gb + crel + e] = 0;
-                } else {                                                    // adopt the source's source
-                    const uint64_t nd = (uint64_t)dist + gs;
-                    if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[gb + crel + e] = 0; continue; }
-                    G[gb + crel + e] = (uint32_t)nd;
-                    left++;
+            for (uint32_t t0 = 0; t0 < FIN_C; t0 += FIN2_TILE) {
+                const uint32_t word = xb[(t0 >> 5) + tid];
+                if (!__syncthreads_or(word != 0)) continue;                  // (roots sit at the start of a chunk: most tiles have none)
+                // compact the tile's roots: exclusive scan of the words' bit counts
+                const uint32_t cnt = __popc(word);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += v; }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                uint32_t before = inc - cnt, total = 0;
+                for (uint32_t w = 0; w < FIN2_T / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; total += v; }
+                for (uint32_t m = word, k = before; m; m &= m - 1, k++) s_root[k] = (uint16_t)(t0 + tid * 32 + (uint32_t)(__ffs(m) - 1));
+                __syncthreads();
+                for (uint32_t k = tid; k < total; k += FIN2_T) {
+                    const uint32_t e = s_root[k];
+                    const uint32_t dist = G[gb + crel + e];
+                    if (dist == 0) continue;                                // final since an earlier round
+                    const uint64_t prel = crel + e;                         // my position and my source, relative to the frame
+                    if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[gb + crel + e] = 0; continue; }
+                    const uint64_t srel = prel - dist;
+                    const uint32_t sc = cf + (uint32_t)(srel >> 16);
+                    uint32_t gs = 0;
+                    if (flag[sc] != 0) gs = G[gb + srel];
+                    if (gs == 0) {                                          // the source is final: take its value
+                        __threadfence();
+                        const uint8_t v = *(volatile const uint8_t*)(J.out + f0 + srel);
+                        J.out[f0 + prel] = v;
+                        __threadfence();
+                        G[gb + crel + e] = 0;
+                    } else {                                                // adopt the source's source (a root's, or the root of a byte under one)
+                        const uint64_t nd = (uint64_t)dist + gs;
+                        if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[gb + crel + e] = 0; continue; }
+                        G[gb + crel + e] = (uint32_t)nd;
+                        left++;
+                    }
                 }
+                __syncthreads();                                            // the list is reused by the next tile
             }
             if (left) atomicAdd(&s_left, left);
             __syncthreads();
             if (tid == 0) {
-                if (s_left == 0) { __threadfence(); flag[c] = 0; }          // every byte of the chunk is final now
+                if (s_left == 0) { __threadfence(); flag[c] = 2; }          // every root of the chunk is final now
                 left_total += s_left;
             }
         }
         if (tid == 0 && left_total) atomicAdd(&J.fin_count[cur], left_total);
         NAF_GRID_SYNC();
         if (J.fin_count[cur] == 0) break;
+    }
+    // every root is final and written (the barrier above): the bytes under a root take its value
+    for (uint32_t c = blockIdx.x; c < J.fin_total_chunks; c += gridDim.x) {
+        if (flag[c] == 0) continue;
+        const uint32_t f = fin_frame_of(J, c);
+        const uint64_t f0 = J.frames[f].dst_off, fend = f0 + J.frames[f].dst_size;
+        const uint64_t crel = (uint64_t)(c - J.fin_chunk_first[f]) * FIN_C;
+        const uint32_t cn = (uint32_t)((crel + FIN_C < fend - f0) ? FIN_C : fend - f0 - crel);
+        const uint32_t* g = J.fin_g + J.fin_g_base[f] + crel;
+        uint8_t* o = J.out + f0 + crel;
+        for (uint32_t e0 = tid * 4; e0 < cn; e0 += FIN2_T * 4) {           // (cn may end inside the last group: fin_g is padded per frame)
+            const uint4 d = __ldcg((const uint4*)(g + e0));
+            const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+                if (dd[k] != 0 && e0 + k < cn && dd[k] <= e0 + k) o[e0 + k] = __ldcg(o + e0 + k - dd[k]);
+        }
     }
 }
 
@@ -2623,7 +2860,8 @@ void lz_finish_ctas(int device, uint32_t* level1, uint32_t* level2) {
 #endif
 }
 
-int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev) {
+int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev,
+                      cudaStream_t st3, cudaEvent_t fork3, cudaEvent_t join3) {
     StageEvents none;
     if (!ev) ev = &none;
     int launches = 0;
@@ -2635,6 +2873,16 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) { cudaEventRecord(fork, st); cudaStreamWaitEvent(st2, fork, 0); }
     if (J.n_huf_items) {
         NAF_LAUNCH(k_build_tables<1>, J.n_blocks, 32, 0, sb, J); launches++;
+        // a job with both kinds of streams (one archive: the big blocks of the sequence, the short ids / lengths / last block):
+        // the two decodes side by side -- for a single small archive this branch is the critical path (25 us each)
+        const bool side = st2 && st3 && J.n_huf_big && J.n_huf_items > J.n_huf_big;
+        (void)side;
+        if (side) {
+            cudaEventRecord(fork3, sb); cudaStreamWaitEvent(st3, fork3, 0);
+            const uint32_t smem = huf_fixed_smem(HUF_T_SMALL) + ((J.max_huf_small + 15 + 16 + 16 + 15) & ~15u);
+            NAF_LAUNCH((k_huf_decode<HUF_T_SMALL>), J.n_huf_items - J.n_huf_big, HUF_T_SMALL, smem, st3, J, J.huf_items + J.n_huf_big); launches++;
+            cudaEventRecord(join3, st3);
+        }
         if (J.n_huf_big) {   // items [0, n_huf_big): the streams of 4-stream blocks, four consecutive items (= one cluster) per block
             const uint32_t smem = hb_smem_bytes(J.max_huf_stream);
             if (!st2) ev->kernel_begin();
@@ -2653,7 +2901,8 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
             }
             if (!st2) ev->kernel_end();
         }
-        if (J.n_huf_items > J.n_huf_big) {
+        if (side) cudaStreamWaitEvent(sb, join3, 0);
+        else if (J.n_huf_items > J.n_huf_big) {
             const uint32_t smem = huf_fixed_smem(HUF_T_SMALL) + ((J.max_huf_small + 15 + 16 + 16 + 15) & ~15u);
             NAF_LAUNCH((k_huf_decode<HUF_T_SMALL>), J.n_huf_items - J.n_huf_big, HUF_T_SMALL, smem, sb, J, J.huf_items + J.n_huf_big); launches++;
         }
@@ -2674,9 +2923,17 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
     if (J.tiny_blocks) { NAF_LAUNCH(k_lz_literals_tiny, (J.n_blocks + 7) / 8, 256, 0, st, J); launches++; }
-    NAF_LAUNCH(k_lz_literals, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; ev->mark();
+    if (J.n_blocks <= 64u) { NAF_LAUNCH(k_lz_literals<4>, dim3(J.n_blocks, 4 * LZLIT_SPLIT), 256, 0, st, J); }
+    else { NAF_LAUNCH(k_lz_literals<1>, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); }
+    launches++; ev->mark();
     if (J.n_seq > 0) {
         // (small jobs: one entry per thread, as many CTAs as entries need -- latency; big jobs: LZ_U entries per thread)
+        if (J.lz_small) {
+            const uint32_t smem = lzs_smem_bytes((uint32_t)J.n_seq);
+            NAF_SET_MAX_SMEM(k_lz_small, smem);
+            NAF_LAUNCH(k_lz_small, 1, LZS_T, smem, st, J); launches++;
+            ev->mark(); ev->mark();
+        } else {
         uint32_t grid = (uint32_t)((J.n_seq + LZ_CTA - 1) / LZ_CTA);
         if (grid > 148u * 8u) grid = std::max<uint32_t>(148u * 8u, (uint32_t)((J.n_seq + LZ_CTA * LZ_U - 1) / (LZ_CTA * LZ_U)));
         if (grid > 148u * 64u) grid = 148u * 64u;
@@ -2691,6 +2948,8 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
         ev->mark();
+        }
+        JobDev Jc = J;
         const uint32_t fin_grid = J.fin_total_chunks < J.fin_ctas ? J.fin_total_chunks : J.fin_ctas;
         if (fin_grid && J.n_seq > LZ_MIN_PENDING) {       // (k_lz_resolve never hands over fewer than LZ_MIN_PENDING matches)
             NAF_SET_MAX_SMEM(k_lz_finish, FIN_SMEM);

@@ -23,6 +23,7 @@ struct JobDev {
     uint8_t* huf_weights;             // n_huf_slots x 256 weights (k_build_tables decodes every tree description once)
     uint8_t* huf_meta;                // n_huf_slots x {n_symbols - 1, max_bits}; max_bits == 0: bad tree
     zf::SeqRec* seq;                  // one 32-byte record per sequence (written by k_decode_sequences / k_lz_literals)
+    uint32_t lz_small;                // nonzero: the match stage runs in one CTA (k_lz_small): at most 8192 matches, arena below 4 GB
     uint32_t tiny_blocks;             // nonzero: blocks of at most 32 sequences / 2 KiB of literals go through the warp-per-block kernels
     uint32_t seq_stage_bytes;         // shared-memory staging size of k_decode_sequences (largest sequence bitstream, capped)
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
@@ -44,6 +45,7 @@ struct JobDev {
     uint32_t fin_total_chunks;
     uint32_t fin_ctas, fin2_ctas;     // grid sizes (one CTA per SM; co-resident CTAs of the cooperative level 2)
     uint32_t* fin_g;                  // one u32 per byte of every frame: distance of an unresolved byte to its source, 0 = final
+    uint32_t* fin_ext;                // [fin_total_chunks x 2048] bitmap of a chunk's external roots (written by level 1 for chunks it flags)
     const uint64_t* fin_g_base;       // [n_frames] first entry of every frame in fin_g (host-filled; frames are packed, 16-entry aligned)
     uint32_t* fin_chunk_flag;         // [fin_total_chunks] chunk has unresolved bytes (zeroed every run)
     uint32_t* fin_unresolved;         // unresolved bytes after level 1
@@ -65,7 +67,9 @@ struct JobDev {
 // Enqueues the whole zstd stage for a job on `stream` (no host synchronisation).
 // Returns the number of kernels launched.  `ev` (optional) gets one mark per stage (7 stages).
 // st2 (optional) runs the Huffman branch concurrently with the FSE branch; fork/join are events owned by the caller.
-int launch_zstd_stage(const JobDev& job, cudaStream_t stream, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev);
+// st3 (optional, with st2): the small Huffman streams run beside the big ones instead of after them (fork3/join3).
+int launch_zstd_stage(const JobDev& job, cudaStream_t stream, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev,
+                      cudaStream_t st3 = 0, cudaEvent_t fork3 = nullptr, cudaEvent_t join3 = nullptr);
 // Co-resident CTAs (whole device) for the cooperative match-resolution kernel.
 uint32_t lz_resolve_max_ctas(int device);
 void lz_finish_ctas(int device, uint32_t* level1, uint32_t* level2);

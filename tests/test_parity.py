@@ -200,9 +200,12 @@ def _generations(rng, gens, blen, far_every=0, long_every=0):
     return bytes(q)
 
 
-def test_ordered_finisher_on_dependency_chains(backend):
+@pytest.mark.parametrize("lz_small", ["8192", "0"])
+def test_ordered_finisher_on_dependency_chains(backend, monkeypatch, lz_small):
     """Sections that are one long LZ dependency chain are handed to k_lz_finish (shared-memory ring); the job stats
-    say so, and the bytes must still be libzstd's."""
+    say so, and the bytes must still be libzstd's.  Small jobs run their rounds in one CTA (k_lz_small: up to 8192 matches,
+    2048 by default), the others in k_lz_first / k_lz_resolve: both hand over here (frames of 3000 to 40000 matches)."""
+    monkeypatch.setenv("NAFGPU_LZ_SMALL", lz_small)
     ctx = N.shared_context(0, library(backend))
     rng = np.random.default_rng(7)
     gens = 3000 if backend == "emul" else 40000
@@ -328,6 +331,22 @@ def test_both_huffman_kernels(backend, monkeypatch, block_min):
     p = bytes(np.random.default_rng(3).integers(0, 16, size=300_000).astype(np.uint8))        # fixed-length codes
     frame = K.zstd_frame(p, 3)
     assert ctx.zstd_decompress(frame, len(p)) == p
+
+
+def test_match_rounds_of_small_jobs_in_both_kernels(backend, monkeypatch):
+    """A job of at most 2048 matches resolves them in one CTA (k_lz_small: every other test with a small input); the same
+    inputs through the general rounds (k_lz_index, k_lz_first, k_lz_resolve) here."""
+    monkeypatch.setenv("NAFGPU_LZ_SMALL", "0")
+    for name in ("NZ_AAEN01000029.naf", "phix.naf", "LuxC.naf", "masked.naf"):
+        check_parity(backend, read_golden(name), name + ", general rounds")
+    check_parity(backend, K.genome(5, 400_000, level=19), "genome, general rounds")
+    monkeypatch.delenv("NAFGPU_LZ_SMALL")
+    ctx = N.shared_context(0, library(backend))
+    monkeypatch.setenv("NAFGPU_LZ_SMALL", "8192")
+    check_parity(backend, K.genome(6, 1_500_000 if backend != "emul" else 600_000, level=19), "genome, one CTA, several matches per thread")
+    monkeypatch.delenv("NAFGPU_LZ_SMALL")
+    res, d = check_parity(backend, K.genome(5, 400_000, level=19), "genome, one CTA")
+    assert ctx.stats().lz_rounds >= 1 and ctx.stats().n_sequences <= 2048
 
 
 @pytest.mark.parametrize("tiny", ["0", "1"])

@@ -4,9 +4,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _cases as K
 import nafcodec_b200 as N
-mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 20
+fastq = len(sys.argv) > 1 and sys.argv[1] == "fastq"          # python tools/lz_probe.py fastq [reads] [quality 0/1]
+mbp = float(sys.argv[2 if fastq else 1]) if len(sys.argv) > (2 if fastq else 1) else 20
 p = os.path.join(ROOT, "bench_cache", "cfg3_n250000000_s3_l19.naf")
-data = open(p, "rb").read() if mbp >= 250 and os.path.exists(p) else K.cfg3_chromosome(int(mbp * 1e6), workers=0)
+if fastq:
+    data = K.cfg4_fastq(int(mbp))
+else:
+    data = open(p, "rb").read() if mbp >= 250 and os.path.exists(p) else K.cfg3_chromosome(int(mbp * 1e6), workers=0)
 ctx = N.Context(0)
 arc = N.parse_archive(data)
 ctx.prepare([arc]); ctx.sync()
