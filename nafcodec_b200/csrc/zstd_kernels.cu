@@ -1955,9 +1955,15 @@ __device__ __forceinline__ void copy_g2g_plain(uint8_t* __restrict__ dst, const 
 // 4 where a lone CTA or warp copies kilobytes and would otherwise pay a round trip to memory per chunk (a single small
 // archive): every load of a pass is issued before its first store -- head and tail bytes (fewer than 16 each: one per lane)
 // and up to U chunks per lane: one round trip for a match of up to U x nlanes x 16 bytes.  nlanes >= 32.
+template <int U>
+__device__ __forceinline__ void copy_g2g_1rt(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes);
 template <int U = 1>
 __device__ __forceinline__ void copy_g2g(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
-    if (U == 1) { copy_g2g_plain(dst, src, n, lane, nlanes); return; }
+    if (U == 1) copy_g2g_plain(dst, src, n, lane, nlanes);
+    else copy_g2g_1rt<U>(dst, src, n, lane, nlanes);
+}
+template <int U>
+__device__ __forceinline__ void copy_g2g_1rt(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, int lane, int nlanes) {
     if (n < 64) {                                      // both bytes of a lane loaded before either is stored
         const uint32_t k0 = lane, k1 = lane + nlanes;
         uint8_t v0 = 0, v1 = 0;
@@ -2069,7 +2075,7 @@ __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
         if (ll > LZLIT_LONG && B.lit_type != LT_RLE) {                    // a long run (often the literals after the last sequence of a block
             if (lane == 0) { const uint32_t q = atomicAdd(&lq_n, 1u); lq_lp[q] = lp; lq_op[q] = op; lq_ll[q] = ll; }   // with few sequences): whole CTA
         } else if (B.lit_type == LT_RLE) for (uint32_t k = lane; k < ll; k += LZLIT_G) out[op + k] = rle;
-        else copy_g2g(out + op, lsrc + lp, ll, lane, LZLIT_G);
+        else copy_g2g(out + op, lsrc + lp, ll, lane, LZLIT_G);            // (head, body and tail loaded together, copy_g2g_1rt<1>: measured the same 0.52 ms on the 256-archive job)
         lp = nlp; op = nop; ll = nll; ml = nml;
     }
     __syncthreads();
@@ -2689,6 +2695,7 @@ __global__ void __launch_bounds__(FIN_T) k_lz_finish(JobDev J) {
 // per 8 KB tile): in a text-like section the offsets are a few hundred bytes, so a chunk has a few hundred roots at its
 // start and 60 000 bytes hanging off them -- jumping every byte (round 1 of this kernel's life) moved 205 M distances per
 // round for a 10^6-read archive, 15 ms; the roots are 1.5 M.  A last pass gives every other byte the value of its root.
+constexpr uint32_t FIN2_U = 8;                   // roots per thread between two fences
 constexpr uint32_t FIN2_TILE = FIN2_T * 32;      // bytes of a chunk whose roots are compacted at a time (one bitmap word per thread)
 
 __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
@@ -2729,27 +2736,45 @@ __global__ void __launch_bounds__(FIN2_T) k_lz_finish2(JobDev J) {
                 for (uint32_t w = 0; w < FIN2_T / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; total += v; }
                 for (uint32_t m = word, k = before; m; m &= m - 1, k++) s_root[k] = (uint16_t)(t0 + tid * 32 + (uint32_t)(__ffs(m) - 1));
                 __syncthreads();
-                for (uint32_t k = tid; k < total; k += FIN2_T) {
-                    const uint32_t e = s_root[k];
-                    const uint32_t dist = G[gb + crel + e];
-                    if (dist == 0) continue;                                // final since an earlier round
-                    const uint64_t prel = crel + e;                         // my position and my source, relative to the frame
-                    if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[gb + crel + e] = 0; continue; }
-                    const uint64_t srel = prel - dist;
-                    const uint32_t sc = cf + (uint32_t)(srel >> 16);
-                    uint32_t gs = 0;
-                    if (flag[sc] != 0) gs = G[gb + srel];
-                    if (gs == 0) {                                          // the source is final: take its value
-                        __threadfence();
-                        const uint8_t v = *(volatile const uint8_t*)(J.out + f0 + srel);
-                        J.out[f0 + prel] = v;
-                        __threadfence();
-                        G[gb + crel + e] = 0;
-                    } else {                                                // adopt the source's source (a root's, or the root of a byte under one)
-                        const uint64_t nd = (uint64_t)dist + gs;
-                        if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[gb + crel + e] = 0; continue; }
-                        G[gb + crel + e] = (uint32_t)nd;
-                        left++;
+                // FIN2_U roots per thread at a time, so that the two fences (sources seen final -> their bytes; my bytes -> my
+                // zeroed distances) are paid once per batch instead of once per root (10.4 ms -> see profiles for a 10^6-read archive)
+                for (uint32_t k0 = tid; k0 < total; k0 += FIN2_T * FIN2_U) {
+                    uint32_t re[FIN2_U], rd[FIN2_U], rs[FIN2_U];            // root, its distance, what to do: 0 nothing, 1 take the source's byte, 2 adopt
+                    uint8_t rv[FIN2_U];
+#pragma unroll
+                    for (uint32_t u = 0; u < FIN2_U; u++) {
+                        const uint32_t k = k0 + u * FIN2_T;
+                        rs[u] = 0; re[u] = 0; rd[u] = 0; rv[u] = 0;
+                        if (k >= total) continue;
+                        const uint32_t e = s_root[k];
+                        const uint32_t dist = G[gb + crel + e];
+                        if (dist == 0) continue;                            // final since an earlier round
+                        const uint64_t prel = crel + e;                     // my position and my source, relative to the frame
+                        if (dist > prel) { flag_error(J, f, zc::E_OFFSET); G[gb + crel + e] = 0; continue; }
+                        const uint64_t srel = prel - dist;
+                        const uint32_t sc = cf + (uint32_t)(srel >> 16);
+                        uint32_t gs = 0;
+                        if (flag[sc] != 0) gs = G[gb + srel];
+                        re[u] = e;
+                        if (gs == 0) { rs[u] = 1; rd[u] = dist; }
+                        else {                                              // adopt the source's source (a root's, or the root of a byte under one)
+                            const uint64_t nd = (uint64_t)dist + gs;
+                            if (nd > 0xFFFFFFFFull) { flag_error(J, f, zc::E_SIZE); G[gb + crel + e] = 0; continue; }
+                            rs[u] = 2; rd[u] = (uint32_t)nd;
+                        }
+                    }
+                    __threadfence();                                        // a source seen final has its byte written
+#pragma unroll
+                    for (uint32_t u = 0; u < FIN2_U; u++)
+                        if (rs[u] == 1) rv[u] = *(volatile const uint8_t*)(J.out + f0 + crel + re[u] - rd[u]);
+#pragma unroll
+                    for (uint32_t u = 0; u < FIN2_U; u++)
+                        if (rs[u] == 1) J.out[f0 + crel + re[u]] = rv[u];
+                    __threadfence();                                        // my bytes before my zeroed distances
+#pragma unroll
+                    for (uint32_t u = 0; u < FIN2_U; u++) {
+                        if (rs[u] == 1) G[gb + crel + re[u]] = 0;
+                        else if (rs[u] == 2) { G[gb + crel + re[u]] = rd[u]; left++; }
                     }
                 }
                 __syncthreads();                                            // the list is reused by the next tile
