@@ -20,7 +20,16 @@
 #define NAF_LAUNCH_COOP(kernel, grid, block, stream, arg) \
     do { void* _args[] = {(void*)&(arg)}; cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(block), _args, 0, (stream)); } while (0)
 #define NAF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define NAF_SET_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+// The attribute belongs to the function (per device), not to the launch: contexts on several host threads (pipeline lanes) launch
+// the same kernels with job-dependent sizes, and a lane that LOWERED the limit between another lane's call here and its launch
+// made that launch fail with "invalid argument".  The limit only ever grows.
+#include <mutex>
+#define NAF_SET_MAX_SMEM(kernel, bytes) do { \
+    static std::mutex _m; static int _cur[64]; \
+    int _d = 0; cudaGetDevice(&_d); \
+    std::lock_guard<std::mutex> _g(_m); \
+    if ((int)(bytes) > _cur[_d & 63]) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); _cur[_d & 63] = (int)(bytes); } \
+} while (0)
 #define NAF_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char _naf_dyn_smem[]; type* name = reinterpret_cast<type*>(_naf_dyn_smem)
 #endif
 

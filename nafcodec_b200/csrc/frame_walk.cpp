@@ -180,6 +180,8 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
             b.seq_src = q;
         }
         known_total += b.known_regen;
+        if (zf::needs_seq_kernel(b)) plan.big_seq.push_back((uint32_t)plan.blocks.size());
+        if (!zf::tiny_lit_block(b)) plan.big_lit.push_back((uint32_t)plan.blocks.size());
         plan.blocks.push_back(b);
         p += content;
         if (last) break;

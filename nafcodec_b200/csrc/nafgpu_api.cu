@@ -121,10 +121,10 @@ void parallel_for(size_t n, unsigned max_threads, F fn) {
 struct nafgpu_ctx {
     int device = 0;
     cudaStream_t st = 0, st2 = 0, st3 = 0;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr, ev_block = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr, ev_fork4 = nullptr, ev_join4 = nullptr, ev_block = nullptr;
     std::string err;
     DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, lzidx, scanagg, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
-    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
+    size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0, o_bigseq = 0, o_biglit = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
     PinBuf stage, result, misc_host, text_host, text_stage, pack_host;
     fw::JobPlan plan;                  // frames, Huffman items and totals of the job (block descriptors live in the tasks)
     std::vector<WalkTask> tasks;       // [0, n_tasks) belong to the current job
@@ -176,7 +176,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     CUDA_TRY(c, cudaMemsetAsync(c->arena.p, 0, c->counts_size, st));
     if (c->z2_size) CUDA_TRY(c, cudaMemsetAsync((uint8_t*)c->arena.p + c->z2_off, 0, c->z2_size, st));
     // profiled runs (ev != null) are serial so that every stage has its own interval
-    int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev, c->st3, c->ev_fork3, c->ev_join3);
+    int launches = zk::launch_zstd_stage(c->J, st, ev ? (cudaStream_t)0 : c->st2, c->ev_fork, c->ev_join, ev, c->st3, c->ev_fork3, c->ev_join3, c->ev_fork4, c->ev_join4);
     launches += nk::launch_naf_stage((uint8_t*)c->arena.p, (const nk::NafDev*)((const uint8_t*)c->desc.p + c->o_naf), (uint32_t)c->arch.size(), c->max_records, c->max_scan, c->scanagg.p,
                                      c->max_chunks, c->max_text, c->any_mask, c->any_text_mask, c->J.status, st, ev);
     c->stats.kernel_launches = (uint32_t)launches;
@@ -252,6 +252,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         if (G.seq_total + L.seq_total > 0xFFFFFFF0ull || nb + L.blocks.size() > 0xFFFFFFF0ull) return fail(c, NAFGPU_ERR_UNSUPPORTED, "job has too many blocks or sequences: split the batch");
         for (zf::FrameDesc F : L.frames) { F.first_block += (uint32_t)T.bo; F.first_seq += T.so; G.frames.push_back(F); }
         for (zf::HufItem it : L.huf_items) { it.block += (uint32_t)T.bo; G.huf_items.push_back(it); }
+        for (uint32_t b : L.big_seq) G.big_seq.push_back(b + (uint32_t)T.bo);
+        for (uint32_t b : L.big_lit) G.big_lit.push_back(b + (uint32_t)T.bo);
         G.seq_total += L.seq_total; G.lit_total += L.lit_total - 16; G.n_slots += L.n_slots - 3; G.n_huf_slots += L.n_huf_slots;
         G.n_huf_blocks += L.n_huf_blocks; G.n_seq_blocks += L.n_seq_blocks; G.n_checksums += L.n_checksums;
         G.max_seq_section = std::max(G.max_seq_section, L.max_seq_section);
@@ -297,7 +299,9 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     }
     c->o_tiles = c->o_gbase + align_up((nf + 1) * 8, 16);
     c->o_big = c->o_tiles + align_up(tiles.size() * sizeof(zf::FsTile), 16);
-    const size_t stage_bytes = c->o_big + align_up(bigs.size() * sizeof(zf::FsBigFrame), 16);
+    c->o_bigseq = c->o_big + align_up(bigs.size() * sizeof(zf::FsBigFrame), 16);
+    c->o_biglit = c->o_bigseq + align_up(pl.big_seq.size() * 4, 16);
+    const size_t stage_bytes = c->o_biglit + align_up(pl.big_lit.size() * 4, 16);
     c->misc_words = 1 + 3 + 1 + 1 + 1 + 3 + nf + total_chunks + 8 + 24;
     bool ok = c->comp.ensure(comp_off + 64) && c->arena.ensure(c->arena_size) && c->lit.ensure(pl.lit_total + 64) &&
               c->desc.ensure(stage_bytes + 64) && c->fin_g.ensure((size_t)g_base[nf] * 4 + 256 + (size_t)total_chunks * 8192) &&
@@ -349,6 +353,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (nh) memcpy(sp + c->o_huf, pl.huf_items.data(), nh * sizeof(zf::HufItem));
     memcpy(sp + c->o_chunks, chunk_first.data(), (nf + 1) * 4);
     memcpy(sp + c->o_gbase, g_base.data(), (nf + 1) * 8);
+    if (!pl.big_seq.empty()) memcpy(sp + c->o_bigseq, pl.big_seq.data(), pl.big_seq.size() * 4);
+    if (!pl.big_lit.empty()) memcpy(sp + c->o_biglit, pl.big_lit.data(), pl.big_lit.size() * 4);
     if (!tiles.empty()) { memcpy(sp + c->o_tiles, tiles.data(), tiles.size() * sizeof(zf::FsTile)); memcpy(sp + c->o_big, bigs.data(), bigs.size() * sizeof(zf::FsBigFrame)); }
     if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
     uint64_t h2d = stage_bytes;
@@ -369,6 +375,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     // the others do not carry the shared memory of ... the others
     J.tiny_blocks = pl.n_tiny_seq_blocks >= 4096u ? 1u : 0u;
     if (const char* e = getenv("NAFGPU_TINY_BLOCKS")) J.tiny_blocks = (uint32_t)atoi(e);      // (tests: both paths on small inputs)
+    J.seq_big_list = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_bigseq); J.n_seq_big = (uint32_t)pl.big_seq.size();
+    J.lit_big_list = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_biglit); J.n_lit_big = (uint32_t)pl.big_lit.size();
     {   // one CTA for the matches of a small job (k_lz_small holds up to 8192; beyond ~2000 the general rounds are faster)
         uint64_t small_max = 2048;
         if (const char* e = getenv("NAFGPU_LZ_SMALL")) small_max = (uint64_t)std::min(8192, std::max(0, atoi(e)));      // (tests: either path)
@@ -445,6 +453,7 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_fork4, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join4, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { c->ev_block = nullptr; cudaGetLastError(); }
     for (int i = 0; i < N_STAGES + 3; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
@@ -468,6 +477,8 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+    if (c->ev_fork4) cudaEventDestroy(c->ev_fork4);
+    if (c->ev_join4) cudaEventDestroy(c->ev_join4);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     cudaStreamDestroy(c->st2);
     if (c->st3) cudaStreamDestroy(c->st3);

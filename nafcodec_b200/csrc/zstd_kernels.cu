@@ -526,10 +526,9 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
     __shared__ __align__(8) SeqCell stab[3][FSE_SLOT_CELLS];
     __shared__ uint32_t r_ov[2][SEQ_BATCH], r_ml[2][SEQ_BATCH], r_ll[2][SEQ_BATCH];
     __shared__ int s_left;
-    const uint32_t bi = blockIdx.x;
-    const BlockDesc& B = J.blocks[bi];
+    const uint32_t bi = J.tiny_blocks ? J.seq_big_list[blockIdx.x] : blockIdx.x;      // (with tiny_blocks: a list of the blocks that are not
+    const BlockDesc& B = J.blocks[bi];                                                  //  k_decode_sequences_tiny's -- 2 x 10^6 CTAs that exit at once cost 2.9 ms)
     if (B.btype != BT_COMPRESSED || B.n_seq == 0) return;
-    if (J.tiny_blocks && B.n_seq <= SEQ_BATCH) return;      // k_decode_sequences_tiny's
     if (J.frame_bad[B.frame]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     BlockState& S = J.bstate[bi];
@@ -638,7 +637,7 @@ __global__ void __launch_bounds__(SEQ_TINY_WARPS * 32) k_decode_sequences_tiny(J
     const uint32_t bi = blockIdx.x * SEQ_TINY_WARPS + warp;
     if (bi >= J.n_blocks) return;
     const BlockDesc& B = J.blocks[bi];
-    if (B.btype != BT_COMPRESSED || B.n_seq == 0 || B.n_seq > SEQ_BATCH) return;
+    if (!tiny_seq_block(B)) return;
     if (J.frame_bad[B.frame]) return;
     BlockState& S = J.bstate[bi];
     if (S.seq_bits_off >= B.src_size) { if (lane == 0) flag_error(J, B.frame, zc::E_SEQ_STREAM); return; }
@@ -2009,20 +2008,12 @@ constexpr int LZLIT_G = 32;                        // lanes per literal run (8-l
 constexpr int LZLIT_SPLIT = 4;                     // CTAs that share the runs of one block
 constexpr uint32_t LZLIT_LONG = 4096;              // longer runs are copied by the whole CTA (at most 32 per block)
 
-// tiny blocks (a FASTQ section flushed per record: 2 x 10^6 blocks of ~100 bytes): one warp each, see k_lz_literals_tiny
-constexpr uint32_t LZLIT_TINY = 2048;
-__device__ __forceinline__ bool lz_lit_tiny(const BlockDesc& B) {
-    if (B.btype != BT_COMPRESSED) return B.src_size <= LZLIT_TINY;
-    return B.n_seq <= 32 && B.lit_regen <= LZLIT_TINY;
-}
-
 // U: see copy_g2g (4 for a job of a few blocks, where the long runs of a block are what the kernel waits for)
 template <int U>
 __global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
     __shared__ uint32_t lq_n, lq_lp[40], lq_op[40], lq_ll[40];
-    const uint32_t bi = blockIdx.x;
+    const uint32_t bi = J.tiny_blocks ? J.lit_big_list[blockIdx.x] : blockIdx.x;       // (with tiny_blocks: the blocks that are not k_lz_literals_tiny's)
     const BlockDesc& B = J.blocks[bi];
-    if (J.tiny_blocks && lz_lit_tiny(B)) return;             // k_lz_literals_tiny's
     if (J.frame_bad[B.frame]) return;
     const BlockState& S = J.bstate[bi];
     uint8_t* out = J.out + S.out_off;
@@ -2090,7 +2081,7 @@ __global__ void __launch_bounds__(256) k_lz_literals_tiny(JobDev J) {
     const uint32_t bi = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (bi >= J.n_blocks) return;
     const BlockDesc& B = J.blocks[bi];
-    if (!lz_lit_tiny(B)) return;
+    if (!tiny_lit_block(B)) return;
     if (J.frame_bad[B.frame]) return;
     const BlockState& S = J.bstate[bi];
     uint8_t* out = J.out + S.out_off;
@@ -2886,7 +2877,7 @@ void lz_finish_ctas(int device, uint32_t* level1, uint32_t* level2) {
 }
 
 int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev,
-                      cudaStream_t st3, cudaEvent_t fork3, cudaEvent_t join3) {
+                      cudaStream_t st3, cudaEvent_t fork3, cudaEvent_t join3, cudaEvent_t fork4, cudaEvent_t join4) {
     StageEvents none;
     if (!ev) ev = &none;
     int launches = 0;
@@ -2935,8 +2926,19 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) cudaEventRecord(join, st2);
     else ev->mark();                                  // serial (profiled) order: the Huffman branch first
     NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
+    // a job with both kinds of blocks (a FASTQ archive: 2 x 10^6 tiny blocks and the ~130 big blocks of the ids, each one chain of
+    // ~10^4 sequences, 2.9 ms): the general kernel on the third stream, beside the tiny blocks' (2.0 ms)
+    const bool seq_side = st2 && st3 && J.tiny_blocks && J.n_seq_big;
+    (void)seq_side;
+    if (seq_side) {
+        cudaEventRecord(fork4, st); cudaStreamWaitEvent(st3, fork4, 0);
+        NAF_LAUNCH(k_decode_sequences, J.n_seq_big, 64, J.seq_stage_bytes, st3, J); launches++;
+        cudaEventRecord(join4, st3);
+    }
     if (J.tiny_blocks) { NAF_LAUNCH(k_decode_sequences_tiny, (J.n_blocks + SEQ_TINY_WARPS - 1) / SEQ_TINY_WARPS, SEQ_TINY_WARPS * 32, 0, st, J); launches++; }
-    NAF_LAUNCH(k_decode_sequences, J.n_blocks, 64, J.seq_stage_bytes, st, J); launches++; ev->mark();
+    if (seq_side) cudaStreamWaitEvent(st, join4, 0);
+    else if (!J.tiny_blocks || J.n_seq_big) { NAF_LAUNCH(k_decode_sequences, J.tiny_blocks ? J.n_seq_big : J.n_blocks, 64, J.seq_stage_bytes, st, J); launches++; }
+    ev->mark();
     NAF_LAUNCH(k_frame_scan, J.n_frames, FSCAN_T, 0, st, J); launches++;
     if (J.n_fs_tiles) {
         NAF_LAUNCH(k_fs_reduce, J.n_fs_tiles, FSCAN_T, 0, st, J);
@@ -2948,9 +2950,11 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     if (st2) { cudaStreamWaitEvent(st, join, 0); ev->mark(); }
     // (jobs of 10^5+ tiny blocks -- FASTQ flushed per record -- have a handful of runs per block: no split, fewer CTAs)
     if (J.tiny_blocks) { NAF_LAUNCH(k_lz_literals_tiny, (J.n_blocks + 7) / 8, 256, 0, st, J); launches++; }
-    if (J.n_blocks <= 64u) { NAF_LAUNCH(k_lz_literals<4>, dim3(J.n_blocks, 4 * LZLIT_SPLIT), 256, 0, st, J); }
-    else { NAF_LAUNCH(k_lz_literals<1>, dim3(J.n_blocks, J.n_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); }
-    launches++; ev->mark();
+    const uint32_t lit_blocks = J.tiny_blocks ? J.n_lit_big : J.n_blocks;
+    if (lit_blocks == 0) {}
+    else if (lit_blocks <= 64u) { NAF_LAUNCH(k_lz_literals<4>, dim3(lit_blocks, 4 * LZLIT_SPLIT), 256, 0, st, J); launches++; }
+    else { NAF_LAUNCH(k_lz_literals<1>, dim3(lit_blocks, lit_blocks > 16384u ? 1 : LZLIT_SPLIT), 256, 0, st, J); launches++; }
+    ev->mark();
     if (J.n_seq > 0) {
         // (small jobs: one entry per thread, as many CTAs as entries need -- latency; big jobs: LZ_U entries per thread)
         if (J.lz_small) {

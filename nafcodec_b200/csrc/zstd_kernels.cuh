@@ -25,6 +25,9 @@ struct JobDev {
     zf::SeqRec* seq;                  // one 32-byte record per sequence (written by k_decode_sequences / k_lz_literals)
     uint32_t lz_small;                // nonzero: the match stage runs in one CTA (k_lz_small): at most 8192 matches, arena below 4 GB
     uint32_t tiny_blocks;             // nonzero: blocks of at most 32 sequences / 2 KiB of literals go through the warp-per-block kernels
+    const uint32_t* seq_big_list;     // with tiny_blocks: the blocks k_decode_sequences takes (more than 32 sequences), host-built
+    const uint32_t* lit_big_list;     // with tiny_blocks: the blocks k_lz_literals takes
+    uint32_t n_seq_big, n_lit_big;
     uint32_t seq_stage_bytes;         // shared-memory staging size of k_decode_sequences (largest sequence bitstream, capped)
     uint32_t* seq_done;               // 0 = pending, else the pass that executed the match
     uint32_t* lz_idx;                 // per frame, per 4 KB of output: first match ending after the start of the cell (k_lz_index)
@@ -69,7 +72,7 @@ struct JobDev {
 // st2 (optional) runs the Huffman branch concurrently with the FSE branch; fork/join are events owned by the caller.
 // st3 (optional, with st2): the small Huffman streams run beside the big ones instead of after them (fork3/join3).
 int launch_zstd_stage(const JobDev& job, cudaStream_t stream, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join, StageEvents* ev,
-                      cudaStream_t st3 = 0, cudaEvent_t fork3 = nullptr, cudaEvent_t join3 = nullptr);
+                      cudaStream_t st3 = 0, cudaEvent_t fork3 = nullptr, cudaEvent_t join3 = nullptr, cudaEvent_t fork4 = nullptr, cudaEvent_t join4 = nullptr);
 // Co-resident CTAs (whole device) for the cooperative match-resolution kernel.
 uint32_t lz_resolve_max_ctas(int device);
 void lz_finish_ctas(int device, uint32_t* level1, uint32_t* level2);
