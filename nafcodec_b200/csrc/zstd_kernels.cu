@@ -2009,8 +2009,10 @@ constexpr int LZLIT_SPLIT = 4;                     // CTAs that share the runs o
 constexpr uint32_t LZLIT_LONG = 4096;              // longer runs are copied by the whole CTA (at most 32 per block)
 
 // U: see copy_g2g (4 for a job of a few blocks, where the long runs of a block are what the kernel waits for)
+// (the batch variant is held to 6 CTAs per SM: at 45 registers instead of 40 -- one more select for the block index -- it lost
+//  an eighth of its rate, 0.52 -> 0.60 ms on the 256-archive job)
 template <int U>
-__global__ void __launch_bounds__(256) k_lz_literals(JobDev J) {
+__global__ void __launch_bounds__(256, U == 1 ? 6 : 1) k_lz_literals(JobDev J) {
     __shared__ uint32_t lq_n, lq_lp[40], lq_op[40], lq_ll[40];
     const uint32_t bi = J.tiny_blocks ? J.lit_big_list[blockIdx.x] : blockIdx.x;       // (with tiny_blocks: the blocks that are not k_lz_literals_tiny's)
     const BlockDesc& B = J.blocks[bi];
