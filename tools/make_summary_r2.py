@@ -84,24 +84,27 @@ Stage times (serial profiled run, CUDA events on the launch stream; in the timed
 |---|---|---|---|---|---|---|---|---|---|---|
 {cfg_tbl}
 
-* cfg1 / cfg2 alone are latency-bound (13-15 kernel launches over an L2-resident working set): 0.20 / 0.24 ms, the same as round 1.  Their
-  serial stage times are in the JSON (`stage_ms_serial`): the FSE stage (one dependent chain per block, ~300 cycles per sequence) and the
-  dependency rounds of the LZ stage (a grid barrier each) are what is left; a single launch for the whole path was not built.
-* cfg3 (250 Mbp, ONE frame per section): 5.87 ms at the start of the round (the byte-level finisher took 3.6 ms of it) -> {d['configs'].get('cfg3_250Mbp', {}).get('device_ms', 0):.2f} ms.  The diverged repeat
+* cfg1 (the reference's own fixture) alone: 0.200 ms in round 1 and at the start of this round -> {d['configs']['cfg1_fixture']['device_ms']:.3f} ms (target 0.09): the match stage of a small job runs
+  in one CTA (`k_lz_small`), the small Huffman streams run beside the big ones, the Huffman weight chain was pipelined, long literal runs are copied with four
+  chunks per lane in flight (steps and what each gained: below).  cfg2 alone: 0.234 -> {d['configs']['cfg2_single']['device_ms']:.3f} ms (target 0.10): bound by the FSE chain of its longest block
+  (93 us: ~580 sequences x ~300 cycles) and four general LZ rounds (67 us); serial stage times are in the JSON (`stage_ms_serial`).
+* cfg3 (250 Mbp, ONE frame per section): 5.87 ms at the start of the round (the byte-level finisher took 3.6 ms of it) -> {d['configs']['cfg3_250Mbp']['device_ms']:.2f} ms.  The diverged repeat
   family makes 78 generations of matches; a round now costs ~25 us (blocker cache, four entries in flight per thread, position index for the probe).
-* cfg4 (10^6 reads, 2 x 10^6 tiny zstd blocks): device + prepare 107 ms at the start of the round (round 1: ~530 ms) -> see the table: tiled frame scan
-  (10.4 -> 0.27 ms), sliced NAF scans (3.5 -> 0.1 ms), threaded header walk with descriptors written straight into pinned staging (45 -> 23 ms).
-  What is left is the quality section's single dependency chain (byte-level finisher: 18 ms) and one two-warp CTA per tiny block in the FSE stage.
+* cfg4 (10^6 reads, 2 x 10^6 tiny zstd blocks): device + prepare 107 ms at the start of the round (round 1: ~530 ms) -> {d['configs']['cfg4_1M_all_fields']['device_plus_prepare_ms']:.1f} ms (target 60), {d['configs']['cfg4_1M_all_fields']['e2e']['ms']:.1f} ms for one synchronous
+  host-to-host call: tiled frame scan (10.4 -> 0.27 ms), sliced NAF scans (3.5 -> 0.1 ms), threaded header walk with descriptors written straight into pinned
+  staging (45 -> 23 ms), warp-per-block kernels for the tiny blocks with the general kernels running over lists of the others, level 2 of the finisher over
+  roots only (steps below).  What is left is the quality section's single dependency chain (finisher: 11.7 ms) and the header walk.
 * cfg5: 512 UNIQUE archives (2-6 Mbp, 1-4 records) in one job.
 
-## ncu launch list, 256-archive job (`profiles/r2_launches_job256.csv`: `ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 python tools/profile_job.py 256 3`; cold-cache, serialised: compare shares)
+## ncu launch list, 256-archive job (`profiles/r2_launches_job256.csv`: `ncu --metrics gpu__time_duration.sum --clock-control none -s 16 -c 32 python tools/profile_job.py 256 3`; cold-cache, serialised: compare shares)
 
 | kernel | launches in the window | us / launch | share of one decode |
 |---|---|---|---|
 {launch_tbl}
 
 `k_huf_decode_block` is {huf_share:.0f} % of the serialised decode here and {100 * rf['kernel_ms'] / tot:.0f} % of the serial stage sum in the bench line ({rf['kernel_ms']:.3f} of {tot:.3f} ms): they agree.
-`profiles/r2_launches_bench.csv` is the launch list of the `bench.py` command itself (first 60 KB).
+`profiles/r2_launches_bench.csv` is the launch list of the `bench.py` command itself (`python bench.py --steps 3 --warmup 3 --no-configs`, first 600 launches);
+`r2_launches_single_archive.csv` and `r2_launches_fastq_1M.csv` are those of one cfg1 / cfg2 archive and of the 10^6-read FASTQ archive.
 
 ## Scaling (weak: 256 archives per GPU per step, no collective; `profiles/r2_bench_n{{2,4,8}}.json`)
 
