@@ -407,21 +407,31 @@ __device__ __forceinline__ void seq_produce(RD& rd, const SeqCell* TLL, const Se
 
 // All 32 lanes of the producer warp call this; lanes 0..2 work.  Decodes `cnt` sequences from smem bit position P (counting
 // down); returns false once the stream is over-read (P below x_zero: corrupt) -- uniform, P is the same in every lane.
+// bits [o, o + k) for k <= 31 (field widths of the sequence codes: at most 31 extra bits, 9 state bits): one instruction less than
+// the general form, and no select
+__device__ __forceinline__ uint32_t smem_bits31(const uint32_t* sw, int o, uint32_t k) {
+    const uint32_t lo = sw[o >> 5], hi = sw[(o >> 5) + 1];
+    return __funnelshift_r(lo, hi, (uint32_t)o) & ~(0xFFFFFFFFu << k);
+}
+
 __device__ __forceinline__ bool seq_produce3(const uint32_t* sw, int& P, int x_zero, const SeqCell* T, uint32_t& state, int lane, uint32_t cnt,
                                              bool last_batch, uint32_t* r_mine) {
+    // the widths travel as  nb | add_bits << 8  = the top half of the cell's second word, as it is
+    const uint32_t j_last = last_batch ? cnt - 1u : 0xFFFFFFFFu;       // no state update after the last sequence of the block
+    const bool mine = lane < 3;
     for (uint32_t j = 0; j < cnt; j++) {
         if (P < x_zero) return false;
         const uint2 q = *(const uint2*)&T[state];                       // base_value | next_base (16) | nb (8) | add_bits (8)
-        const uint32_t a = q.y >> 24;
-        const uint32_t n = (last_batch && j + 1 == cnt) ? 0u : ((q.y >> 16) & 0xFFu);       // no state update after the last sequence
-        const uint32_t pk = lane < 3 ? (a | (n << 8)) : 0u;
+        uint32_t pk = mine ? q.y >> 16 : 0u;
+        if (j == j_last) pk &= 0xFF00u;
         const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, pk, 0), p1 = __shfl_sync(0xFFFFFFFFu, pk, 1), p2 = __shfl_sync(0xFFFFFFFFu, pk, 2);
-        const uint32_t tot = p0 + p1 + p2;                              // sums stay inside their bytes (3 x 31, 3 x 9)
+        const uint32_t tot = p0 + p1 + p2;                              // sums stay inside their bytes (3 x 9, 3 x 31)
         const uint32_t pre = (lane > 0 ? p0 : 0u) + (lane > 1 ? p1 : 0u);
         const int Pend = P - (int)(tot & 0xFFu) - (int)(tot >> 8);
-        if (lane < 3) {
-            r_mine[j] = q.x + smem_bits(sw, P - (int)(pre & 0xFFu) - (int)a, a);
-            state = (q.y & 0xFFFFu) + smem_bits(sw, Pend + (int)(pre >> 8), n);
+        if (mine) {
+            const uint32_t a = pk >> 8, n = pk & 0xFFu;
+            r_mine[j] = q.x + smem_bits31(sw, P - (int)(pre >> 8) - (int)a, a);
+            state = (q.y & 0xFFFFu) + smem_bits31(sw, Pend + (int)(pre & 0xFFu), n);
         }
         P = Pend;
     }
