@@ -113,6 +113,8 @@ typedef struct nafgpu_job_stats {
     float text_kernel_ms;               /* device time of the last nafgpu_job_format's kernels (CUDA events on the context's stream) */
     uint64_t text_bytes;                /* bytes of text the last nafgpu_job_format produced */
     uint32_t lz_pending[24];            /* matches still waiting after dependency round 1, 2, ... of the last fetched run (0 past the last round) */
+    uint32_t lz_flow;                   /* nonzero if the last fetched run finished its matches in the in-order kernel (k_lz_flow: chains of a few dozen generations) */
+    uint32_t _pad;
 } nafgpu_job_stats;
 
 /* ---- host-only helpers -------------------------------------------------------------------------------- */

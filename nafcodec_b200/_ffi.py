@@ -65,7 +65,8 @@ class JobStats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("n_stages", C.c_uint32), ("lz_handover", C.c_uint32),
                 ("lz_rounds", C.c_uint32), ("lz_unresolved", C.c_uint32),
-                ("text_kernel_ms", C.c_float), ("text_bytes", C.c_uint64), ("lz_pending", C.c_uint32 * 24)]
+                ("text_kernel_ms", C.c_float), ("text_bytes", C.c_uint64), ("lz_pending", C.c_uint32 * 24),
+                ("lz_flow", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 # every symbol include/nafgpu.h declares (tests check the library exports all of them)

@@ -188,6 +188,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
 void read_lz_stats(nafgpu_ctx* c) {
     const uint32_t* m = (const uint32_t*)c->misc_host.p;
     c->stats.lz_handover = m[4]; c->stats.lz_rounds = m[5]; c->stats.lz_unresolved = m[6];
+    c->stats.lz_flow = c->misc_words >= 32 ? m[c->misc_words - 32] : 0;
     if (c->misc_words >= 24) memcpy(c->stats.lz_pending, m + c->misc_words - 24, 24 * 4);
 }
 
@@ -386,6 +387,10 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     uint32_t* misc = (uint32_t*)c->misc.p;
     J.status = misc; J.lz_count = misc + 1; J.lz_handover = misc + 4; J.lz_rounds = misc + 5; J.fin_unresolved = misc + 6; J.fin_count = misc + 7;
     J.frame_bad = misc + 10; J.fin_chunk_flag = misc + 10 + nf; J.lz_pending = misc + 10 + nf + total_chunks + 8;
+    J.lz_flow = misc + 10 + nf + total_chunks;          // (three of the eight spare words before lz_pending)
+    J.lz_flow_on = nseq > 8192 ? 1u : 0u;
+    if (const char* e = getenv("NAFGPU_LZ_FLOW")) J.lz_flow_on = (uint32_t)atoi(e);          // (0: never; 2: tests force it whenever the rounds would go on)
+    J.flow_ctas = (uint32_t)std::min<uint64_t>((nseq + 255) / 256, 148u * 8u);
     J.fin_chunk_first = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_chunks); J.fin_total_chunks = total_chunks;
     J.lz_idx = (uint32_t*)c->lzidx.p;
     J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p; J.fin_ext = (uint32_t*)c->fin_g.p + g_base[nf] + 64;

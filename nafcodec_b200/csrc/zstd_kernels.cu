@@ -2382,11 +2382,124 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         // the bytes of the frame, not on the depth of the chain), the section is text-like: hand it over.
         const uint32_t progress = n - n_next;
         const uint64_t round_ns = 5000 + n_next / 25;                      // measured: ~30 us per round at 600 K entries (most of them one load: still blocked)
+        // chains of a few dozen generations (at this rate the rest needs 8..256 more rounds): k_lz_flow, where a generation
+        // costs a visibility latency instead of a round.  Endless chains (text-like sections: thousands of rounds) go to the finisher.
+        if (round >= LZ_MIN_ROUNDS && n_next > LZ_MIN_PENDING && J.lz_flow_on) {
+            const uint64_t est = (uint64_t)n_next / (progress ? progress : 1u);
+            if ((est >= 8 && est <= 256) || J.lz_flow_on == 2u) {       // (2: tests force the kernel on small inputs)
+                if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_flow = 1;
+                break;
+            }
+        }
         if (round >= LZ_MIN_ROUNDS && n_next > LZ_MIN_PENDING &&
             (uint64_t)n_next * round_ns > (uint64_t)(progress ? progress : 1u) * J.fin_cost_us * 1000u) {
             if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = round;
             break;
         }
+    }
+}
+
+// k_lz_flow: the matches that k_lz_resolve's rounds leave when the dependency chains are DEEP BUT NOT ENDLESS -- a diverged repeat
+// family in a chromosome (cfg3): 78 generations of matches, ~2 % of the pending ones becoming ready per round, every round a
+// grid barrier and a pass over the worklist (25 us each, 1.9 ms).  Here the matches are taken IN ORDER, 32 per warp by a ticket,
+// and a match simply waits for the matches its source range needs (they have smaller indices: finished, or held by a warp
+// that took an earlier ticket and is therefore running -- no deadlock, no co-residency requirement beyond "a warp that holds
+// a ticket runs").  A generation then costs one visibility latency (~1-2 us) instead of a round.  The waiting is a CONVERGENT
+// loop of the warp (every lane polls once per iteration; no lane ever spins inside a divergent branch that a peer lane would
+// have to leave first), bounded by a deadline: a section whose chain is as long as the section (quality strings) would
+// serialise here, so k_lz_resolve only chooses this kernel when the remaining depth looks small, and when the deadline
+// passes anyway the kernel gives up and hands what is left to the byte-level finisher.
+__device__ __forceinline__ unsigned long long flow_now_ns() {
+#if defined(__CUDA_ARCH__)
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+#else
+    return 0ull;
+#endif
+}
+
+constexpr int LZF_T = 256;
+
+__global__ void __launch_bounds__(LZF_T) k_lz_flow(JobDev J) {
+    if (*J.lz_flow == 0) return;
+    volatile uint32_t* done = J.seq_done;
+    volatile uint32_t* abort_flag = J.lz_flow + 2;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = (uint32_t)J.n_seq;
+    const uint32_t stamp = 0x7FFFFFFFu;                                // "done" value of matches executed here
+    const unsigned long long deadline = flow_now_ns() + (unsigned long long)J.fin_cost_us * 1000ull;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(J.lz_flow + 1, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) return;
+        const uint32_t i = base + (uint32_t)lane;
+        bool active = i < n && done[i] == 0;
+        uint64_t d = 0, e = 0;
+        uint32_t off = 0, ml = 0, j = 0, frame = 0;
+        if (active) {
+            const SeqRec& R = J.seq[i];
+            const BlockDesc& B = J.blocks[R.block];
+            frame = B.frame;
+            const FrameDesc& F = J.frames[frame];
+            if (J.frame_bad[frame]) { done[i] = stamp; active = false; }
+            else {
+                ml = R.ml; d = R.match_pos; off = resolve_offset(J, R.off, R.block);       // (possibly redirected by the rounds: any value it had is valid)
+                if (off == 0 || (uint64_t)off > d - F.dst_off) { flag_error(J, frame, zc::E_OFFSET); done[i] = stamp; active = false; }
+                else {
+                    const uint64_t sp = d - off;
+                    e = off < ml ? d : sp + ml;                                            // external source range [sp, e)
+                    uint32_t lo = F.first_seq, hi = i;
+                    const uint32_t* ix = J.lz_idx + (size_t)J.fin_chunk_first[frame] * LZ_IDX_PER_CHUNK + frame + ((sp - F.dst_off) >> LZ_IDX_SHIFT);
+                    const uint32_t a = ix[0], b = ix[1];
+                    if (a > lo) lo = a;
+                    if (b < hi) hi = b;
+                    if (lo > hi) lo = hi;
+                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (J.seq[mid].match_pos + J.seq[mid].ml > sp) hi = mid; else lo = mid + 1; }
+                    j = lo;                                                                // first match that ends after the start of my source
+                }
+            }
+        }
+        uint32_t idle = 0;
+        while (__any_sync(0xFFFFFFFFu, active)) {
+            bool ready = false;
+            if (active) {
+                // the cursor moves over the finished matches of my source range; it stops at the first unfinished one
+                while (j < i && J.seq[j].match_pos < e && done[j] != 0) j++;
+                ready = !(j < i && J.seq[j].match_pos < e);
+            }
+            const uint32_t rb = __ballot_sync(0xFFFFFFFFu, ready);
+            if (rb) {
+                // the ready matches one after the other, each copied by the WHOLE warp with its loads issued before its stores
+                // (a lane copying its own 150 bytes pays a round trip to memory per 8 of them, and the next generation waits for it)
+                __threadfence();                                                           // their bytes before mine
+                for (uint32_t m = rb; m; m &= m - 1) {
+                    const int src = __ffs((int)m) - 1;
+                    const uint64_t dd = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(d >> 32), src) << 32) | __shfl_sync(0xFFFFFFFFu, (uint32_t)d, src);
+                    const uint32_t oo = __shfl_sync(0xFFFFFFFFu, off, src), mm = __shfl_sync(0xFFFFFFFFu, ml, src);
+                    if (oo >= mm) copy_g2g_1rt<4>(J.out + dd, J.out + dd - oo, mm, lane, 32);
+                    else copy_long_match(J.out, dd, oo, mm, lane, 32);
+                }
+                __threadfence();
+                if (ready) { done[i] = stamp; active = false; }
+                idle = 0;
+                continue;
+            }
+            // nobody moved: the warp waits for matches of other warps.  Check the clock now and then.
+            if ((++idle & 63u) == 0) {
+                uint32_t stop = 0;
+                if (lane == 0) { stop = *abort_flag; if (!stop && flow_now_ns() > deadline) { *abort_flag = 1; stop = 1; } }
+                if (__shfl_sync(0xFFFFFFFFu, stop, 0)) {
+                    if (lane == 0) atomicMax(J.lz_handover, *J.lz_rounds + 1u);            // what is left goes to k_lz_finish
+                    return;
+                }
+            }
+#if defined(__CUDA_ARCH__)
+            __nanosleep(100);
+#endif
+        }
+        uint32_t stop = 0;
+        if (lane == 0) stop = *abort_flag;
+        if (__shfl_sync(0xFFFFFFFFu, stop, 0)) { if (lane == 0) atomicMax(J.lz_handover, *J.lz_rounds + 1u); return; }     // (uniform)
     }
 }
 
@@ -2988,6 +3101,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         (void)cg;
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
+        if (J.lz_flow_on) { NAF_LAUNCH(k_lz_flow, J.flow_ctas ? J.flow_ctas : 1u, LZF_T, 0, st, J); launches++; }
         ev->mark();
         }
         JobDev Jc = J;

@@ -40,6 +40,8 @@ struct JobDev {
     uint32_t* lz_count;               // [3] their lengths
     uint32_t* lz_rounds;              // rounds k_lz_first + k_lz_resolve ran (statistics)
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
+    uint32_t* lz_flow;                // [0] set by k_lz_resolve: k_lz_flow takes the rest; [1] its ticket counter; [2] its abort flag
+    uint32_t lz_flow_on, flow_ctas;   // host: launch k_lz_flow (jobs with more than a few thousand matches); its grid
     uint32_t* lz_pending;             // [24] matches still pending after round 1, 2, ... (statistics)
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier
     uint32_t fin_cost_us;             // estimated cost of the finisher kernels on this job (hand-over decision)

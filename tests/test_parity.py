@@ -349,6 +349,33 @@ def test_match_rounds_of_small_jobs_in_both_kernels(backend, monkeypatch):
     assert ctx.stats().lz_rounds >= 1 and ctx.stats().n_sequences <= 2048
 
 
+def test_in_order_kernel_for_chains_of_some_depth(backend, monkeypatch):
+    """Chains of a few dozen generations of matches (a diverged repeat family) leave k_lz_resolve's rounds for k_lz_flow: the
+    matches in order, 32 per warp by a ticket, each waiting for the ones its source needs.  Forced here on small inputs
+    (NAFGPU_LZ_FLOW=2), with the one-CTA stage off; then with a deadline of zero, which must hand what is left to the finisher."""
+    monkeypatch.setenv("NAFGPU_LZ_SMALL", "0")
+    monkeypatch.setenv("NAFGPU_LZ_FLOW", "2")
+    ctx = N.shared_context(0, library(backend))
+    rng = np.random.default_rng(11)
+    gens = 400 if backend == "emul" else 6000
+    p = _generations(rng, gens, 120, far_every=7, long_every=90)
+    for level in (3, 19):
+        frame = K.zstd_frame(p, level)
+        assert ctx.zstd_decompress(frame, len(p)) == p, level
+        # (thousands of generations: on the device the deadline passes and the finisher takes the rest -- the bytes above are
+        #  the point; the emulator has no clock and finishes in the kernel)
+        assert ctx.stats().lz_flow == 1, (level, ctx.stats().lz_rounds)
+    res, d = check_parity(backend, K.cfg3_chromosome(300_000 if backend == "emul" else 4_000_000, workers=0), "repeat family, in-order kernel")
+    st = N.shared_context(0, library(backend)).stats()
+    assert st.lz_flow == 0 or st.lz_handover == 0, "a few dozen generations: finished in the in-order kernel"
+    check_parity(backend, read_golden("NZ_AAEN01000029.naf"), "fixture, in-order kernel allowed")
+    if backend != "emul":                                  # (the emulator has no clock: its deadline never passes)
+        monkeypatch.setenv("NAFGPU_FIN_COST_US", "0")
+        frame = K.zstd_frame(p, 3)
+        assert ctx.zstd_decompress(frame, len(p)) == p
+        assert ctx.stats().lz_handover > 0, "deadline of zero: the finisher takes over"
+
+
 @pytest.mark.parametrize("tiny", ["0", "1"])
 def test_tiny_blocks_take_the_warp_per_block_kernels(backend, monkeypatch, tiny):
     """Blocks of at most 32 sequences / 2 KiB of literals (a FASTQ archive in the reference encoder's framing: one flush per
