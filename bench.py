@@ -258,7 +258,7 @@ def measure_config(ctx, lib, name, blobs, want, peak, fields, note, iters=10, pa
             "frac_of_hbm_peak": int(st.algorithmic_bytes) / (ms * 1e-3) / 1e9 / peak,
             "e2e": {"ms": e2e_s * 1e3, "output_GBps": out_bytes / e2e_s / 1e9, "h2d_bytes": int(st.h2d_bytes), "d2h_bytes": int(st.d2h_bytes),
                     "first_call_ms": t_first * 1e3},
-            "lz_rounds": int(st2.lz_rounds), "lz_handover_round": int(st2.lz_handover), "stage_ms_serial": stages,
+            "lz_rounds": int(st2.lz_rounds), "lz_handover_round": int(st2.lz_handover), "lz_in_order_kernel": int(st2.lz_flow), "stage_ms_serial": stages,
             "cpu_oracle": {"ms": t_cpu * 1e3, "threads": min(len(idx), os.cpu_count() or 1), "archives": len(idx)}}
 
 

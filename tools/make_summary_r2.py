@@ -36,7 +36,7 @@ def cfg_row(name, v):
         return f"| {name} | error: {v['error']} |"
     return (f"| `{name}` | {v['archives']} | {v['zstd_blocks']} / {v['sequences']} | {v['ascii_bytes'] / 1e6:.1f} | **{v['device_ms']:.3f}** | {v['host_prepare_ms']:.2f} | "
             f"{v['ascii_GBps']:.1f} | {100 * v['frac_of_hbm_peak']:.2f} % | {v['e2e']['ms']:.2f} | {v['cpu_oracle']['ms']:.0f} ({v['cpu_oracle']['threads']} thr) | "
-            f"{v['lz_rounds']}{' -> finisher' if v['lz_handover_round'] else ''} |")
+            f"{v['lz_rounds']}{' -> in-order kernel' if v.get('lz_in_order_kernel') else ''}{' -> finisher' if v['lz_handover_round'] else ''} |")
 
 
 cfg_tbl = "\n".join(cfg_row(k, v) for k, v in d["configs"].items())
@@ -88,8 +88,9 @@ Stage times (serial profiled run, CUDA events on the launch stream; in the timed
   in one CTA (`k_lz_small`), the small Huffman streams run beside the big ones, the Huffman weight chain was pipelined, long literal runs are copied with four
   chunks per lane in flight (steps and what each gained: below).  cfg2 alone: 0.234 -> {d['configs']['cfg2_single']['device_ms']:.3f} ms (target 0.10): bound by the FSE chain of its longest block
   (93 us: ~580 sequences x ~300 cycles) and four general LZ rounds (67 us); serial stage times are in the JSON (`stage_ms_serial`).
-* cfg3 (250 Mbp, ONE frame per section): 5.87 ms at the start of the round (the byte-level finisher took 3.6 ms of it) -> {d['configs']['cfg3_250Mbp']['device_ms']:.2f} ms.  The diverged repeat
-  family makes 78 generations of matches; a round now costs ~25 us (blocker cache, four entries in flight per thread, position index for the probe).
+* cfg3 (250 Mbp, ONE frame per section): 5.87 ms at the start of the round -> {d['configs']['cfg3_250Mbp']['device_ms']:.2f} ms = {d['configs']['cfg3_250Mbp']['ascii_GBps']:.0f} GB/s ASCII (target 250).  The diverged repeat
+  family makes 78 generations of matches: after three rounds the in-order kernel `k_lz_flow` takes them (a generation costs a visibility latency instead of
+  a round: 1.93 -> 0.39 ms for the match stage; steps below).
 * cfg4 (10^6 reads, 2 x 10^6 tiny zstd blocks): device + prepare 107 ms at the start of the round (round 1: ~530 ms) -> {d['configs']['cfg4_1M_all_fields']['device_plus_prepare_ms']:.1f} ms (target 60), {d['configs']['cfg4_1M_all_fields']['e2e']['ms']:.1f} ms for one synchronous
   host-to-host call: tiled frame scan (10.4 -> 0.27 ms), sliced NAF scans (3.5 -> 0.1 ms), threaded header walk with descriptors written straight into pinned
   staging (45 -> 23 ms), warp-per-block kernels for the tiny blocks with the general kernels running over lists of the others, level 2 of the finisher over
