@@ -121,7 +121,7 @@ void parallel_for(size_t n, unsigned max_threads, F fn) {
 struct nafgpu_ctx {
     int device = 0;
     cudaStream_t st = 0, st2 = 0, st3 = 0;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr, ev_fork4 = nullptr, ev_join4 = nullptr, ev_block = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr, ev_fork4 = nullptr, ev_join4 = nullptr, ev_block = nullptr, ev_d2h = nullptr;
     std::string err;
     DevBuf comp, arena, lit, desc, bstate, hufw, fsstate, lzidx, scanagg, debug, tables, table_al, seq32, seq64, misc, flush, text, fin_g, pack_in, pack_out;
     size_t o_frames = 0, o_naf = 0, o_huf = 0, o_chunks = 0, o_gbase = 0, o_tiles = 0, o_big = 0, o_bigseq = 0, o_biglit = 0;   // layout of `desc` (blocks at 0): one H2D copy for all descriptors
@@ -226,11 +226,22 @@ static cudaError_t wait_stream(nafgpu_ctx* c) {
     return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
 }
 
+// The turns are taken on the DEVICE: a lane enqueues its copy behind the previous lane's (an event of that lane's stream), so the
+// copy engine goes from one result to the next without waiting for a host thread to wake up, release a lock and enqueue
+// (blocking-sync wake-ups cost tens of microseconds each).  The mutex only orders the enqueues.
+static cudaEvent_t g_last_d2h[16];
+
 static int d2h_results(nafgpu_ctx* c) {
-    CUDA_TRY(c, wait_stream(c));                                // kernels first: do not hold the turn while they run
-    std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
-    CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
-    CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, wait_stream(c));                                // kernels first: a copy queued behind running kernels would hold up the lanes behind it
+    {
+        std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
+        cudaEvent_t prev = g_last_d2h[c->device & 15];
+        if (prev && prev != c->ev_d2h && c->ev_d2h) CUDA_TRY(c, cudaStreamWaitEvent(c->st, prev, 0));
+        CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->z1_size, cudaMemcpyDeviceToHost, c->st));
+        if (c->ev_d2h) { CUDA_TRY(c, cudaEventRecord(c->ev_d2h, c->st)); g_last_d2h[c->device & 15] = c->ev_d2h; }
+        else { CUDA_TRY(c, wait_stream(c)); return NAFGPU_OK; }   // (no event: the old way, the turn held until the copy is done)
+    }
     CUDA_TRY(c, wait_stream(c));
     return NAFGPU_OK;
 }
@@ -461,6 +472,7 @@ int nafgpu_ctx_create(int device, nafgpu_ctx** out) {
     if (cudaEventCreateWithFlags(&c->ev_fork4, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join4, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { c->ev_block = nullptr; cudaGetLastError(); }
+    if (cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming) != cudaSuccess) { c->ev_d2h = nullptr; cudaGetLastError(); }
     for (int i = 0; i < N_STAGES + 3; i++) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return NAFGPU_ERR_CUDA; }
     c->ev_ok = true;
     c->coop_ctas = zk::lz_resolve_max_ctas(device);
@@ -485,6 +497,10 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     if (c->ev_fork4) cudaEventDestroy(c->ev_fork4);
     if (c->ev_join4) cudaEventDestroy(c->ev_join4);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
+    if (c->ev_d2h) {
+        { std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]); if (g_last_d2h[c->device & 15] == c->ev_d2h) g_last_d2h[c->device & 15] = nullptr; }
+        cudaEventDestroy(c->ev_d2h);
+    }
     cudaStreamDestroy(c->st2);
     if (c->st3) cudaStreamDestroy(c->st3);
     cudaStreamDestroy(c->st);
