@@ -3,18 +3,24 @@
 // nafcodec/src/decoder/mod.rs:32,221-223).  No library decompressor, no CPU fallback.
 //
 // One job = any number of frames (NAF sections, possibly of many archives).  Two branches run on two streams and join
-// before the LZ stage:
-//   FSE branch      k_build_tables<0>   per block: parse the FSE table descriptions, build LL/OF/ML decode tables (whole warp)
-//                   k_decode_sequences  per block: tANS decode of (ll, ml, offset), producer / consumer warps, symbolic repeat offsets
-//                   k_frame_scan        per frame: block output offsets (prefix sum) + repeat-offset carry across blocks
-//   Huffman branch  k_build_tables<1>   per block: Huffman tree description -> 256 weights, once per tree
-//                   k_huf_tables        per tree used by long streams: decode / boundary / 3-symbol tables, once
-//                   k_huf_decode<512|128> per bitstream: intra-stream parallel decode into the literal staging buffer
-//   LZ stage        k_lz_literals       per block: raw / RLE blocks, literal runs -> their output positions
-//                   k_lz_first          per match: round 1 of the dependency-resolving match execution (+ redirect through copies)
-//                   k_lz_resolve        persistent cooperative kernel: further rounds over a worklist, one grid barrier per round
-//                   k_lz_finish, k_lz_finish2  after a hand-over (text-like sections): byte-level pointer jumping inside 64 KB
-//                                       chunks on all SMs, then across chunks
+// before the LZ stage (a third stream carries a kernel of either branch beside its sibling where a job has both kinds of work):
+//   FSE branch      k_build_tables<0>        per block: parse the FSE table descriptions, build LL/OF/ML decode tables (whole warp)
+//                   k_decode_sequences       per block: tANS decode of (ll, ml, offset): three-lane producer / consumer warp, symbolic repeat offsets
+//                   k_decode_sequences_tiny  blocks of at most 32 sequences, one warp each (jobs with thousands of them: FASTQ flushed per record)
+//                   k_frame_scan (+ k_fs_reduce / k_fs_prefix / k_fs_apply for frames of 10^4+ blocks)
+//                                            per frame: block output offsets (prefix sum) + repeat-offset carry across blocks
+//   Huffman branch  k_build_tables<1>        per block: Huffman tree description -> 256 weights, once per tree
+//                   k_huf_decode_block       per big block: intra-stream parallel decode of its four streams into the literal staging buffer
+//                   k_huf_decode_big         the same per stream, four CTAs of a block as a cluster (DSMEM): a job of a few blocks
+//                   k_huf_decode<128>        short streams
+//   LZ stage        k_lz_literals (+ _tiny)  per block: raw / RLE blocks, literal runs -> their output positions
+//                   k_lz_small               a job of at most 2048 matches: the whole match stage in one CTA
+//                   k_lz_index, k_lz_first   per match: position index; round 1 of the dependency-resolving match execution (+ redirect through copies)
+//                   k_lz_resolve             persistent cooperative kernel: further rounds over a worklist, one grid barrier per round
+//                   k_lz_flow                chains of a few dozen generations: matches in order by ticket, each waiting for the ones it needs
+//                   k_lz_finish, k_lz_finish2  endless chains (text-like sections): byte-level pointer jumping inside 64 KB chunks on all SMs,
+//                                            then across chunks over the chunks' roots
+//                   k_frame_checksum         frames that carry a content checksum (XXH64)
 #include "zstd_kernels.cuh"
 
 #include <algorithm>
