@@ -58,6 +58,27 @@ struct SmemBits {
     __device__ __forceinline__ int remaining() const { return (qi << 5) + rr - x_zero; }   // unread payload bits (negative: over-read)
 };
 
+// ---- shared-memory access by explicit shared-space address ---------------------------------------------------------
+// The hot loops below address shared memory through 32-bit shared-space addresses and ld.shared PTX: with generic
+// pointers nvcc re-derives the shared window base inside the loops (S2R SR_CgaCtaId + LEA per access, seen in SASS).
+#if defined(__CUDA_ARCH__)
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t to_saddr(const void* p) { return (saddr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(saddr_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ void sts32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+#else
+typedef uintptr_t saddr_t;
+static inline saddr_t to_saddr(const void* p) { return (saddr_t)p; }
+static inline uint32_t lds32(saddr_t a) { return *(const uint32_t*)a; }
+static inline uint2 lds64(saddr_t a) { return *(const uint2*)a; }
+static inline uint32_t lds16(saddr_t a) { return *(const uint16_t*)a; }
+static inline void sts8(saddr_t a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
+static inline void sts32(saddr_t a, uint32_t v) { *(uint32_t*)a = v; }
+#endif
+
 // bits [o, o + k) of a shared-memory image of a bitstream (32-bit words), k <= 32: no reader state
 __device__ __forceinline__ uint32_t smem_bits(const uint32_t* sw, int o, uint32_t k) {         // bits [o, o + k) of the image, k <= 32
     const uint32_t lo = sw[o >> 5], hi = sw[(o >> 5) + 1];
@@ -336,18 +357,32 @@ struct RepMap { int32_t s[3]; uint32_t v[3]; };
 
 __device__ __forceinline__ void rep_identity(RepMap& m) { m.s[0] = 0; m.s[1] = 1; m.s[2] = 2; m.v[0] = m.v[1] = m.v[2] = 0; }
 
-// m <- (m after f)
+// m <- (m after f).  Branch-free: the consumer warp of k_decode_sequences runs this inside a shuffle scan, and a lone warp pays
+// for every divergent branch (the same rewrite of the producer's loop took it from 284 to 189 cycles per sequence).
 __device__ __forceinline__ void rep_compose(RepMap& m, const RepMap& f, bool& bad) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        if (m.s[k] >= 0) {
-            const int sk = m.s[k];
-            const int32_t es = sk == 0 ? f.s[0] : (sk == 1 ? f.s[1] : f.s[2]);
-            const uint32_t ev = sk == 0 ? f.v[0] : (sk == 1 ? f.v[1] : f.v[2]);
-            if (es < 0) { if (ev <= m.v[k]) { bad = true; m.v[k] = 1; } else m.v[k] = ev - m.v[k]; m.s[k] = -1; }
-            else { m.s[k] = es; m.v[k] = ev + m.v[k]; }
-        }
+        const int sk = m.s[k];
+        const bool has = sk >= 0;
+        const int32_t es = sk == 0 ? f.s[0] : (sk == 1 ? f.s[1] : f.s[2]);
+        const uint32_t ev = sk == 0 ? f.v[0] : (sk == 1 ? f.v[1] : f.v[2]);
+        const bool cst = es < 0;
+        const bool badk = has && cst && ev <= m.v[k];
+        const uint32_t nv = cst ? ev - m.v[k] : ev + m.v[k];
+        m.v[k] = has ? (badk ? 1u : nv) : m.v[k];
+        m.s[k] = has ? (cst ? -1 : es) : sk;
+        bad = bad || badk;
     }
+}
+
+// m <- (m after f) where `take` holds, m otherwise (no branch)
+__device__ __forceinline__ void rep_compose_if(RepMap& m, const RepMap& f, bool take, bool& bad) {
+    RepMap t = m;
+    bool b = false;
+    rep_compose(t, f, b);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { m.s[k] = take ? t.s[k] : m.s[k]; m.v[k] = take ? t.v[k] : m.v[k]; }
+    bad = bad || (take && b);
 }
 
 // out <- m(in); returns false if an offset would not be positive
@@ -371,7 +406,7 @@ __device__ __forceinline__ void rep_warp_scan(RepMap& m, int lane, bool& bad) {
         RepMap f;
 #pragma unroll
         for (int k = 0; k < 3; k++) { f.s[k] = __shfl_up_sync(0xFFFFFFFFu, m.s[k], d); f.v[k] = __shfl_up_sync(0xFFFFFFFFu, m.v[k], d); }
-        if (lane >= d) rep_compose(m, f, bad);
+        rep_compose_if(m, f, lane >= d, bad);
     }
 }
 
@@ -444,6 +479,39 @@ __device__ __forceinline__ bool seq_produce3(const uint32_t* sw, int& P, int x_z
     return true;
 }
 
+// The same loop with everything it touches (bit image, the lane's table, the lane's output array) addressed by 32-bit
+// shared-space addresses: with generic pointers nvcc re-derived the shared window base inside the loop (S2R SR_CgaCtaId + LEA in
+// front of every load -- on the dependent chain of every sequence).  k_decode_sequences' producer; the tiny-block kernel, whose
+// tables stay in global memory, keeps the generic form above.
+__device__ __forceinline__ uint32_t sbits31(saddr_t sw, int o, uint32_t k) {
+    const saddr_t a = sw + (saddr_t)(4 * (o >> 5));
+    return __funnelshift_r(lds32(a), lds32(a + 4), (uint32_t)o) & ~(0xFFFFFFFFu << k);
+}
+
+__device__ __forceinline__ bool seq_produce3s(saddr_t sw, int& P, int x_zero, saddr_t T, uint32_t& state, int lane, uint32_t cnt,
+                                              bool last_batch, saddr_t r_mine) {
+    const uint32_t j_last = last_batch ? cnt - 1u : 0xFFFFFFFFu;
+    const bool mine = lane < 3;
+    for (uint32_t j = 0; j < cnt; j++) {
+        if (P < x_zero) return false;
+        const uint2 q = lds64(T + 8u * state);
+        uint32_t pk = mine ? q.y >> 16 : 0u;
+        if (j == j_last) pk &= 0xFF00u;
+        const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, pk, 0), p1 = __shfl_sync(0xFFFFFFFFu, pk, 1), p2 = __shfl_sync(0xFFFFFFFFu, pk, 2);
+        const uint32_t tot = p0 + p1 + p2;
+        const uint32_t pre = (lane > 0 ? p0 : 0u) + (lane > 1 ? p1 : 0u);
+        const int Pend = P - (int)(tot & 0xFFu) - (int)(tot >> 8);
+        // (no branch around the three working lanes: the others cut empty fields at valid addresses and keep state 0)
+        const uint32_t a = pk >> 8, n = pk & 0xFFu;
+        const uint32_t v = q.x + sbits31(sw, P - (int)(pre >> 8) - (int)a, a);
+        const uint32_t ns = (q.y & 0xFFFFu) + sbits31(sw, Pend + (int)(pre & 0xFFu), n);
+        if (mine) sts32(r_mine + 4u * j, v);
+        state = mine ? ns : 0u;
+        P = Pend;
+    }
+    return true;
+}
+
 // CONSUMER side, one batch of at most 32 sequences held by a warp (lane j: sequence j): repeat offsets, positions, records.
 struct SeqTotals {
     RepMap carry;                    // the block's repeat-offset map up to the current batch (uniform over the warp)
@@ -471,14 +539,14 @@ __device__ __forceinline__ void seq_consume_batch(uint32_t* b_ov, const uint32_t
                 else if (idx == 3) { m.v[0] = 1; m.s[1] = 0; m.s[2] = 1; }
             }
         }
-        if (lane == 0) rep_compose(m, t.carry, t.bad);
+        rep_compose_if(m, t.carry, lane == 0, t.bad);
         if (cnt <= 8) {
             // a handful of sequences (the tiny blocks of a FASTQ section flushed per record): a short chain of shuffles is
             // cheaper than the five-step scan
             for (uint32_t j = 1; j < cnt; j++) {
                 RepMap f;
                 rep_shfl(f, m, (int)j - 1);
-                if ((uint32_t)lane == j) rep_compose(m, f, t.bad);
+                rep_compose_if(m, f, (uint32_t)lane == j, t.bad);
             }
             RepMap last;
             rep_shfl(last, m, (int)cnt - 1);
@@ -585,6 +653,11 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
         const int kind = lane == 0 ? 1 : (lane == 1 ? 2 : 0);                               // stab / al / r_* index of the lane's state
         uint32_t* const r_base = lane == 0 ? &r_ov[0][0] : (lane == 1 ? &r_ml[0][0] : &r_ll[0][0]);
         bool dead = false;
+        saddr_t s_bits_a = to_saddr(sbits), s_tab_a = to_saddr(stab[kind]), s_out_a = to_saddr(r_base);
+#if defined(__CUDA_ARCH__)
+        // (opaque to the compiler, or it rematerialises the three addresses from SR_CgaCtaId inside the loop)
+        asm volatile("" : "+r"(s_bits_a), "+r"(s_tab_a), "+r"(s_out_a));
+#endif
         if (staged) {
             // the three initial states: AL_ll, AL_of, AL_ml bits from the top, in that order
             const int before = lane == 2 ? 0 : (lane == 0 ? al[0] : al[0] + al[1]);
@@ -597,7 +670,7 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
             SEQ_CLK(t0);
             if (staged) {
                 if (!dead) {
-                    const bool ok = seq_produce3(sbits, P, xz, stab[kind], state, lane, cnt, k + 1 == nbatch, r_base + (k & 1) * SEQ_BATCH);
+                    const bool ok = seq_produce3s(s_bits_a, P, xz, s_tab_a, state, lane, cnt, k + 1 == nbatch, s_out_a + (saddr_t)((k & 1) * SEQ_BATCH * 4));
                     // a corrupt stream over-reads: the reader stops at the first sequence that starts below bit 0 (it has read at
                     // most 90 bits of the zero padding by then); the block is flagged
                     const int left = ok ? P - xz : -1;
@@ -868,25 +941,6 @@ __host__ __device__ constexpr uint32_t huf_sout_bytes(int T) { return (T == HUF_
 // the boundary-mask table (8 KB, phase 1 only) shares its space with the output image (phase 2 and flush only)
 __host__ __device__ constexpr uint32_t huf_multi_bytes(int T) { return T == HUF_T_BIG ? 16384u : 0u; }
 __host__ __device__ constexpr uint32_t huf_fixed_smem(int T) { return 4096u + 768u + huf_multi_bytes(T) + huf_sout_bytes(T); }
-
-// ---- shared-memory access by explicit shared-space address ---------------------------------------------------------
-// The hot loops below address shared memory through 32-bit shared-space addresses and ld.shared PTX: with generic
-// pointers nvcc re-derives the shared window base inside the loops (S2R SR_CgaCtaId + LEA per access, seen in SASS).
-#if defined(__CUDA_ARCH__)
-typedef uint32_t saddr_t;
-__device__ __forceinline__ saddr_t to_saddr(const void* p) { return (saddr_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds16(saddr_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
-__device__ __forceinline__ void sts32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
-#else
-typedef uintptr_t saddr_t;
-static inline saddr_t to_saddr(const void* p) { return (saddr_t)p; }
-static inline uint32_t lds32(saddr_t a) { return *(const uint32_t*)a; }
-static inline uint32_t lds16(saddr_t a) { return *(const uint16_t*)a; }
-static inline void sts8(saddr_t a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
-static inline void sts32(saddr_t a, uint32_t v) { *(uint32_t*)a = v; }
-#endif
 
 constexpr int HUF_W = 12;                          // index width of the multi-symbol tables
 
