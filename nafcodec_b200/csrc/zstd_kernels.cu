@@ -217,22 +217,27 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
                     pos -= al; uint32_t s2 = smem_bits(sb, 128 + pos, (uint32_t)al);
                     ok = pos >= 0;
                     int k = 0;
-                    while (ok) {
-                        if (k > 253) { ok = false; break; }
+                    bool ended = false;
+                    // (one test per pair of weights: at most 254 weights before the last one = 127 pairs; both weights of a pair are
+                    //  stored whatever happens -- when the stream ends inside the pair they are exactly what the serial reader emits)
+                    if (ok) for (int it = 0; it < 127; it++) {
                         const uint32_t c1 = cells[s1], c2 = cells[s2];
                         const int n1 = (int)((c1 >> 8) & 0xFF), n2 = (int)((c2 >> 8) & 0xFF);
                         const int p1 = pos - n1, p2 = p1 - n2;
                         const uint32_t b1 = smem_bits(sb, 128 + p1, (uint32_t)n1);
                         const uint32_t b2 = smem_bits(sb, 128 + (p2 < -96 ? -96 : p2), (uint32_t)n2);
-                        w[k++] = (uint8_t)c1;
+                        w[k] = (uint8_t)c1; w[k + 1] = (uint8_t)c2;
                         s1 = (c1 >> 16) + b1;
-                        if (p1 < 0) { w[k++] = (uint8_t)c2; break; }
-                        if (k > 253) { ok = false; break; }
-                        w[k++] = (uint8_t)c2;
                         s2 = (c2 >> 16) + b2;
-                        if (p2 < 0) { w[k++] = (uint8_t)cells[s1]; break; }
-                        pos = p2;
+                        if (p2 < 0) {
+                            if (p1 < 0) k += 2;                                            // the stream ended with the first of the pair
+                            else { w[k + 2] = (uint8_t)cells[s1]; k += 3; }                // ... with the second
+                            ended = true;
+                            break;
+                        }
+                        k += 2; pos = p2;
                     }
+                    ok = ok && ended;
                     s_n = ok ? k : 0;
                 }
                 if (!ok) s_n = 0;
@@ -469,11 +474,13 @@ __device__ __forceinline__ bool seq_produce3(const uint32_t* sw, int& P, int x_z
         const uint32_t tot = p0 + p1 + p2;                              // sums stay inside their bytes (3 x 9, 3 x 31)
         const uint32_t pre = (lane > 0 ? p0 : 0u) + (lane > 1 ? p1 : 0u);
         const int Pend = P - (int)(tot & 0xFFu) - (int)(tot >> 8);
-        if (mine) {
-            const uint32_t a = pk >> 8, n = pk & 0xFFu;
-            r_mine[j] = q.x + smem_bits31(sw, P - (int)(pre >> 8) - (int)a, a);
-            state = (q.y & 0xFFFFu) + smem_bits31(sw, Pend + (int)(pre & 0xFFu), n);
-        }
+        // (no branch around the three working lanes -- a lone warp pays dearly for divergence: the others cut empty fields at
+        //  valid addresses and keep state 0)
+        const uint32_t a = pk >> 8, n = pk & 0xFFu;
+        const uint32_t v = q.x + smem_bits31(sw, P - (int)(pre >> 8) - (int)a, a);
+        const uint32_t ns = (q.y & 0xFFFFu) + smem_bits31(sw, Pend + (int)(pre & 0xFFu), n);
+        if (mine) r_mine[j] = v;
+        state = mine ? ns : 0u;
         P = Pend;
     }
     return true;
