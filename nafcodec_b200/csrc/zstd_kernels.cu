@@ -149,8 +149,10 @@ __device__ __forceinline__ bool fse_build_warp(const int16_t* norm, int max_symb
 // k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
 // part 0: FSE tables (32 threads, grid n_blocks + 1); part 1: Huffman weights (32 threads, grid n_blocks).  Two launches so
 // that the Huffman branch and the FSE branch of the zstd stage can run on different streams.
+// part 0 runs three warps: the three table descriptions are parsed one after the other by one lane (each starts where the one
+// before ends), then every warp builds one table (a single small archive waits for this kernel: 21 -> see profiles).
 template <int PART>
-__global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
+__global__ void __launch_bounds__(PART == 0 ? 96 : 32) k_build_tables(JobDev J) {
     if (PART == 1) {
         // warp 1: the block's Huffman tree description -> 256 weights, decoded ONCE per tree (streams and treeless
         // blocks that reuse the tree read the weights back and build their decode table in parallel).
@@ -277,18 +279,18 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
     __shared__ int mode[3];
     __shared__ int rle_sym[3];
     __shared__ int ok;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t bi = blockIdx.x;
     uint32_t slot[3];
     uint32_t frame = 0;
     if (bi == J.n_blocks) {                 // predefined tables
-        if (lane < 3) {
-            int k = lane;
+        if (threadIdx.x < 3) {
+            int k = (int)threadIdx.x;
             for (int s = 0; s <= zc::kind_max_symbol(k); s++) norm[k][s] = zc::predef_norm(k, s);
             al[k] = zc::predef_al(k);
             mode[k] = SM_FSE;
         }
-        if (lane == 0) ok = 1;
+        if (threadIdx.x == 0) ok = 1;
         slot[0] = 0; slot[1] = 1; slot[2] = 2;
     } else {
         const BlockDesc& B = J.blocks[bi];
@@ -298,9 +300,9 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
         // stage the table descriptions (at most ~3 x 64 bytes) in shared memory for the serial bit parser
         __shared__ __align__(16) uint8_t desc[256];
         const uint32_t dsize = (B.src_size - B.seq_src) < 240u ? (B.src_size - B.seq_src) : 240u;
-        for (uint32_t i = lane; i < 256; i += 32) desc[i] = i < dsize ? J.comp[B.src_off + B.seq_src + i] : 0;
-        __syncwarp();
-        if (lane == 0) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) desc[i] = i < dsize ? J.comp[B.src_off + B.seq_src + i] : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
             ok = 1;
             const uint8_t* src = desc - B.seq_src;      // so that src[p] addresses the staged copy for p >= seq_src
             uint32_t p = B.seq_src;
@@ -324,13 +326,14 @@ __global__ void __launch_bounds__(32) k_build_tables(JobDev J) {
             J.bstate[bi].seq_bits_off = p;
         }
     }
-    __syncwarp();
+    __syncthreads();
     if (!ok) {
-        if (lane == 0) flag_error(J, frame, zc::E_FSE_TABLE);
+        if (threadIdx.x == 0) flag_error(J, frame, zc::E_FSE_TABLE);
         return;
     }
-    __shared__ uint16_t cum[60];
-    for (int k = 0; k < 3; k++) {                          // (mode, al, norm are uniform: shared memory)
+    __shared__ uint16_t cum3[3][60];
+    for (int k = warp; k < 3; k += (int)(blockDim.x >> 5)) {            // (mode, al, norm are uniform: shared memory) one table per warp
+        uint16_t* cum = cum3[k];
         if (mode[k] < 0) continue;
         SeqCell* T = J.tables + (size_t)slot[k] * FSE_SLOT_CELLS;
         if (mode[k] == SM_RLE) {
@@ -491,6 +494,7 @@ __device__ __forceinline__ bool seq_produce3(const uint32_t* sw, int& P, int x_z
 // front of every load -- on the dependent chain of every sequence).  k_decode_sequences' producer; the tiny-block kernel, whose
 // tables stay in global memory, keeps the generic form above.
 __device__ __forceinline__ uint32_t sbits31(saddr_t sw, int o, uint32_t k) {
+    o = o < 0 ? 0 : o;                                 // (a corrupt stream over-reads: it is caught after the batch, P below the zero padding)
     const saddr_t a = sw + (saddr_t)(4 * (o >> 5));
     return __funnelshift_r(lds32(a), lds32(a + 4), (uint32_t)o) & ~(0xFFFFFFFFu << k);
 }
@@ -499,8 +503,8 @@ __device__ __forceinline__ bool seq_produce3s(saddr_t sw, int& P, int x_zero, sa
                                               bool last_batch, saddr_t r_mine) {
     const uint32_t j_last = last_batch ? cnt - 1u : 0xFFFFFFFFu;
     const bool mine = lane < 3;
+    (void)x_zero;
     for (uint32_t j = 0; j < cnt; j++) {
-        if (P < x_zero) return false;
         const uint2 q = lds64(T + 8u * state);
         uint32_t pk = mine ? q.y >> 16 : 0u;
         if (j == j_last) pk &= 0xFF00u;
@@ -678,8 +682,8 @@ __global__ void __launch_bounds__(64) k_decode_sequences(JobDev J) {
             if (staged) {
                 if (!dead) {
                     const bool ok = seq_produce3s(s_bits_a, P, xz, s_tab_a, state, lane, cnt, k + 1 == nbatch, s_out_a + (saddr_t)((k & 1) * SEQ_BATCH * 4));
-                    // a corrupt stream over-reads: the reader stops at the first sequence that starts below bit 0 (it has read at
-                    // most 90 bits of the zero padding by then); the block is flagged
+                    // a corrupt stream over-reads: bit addresses are clamped to the image (no test inside the chain), P ends below
+                    // bit 0, the block is flagged and the batches after this one are not decoded
                     const int left = ok ? P - xz : -1;
                     if (left < 0) { dead = true; if (lane == 0) s_left = left; }
                     else if (k + 1 == nbatch && lane == 0) s_left = left;
@@ -3117,7 +3121,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
     }
     if (st2) cudaEventRecord(join, st2);
     else ev->mark();                                  // serial (profiled) order: the Huffman branch first
-    NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 32, 0, st, J); launches++; ev->mark();
+    NAF_LAUNCH(k_build_tables<0>, J.n_blocks + 1, 96, 0, st, J); launches++; ev->mark();
     // a job with both kinds of blocks (a FASTQ archive: 2 x 10^6 tiny blocks and the ~130 big blocks of the ids, each one chain of
     // ~10^4 sequences, 2.9 ms): the general kernel on the third stream, beside the tiny blocks' (2.0 ms)
     const bool seq_side = st2 && st3 && J.tiny_blocks && J.n_seq_big;
