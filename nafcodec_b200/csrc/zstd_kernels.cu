@@ -146,6 +146,46 @@ __device__ __forceinline__ bool fse_build_warp(const int16_t* norm, int max_symb
     return true;
 }
 
+// zc::fse_read_ncount over the staged (word-aligned, zero-padded) copy of the table descriptions, for the one lane that parses
+// them: fields cut out of the image with a funnel shift, the two cases of a field as selects (the restatement's byte reader and
+// branches cost ~240 cycles per symbol on a lone lane: 15 us for the three tables of a block, on the critical path of a single
+// archive).  `norm` must be zeroed by the caller.  Returns bytes consumed, or 0 on error, like the restatement.
+__device__ __forceinline__ uint32_t fse_read_ncount_staged(const uint32_t* dw, uint32_t byte0, uint32_t src_len, int max_symbol, int max_al,
+                                                           int16_t* norm, int* al_out) {
+    uint32_t pos = byte0 * 8u;
+    const uint32_t limit = pos + src_len * 8u;
+    auto peek = [&](uint32_t k) { const uint32_t i = pos >> 5; return __funnelshift_r(dw[i], dw[i + 1], pos) & ((1u << k) - 1u); };
+    const int al = (int)peek(4) + 5;
+    pos += 4;
+    if (al > max_al) return 0;
+    int rem = 1 << al, sym = 0;
+    while (rem > 0 && sym <= max_symbol) {
+        const uint32_t bits = 32u - (uint32_t)__clz(rem + 1);
+        uint32_t v = peek(bits);
+        const uint32_t low = (1u << (bits - 1)) - 1u, thr = (1u << bits) - 1u - (uint32_t)(rem + 1);
+        const bool small = (v & low) < thr;
+        pos += bits - (small ? 1u : 0u);
+        v = small ? (v & low) : (v > low ? v - thr : v);
+        const int pr = (int)v - 1;
+        rem -= pr < 0 ? -pr : pr;
+        norm[sym++] = (int16_t)pr;
+        if (pr == 0) {
+            for (;;) {
+                const uint32_t r = peek(2);
+                pos += 2;
+                sym += (int)r;                      // r extra zero-probability symbols
+                if (r != 3) break;
+                if (pos > limit) return 0;
+            }
+            if (sym > max_symbol + 1) return 0;
+        }
+        if (pos > limit) return 0;
+    }
+    if (rem != 0 || sym > max_symbol + 1) return 0;
+    *al_out = al;
+    return ((pos + 7u) >> 3) - byte0;
+}
+
 // k_build_tables: one warp per block (+ one extra CTA that builds the three predefined tables into slots 0..2).
 // part 0: FSE tables (32 threads, grid n_blocks + 1); part 1: Huffman weights (32 threads, grid n_blocks).  Two launches so
 // that the Huffman branch and the FSE branch of the zstd stage can run on different streams.
@@ -298,9 +338,10 @@ __global__ void __launch_bounds__(PART == 0 ? 96 : 32) k_build_tables(JobDev J) 
         frame = B.frame;
         slot[0] = B.tbl[0]; slot[1] = B.tbl[1]; slot[2] = B.tbl[2];
         // stage the table descriptions (at most ~3 x 64 bytes) in shared memory for the serial bit parser
-        __shared__ __align__(16) uint8_t desc[256];
+        __shared__ __align__(16) uint8_t desc[272];
         const uint32_t dsize = (B.src_size - B.seq_src) < 240u ? (B.src_size - B.seq_src) : 240u;
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) desc[i] = i < dsize ? J.comp[B.src_off + B.seq_src + i] : 0;
+        for (uint32_t i = threadIdx.x; i < 272; i += blockDim.x) desc[i] = i < dsize ? J.comp[B.src_off + B.seq_src + i] : 0;
+        for (uint32_t i = threadIdx.x; i < 3 * 56; i += blockDim.x) (&norm[0][0])[i] = 0;
         __syncthreads();
         if (threadIdx.x == 0) {
             ok = 1;
@@ -316,7 +357,9 @@ __global__ void __launch_bounds__(PART == 0 ? 96 : 32) k_build_tables(JobDev J) 
                     if (rle_sym[k] > zc::kind_max_symbol(k)) { ok = 0; break; }
                 } else if (m == SM_FSE) {
                     int a = 0;
-                    uint32_t used = zc::fse_read_ncount(src + p, B.src_size - p, zc::kind_max_symbol(k), zc::kind_max_al(k), norm[k], &a);
+                    const bool in_stage = src != J.comp + B.src_off;         // (else: oversized descriptions, read from global memory)
+                    uint32_t used = in_stage ? fse_read_ncount_staged((const uint32_t*)desc, p - B.seq_src, B.src_size - p, zc::kind_max_symbol(k), zc::kind_max_al(k), norm[k], &a)
+                                             : zc::fse_read_ncount(src + p, B.src_size - p, zc::kind_max_symbol(k), zc::kind_max_al(k), norm[k], &a);
                     if (used == 0 || p + used > B.src_size) { ok = 0; break; }
                     al[k] = a;
                     p += used;
