@@ -113,7 +113,8 @@ typedef struct nafgpu_job_stats {
     float text_kernel_ms;               /* device time of the last nafgpu_job_format's kernels (CUDA events on the context's stream) */
     uint64_t text_bytes;                /* bytes of text the last nafgpu_job_format produced */
     uint32_t lz_pending[24];            /* matches still waiting after dependency round 1, 2, ... of the last fetched run (0 past the last round) */
-    uint32_t lz_flow;                   /* nonzero if the last fetched run finished its matches in the in-order kernel (k_lz_flow: chains of a few dozen generations) */
+    uint32_t lz_flow;                   /* the in-order match kernel (k_lz_flow) in the last fetched run: bit 0 = the rounds handed chains of a few dozen generations to it;
+                                           bit 1 = it ran before the rounds (a job of a few thousand matches) and met its deadline */
     uint32_t _pad;
 } nafgpu_job_stats;
 

@@ -188,7 +188,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
 void read_lz_stats(nafgpu_ctx* c) {
     const uint32_t* m = (const uint32_t*)c->misc_host.p;
     c->stats.lz_handover = m[4]; c->stats.lz_rounds = m[5]; c->stats.lz_unresolved = m[6];
-    c->stats.lz_flow = c->misc_words >= 32 ? m[c->misc_words - 32] : 0;
+    c->stats.lz_flow = c->misc_words >= 32 ? (m[c->misc_words - 32] | ((c->J.lz_flow_early && m[c->misc_words - 32 + 4] == 0) ? 2u : 0u)) : 0;   // bit 0: chosen by the rounds; bit 1: ran before them to the end
     if (c->misc_words >= 24) memcpy(c->stats.lz_pending, m + c->misc_words - 24, 24 * 4);
 }
 
@@ -402,6 +402,8 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     J.lz_flow_on = nseq > 8192 ? 1u : 0u;
     if (const char* e = getenv("NAFGPU_LZ_FLOW")) J.lz_flow_on = (uint32_t)atoi(e);          // (0: never; 2: tests force it whenever the rounds would go on)
     J.flow_ctas = (uint32_t)std::min<uint64_t>((nseq + 255) / 256, 148u * 8u);
+    J.lz_flow_early = (nseq > 2048 && nseq <= 65536 && !getenv("NAFGPU_LZ_SMALL")) ? 1u : 0u;      // (tests that force the general rounds keep them)
+    if (const char* e = getenv("NAFGPU_LZ_FLOW_EARLY")) J.lz_flow_early = (uint32_t)atoi(e);
     J.fin_chunk_first = (const uint32_t*)((const uint8_t*)c->desc.p + c->o_chunks); J.fin_total_chunks = total_chunks;
     J.lz_idx = (uint32_t*)c->lzidx.p;
     J.fin_ctas = c->fin_ctas; J.fin2_ctas = c->fin2_ctas; J.fin_g = (uint32_t*)c->fin_g.p; J.fin_ext = (uint32_t*)c->fin_g.p + g_base[nf] + 64;

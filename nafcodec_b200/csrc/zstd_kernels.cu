@@ -2419,7 +2419,7 @@ __device__ __forceinline__ void lz_round(const JobDev& J, const uint32_t* list, 
                 idx[u] = i;
                 if (J.seq_done[i] == 0) {
                     look[u] = true;
-                    if (round > 1) {
+                    if (round > 1u + J.lz_flow_early) {
                         const uint32_t b = J.lz_blocker[i];
                         if (b != 0xFFFFFFFFu) { const uint32_t dn = J.seq_done[b]; if (dn == 0 || dn >= round) { look[u] = false; pend[u] = true; } }
                     }
@@ -2471,7 +2471,7 @@ __device__ __forceinline__ void lz_round(const JobDev& J, const uint32_t* list, 
 // Round 1: every match of the job, one thread each.
 __global__ void __launch_bounds__(LZ_CTA, 4) k_lz_first(JobDev J) {
     LZ_SHARED_QUEUE;
-    lz_round(J, nullptr, (uint32_t)J.n_seq, 1u, J.lz_list[0], &J.lz_count[0], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
+    lz_round(J, nullptr, (uint32_t)J.n_seq, 1u + J.lz_flow_early, J.lz_list[0], &J.lz_count[0], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
              &q_n, q_d, q_off, q_ml, q_i);
 }
 
@@ -2480,10 +2480,11 @@ __global__ void __launch_bounds__(LZ_CTA, 4) k_lz_first(JobDev J) {
 __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
     LZ_SHARED_QUEUE;
     uint32_t cur = 0;
-    for (uint32_t round = 2;; round++) {
+    const uint32_t r0 = J.lz_flow_early;                             // (round numbers are one higher after an early k_lz_flow, whose matches carry 1)
+    for (uint32_t round = 2 + r0;; round++) {
         const uint32_t nxt = cur == 2 ? 0 : cur + 1, clr = nxt == 2 ? 0 : nxt + 1;
         const uint32_t n = J.lz_count[cur];                          // stable: written before the last grid barrier
-        if (blockIdx.x == 0 && threadIdx.x == 0) { *J.lz_rounds = round - 1; if (round - 2 < 24) J.lz_pending[round - 2] = n; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { *J.lz_rounds = round - 1 - r0; if (round - 2 - r0 < 24) J.lz_pending[round - 2 - r0] = n; }
         if (n == 0) break;
         if (blockIdx.x == 0 && threadIdx.x == 0) J.lz_count[clr] = 0; // append target of the NEXT round; idle in this one
         lz_round(J, J.lz_list[cur], n, round, J.lz_list[nxt], &J.lz_count[nxt], blockIdx.x * LZ_CTA, gridDim.x * LZ_CTA,
@@ -2498,16 +2499,16 @@ __global__ void __launch_bounds__(LZ_CTA) k_lz_resolve(JobDev J) {
         const uint64_t round_ns = 5000 + n_next / 25;                      // measured: ~30 us per round at 600 K entries (most of them one load: still blocked)
         // chains of a few dozen generations (at this rate the rest needs 8..256 more rounds): k_lz_flow, where a generation
         // costs a visibility latency instead of a round.  Endless chains (text-like sections: thousands of rounds) go to the finisher.
-        if (round >= LZ_MIN_ROUNDS && n_next > LZ_MIN_PENDING && J.lz_flow_on) {
+        if (round >= LZ_MIN_ROUNDS + r0 && n_next > LZ_MIN_PENDING && J.lz_flow_on) {
             const uint64_t est = (uint64_t)n_next / (progress ? progress : 1u);
             if ((est >= 8 && est <= 256) || J.lz_flow_on == 2u) {       // (2: tests force the kernel on small inputs)
                 if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_flow = 1;
                 break;
             }
         }
-        if (round >= LZ_MIN_ROUNDS && n_next > LZ_MIN_PENDING &&
+        if (round >= LZ_MIN_ROUNDS + r0 && n_next > LZ_MIN_PENDING &&
             (uint64_t)n_next * round_ns > (uint64_t)(progress ? progress : 1u) * J.fin_cost_us * 1000u) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = round;
+            if (blockIdx.x == 0 && threadIdx.x == 0) *J.lz_handover = round - r0;
             break;
         }
     }
@@ -2533,17 +2534,26 @@ __device__ __forceinline__ unsigned long long flow_now_ns() {
 
 constexpr int LZF_T = 256;
 
-__global__ void __launch_bounds__(LZF_T) k_lz_flow(JobDev J) {
-    if (*J.lz_flow == 0) return;
+// `early`: the kernel runs BEFORE the rounds, over every match, for jobs of a few thousand to a few ten thousand matches (one
+// genome alone): their three or four generations then cost a launch, a probe and a few visibility latencies instead of a launch
+// plus a grid barrier and a dozen dependent loads per round (one cfg2 archive: 78 -> see profiles).  Its deadline is short; what it
+// leaves (a text-like section) goes through k_lz_first / k_lz_resolve as before, which skip what is done.
+constexpr unsigned long long LZF_EARLY_NS = 60000ull;
+
+__global__ void __launch_bounds__(LZF_T) k_lz_flow(JobDev J, int early) {
+    if (!early && *J.lz_flow == 0) return;
     volatile uint32_t* done = J.seq_done;
-    volatile uint32_t* abort_flag = J.lz_flow + 2;
+    volatile uint32_t* abort_flag = J.lz_flow + (early ? 4 : 2);
+    uint32_t* const ticket = J.lz_flow + (early ? 3 : 1);
     const int lane = threadIdx.x & 31;
     const uint32_t n = (uint32_t)J.n_seq;
-    const uint32_t stamp = 0x7FFFFFFFu;                                // "done" value of matches executed here
-    const unsigned long long deadline = flow_now_ns() + (unsigned long long)J.fin_cost_us * 1000ull;
+    // "done" value of the matches executed here: to the rounds that may follow the early run, a match is finished when its value is
+    // below their round number (they start at 2 then, k_lz_first); nothing runs after the late one
+    const uint32_t stamp = early ? 1u : 0x7FFFFFFFu;
+    const unsigned long long deadline = flow_now_ns() + (early ? LZF_EARLY_NS : (unsigned long long)J.fin_cost_us * 1000ull);
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(J.lz_flow + 1, 32u);
+        if (lane == 0) base = atomicAdd(ticket, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n) return;
         const uint32_t i = base + (uint32_t)lane;
@@ -2603,7 +2613,7 @@ __global__ void __launch_bounds__(LZF_T) k_lz_flow(JobDev J) {
                 uint32_t stop = 0;
                 if (lane == 0) { stop = *abort_flag; if (!stop && flow_now_ns() > deadline) { *abort_flag = 1; stop = 1; } }
                 if (__shfl_sync(0xFFFFFFFFu, stop, 0)) {
-                    if (lane == 0) atomicMax(J.lz_handover, *J.lz_rounds + 1u);            // what is left goes to k_lz_finish
+                    if (lane == 0 && !early) atomicMax(J.lz_handover, *J.lz_rounds + 1u);  // what is left goes to k_lz_finish (early: to the rounds)
                     return;
                 }
             }
@@ -2613,7 +2623,7 @@ __global__ void __launch_bounds__(LZF_T) k_lz_flow(JobDev J) {
         }
         uint32_t stop = 0;
         if (lane == 0) stop = *abort_flag;
-        if (__shfl_sync(0xFFFFFFFFu, stop, 0)) { if (lane == 0) atomicMax(J.lz_handover, *J.lz_rounds + 1u); return; }     // (uniform)
+        if (__shfl_sync(0xFFFFFFFFu, stop, 0)) { if (lane == 0 && !early) atomicMax(J.lz_handover, *J.lz_rounds + 1u); return; }     // (uniform)
     }
 }
 
@@ -3206,6 +3216,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         if (grid > 148u * 8u) grid = std::max<uint32_t>(148u * 8u, (uint32_t)((J.n_seq + LZ_CTA * LZ_U - 1) / (LZ_CTA * LZ_U)));
         if (grid > 148u * 64u) grid = 148u * 64u;
         NAF_LAUNCH(k_lz_index, (uint32_t)((J.n_seq + 255) / 256), 256, 0, st, J); launches++;
+        if (J.lz_flow_early) { NAF_LAUNCH(k_lz_flow, J.flow_ctas ? J.flow_ctas : 1u, LZF_T, 0, st, J, 1); launches++; }
         NAF_LAUNCH(k_lz_first, grid, LZ_CTA, 0, st, J); launches++;
         ev->mark();
         // co-resident CTAs for the grid barrier (queried by the API); a small job takes no more than its matches can use: a
@@ -3215,7 +3226,7 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         (void)cg;
         JobDev Jc = J;
         NAF_LAUNCH_COOP(k_lz_resolve, cg, LZ_CTA, st, Jc); launches++;
-        if (J.lz_flow_on) { NAF_LAUNCH(k_lz_flow, J.flow_ctas ? J.flow_ctas : 1u, LZF_T, 0, st, J); launches++; }
+        if (J.lz_flow_on) { NAF_LAUNCH(k_lz_flow, J.flow_ctas ? J.flow_ctas : 1u, LZF_T, 0, st, J, 0); launches++; }
         ev->mark();
         }
         JobDev Jc = J;
@@ -3223,7 +3234,11 @@ int launch_zstd_stage(const JobDev& J, cudaStream_t st, cudaStream_t st2, cudaEv
         if (fin_grid && J.n_seq > LZ_MIN_PENDING) {       // (k_lz_resolve never hands over fewer than LZ_MIN_PENDING matches)
             NAF_SET_MAX_SMEM(k_lz_finish, FIN_SMEM);
             NAF_LAUNCH(k_lz_finish, fin_grid, FIN_T, FIN_SMEM, st, J); launches++;
-            const uint32_t cg2 = J.fin2_ctas ? J.fin2_ctas : 1u;
+            // (a small job: no more CTAs than its chunks can use -- a cooperative grid of 592 CTAs costs microseconds to launch
+            //  even when it has nothing to do, which is the normal case)
+            uint32_t cg2 = J.fin2_ctas ? J.fin2_ctas : 1u;
+            if (J.fin_total_chunks * 2u < cg2) cg2 = J.fin_total_chunks * 2u < 8u ? 8u : J.fin_total_chunks * 2u;
+            if (cg2 > (J.fin2_ctas ? J.fin2_ctas : 1u)) cg2 = J.fin2_ctas ? J.fin2_ctas : 1u;
             (void)cg2;
             NAF_LAUNCH_COOP(k_lz_finish2, cg2, FIN2_T, st, Jc); launches++;
         }

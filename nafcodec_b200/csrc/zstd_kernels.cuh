@@ -41,6 +41,7 @@ struct JobDev {
     uint32_t* lz_rounds;              // rounds k_lz_first + k_lz_resolve ran (statistics)
     uint32_t* lz_handover;            // set by k_lz_resolve when it leaves work to k_lz_finish
     uint32_t* lz_flow;                // [0] set by k_lz_resolve: k_lz_flow takes the rest; [1] its ticket counter; [2] its abort flag
+    uint32_t lz_flow_early;           // host: k_lz_flow also runs before the rounds (jobs of 2 K .. 64 K matches), words [3] ticket, [4] abort
     uint32_t lz_flow_on, flow_ctas;   // host: launch k_lz_flow (jobs with more than a few thousand matches); its grid
     uint32_t* lz_pending;             // [24] matches still pending after round 1, 2, ... (statistics)
     uint32_t coop_ctas;               // co-resident CTAs for k_lz_resolve's grid barrier

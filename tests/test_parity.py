@@ -376,6 +376,27 @@ def test_in_order_kernel_for_chains_of_some_depth(backend, monkeypatch):
         assert ctx.stats().lz_handover > 0, "deadline of zero: the finisher takes over"
 
 
+@pytest.mark.parametrize("early", ["1", "0"])
+def test_in_order_kernel_before_the_rounds(backend, monkeypatch, early):
+    """Jobs of a few thousand matches (one genome alone) run k_lz_flow BEFORE the rounds, over every match, with a short deadline;
+    what it leaves goes through the rounds, which then count from 2.  With and without it on the same inputs: genomes (finished
+    in the kernel), a text-like chain (on the device the deadline passes: rounds, then the finisher)."""
+    monkeypatch.setenv("NAFGPU_LZ_FLOW_EARLY", early)
+    monkeypatch.setenv("NAFGPU_LZ_SMALL", "0")                     # (also the small inputs below take the general path)
+    monkeypatch.setenv("NAFGPU_LZ_FLOW_EARLY", early)
+    ctx = N.shared_context(0, library(backend))
+    for name in ("NZ_AAEN01000029.naf", "phix.naf", "masked.naf"):
+        check_parity(backend, read_golden(name), name + ", early in-order kernel " + early)
+    res, d = check_parity(backend, K.genome(9, 600_000 if backend == "emul" else 5_000_000, level=19), "genome, early " + early)
+    st = ctx.stats()
+    if early == "1" and st.n_sequences > 0: assert st.lz_flow & 2, "a genome's few generations finish before the deadline"
+    rng = np.random.default_rng(13)
+    p = _generations(rng, 500 if backend == "emul" else 20000, 100, far_every=9)
+    frame = K.zstd_frame(p, 3)
+    assert ctx.zstd_decompress(frame, len(p)) == p
+    if backend != "emul" and early == "1": assert ctx.stats().lz_handover > 0 and not (ctx.stats().lz_flow & 2)
+
+
 @pytest.mark.parametrize("tiny", ["0", "1"])
 def test_tiny_blocks_take_the_warp_per_block_kernels(backend, monkeypatch, tiny):
     """Blocks of at most 32 sequences / 2 KiB of literals (a FASTQ archive in the reference encoder's framing: one flush per
