@@ -87,7 +87,8 @@ Stage times (serial profiled run, CUDA events on the launch stream; in the timed
 * cfg1 (the reference's own fixture) alone: 0.200 ms in round 1 and at the start of this round -> {d['configs']['cfg1_fixture']['device_ms']:.3f} ms (target 0.09): the match stage of a small job runs
   in one CTA (`k_lz_small`), the small Huffman streams run beside the big ones, the Huffman weight chain was pipelined, long literal runs are copied with four
   chunks per lane in flight (steps and what each gained: below).  cfg2 alone: 0.234 -> {d['configs']['cfg2_single']['device_ms']:.3f} ms (target 0.10): bound by the FSE chain of its longest block
-  (93 us: ~580 sequences x ~300 cycles) and four general LZ rounds (67 us); serial stage times are in the JSON (`stage_ms_serial`).
+  (61 us after the control flow was taken out of its loop: ~580 sequences x 182 cycles) and the match stage (the in-order kernel before the rounds);
+  serial stage times are in the JSON (`stage_ms_serial`).
 * cfg3 (250 Mbp, ONE frame per section): 5.87 ms at the start of the round -> {d['configs']['cfg3_250Mbp']['device_ms']:.2f} ms = {d['configs']['cfg3_250Mbp']['ascii_GBps']:.0f} GB/s ASCII (target 250).  The diverged repeat
   family makes 78 generations of matches: after three rounds the in-order kernel `k_lz_flow` takes them (a generation costs a visibility latency instead of
   a round: 1.93 -> 0.39 ms for the match stage; steps below).
