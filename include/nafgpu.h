@@ -169,6 +169,14 @@ int nafgpu_job_prepare(nafgpu_ctx* ctx, const nafgpu_archive* archives, uint32_t
 int nafgpu_job_run(nafgpu_ctx* ctx);
 int nafgpu_job_fetch(nafgpu_ctx* ctx, nafgpu_result* out, uint32_t n);
 int nafgpu_job_sync(nafgpu_ctx* ctx);
+/* Bounded-memory fetch: records [first, first + count) of archive `archive` of the job that was run, as a result of their
+ * own (out->n_records = records in the window, offsets relative to the window's first byte, first_bad_record relative to
+ * `first`), through a pinned buffer that holds this window only.  max_bytes != 0 shrinks the window to the records that fit
+ * in max_bytes of decoded data (never below one record).  The decoded archive stays in device memory between calls, so a
+ * consumer that walks the archive in windows needs host memory for one window, as the reference needs it for its 4 KiB
+ * BufReaders (decoder/mod.rs:69,105-112,221-223: DecoderBuilder::buffer_size), and gets record `first` after one window has
+ * crossed PCIe.  Pointers are valid until the next fetch of either kind on the context.  Returns the archive's status. */
+int nafgpu_job_fetch_window(nafgpu_ctx* ctx, uint32_t archive, uint64_t first, uint64_t count, uint64_t max_bytes, nafgpu_result* out);
 int nafgpu_job_get_stats(const nafgpu_ctx* ctx, nafgpu_job_stats* out);
 
 /* Runs the prepared job `iters` times back to back and returns the elapsed device time in milliseconds, measured

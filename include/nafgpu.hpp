@@ -112,7 +112,7 @@ public:
         if (this != &o) {
             if (ctx_) nafgpu_ctx_destroy(ctx_);
             bytes_ = std::move(o.bytes_); arc_ = o.arc_; header_ = o.header_; want_ = o.want_; device_ = o.device_;
-            ctx_ = o.ctx_; o.ctx_ = nullptr; res_ = o.res_; decoded_ = o.decoded_; n_ = o.n_;   // (a moved vector keeps its buffer: arc_'s section pointers stay valid)
+            ctx_ = o.ctx_; o.ctx_ = nullptr; res_ = o.res_; decoded_ = o.decoded_; n_ = o.n_; window_bytes_ = o.window_bytes_; window_first_ = o.window_first_; ran_ = o.ran_;   // (a moved vector keeps its buffer: arc_'s section pointers stay valid)
         }
         return *this;
     }
@@ -130,8 +130,9 @@ public:
     // reference yields Some(Err(_)).
     std::optional<Record> next() {
         if (n_ >= header_.number_of_sequences()) return std::nullopt;
-        decode_once();
-        const uint64_t i = n_++;
+        uint64_t i = n_;
+        if (window_bytes_) { fetch_window(n_); i = n_ - window_first_; } else decode_once();
+        n_++;
         if (res_.record_status != 0 && res_.first_bad_record == i) detail::check(res_.record_status, nullptr, "record text");
         Record r;
         if (res_.ids && i < res_.n_ids) r.id = slice(res_.ids, res_.id_offsets[i], res_.id_offsets[i + 1] - 1);
@@ -181,6 +182,22 @@ private:
         detail::check(nafgpu_decode(ctx_, &arc_, want_, &res_), ctx_, "decode");
         decoded_ = true;
     }
+    // buffer_size mode: the archive is decoded into device memory once; records cross PCIe in windows of about window_bytes_
+    // decoded bytes (nafgpu_job_fetch_window), so host memory is bounded as with the reference's BufReaders (mod.rs:69,105-112).
+    void fetch_window(uint64_t i) {
+        if (!ctx_) detail::check(nafgpu_ctx_create(device_, &ctx_), nullptr, "nafgpu_ctx_create");
+        if (!ran_) {
+            detail::check(nafgpu_job_prepare(ctx_, &arc_, 1, want_), ctx_, "decode");
+            detail::check(nafgpu_job_run(ctx_), ctx_, "decode");
+            ran_ = true;
+        }
+        if (decoded_ && i >= window_first_ && i < window_first_ + res_.n_records) return;
+        detail::check(nafgpu_job_fetch_window(ctx_, 0, i, header_.number_of_sequences() - i, window_bytes_, &res_), ctx_, "decode");
+        window_first_ = i;
+        decoded_ = true;
+    }
+    uint64_t window_bytes_ = 0, window_first_ = 0;
+    bool ran_ = false;
     std::vector<uint8_t> bytes_;
     nafgpu_archive arc_{};
     Header header_;
@@ -201,7 +218,7 @@ public:
         b.comment_ = flags.test(Flag::Comment);
         return b;
     }
-    DecoderBuilder& buffer_size(size_t n) { buffer_size_ = n; return *this; }  // mod.rs:104-108 (kept for source compatibility; unused)
+    DecoderBuilder& buffer_size(size_t n) { buffer_size_ = n; return *this; }  // mod.rs:104-108: records are fetched in windows of about n decoded bytes (bounded host memory)
     DecoderBuilder& id(bool v) { id_ = v; return *this; }                      // mod.rs:117-121
     DecoderBuilder& comment(bool v) { comment_ = v; return *this; }
     DecoderBuilder& sequence(bool v) { sequence_ = v; return *this; }
@@ -215,6 +232,7 @@ public:
         d.want_ = (id_ ? NAFGPU_WANT_ID : 0u) | (comment_ ? NAFGPU_WANT_COMMENT : 0u) | (sequence_ ? NAFGPU_WANT_SEQUENCE : 0u) |
                   (quality_ ? NAFGPU_WANT_QUALITY : 0u) | (mask_ ? NAFGPU_WANT_MASK : 0u);
         d.device_ = device_;
+        d.window_bytes_ = buffer_size_;
         detail::check(nafgpu_parse_archive(d.bytes_.data(), d.bytes_.size(), &d.arc_), nullptr, "header");
         d.header_ = Header(d.arc_.header);
         return d;

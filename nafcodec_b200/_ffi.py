@@ -72,7 +72,7 @@ class JobStats(C.Structure):
 # every symbol include/nafgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["nafgpu_parse_archive", "nafgpu_variable_u64", "nafgpu_strerror", "nafgpu_version", "nafgpu_ctx_create",
            "nafgpu_ctx_destroy", "nafgpu_last_error", "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_decode",
-           "nafgpu_decode_batch", "nafgpu_job_prepare", "nafgpu_job_run", "nafgpu_job_fetch", "nafgpu_job_sync",
+           "nafgpu_decode_batch", "nafgpu_job_prepare", "nafgpu_job_run", "nafgpu_job_fetch", "nafgpu_job_fetch_window", "nafgpu_job_sync",
            "nafgpu_job_get_stats", "nafgpu_job_time", "nafgpu_job_run_profiled", "nafgpu_stage_name",
            "nafgpu_job_device_result", "nafgpu_zstd_decompress", "nafgpu_job_format", "nafgpu_format_batch", "nafgpu_pack", "nafgpu_pipeline_create", "nafgpu_pipeline_destroy", "nafgpu_pipeline_submit",
            "nafgpu_pipeline_wait", "nafgpu_pipeline_release", "nafgpu_pipeline_last_error", "nafgpu_pipeline_lanes", "nafgpu_pipeline_lane_stats"]
@@ -106,6 +106,7 @@ class Library:
         L.nafgpu_job_prepare.argtypes = [C.c_void_p, C.POINTER(Archive), C.c_uint32, C.c_uint32]
         L.nafgpu_job_run.argtypes = [C.c_void_p]
         L.nafgpu_job_fetch.argtypes = [C.c_void_p, C.POINTER(Result), C.c_uint32]
+        L.nafgpu_job_fetch_window.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Result)]
         L.nafgpu_job_sync.argtypes = [C.c_void_p]
         L.nafgpu_job_get_stats.argtypes = [C.c_void_p, C.POINTER(JobStats)]
         L.nafgpu_job_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]

@@ -140,6 +140,8 @@ struct nafgpu_ctx {
     size_t misc_words = 0;
     nafgpu_job_stats stats;
     bool prepared = false, ran = false;
+    bool win_counts = false;           // counts + status of the last run are on the host (windowed fetch)
+    PinBuf win;                        // the current window of a job that is read in windows (nafgpu_job_fetch_window)
     cudaEvent_t ev[N_STAGES + 3];
     bool ev_ok = false;
 #if !defined(NAFGPU_EMULATE)
@@ -182,6 +184,7 @@ int enqueue_run(nafgpu_ctx* c, StageEvents* ev) {
     c->stats.kernel_launches = (uint32_t)launches;
     CUDA_TRY(c, cudaGetLastError());
     c->ran = true;
+    c->win_counts = false;
     return NAFGPU_OK;
 }
 
@@ -232,6 +235,8 @@ static cudaError_t wait_stream(nafgpu_ctx* c) {
 static cudaEvent_t g_last_d2h[16];
 
 static int d2h_results(nafgpu_ctx* c) {
+    if (!c->result.ensure(c->z1_size + 64)) return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+    c->win_counts = false;
     CUDA_TRY(c, wait_stream(c));                                // kernels first: a copy queued behind running kernels would hold up the lanes behind it
     {
         std::lock_guard<std::mutex> turn(g_d2h_turn[c->device & 15]);
@@ -323,7 +328,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
               c->seq32.ensure(nseq * 5 * 4 + 64) && c->seq64.ensure(nseq * sizeof(zf::SeqRec) + 64) && c->misc.ensure(c->misc_words * 4);
     if (!ok) return fail(c, NAFGPU_ERR_NOMEM, "device allocation failed");
     clk.lap("merge + device buffers");
-    if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->z1_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))
+    if (!c->stage.ensure(stage_bytes + 64) || !c->result.ensure(c->counts_size + 64) || !c->misc_host.ensure(c->misc_words * 4 + 64))   // (the whole-result buffer is taken at the first full fetch: a job read in windows never needs it)
         return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
 
     // ---- H2D ---------------------------------------------------------------------------------------------------------
@@ -490,7 +495,7 @@ void nafgpu_ctx_destroy(nafgpu_ctx* c) {
     drop_graph(c);
     DevBuf* d[] = {&c->comp, &c->arena, &c->lit, &c->desc, &c->bstate, &c->hufw, &c->fsstate, &c->lzidx, &c->scanagg, &c->debug, &c->tables, &c->table_al, &c->seq32, &c->seq64, &c->misc, &c->flush, &c->text, &c->fin_g, &c->pack_in, &c->pack_out};
     for (DevBuf* b : d) b->release();
-    c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release(); c->pack_host.release();
+    c->stage.release(); c->result.release(); c->misc_host.release(); c->text_host.release(); c->text_stage.release(); c->pack_host.release(); c->win.release();
     if (c->ev_ok) for (int i = 0; i < N_STAGES + 3; i++) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1096,6 +1101,102 @@ int nafgpu_pack(nafgpu_ctx* c, const nafgpu_pack_input* in, nafgpu_pack_result* 
         snprintf(b, sizeof b, "unexpected sequence character at residue %llu", (unsigned long long)cnt[0]);
         return fail(c, NAFGPU_ERR_INVALID_DATA, b);
     }
+    return NAFGPU_OK;
+}
+
+// Records [first, first + count) of one archive of the job that was run, through a pinned buffer that holds this window only:
+// the result stays in HBM and crosses PCIe a window at a time, so the host memory a decode needs is bounded by the window,
+// as the reference's is by its 4 KiB BufReaders (decoder/mod.rs:69,221-223), and record `first` is available after
+// copying one window instead of the whole archive.  Two copies: the slices of the offset tables, then the bytes they span.
+int nafgpu_job_fetch_window(nafgpu_ctx* c, uint32_t archive, uint64_t first, uint64_t count, uint64_t max_bytes, nafgpu_result* out) {
+    if (!c || !out) return NAFGPU_ERR_ARGUMENT;
+    if (!c->prepared || !c->ran) return fail(c, NAFGPU_ERR_ARGUMENT, "job has not been run");
+    if (archive >= c->arch.size()) return fail(c, NAFGPU_ERR_ARGUMENT, "bad archive index");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->win_counts) {                // once per run: status words and the archives' counters
+        CUDA_TRY(c, wait_stream(c));
+        CUDA_TRY(c, cudaMemcpyAsync(c->misc_host.p, c->misc.p, c->misc_words * 4, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->result.p, c->arena.p, c->counts_size, cudaMemcpyDeviceToHost, c->st));
+        CUDA_TRY(c, cudaStreamSynchronize(c->st));
+        read_lz_stats(c);
+        c->win_counts = true;
+    }
+    const nk::NafDev& D = c->arch[archive];
+    const ArchPlan& P = c->aplan[archive];
+    const nk::NafCounts* C = (const nk::NafCounts*)((const uint8_t*)c->result.p + D.counts_off);
+    nafgpu_result& r = *out;
+    memset(&r, 0, sizeof r);
+    r.first_bad_record = nk::NO_RECORD;
+    std::string msg;
+    const int code = archive_status(c, archive, msg);
+    if (code) { r.status = code; r.n_records = P.n_records; char b[48]; snprintf(b, sizeof b, "archive %u: ", archive); return fail(c, code, b + msg); }
+    first = std::min<uint64_t>(first, P.n_records);
+    count = std::min<uint64_t>(count, P.n_records - first);
+    if (max_bytes) count = std::min<uint64_t>(count, max_bytes / 32 + 1);       // (a record takes 32 bytes of tables at least)
+    const uint64_t n_ids = std::min<uint64_t>(C->n_ids, P.n_records), n_com = std::min<uint64_t>(C->n_comments, P.n_records), n_len = C->n_lengths;
+    struct Slice { bool on; uint64_t lo, hi, src, dst; } id{P.dec[0], 0, 0, D.id_offsets_off, 0}, co{P.dec[1], 0, 0, D.com_offsets_off, 0}, le{P.dec[2], 0, 0, D.rec_offsets_off, 0};
+    auto clampw = [&](Slice& s, uint64_t n) { s.lo = std::min(first, n); s.hi = std::min(first + count, n); };
+    clampw(id, n_ids); clampw(co, n_com); clampw(le, n_len);
+    // ---- copy 1: table slices (hi - lo + 1 offsets each; lengths hi - lo) ----
+    uint64_t need = 0;
+    for (Slice* s : {&id, &co, &le}) if (s->on) { s->dst = need; need += align_up((s->hi - s->lo + 1) * 8, 64); }
+    const uint64_t len_dst = need;
+    if (le.on) need += align_up((le.hi - le.lo) * 8 + 8, 64);
+    const uint64_t tables_bytes = need;
+    if (!c->win.ensure(tables_bytes + 64)) return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+    uint8_t* W = (uint8_t*)c->win.p;
+    const uint8_t* A = (const uint8_t*)c->arena.p;
+    for (Slice* s : {&id, &co, &le}) if (s->on) CUDA_TRY(c, cudaMemcpyAsync(W + s->dst, A + s->src + s->lo * 8, (s->hi - s->lo + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+    if (le.on && le.hi > le.lo) CUDA_TRY(c, cudaMemcpyAsync(W + len_dst, A + D.lengths_off + le.lo * 8, (le.hi - le.lo) * 8, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    // ---- fit the window to max_bytes (never less than one record) ----
+    auto span = [&](const Slice& s, uint64_t k) -> uint64_t {      // bytes of the first k records of the window in this field
+        if (!s.on) return 0;
+        const uint64_t* o = (const uint64_t*)(W + s.dst);
+        const uint64_t kk = std::min(k, s.hi - s.lo);
+        return o[kk] - o[0];
+    };
+    const uint64_t per_res = (P.dec[4] ? 1 : 0) + (P.dec[5] ? 1 : 0);
+    auto bytes_of = [&](uint64_t k) { return span(id, k) + span(co, k) + span(le, k) * per_res + k * 32; };
+    if (max_bytes && count > 1 && bytes_of(count) > max_bytes) {
+        uint64_t lo = 1, hi = count;                                 // largest k in [1, count] with bytes_of(k) <= max_bytes (bytes_of is monotone)
+        while (lo < hi) { const uint64_t mid = (lo + hi + 1) / 2; if (bytes_of(mid) <= max_bytes) lo = mid; else hi = mid - 1; }
+        count = lo;
+        clampw(id, n_ids); clampw(co, n_com); clampw(le, n_len);
+    }
+    // ---- copy 2: the bytes the slices span ----
+    const uint64_t id_bytes = span(id, count), co_bytes = span(co, count), res = span(le, count);
+    const uint64_t id0 = id.on ? *(const uint64_t*)(W + id.dst) : 0, co0 = co.on ? *(const uint64_t*)(W + co.dst) : 0, r0 = le.on ? *(const uint64_t*)(W + le.dst) : 0;
+    if (id0 + id_bytes > D.ids_size || co0 + co_bytes > D.com_size || (P.dec[4] && r0 + res > D.seq_residues) || (P.dec[5] && r0 + res > D.qual_size)) return fail(c, NAFGPU_ERR_INVALID_DATA, "offset tables exceed their sections");
+    uint64_t o_ids = tables_bytes, o_com = o_ids + align_up(id_bytes + 1, 64), o_seq = o_com + align_up(co_bytes + 1, 64), o_qual = o_seq + (P.dec[4] ? align_up(res + 1, 64) : 0);
+    need = o_qual + (P.dec[5] ? align_up(res + 1, 64) : 0);
+    if (need + 64 > c->win.cap) {           // grow, keeping the tables
+        std::vector<uint8_t> keep(W, W + tables_bytes);
+        if (!c->win.ensure(need + 64)) return fail(c, NAFGPU_ERR_NOMEM, "pinned host allocation failed");
+        W = (uint8_t*)c->win.p;
+        memcpy(W, keep.data(), tables_bytes);
+    }
+    if (id_bytes) CUDA_TRY(c, cudaMemcpyAsync(W + o_ids, A + D.ids_off + id0, id_bytes, cudaMemcpyDeviceToHost, c->st));
+    if (co_bytes) CUDA_TRY(c, cudaMemcpyAsync(W + o_com, A + D.com_off + co0, co_bytes, cudaMemcpyDeviceToHost, c->st));
+    if (P.dec[4] && res) CUDA_TRY(c, cudaMemcpyAsync(W + o_seq, A + D.ascii_off + r0, res, cudaMemcpyDeviceToHost, c->st));
+    if (P.dec[5] && res) CUDA_TRY(c, cudaMemcpyAsync(W + o_qual, A + D.qual_off + r0, res, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(c, cudaStreamSynchronize(c->st));
+    // ---- the window as a result of its own: offsets rebased to the window's first byte ----
+    for (Slice* s : {&id, &co, &le}) if (s->on) {
+        uint64_t* o = (uint64_t*)(W + s->dst);
+        const uint64_t base = o[0], n = s->hi - s->lo;
+        for (uint64_t k = 0; k <= n; k++) o[k] -= base;
+    }
+    r.n_records = count;
+    r.n_ids = id.hi - id.lo; r.n_comments = co.hi - co.lo; r.n_lengths = le.hi - le.lo;
+    r.total_residues = res;
+    if (id.on) { r.ids = W + o_ids; r.id_offsets = (const uint64_t*)(W + id.dst); }
+    if (co.on) { r.comments = W + o_com; r.comment_offsets = (const uint64_t*)(W + co.dst); }
+    if (le.on) { r.lengths = (const uint64_t*)(W + len_dst); r.record_offsets = (const uint64_t*)(W + le.dst); }
+    if (P.dec[4]) r.sequence = W + o_seq;
+    if (P.dec[5]) r.quality = W + o_qual;
+    const uint64_t fb = C->first_bad_record;
+    if (fb != nk::NO_RECORD && fb >= first && fb < first + count) { r.first_bad_record = fb - first; r.record_status = NAFGPU_ERR_UTF8; }
     return NAFGPU_OK;
 }
 

@@ -112,6 +112,15 @@ class Context:
         raise_for_status(self.lib, self.lib.dll.nafgpu_job_fetch(self._ctx, res, self._n), self._ctx)
         return res
 
+    def fetch_window(self, archive: int, first: int, count: int, max_bytes: int = 0) -> "ArchiveResult":
+        """Records [first, first + count) of one archive of the job that was run, through a pinned buffer of that window only
+        (nafgpu_job_fetch_window): the decoded archive stays in HBM between calls."""
+        res = _ffi.Result()
+        with self._lock:
+            rc = self.lib.dll.nafgpu_job_fetch_window(self._ctx, archive, first, count, max_bytes, C.byref(res))
+            raise_for_status(self.lib, rc, self._ctx)
+            return ArchiveResult._copy_from(self._arr[archive].header, res)
+
     def fetch(self):
         res = self.fetch_raw()
         return [ArchiveResult._copy_from(self._arr[i].header, res[i]) for i in range(self._n)]
@@ -233,15 +242,25 @@ class Decoder:
 
     def __init__(self, file, *, id: bool = True, comment: bool = True, sequence: bool = True, quality: bool = True,
                  mask: bool = True, buffer_size: Optional[int] = None, device: int = 0, _library=None):
-        # buffer_size is accepted for surface compatibility (decoder/mod.rs:105-112); whole sections are read at once.
+        # buffer_size (DecoderBuilder::buffer_size, decoder/mod.rs:105-112): the reference reads every section through
+        # BufReaders of this many bytes, so its memory is bounded whatever the archive.  Here an explicit buffer_size bounds the
+        # HOST side the same way: the archive is decoded once into HBM and the records cross PCIe in windows of about
+        # buffer_size decoded bytes (at least one record), a path is mapped instead of read, and the first record is
+        # yielded after the first window.  Without it the whole result is copied back in one go (fastest for whole-file reads).
         self._buffer_size = buffer_size if buffer_size is not None else io.DEFAULT_BUFFER_SIZE
+        self._window_bytes = max(int(buffer_size), 1) if buffer_size is not None else 0
+        self._window_first = 0
+        self._window_ctx: Optional[Context] = None
         self._file = file
         if hasattr(file, "read"):
             data = file.read()
         else:
             path = os.fspath(file)
             with open(path, "rb") as f:      # FileNotFoundError / IsADirectoryError as in lib.rs:363-376
-                data = f.read()
+                if self._window_bytes and os.fstat(f.fileno()).st_size:
+                    data = np.memmap(f, dtype=np.uint8, mode="r")     # compressed sections go page cache -> device
+                else:
+                    data = f.read()
         self._library = _library or _ffi.default_library()
         if len(data) == 0:
             # Decoder::new on empty input: Io(UnexpectedEof) "failed to read header" (mod.rs:181-186, test mod.rs:470-476)
@@ -300,6 +319,25 @@ class Decoder:
             self._result = ctx.decode([self._archive], self._want)[0]
         return self._result
 
+    def _window(self, i: int) -> ArchiveResult:
+        """The window holding record i (windowed mode): the archive is decoded into HBM at the first call and stays there, on a
+        context of this decoder's own, until the last record has been fetched."""
+        if self._window_ctx is None:
+            self._window_ctx = Context(self._device, self._library)
+            self._window_ctx.prepare([self._archive], self._want)
+            self._window_ctx.run()
+        r = self._result
+        if r is None or not (self._window_first <= i < self._window_first + r.n_records):
+            r = self._result = self._window_ctx.fetch_window(0, i, self._header.number_of_sequences - i, self._window_bytes)
+            self._window_first = i
+        return r
+
+    def close(self):
+        """Releases the device memory of a windowed decoder early (otherwise released with the object)."""
+        if self._window_ctx is not None:
+            self._window_ctx.close()
+            self._window_ctx = None
+
     def __iter__(self):
         return self
 
@@ -309,12 +347,18 @@ class Decoder:
     def __next__(self) -> Record:
         if self._n >= self._header.number_of_sequences:    # mod.rs:447-449
             raise StopIteration
-        r = self._decoded()
-        i = self._n
+        if self._window_bytes:
+            r = self._window(self._n)
+            i = self._n - self._window_first
+        else:
+            r = self._decoded()
+            i = self._n
         if r.first_bad_record is not None and i == r.first_bad_record:
             self._n += 1
             raise_for_status(self._library, r.record_status)
         self._n += 1
+        if self._window_bytes and self._n >= self._header.number_of_sequences:
+            self.close()
 
         def s(b):
             return None if b is None else b.decode("utf-8")

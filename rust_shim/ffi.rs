@@ -152,6 +152,17 @@ extern "C" {
         line_length: u64,
         out: *mut nafgpu_text,
     ) -> c_int;
+    pub fn nafgpu_job_prepare(ctx: *mut nafgpu_ctx, archives: *const nafgpu_archive, n: u32, want: u32) -> c_int;
+    pub fn nafgpu_job_run(ctx: *mut nafgpu_ctx) -> c_int;
+    /// Bounded-memory fetch of records [first, first + count) of one archive of the job that was run (nafgpu.h).
+    pub fn nafgpu_job_fetch_window(
+        ctx: *mut nafgpu_ctx,
+        archive: u32,
+        first: u64,
+        count: u64,
+        max_bytes: u64,
+        out: *mut nafgpu_result,
+    ) -> c_int;
     pub fn nafgpu_pipeline_create(device: c_int, lanes: u32, out: *mut *mut nafgpu_pipeline) -> c_int;
     pub fn nafgpu_pipeline_destroy(p: *mut nafgpu_pipeline);
     /// returns a ticket (>= 0) or a negative status; the archives are borrowed until `wait` returns

@@ -3,6 +3,7 @@
 //   nafcodec/tests/decoder/fastq.rs    decode_header, decode, decode_no_id / no_seq / no_comment / no_quality
 //   nafcodec/tests/decoder/protein.rs  decode
 //   nafcodec/src/decoder/mod.rs:478-504  error on a truncated archive
+//   nafcodec/src/decoder/mod.rs:104-112  buffer_size: same records through windows of any size
 // Usage: test_decoder <directory with the .naf fixtures>.  Exit code 0 = all passed.
 #include <algorithm>
 #include <cctype>
@@ -168,6 +169,28 @@ static void errors() {                                           // decoder/mod.
     CHECK(threw);
 }
 
+// DecoderBuilder::buffer_size (mod.rs:104-112): the same records whatever the buffer; here it bounds the host side, the records
+// crossing PCIe in windows (nafgpu_job_fetch_window).
+static void buffer_size_windows() {
+    for (const char* name : {"/phix.naf", "/masked.naf", "/LuxC.naf", "/CP040672.naf"}) {
+        const std::vector<uint8_t> ARCHIVE = read_file(DIR + name);
+        std::vector<Record> whole = Decoder::from_bytes(ARCHIVE.data(), ARCHIVE.size()).collect();
+        for (size_t bs : {size_t(1), size_t(4096), size_t(1) << 20}) {
+            Decoder d = DecoderBuilder().buffer_size(bs).with_bytes(ARCHIVE);
+            CHECK_EQ(d.len(), whole.size());
+            std::vector<Record> got = d.collect();
+            CHECK_EQ(got.size(), whole.size());
+            for (size_t i = 0; i < got.size() && i < whole.size(); i++) {
+                CHECK(got[i].id == whole[i].id);
+                CHECK(got[i].comment == whole[i].comment);
+                CHECK(got[i].sequence == whole[i].sequence);
+                CHECK(got[i].quality == whole[i].quality);
+                CHECK(got[i].length == whole[i].length);
+            }
+        }
+    }
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { std::fprintf(stderr, "usage: %s <fixture directory>\n", argv[0]); return 2; }
     DIR = argv[1];
@@ -177,6 +200,7 @@ int main(int argc, char** argv) {
         fastq_skip("id"); fastq_skip("sequence"); fastq_skip("comment"); fastq_skip("quality");
         protein_decode();
         errors();
+        buffer_size_windows();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "unexpected exception: %s\n", e.what());
         return 1;
