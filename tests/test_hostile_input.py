@@ -138,3 +138,51 @@ def test_window_beyond_the_offset_encoding_is_refused(backend):
         ctx.zstd_decompress(bytes(frame), len(p))
     frame[1] = (19 << 3)                                              # 2^29: still representable
     assert ctx.zstd_decompress(bytes(frame), len(p)) == p
+
+
+@pytest.mark.parametrize("max_bytes", [0, 1, 4096])
+def test_windows_over_an_absurd_record_count(backend, max_bytes):
+    # nafgpu_job_fetch_window: windows are clamped by what the streams hold, not by number_of_sequences (2^61 here); a window
+    # far past the stored ids is empty-handed (id None), not out of bounds
+    lib = library(backend)
+    ids = b"".join(b"id%d\0" % k for k in range(5000))
+    data = _header(0x20 | 0x08, 2 ** 61) + _section(ids) + _section(b"")
+    ctx = N.Context(0, lib)
+    ctx.prepare([N.parse_archive(data, lib)])
+    ctx.run()
+    w = ctx.fetch_window(0, 4990, 2 ** 61 - 4990, max_bytes)
+    assert w.n_records >= 1 and w.id_bytes(0) == b"id4990"
+    if max_bytes == 0:
+        assert w.n_records == 2 ** 61 - 4990 and w.n_ids == 10 and w.id_bytes(9) == b"id4999" and w.id_bytes(10) is None
+    w = ctx.fetch_window(0, 2 ** 60, 1000, max_bytes)
+    assert w.n_ids == 0 and w.id_bytes(0) is None and w.n_records >= 1
+    w = ctx.fetch_window(0, 2 ** 64 - 1, 2 ** 64 - 1, max_bytes)        # first past the end: empty window
+    assert w.n_records == 0
+    ctx.close()
+
+
+def test_window_of_a_corrupt_archive_reports_its_status(backend):
+    lib = library(backend)
+    good = O.encode(ids=[b"a", b"b"], sequences=[b"ACGT" * 300, b"GGCC" * 200], level=3)
+    L = O.parse(good)
+    bad = bytearray(good)
+    s = L.sec[4]
+    for k in range(s.offset + 6, s.offset + s.compressed_size - 2):
+        bad[k] ^= 0xA5
+    dec = N.Decoder(__import__("io").BytesIO(bytes(bad)), buffer_size=64, _library=lib)
+    with pytest.raises(N.NafIoError):
+        next(dec)
+    # and a header-level lie is refused by prepare, before any window
+    data = _header(0x20 | 0x08, 3) + _section(b"a\0b\0c\0", 2 ** 40) + _section(b"")
+    with pytest.raises(N.NafIoError):
+        next(N.Decoder(__import__("io").BytesIO(data), buffer_size=64, _library=lib))
+
+
+def test_windows_when_the_header_overstates_the_records(backend):
+    # test_edge_cases.py::test_header_says_more_records_than_the_streams_hold, through windows of one record
+    data = bytearray(O.encode(ids=[b"r1", b"r2"], comments=[b"c1", b"c2"], sequences=[b"ACGT", b"GG"]))
+    L = O.parse(bytes(data))
+    data[L.header_size - 1] = 5
+    recs = list(N.Decoder(__import__("io").BytesIO(bytes(data)), buffer_size=1, _library=library(backend)))
+    assert len(recs) == 5 and recs[2].id is None and recs[2].sequence is None and recs[1].sequence == "GG"
+    assert [r.length for r in recs] == [4, 2, None, None, None]
