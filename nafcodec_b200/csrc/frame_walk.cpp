@@ -3,6 +3,7 @@
 #include "frame_walk.h"
 
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -14,15 +15,15 @@ static const int ERR_UNSUPPORTED = -9;
 
 #define FAIL(code, ...) do { char _b[160]; snprintf(_b, sizeof _b, __VA_ARGS__); err = _b; return (code); } while (0)
 
-int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64_t dst_off, uint64_t dst_size,
-               JobPlan& plan, std::string& err) {
-    const uint8_t* s = frame;
-    uint64_t n = src_size, p = 0;
+// Frame header: returns its size through p, the window through `window`, whether a content checksum follows the blocks.
+static int frame_header(const uint8_t* s, uint64_t n, uint64_t dst_size, uint64_t& p, uint64_t& window, int& checksum, std::string& err) {
+    p = 0;
     if (n < 1) FAIL(ERR_EOF, "zstd frame: empty");
     uint8_t fhd = s[p++];
-    int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, dict_flag = fhd & 3;
+    int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, dict_flag = fhd & 3;
+    checksum = (fhd >> 2) & 1;
     if (fhd & 0x08) FAIL(ERR_INVALID, "zstd frame: reserved bit set");
-    uint64_t window = 0;
+    window = 0;
     if (!single) {
         if (p >= n) FAIL(ERR_EOF, "zstd frame: truncated header");
         uint8_t wd = s[p++];
@@ -46,15 +47,71 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
     if (fcs_sz && fcs != dst_size) FAIL(ERR_INVALID, "zstd frame: content size %llu differs from the section size %llu",
                                         (unsigned long long)fcs, (unsigned long long)dst_size);
 
-    zf::FrameDesc fd{};
-    fd.src_off = src_off; fd.src_size = src_size; fd.dst_off = dst_off; fd.dst_size = dst_size;
-    fd.first_block = (uint32_t)plan.blocks.size(); fd.first_seq = (uint32_t)plan.seq_total; fd.window = window;
-    uint32_t frame_idx = (uint32_t)plan.frames.size();
+    return 0;
+}
 
-    uint32_t last_huf = zf::NO_BLOCK, last_huf_slot = 0;
-    uint32_t cur_tbl[3] = {zf::NO_SLOT, zf::NO_SLOT, zf::NO_SLOT};
-    uint64_t known_total = 0;
+int chain_blocks(const uint8_t* s, uint64_t n, uint64_t dst_size, uint32_t every, std::vector<uint64_t>& cuts, uint64_t& n_blocks, std::string& err) {
+    uint64_t p, window;
+    int checksum;
+    if (int rc = frame_header(s, n, dst_size, p, window, checksum, err)) return rc;
+    cuts.clear();
+    n_blocks = 0;
+    // the serial dependency of the whole walk: position -> header -> next position.  Nothing else is looked at here (reserved
+    // block types, sizes beyond the maximum and truncated contents are reported by the parts).
+    while (p + 4 <= n) {
+        uint32_t left = every;
+        uint32_t bh = 0;
+        do {
+            memcpy(&bh, s + p, 4);                               // (little-endian host; the fourth byte is masked off)
+            bh &= 0xFFFFFF;
+            p += 3 + (((bh >> 1) & 3) == zf::BT_RLE ? 1u : (bh >> 3));
+            n_blocks++;
+        } while (!(bh & 1) && --left && p + 4 <= n);
+        if (bh & 1) return 0;
+        if (!left) cuts.push_back(p);
+    }
+    // fewer than 4 bytes left: the last header of a frame without content after it, or a truncated frame
     for (;;) {
+        if (p + 3 > n) FAIL(ERR_EOF, "zstd frame: truncated block header");
+        const uint32_t bh = s[p] | (s[p + 1] << 8) | (s[p + 2] << 16);
+        p += 3 + (((bh >> 1) & 3) == zf::BT_RLE ? 1u : (bh >> 3));
+        n_blocks++;
+        if (bh & 1) break;
+    }
+    return 0;
+}
+
+int walk_frame_part(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64_t dst_off, uint64_t dst_size,
+                    uint64_t p_begin, uint64_t p_end, bool first, bool last_part, RangeState& st, JobPlan& plan, std::string& err) {
+    const uint8_t* s = frame;
+    uint64_t n = src_size, p = p_begin;
+    int checksum = 0;
+    uint32_t frame_idx = 0;                                    // (a continuation part has no frame of its own: the merge points its blocks at the first part's)
+    size_t fd_at = (size_t)-1;
+    st = RangeState();
+    if (first) {
+        uint64_t window;
+        if (int rc = frame_header(s, n, dst_size, p, window, checksum, err)) return rc;
+        zf::FrameDesc fd{};
+        fd.src_off = src_off; fd.src_size = src_size; fd.dst_off = dst_off; fd.dst_size = dst_size;
+        fd.first_block = (uint32_t)plan.blocks.size(); fd.first_seq = (uint32_t)plan.seq_total; fd.window = window;
+        frame_idx = (uint32_t)plan.frames.size();
+        fd_at = plan.frames.size();
+        plan.frames.push_back(fd);
+    } else {
+        checksum = (s[0] >> 2) & 1;
+        st.last_huf = PREV_BLOCK;
+        st.cur_tbl[0] = st.cur_tbl[1] = st.cur_tbl[2] = PREV_SLOT;
+    }
+    const size_t first_block = plan.blocks.size();
+    const uint64_t first_seq = plan.seq_total;
+    uint32_t& last_huf = st.last_huf;
+    uint32_t& last_huf_slot = st.last_huf_slot;
+    uint32_t* cur_tbl = st.cur_tbl;
+    uint64_t& known_total = st.known_total;
+    for (;;) {
+        if (!last_part && p == p_end) break;
+        if (!last_part && p > p_end) FAIL(ERR_INVALID, "zstd frame: block chain changed between the passes");
         if (p + 3 > n) FAIL(ERR_EOF, "zstd frame: truncated block header");
         uint32_t bh = s[p] | (s[p + 1] << 8) | (s[p + 2] << 16);
         p += 3;
@@ -103,6 +160,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
             if (lt == zf::LT_HUF) { last_huf = self; b.huf_block = self; last_huf_slot = plan.n_huf_slots++; b.huf_slot = last_huf_slot; }
             else if (lt == zf::LT_TREELESS) {
                 if (last_huf == zf::NO_BLOCK) FAIL(ERR_INVALID, "zstd literals: treeless block without a previous tree");
+                if (last_huf == PREV_BLOCK) st.used_prev_huf = true;     // (a tree from before this part: the merge fills it in)
                 b.huf_block = last_huf; b.huf_slot = last_huf_slot;
             }
             if (lt >= zf::LT_HUF) {
@@ -166,6 +224,7 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
                     if (m == zf::SM_PREDEF) { b.tbl[k] = (uint32_t)k; cur_tbl[k] = (uint32_t)k; }
                     else if (m == zf::SM_REPEAT) {
                         if (cur_tbl[k] == zf::NO_SLOT) FAIL(ERR_INVALID, "zstd sequences: repeat mode without a previous table");
+                        if (cur_tbl[k] == PREV_SLOT) st.used_prev_tbl[k] = true;
                         b.tbl[k] = cur_tbl[k];
                     } else { b.tbl[k] = plan.n_slots++; b.defines |= (uint8_t)(1 << k); cur_tbl[k] = b.tbl[k]; }
                 }
@@ -184,21 +243,36 @@ int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64
         if (!zf::tiny_lit_block(b)) plan.big_lit.push_back((uint32_t)plan.blocks.size());
         plan.blocks.push_back(b);
         p += content;
-        if (last) break;
+        if (last) { if (!last_part) FAIL(ERR_INVALID, "zstd frame: block chain changed between the passes"); break; }
     }
-    if (checksum) {
+    if (last_part && checksum) {
         if (p + 4 > n) FAIL(ERR_EOF, "zstd frame: truncated checksum");
-        fd.has_checksum = 1; fd.checksum = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+        st.has_checksum = 1; st.checksum = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
         p += 4;
         plan.n_checksums++;
     }
-    fd.n_blocks = (uint32_t)plan.blocks.size() - fd.first_block;
-    fd.n_seq = (uint32_t)plan.seq_total - fd.first_seq;
-    if (fd.n_seq == 0 && known_total != dst_size)
+    st.n_blocks = (uint32_t)(plan.blocks.size() - first_block);
+    st.n_seq = (uint32_t)(plan.seq_total - first_seq);
+    if (first) {
+        zf::FrameDesc& fd = plan.frames[fd_at];
+        fd.n_blocks = st.n_blocks; fd.n_seq = st.n_seq;
+        fd.has_checksum = st.has_checksum; fd.checksum = st.checksum;
+    }
+    return 0;
+}
+
+int check_frame_total(uint64_t n_seq, uint64_t known_total, uint64_t dst_size, std::string& err) {
+    if (n_seq == 0 && known_total != dst_size)
         FAIL(ERR_INVALID, "zstd frame regenerates %llu bytes but the section header says %llu",
              (unsigned long long)known_total, (unsigned long long)dst_size);
-    plan.frames.push_back(fd);
     return 0;
+}
+
+int walk_frame(const uint8_t* frame, uint64_t src_off, uint64_t src_size, uint64_t dst_off, uint64_t dst_size,
+               JobPlan& plan, std::string& err) {
+    RangeState st;
+    if (int rc = walk_frame_part(frame, src_off, src_size, dst_off, dst_size, 0, 0, true, true, st, plan, err)) return rc;
+    return check_frame_total(st.n_seq, st.known_total, dst_size, err);
 }
 
 void JobPlan::finalize(uint32_t small_max_symbols) {

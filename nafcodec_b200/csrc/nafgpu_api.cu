@@ -89,6 +89,15 @@ struct WalkTask {
     size_t bo = 0;                     // first block of the task among the job's blocks
     uint32_t so = 0, slot_off = 0, ho = 0;
     uint64_t lo = 0;
+    // a long section walked in parts (frame_walk.h): [p_begin, p_end) of the frame, and what the part inherits from the parts
+    // before it: the task that last defined a Huffman tree / an FSE table of each kind (-1: none, -2: a predefined table) and the
+    // index there; made absolute (abs_*) once the tasks' offsets are known
+    uint64_t p_begin = 0, p_end = 0;
+    bool first = true, last = true, heavy = false;
+    fw::RangeState st;
+    int carry_huf_task = -1, carry_tbl_task[3] = {-1, -1, -1};
+    uint32_t carry_huf_block = 0, carry_huf_slot = 0, carry_tbl_slot[3] = {0, 0, 0};
+    uint32_t abs_huf_block = zf::NO_BLOCK, abs_huf_slot = 0, abs_tbl[3] = {zf::NO_SLOT, zf::NO_SLOT, zf::NO_SLOT};
 };
 
 // NAFGPU_DEBUG_PREP=1: phase times of nafgpu_job_prepare on stderr
@@ -268,6 +277,16 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         T.bo = nb; T.so = (uint32_t)G.seq_total; T.lo = G.lit_total - 16; T.slot_off = G.n_slots - 3; T.ho = G.n_huf_slots;
         if (G.seq_total + L.seq_total > 0xFFFFFFF0ull || nb + L.blocks.size() > 0xFFFFFFF0ull) return fail(c, NAFGPU_ERR_UNSUPPORTED, "job has too many blocks or sequences: split the batch");
         for (zf::FrameDesc F : L.frames) { F.first_block += (uint32_t)T.bo; F.first_seq += T.so; G.frames.push_back(F); }
+        if (!T.first) {                // a continuation part: its blocks and sequences belong to the frame the first part opened
+            zf::FrameDesc& F = G.frames.back();
+            F.n_blocks += T.st.n_blocks; F.n_seq += T.st.n_seq;
+            if (T.last) { F.has_checksum = T.st.has_checksum; F.checksum = T.st.checksum; }
+            if (T.carry_huf_task >= 0) { const WalkTask& S = c->tasks[T.carry_huf_task]; T.abs_huf_block = (uint32_t)S.bo + T.carry_huf_block; T.abs_huf_slot = S.ho + T.carry_huf_slot; }
+            for (int k = 0; k < 3; k++) {
+                if (T.carry_tbl_task[k] == -2) T.abs_tbl[k] = T.carry_tbl_slot[k];
+                else if (T.carry_tbl_task[k] >= 0) T.abs_tbl[k] = c->tasks[T.carry_tbl_task[k]].slot_off + T.carry_tbl_slot[k];
+            }
+        }
         for (zf::HufItem it : L.huf_items) { it.block += (uint32_t)T.bo; G.huf_items.push_back(it); }
         for (uint32_t b : L.big_seq) G.big_seq.push_back(b + (uint32_t)T.bo);
         for (uint32_t b : L.big_lit) G.big_lit.push_back(b + (uint32_t)T.bo);
@@ -337,7 +356,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         // block descriptors: every task's blocks to their place, indices rebased to the job (frames, sequences, literal staging,
         // FSE table slots, Huffman weight records)
         std::vector<uint32_t> frame_off(c->n_tasks, 0);
-        { uint32_t fo = 0; for (size_t t = 0; t < c->n_tasks; t++) { frame_off[t] = fo; if (c->tasks[t].live) fo += (uint32_t)c->tasks[t].plan.frames.size(); } }
+        { uint32_t fo = 0; for (size_t t = 0; t < c->n_tasks; t++) { frame_off[t] = c->tasks[t].first ? fo : fo - 1; if (c->tasks[t].live) fo += (uint32_t)c->tasks[t].plan.frames.size(); } }
         (void)walked_bytes;
         const unsigned threads = nb > 200000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
         struct Chunk { size_t task, begin, end; };
@@ -357,9 +376,15 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
                 zf::BlockDesc b = in[i];
                 b.frame += fo;
                 if (b.n_seq) b.seq_base += T.so;
-                if (b.lit_type >= zf::LT_HUF && b.btype == zf::BT_COMPRESSED) { b.lit_base += T.lo; b.huf_slot += T.ho; }
-                if (b.huf_block != zf::NO_BLOCK) b.huf_block += (uint32_t)T.bo;
-                for (int k = 0; k < 3; k++) if (b.tbl[k] != zf::NO_SLOT && b.tbl[k] >= 3) b.tbl[k] += T.slot_off;
+                if (b.huf_block == fw::PREV_BLOCK) { b.lit_base += T.lo; b.huf_block = T.abs_huf_block; b.huf_slot = T.abs_huf_slot; }     // treeless, the tree from an earlier part
+                else {
+                    if (b.lit_type >= zf::LT_HUF && b.btype == zf::BT_COMPRESSED) { b.lit_base += T.lo; b.huf_slot += T.ho; }
+                    if (b.huf_block != zf::NO_BLOCK) b.huf_block += (uint32_t)T.bo;
+                }
+                for (int k = 0; k < 3; k++) {
+                    if (b.tbl[k] == fw::PREV_SLOT) b.tbl[k] = T.abs_tbl[k];
+                    else if (b.tbl[k] != zf::NO_SLOT && b.tbl[k] >= 3) b.tbl[k] += T.slot_off;
+                }
                 out[i] = b;
             }
         });
@@ -660,8 +685,8 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
 
     // ---- host frame walk (north star: "The host walks the frame and block headers") --------------------------------
     std::vector<Copy> copies;
-    size_t n_tasks = 0;                                         // (tasks are reused from call to call: their plans keep their capacity)
-    uint32_t big_sections = 0;
+    struct SecRef { uint32_t arch; int sec; const uint8_t* data; uint64_t comp_off, comp_size, dst_off, dst_size; std::vector<uint64_t> cuts; uint64_t n_blocks; int chain_rc; std::string chain_err; };
+    std::vector<SecRef> secs;
     for (uint32_t a = 0; a < n; a++) {
         const nafgpu_archive& A = archives[a];
         ArchPlan& P = c->aplan[a];
@@ -685,31 +710,100 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
                 if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
                 copies.push_back({S.data, comp_off, S.compressed_size});
             }
+            secs.push_back({a, s, S.data, comp_off, S.compressed_size, P.blob_off[s], P.blob_size[s], {}, 0, 0, {}});
+        }
+    }
+    PrepClock clk;
+    // ---- pass 1 over the long sections: the chain of block headers alone, a cut every `every` blocks ---------------------------
+    uint32_t split_min = 200000, every = 16384;                  // (sections of fewer blocks are walked in one piece)
+    uint64_t long_bytes = 4u << 20;
+    const char* split_env = getenv("NAFGPU_WALK_SPLIT");           // (test hook: parts of a few blocks; 0 = never split)
+    if (split_env && atoi(split_env) <= 0) long_bytes = UINT64_MAX;
+    else if (split_env) { every = (uint32_t)atoi(split_env); split_min = every; long_bytes = 0; }
+    const unsigned hw_threads = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    {
+        std::vector<size_t> longs;
+        for (size_t i = 0; i < secs.size(); i++) if (secs[i].comp_size > long_bytes) longs.push_back(i);
+        parallel_for(longs.size(), hw_threads, [&](size_t i) {
+            SecRef& R = secs[longs[i]];
+            R.chain_rc = fw::chain_blocks(R.data, R.comp_size, R.dst_size, every, R.cuts, R.n_blocks, R.chain_err);
+            if (R.chain_rc || R.n_blocks < split_min) R.cuts.clear();       // (an error is found again, and reported, by the walk proper)
+        });
+    }
+    clk.lap("block chains");
+    // ---- tasks, in section order; a long section as up to 8 parts ------------------------------------------------------------
+    size_t n_tasks = 0;                                         // (tasks are reused from call to call: their plans keep their capacity)
+    uint32_t heavy = 0;
+    for (SecRef& R : secs) {
+        const size_t n_cuts = R.cuts.size();
+        const size_t parts = std::min<size_t>(n_cuts + 1, split_env ? n_cuts + 1 : 8);
+        for (size_t k = 0; k < parts; k++) {
             if (n_tasks == c->tasks.size()) c->tasks.emplace_back();
             WalkTask& T = c->tasks[n_tasks++];
             T.plan.clear(); T.rc = 0; T.err.clear(); T.live = true;
-            T.arch = a; T.sec = s; T.data = S.data; T.comp_off = comp_off; T.comp_size = S.compressed_size;
-            T.dst_off = P.blob_off[s]; T.dst_size = P.blob_size[s];
-            if (S.compressed_size > (8u << 20)) big_sections++;
+            T.arch = R.arch; T.sec = R.sec; T.data = R.data; T.comp_off = R.comp_off; T.comp_size = R.comp_size;
+            T.dst_off = R.dst_off; T.dst_size = R.dst_size;
+            T.first = k == 0; T.last = k + 1 == parts;
+            // part k covers cuts [k * (n_cuts + 1) / parts, (k + 1) * (n_cuts + 1) / parts) of the n_cuts + 1 stretches between cuts
+            const size_t lo = k * (n_cuts + 1) / parts, hi = (k + 1) * (n_cuts + 1) / parts;
+            T.p_begin = lo ? R.cuts[lo - 1] : 0;
+            T.p_end = hi <= n_cuts ? R.cuts[hi - 1] : 0;
+            T.heavy = R.comp_size > (8u << 20) || parts > 1;
+            T.carry_huf_task = -1; T.carry_tbl_task[0] = T.carry_tbl_task[1] = T.carry_tbl_task[2] = -1;
+            T.abs_huf_block = zf::NO_BLOCK; T.abs_tbl[0] = T.abs_tbl[1] = T.abs_tbl[2] = zf::NO_SLOT;
+            if (T.heavy) heavy++;
         }
     }
     c->n_tasks = n_tasks;
-    PrepClock clk;
-    // the frame / block header walk, one task per section; big jobs on several host threads
+    // the frame / block header walk, one task per section or part; big jobs on several host threads
     {
-        // (threads only when at least two sections are big enough to hold 10^5+ block headers: starting threads costs more than
+        auto walk = [&](size_t t) {
+            WalkTask& T = c->tasks[t];
+            T.rc = fw::walk_frame_part(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.p_begin, T.p_end, T.first, T.last, T.st, T.plan, T.err);
+        };
+        // (threads only when at least two tasks are big enough to hold 10^5+ block headers: starting threads costs more than
         // walking the ~30 headers of a genome section)
-        const unsigned threads = big_sections >= 2 ? std::min(std::min(big_sections, 8u), std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+        const unsigned threads = heavy >= 2 ? std::min(heavy, hw_threads) : 1u;
         if (threads > 1) {
             std::vector<size_t> big, small;
-            for (size_t t = 0; t < n_tasks; t++) (c->tasks[t].comp_size > (8u << 20) ? big : small).push_back(t);
-            auto walk = [&](size_t t) { WalkTask& T = c->tasks[t]; T.rc = fw::walk_frame(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.plan, T.err); };
+            for (size_t t = 0; t < n_tasks; t++) (c->tasks[t].heavy ? big : small).push_back(t);
             std::thread rest([&] { for (size_t t : small) walk(t); });
             parallel_for(big.size(), threads, [&](size_t i) { walk(big[i]); });
             rest.join();
         } else {
-            for (size_t t = 0; t < n_tasks; t++) { WalkTask& T = c->tasks[t]; T.rc = fw::walk_frame(T.data, T.comp_off, T.comp_size, T.dst_off, T.dst_size, T.plan, T.err); }
+            for (size_t t = 0; t < n_tasks; t++) walk(t);
         }
+    }
+    // what every part inherits from the parts before it, and the checks that span a whole frame
+    for (size_t t0 = 0; t0 < n_tasks;) {
+        size_t t1 = t0 + 1;
+        while (t1 < n_tasks && !c->tasks[t1].first) t1++;
+        int huf_task = -1, tbl_task[3] = {-1, -1, -1};
+        uint32_t huf_block = 0, huf_slot = 0, tbl_slot[3] = {0, 0, 0};
+        uint64_t n_seq = 0, known = 0;
+        int rc = 0;
+        std::string err;
+        for (size_t t = t0; t < t1 && !rc; t++) {
+            WalkTask& T = c->tasks[t];
+            if (T.rc) { rc = T.rc; err = T.err; break; }
+            if (!T.first) {
+                T.carry_huf_task = huf_task; T.carry_huf_block = huf_block; T.carry_huf_slot = huf_slot;
+                for (int k = 0; k < 3; k++) { T.carry_tbl_task[k] = tbl_task[k]; T.carry_tbl_slot[k] = tbl_slot[k]; }
+                if (T.st.used_prev_huf && huf_task < 0) { rc = NAFGPU_ERR_INVALID_DATA; err = "zstd literals: treeless block without a previous tree"; }
+                for (int k = 0; k < 3; k++) if (T.st.used_prev_tbl[k] && tbl_task[k] == -1) { rc = NAFGPU_ERR_INVALID_DATA; err = "zstd sequences: repeat mode without a previous table"; }
+            }
+            if (T.st.last_huf != fw::PREV_BLOCK && T.st.last_huf != zf::NO_BLOCK) { huf_task = (int)t; huf_block = T.st.last_huf; huf_slot = T.st.last_huf_slot; }
+            for (int k = 0; k < 3; k++) {
+                const uint32_t v = T.st.cur_tbl[k];
+                if (v == fw::PREV_SLOT || v == zf::NO_SLOT) continue;
+                tbl_task[k] = v < 3 ? -2 : (int)t; tbl_slot[k] = v;
+            }
+            n_seq += T.st.n_seq; known += T.st.known_total;
+        }
+        if (!rc) rc = fw::check_frame_total(n_seq, known, c->tasks[t0].dst_size, err);
+        if (rc) { c->tasks[t0].rc = rc; c->tasks[t0].err = err; }
+        for (size_t t = t0 + 1; t < t1; t++) { c->tasks[t].comp_size = 0; c->tasks[t].dst_size = 0; }      // (counted once, with the first part)
+        t0 = t1;
     }
     clk.lap("header walk");
     {
@@ -767,7 +861,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx* c, const uint8_t* frame, uint64_t frame_s
     c->n_tasks = 1;
     {
         WalkTask& T = c->tasks[0];
-        T.plan.clear(); T.rc = 0; T.err.clear(); T.live = true; T.arch = 0; T.sec = 0;
+        T.plan.clear(); T.rc = 0; T.err.clear(); T.live = true; T.arch = 0; T.sec = 0; T.first = true; T.last = true;
         T.data = frame; T.comp_off = 16; T.comp_size = frame_size; T.dst_off = ALIGN; T.dst_size = regen_size;
         T.rc = fw::walk_frame(frame, 16, frame_size, ALIGN, regen_size, T.plan, T.err);
         if (T.rc) return fail(c, T.rc, T.err);
