@@ -10,7 +10,7 @@ import pytest
 import _cases as K
 import _oracle as O
 import nafcodec_b200 as N
-from _harness import BACKENDS, check_parity, library, records
+from _harness import BACKENDS, assert_same_as_oracle, check_parity, decode_soa, library, records
 from conftest import read_golden
 
 pytestmark = pytest.mark.parametrize("backend", BACKENDS)
@@ -318,6 +318,58 @@ def test_long_frames_are_scanned_by_tiles(backend, monkeypatch):
     assert N.shared_context(0, lib).stats().n_blocks > 1400
     monkeypatch.delenv("NAFGPU_FS_TILE")
     check_parity(backend, arc, "default tiles")
+
+
+@pytest.mark.parametrize("part", ["1", "5", "64"])
+def test_long_frames_are_walked_in_parts(backend, monkeypatch, part):
+    """A section of 2 x 10^5+ blocks is walked in parts on several host threads after a pass over the chain of block headers
+    alone (frame_walk.h); a part inherits the last Huffman tree (treeless literals) and the last FSE tables (repeat mode) from
+    the parts before it.  Parts of 1, 5 and 64 blocks here, so that every block, or nearly, inherits across a cut; the result
+    must be what the walk in one piece gives (NAFGPU_WALK_SPLIT=0) and what the oracle gives."""
+    lib = library(backend)
+    arcs = [K.fastq_reads(31, 200 if backend == "emul" else 20000, with_mask=True),
+            K.fastq_reads(32, 120 if backend == "emul" else 5000, level=19),
+            K.multi_record_dna(33, 40, 2000, level=3, flush=True)]
+    monkeypatch.setenv("NAFGPU_WALK_SPLIT", "0")
+    whole = [decode_soa(lib, a) for a in arcs]
+    monkeypatch.setenv("NAFGPU_WALK_SPLIT", part)
+    for a, w in zip(arcs, whole):
+        res, d = check_parity(backend, a, f"parts of {part} blocks")
+        assert res.sequence == w.sequence and res.quality == w.quality and res.ids == w.ids
+    # the pure-zstd boundary: frames whose blocks repeat tables and trees of earlier blocks
+    rng = np.random.default_rng(7)
+    payload = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 300_000))
+    frame = K.zstd_frame(payload, 3, flush_every=997)
+    assert N.shared_context(0, lib).zstd_decompress(frame, len(payload)) == payload
+    # a batch: every archive's sections are cut independently
+    got = N.shared_context(0, lib).decode([N.parse_archive(a, lib) for a in arcs])
+    for r, a in zip(got, arcs):
+        assert_same_as_oracle(r, O.decode(a), "batch walked in parts")
+
+
+def test_corrupt_frames_walked_in_parts_fail_cleanly(backend, monkeypatch):
+    """Bit flips in a long section with the walk in parts: same outcome classes as in one piece (decoded identically, or an
+    error; never a hang or a crash), and a truncated chain is reported."""
+    lib = library(backend)
+    arc = K.fastq_reads(34, 150, with_mask=True)
+    L = O.parse(arc)
+    s = L.sec[4]
+    monkeypatch.setenv("NAFGPU_WALK_SPLIT", "3")
+    rng = np.random.default_rng(11)
+    for pos in rng.integers(s.offset + 2, s.offset + s.compressed_size, size=16):
+        bad = bytearray(arc)
+        bad[int(pos)] ^= 1 << int(rng.integers(0, 8))
+        try:
+            r = decode_soa(lib, bytes(bad))
+        except (N.NafError, UnicodeError):
+            continue
+        try:
+            want = O.decode(bytes(bad))
+        except O.OracleError:
+            continue                      # (libzstd rejects what the device decoded: judged by test_corrupt_input_never_hangs' closed list, in one piece)
+        assert r.sequence == want.sequence
+    with pytest.raises(N.NafError):
+        decode_soa(lib, arc[:s.offset + s.compressed_size // 2])
 
 
 @pytest.mark.parametrize("block_min", ["1", "1000000"])
