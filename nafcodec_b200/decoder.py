@@ -168,6 +168,25 @@ def _np_copy(ptr, count, dtype):
     return np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype)
 
 
+class _FieldView:
+    """One field of an ArchiveResult for iteration: text(i) is record i's string or None (None-ness rules of mod.rs:356-399)."""
+    __slots__ = ("n", "off", "str", "blob", "trim")
+
+    def __init__(self, blob, offsets, n, trim):
+        self.n = n if (blob is not None and offsets is not None) else 0
+        self.off = offsets.tolist() if self.n else None
+        self.blob = blob
+        self.str = blob.decode("ascii") if (self.n and blob.isascii()) else None      # (1 byte = 1 character: slice the text)
+        self.trim = trim                                                                # ids / comments: the NUL
+
+    def text(self, i):
+        if i >= self.n:
+            return None
+        a, b = self.off[i], self.off[i + 1] - self.trim
+        t = self.str
+        return t[a:b] if t is not None else self.blob[a:b].decode("utf-8")
+
+
 class ArchiveResult:
     """Structure-of-arrays result of one archive, copied out of the context's pinned buffers."""
 
@@ -191,6 +210,17 @@ class ArchiveResult:
         self.sequence = C.string_at(r.sequence, r.total_residues) if r.sequence else None
         self.quality = C.string_at(r.quality, r.total_residues) if r.quality else None
         return self
+
+    def views(self):
+        """Per-field views for record iteration (built once): offsets as Python ints and, where a blob is pure ASCII, its text
+        decoded once, so that a record costs four string slices instead of four numpy reads, byte slices and decodes."""
+        v = getattr(self, "_views", None)
+        if v is None:
+            nl = self.n_lengths if self.lengths is not None else 0
+            v = self._views = (_FieldView(self.ids, self.id_offsets, self.n_ids, 1), _FieldView(self.comments, self.comment_offsets, self.n_comments, 1),
+                               _FieldView(self.sequence, self.record_offsets, nl, 0), _FieldView(self.quality, self.record_offsets, nl, 0),
+                               self.lengths.tolist() if self.lengths is not None else [], nl)
+        return v
 
     # field accessors with the reference's None-ness rules (mod.rs:356-399)
     def id_bytes(self, i):
@@ -274,6 +304,7 @@ class Decoder:
         self._want = _want_bits(id, comment, sequence, quality, mask)
         self._device = device
         self._n = 0
+        self._run = None
         self._result: Optional[ArchiveResult] = None
 
     # -- Rust-style constructors -----------------------------------------------------------------------------------
@@ -345,24 +376,67 @@ class Decoder:
         return self._header.number_of_sequences - self._n
 
     def __next__(self) -> Record:
+        run = self._run
+        if run is not None:                                # records [i, stop) of the current result without a stop in between:
+            try:                                           # a generator with everything in locals (~1 us per record)
+                return next(run)
+            except StopIteration:
+                self._run = None
         if self._n >= self._header.number_of_sequences:    # mod.rs:447-449
+            if self._window_bytes:
+                self.close()
             raise StopIteration
         if self._window_bytes:
             r = self._window(self._n)
-            i = self._n - self._window_first
+            base = self._window_first
         else:
             r = self._decoded()
-            i = self._n
-        if r.first_bad_record is not None and i == r.first_bad_record:
+            base = 0
+        i = self._n - base
+        bad = r.first_bad_record
+        if bad is not None and i == bad:
             self._n += 1
             raise_for_status(self._library, r.record_status)
-        self._n += 1
-        if self._window_bytes and self._n >= self._header.number_of_sequences:
-            self.close()
+        stop = min(r.n_records, self._header.number_of_sequences - base)
+        if bad is not None and i < bad < stop:
+            stop = bad
+        self._run = self._records(r, i, stop)
+        return next(self._run)
 
-        def s(b):
-            return None if b is None else b.decode("utf-8")
-        return _make_record(s(r.id_bytes(i)), s(r.comment_bytes(i)), s(r.sequence_bytes(i)), s(r.quality_bytes(i)), r.length(i))
+    def _records(self, r: ArchiveResult, i: int, stop: int):
+        """Records [i, stop) of one result (or window), None-ness as in mod.rs:356-399."""
+        idv, comv, seqv, qualv, lengths, nl = r.views()
+        id_n, id_off, id_str, id_blob = idv.n, idv.off, idv.str, idv.blob
+        com_n, com_off, com_str, com_blob = comv.n, comv.off, comv.str, comv.blob
+        seq_n, seq_str, seq_blob = seqv.n, seqv.str, seqv.blob
+        qual_n, qual_str, qual_blob = qualv.n, qualv.str, qualv.blob
+        rec_off = seqv.off if seq_n else qualv.off
+        new = Record.__new__
+        while i < stop:
+            rec = new(Record)
+            if i < id_n:
+                a, b = id_off[i], id_off[i + 1] - 1
+                rec.id = id_str[a:b] if id_str is not None else id_blob[a:b].decode("utf-8")
+            else:
+                rec.id = None
+            if i < com_n:
+                a, b = com_off[i], com_off[i + 1] - 1
+                rec.comment = com_str[a:b] if com_str is not None else com_blob[a:b].decode("utf-8")
+            else:
+                rec.comment = None
+            if i < nl:
+                rec.length = lengths[i]
+                if rec_off is not None:
+                    a, b = rec_off[i], rec_off[i + 1]
+                    rec.sequence = (seq_str[a:b] if seq_str is not None else seq_blob[a:b].decode("utf-8")) if seq_n else None
+                    rec.quality = (qual_str[a:b] if qual_str is not None else qual_blob[a:b].decode("utf-8")) if qual_n else None
+                else:
+                    rec.sequence = rec.quality = None
+            else:
+                rec.length = rec.sequence = rec.quality = None
+            i += 1
+            self._n += 1
+            yield rec
 
     def read(self) -> Optional[Record]:      # lib.rs:452-460
         try:
