@@ -24,6 +24,7 @@
 #include <cstring>
 #include <fstream>
 #include <istream>
+#include <mutex>
 #include <iterator>
 #include <optional>
 #include <stdexcept>
@@ -99,6 +100,36 @@ inline void check(int rc, const nafgpu_ctx* ctx, const char* what) {
     }
     throw Error(k, rc, msg);
 }
+// Contexts (streams, events, device arenas, pinned result buffers) outlive the Decoders that used them: a Decoder takes an idle
+// one of its device and gives it back when it is dropped, so that a program that opens archive after archive, as callers of
+// nafcodec::Decoder do, allocates device and pinned memory once, not per archive.  (Never torn down at exit: the CUDA runtime
+// may be gone by then.)
+class ContextPool {
+public:
+    static ContextPool& instance() { static ContextPool* p = new ContextPool; return *p; }
+    nafgpu_ctx* take(int device) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            for (size_t i = 0; i < idle_.size(); i++)
+                if (idle_[i].first == device) { nafgpu_ctx* c = idle_[i].second; idle_.erase(idle_.begin() + (std::ptrdiff_t)i); return c; }
+        }
+        nafgpu_ctx* c = nullptr;
+        check(nafgpu_ctx_create(device, &c), nullptr, "nafgpu_ctx_create");
+        return c;
+    }
+    void give(int device, nafgpu_ctx* c) {
+        if (!c) return;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            if (idle_.size() < kMaxIdle) { idle_.emplace_back(device, c); return; }
+        }
+        nafgpu_ctx_destroy(c);
+    }
+private:
+    static constexpr size_t kMaxIdle = 4;
+    std::mutex m_;
+    std::vector<std::pair<int, nafgpu_ctx*>> idle_;
+};
 }  // namespace detail
 
 class DecoderBuilder;
@@ -110,13 +141,13 @@ public:
     Decoder(Decoder&& o) noexcept { *this = std::move(o); }
     Decoder& operator=(Decoder&& o) noexcept {
         if (this != &o) {
-            if (ctx_) nafgpu_ctx_destroy(ctx_);
+            detail::ContextPool::instance().give(device_, ctx_);
             bytes_ = std::move(o.bytes_); arc_ = o.arc_; header_ = o.header_; want_ = o.want_; device_ = o.device_;
             ctx_ = o.ctx_; o.ctx_ = nullptr; res_ = o.res_; decoded_ = o.decoded_; n_ = o.n_; window_bytes_ = o.window_bytes_; window_first_ = o.window_first_; ran_ = o.ran_;   // (a moved vector keeps its buffer: arc_'s section pointers stay valid)
         }
         return *this;
     }
-    ~Decoder() { if (ctx_) nafgpu_ctx_destroy(ctx_); }
+    ~Decoder() { detail::ContextPool::instance().give(device_, ctx_); }
 
     static Decoder from_path(const std::string& path);                        // mod.rs:304-306
     static Decoder from_reader(std::istream& reader);                         // Decoder::new, mod.rs:315-317
@@ -178,14 +209,14 @@ private:
     static std::string slice(const uint8_t* blob, uint64_t b, uint64_t e) { return std::string(reinterpret_cast<const char*>(blob) + b, e - b); }
     void decode_once() {
         if (decoded_) return;
-        if (!ctx_) detail::check(nafgpu_ctx_create(device_, &ctx_), nullptr, "nafgpu_ctx_create");
+        if (!ctx_) ctx_ = detail::ContextPool::instance().take(device_);
         detail::check(nafgpu_decode(ctx_, &arc_, want_, &res_), ctx_, "decode");
         decoded_ = true;
     }
     // buffer_size mode: the archive is decoded into device memory once; records cross PCIe in windows of about window_bytes_
     // decoded bytes (nafgpu_job_fetch_window), so host memory is bounded as with the reference's BufReaders (mod.rs:69,105-112).
     void fetch_window(uint64_t i) {
-        if (!ctx_) detail::check(nafgpu_ctx_create(device_, &ctx_), nullptr, "nafgpu_ctx_create");
+        if (!ctx_) ctx_ = detail::ContextPool::instance().take(device_);
         if (!ran_) {
             detail::check(nafgpu_job_prepare(ctx_, &arc_, 1, want_), ctx_, "decode");
             detail::check(nafgpu_job_run(ctx_), ctx_, "decode");
