@@ -22,6 +22,12 @@ pub struct DeviceRecords {
     result: nafgpu_result,
     next: u64,
     // keeps the compressed sections alive for the duration of nafgpu_decode only
+    // `DecoderBuilder::buffer_size` (mod.rs:104-112) under the device backend: the decoded archive stays in device memory and
+    // `result` holds records [window_first, window_first + result.n_records) only, about `window_bytes` of decoded data
+    // (nafgpu_job_fetch_window); 0 = the whole result was copied back by `decode`.
+    window_bytes: u64,
+    window_first: u64,
+    n_records: u64,
 }
 
 // `arc` feature (lib.rs:25-26): a context has no thread-local CUDA state (cudaSetDevice at every entry).
@@ -57,13 +63,59 @@ impl DeviceRecords {
             unsafe { nafgpu_ctx_destroy(ctx) };
             return Err(e);
         }
-        Ok(Self { ctx, result, next: 0 })
+        let n_records = result.n_records;
+        Ok(Self { ctx, result, next: 0, window_bytes: 0, window_first: 0, n_records })
+    }
+
+    /// Same, with host memory bounded by `buffer_size`: prepare + run once, records fetched a window at a time.
+    pub fn decode_windowed(archive: &nafgpu_archive, want: u32, device: i32, buffer_size: u64) -> Result<Self, Error> {
+        let mut ctx = std::ptr::null_mut();
+        let rc = unsafe { nafgpu_ctx_create(device, &mut ctx) };
+        if rc != NAFGPU_OK {
+            return Err(Error::Io(std::io::Error::new(
+                std::io::ErrorKind::Other,
+                unsafe { CStr::from_ptr(nafgpu_strerror(rc)) }.to_string_lossy().into_owned(),
+            )));
+        }
+        let mut rc = unsafe { nafgpu_job_prepare(ctx, archive, 1, want) };
+        if rc == NAFGPU_OK {
+            rc = unsafe { nafgpu_job_run(ctx) };
+        }
+        if rc != NAFGPU_OK {
+            let e = to_error(ctx, rc);
+            unsafe { nafgpu_ctx_destroy(ctx) };
+            return Err(e);
+        }
+        let mut me = Self {
+            ctx,
+            result: unsafe { std::mem::zeroed() },
+            next: 0,
+            window_bytes: buffer_size.max(1),
+            window_first: 0,
+            n_records: archive.header.number_of_sequences,
+        };
+        me.fetch_window(0)?;
+        Ok(me)
+    }
+
+    fn fetch_window(&mut self, first: u64) -> Result<(), Error> {
+        let rc = unsafe {
+            nafgpu_job_fetch_window(self.ctx, 0, first, self.n_records - first, self.window_bytes, &mut self.result)
+        };
+        if rc != NAFGPU_OK {
+            return Err(to_error(self.ctx, rc));
+        }
+        self.window_first = first;
+        Ok(())
     }
 
     /// The body of `Decoder::next_record` for the device backend.
     pub fn next_record(&mut self) -> Result<Record<'static>, Error> {
+        if self.window_bytes != 0 && self.next >= self.window_first + self.result.n_records {
+            self.fetch_window(self.next)?;
+        }
         let r = &self.result;
-        let i = self.next;
+        let i = self.next - self.window_first;        // (index within the window; the whole archive is one window otherwise)
         self.next += 1;
         if r.record_status != 0 && i == r.first_bad_record {
             return Err(to_error(self.ctx, r.record_status));
