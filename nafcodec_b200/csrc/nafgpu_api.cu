@@ -2,6 +2,9 @@
 // walk), stream orchestration, result marshalling.  The reference-side seam it stands behind is the generic
 // reader parameter of nafcodec/src/decoder/reader.rs instantiated with ZstdDecoder in setup_block!
 // (nafcodec/src/decoder/mod.rs:32,218-226) and consumed by next_record / mask_sequence (mod.rs:356-441).
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -111,6 +114,26 @@ struct PrepClock {
         t = n;
     }
 };
+
+// A block descriptor goes to the pinned staging buffer with non-temporal stores where the host has them: the buffer is written
+// once and read by the copy engine, and a cached store would first read every line it overwrites (160 MB of descriptors for a
+// 10^6-read FASTQ archive: 6.3 ms on 8 threads with plain stores).
+static_assert(sizeof(zf::BlockDesc) % 16 == 0, "store_desc writes 16 bytes at a time");
+#if defined(__SSE2__) && !defined(__CUDA_ARCH__)
+inline void store_desc(zf::BlockDesc* dst, const zf::BlockDesc& b) {
+    if (((uintptr_t)dst & 15) == 0) {
+        const __m128i* s = (const __m128i*)&b;
+        __m128i* d = (__m128i*)dst;
+        for (size_t k = 0; k < sizeof(zf::BlockDesc) / 16; k++) _mm_stream_si128(d + k, _mm_loadu_si128(s + k));
+    } else {
+        *dst = b;
+    }
+}
+inline void desc_fence() { _mm_sfence(); }
+#else
+inline void store_desc(zf::BlockDesc* dst, const zf::BlockDesc& b) { *dst = b; }
+inline void desc_fence() {}
+#endif
 
 // fn(i) for i in [0, n) on up to `max_threads` host threads (inline when that is one).
 template <class F>
@@ -385,8 +408,9 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
                     if (b.tbl[k] == fw::PREV_SLOT) b.tbl[k] = T.abs_tbl[k];
                     else if (b.tbl[k] != zf::NO_SLOT && b.tbl[k] >= 3) b.tbl[k] += T.slot_off;
                 }
-                out[i] = b;
+                store_desc(out + i, b);
             }
+            desc_fence();
         });
     }
     clk.lap("pinned staging + block copy");
