@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -134,6 +135,23 @@ inline void desc_fence() { _mm_sfence(); }
 inline void store_desc(zf::BlockDesc* dst, const zf::BlockDesc& b) { *dst = b; }
 inline void desc_fence() {}
 #endif
+
+// Host threads a big job may use for its header walk and descriptor copy: three quarters of the cores, at most 12, less what the
+// other contexts of the process (the lanes of a pipeline) are using at this moment; never fewer than one.
+static std::atomic<int> g_helpers_busy{0};
+struct HelperLease {
+    unsigned n = 1;
+    HelperLease() {
+        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        const int cap = std::min(12, std::max(1, hw * 3 / 4));
+        const int got = std::max(1, std::min(cap, hw - g_helpers_busy.load(std::memory_order_relaxed)));
+        g_helpers_busy.fetch_add(got, std::memory_order_relaxed);
+        n = (unsigned)got;
+    }
+    ~HelperLease() { g_helpers_busy.fetch_sub((int)n, std::memory_order_relaxed); }
+    HelperLease(const HelperLease&) = delete;
+    HelperLease& operator=(const HelperLease&) = delete;
+};
 
 // fn(i) for i in [0, n) on up to `max_threads` host threads (inline when that is one).
 template <class F>
@@ -381,7 +399,9 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
         std::vector<uint32_t> frame_off(c->n_tasks, 0);
         { uint32_t fo = 0; for (size_t t = 0; t < c->n_tasks; t++) { frame_off[t] = c->tasks[t].first ? fo : fo - 1; if (c->tasks[t].live) fo += (uint32_t)c->tasks[t].plan.frames.size(); } }
         (void)walked_bytes;
-        const unsigned threads = nb > 200000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+        unsigned threads = 1;
+        std::unique_ptr<HelperLease> lease;
+        if (nb > 200000) { lease.reset(new HelperLease); threads = lease->n; }
         struct Chunk { size_t task, begin, end; };
         std::vector<Chunk> chunks;
         for (size_t t = 0; t < c->n_tasks; t++) {
@@ -744,7 +764,11 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     const char* split_env = getenv("NAFGPU_WALK_SPLIT");           // (test hook: parts of a few blocks; 0 = never split)
     if (split_env && atoi(split_env) <= 0) long_bytes = UINT64_MAX;
     else if (split_env) { every = (uint32_t)atoi(split_env); split_min = every; long_bytes = 0; }
-    const unsigned hw_threads = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    bool any_long = false;
+    for (const SecRef& R : secs) any_long = any_long || R.comp_size > long_bytes;
+    std::unique_ptr<HelperLease> walk_lease;
+    if (any_long) walk_lease.reset(new HelperLease);              // (held to the end of the walk)
+    const unsigned hw_threads = walk_lease ? walk_lease->n : 1u;
     {
         std::vector<size_t> longs;
         for (size_t i = 0; i < secs.size(); i++) if (secs[i].comp_size > long_bytes) longs.push_back(i);
@@ -760,7 +784,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     uint32_t heavy = 0;
     for (SecRef& R : secs) {
         const size_t n_cuts = R.cuts.size();
-        const size_t parts = std::min<size_t>(n_cuts + 1, split_env ? n_cuts + 1 : 8);
+        const size_t parts = std::min<size_t>(n_cuts + 1, split_env ? n_cuts + 1 : std::max(8u, hw_threads));
         for (size_t k = 0; k < parts; k++) {
             if (n_tasks == c->tasks.size()) c->tasks.emplace_back();
             WalkTask& T = c->tasks[n_tasks++];
@@ -798,6 +822,7 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
             for (size_t t = 0; t < n_tasks; t++) walk(t);
         }
     }
+    walk_lease.reset();
     // what every part inherits from the parts before it, and the checks that span a whole frame
     for (size_t t0 = 0; t0 < n_tasks;) {
         size_t t1 = t0 + 1;
