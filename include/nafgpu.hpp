@@ -16,6 +16,9 @@
 // the reference yields `Some(Err(e))`: at the record whose text is not valid UTF-8 (reader.rs:108-109), at the first
 // record for corrupt compressed data.  The six per-section streaming zstd readers are replaced by ONE device decode of
 // the whole archive on first access (nafgpu_decode); records are sliced out of the structure-of-arrays result.
+// With DecoderBuilder::buffer_size(n) the decoded archive stays in device memory and the records cross PCIe in windows of about n
+// decoded bytes (nafgpu_job_fetch_window): host memory bounded like the reference's BufReaders (mod.rs:69,104-112).  Contexts
+// are pooled per device and outlive the Decoders that used them.
 // Link with -lnafgpu (nafcodec_b200/csrc/libnafgpu.so).  There is no CPU fallback.
 #ifndef NAFGPU_HPP
 #define NAFGPU_HPP
