@@ -102,10 +102,8 @@ class Encoder:
             # SequenceWriter::encode rejects the record that carries the bad character (encoder/mod.rs:283-286): checked on the
             # host per record so that the error is raised by the `write` that caused it; the device reports the same
             # position again at `close` (nafgpu_pack_result.first_invalid), which the tests compare
-            ok = _VALID_RNA if self._type == SequenceType.Rna else _VALID_DNA
-            if self._mask:
-                ok = ok | {c + 32 for c in ok if 65 <= c <= 90}
-            if not ok.issuperset(record.sequence.encode("latin-1", "replace")):
+            # (bytes.translate with a delete table: one C loop over the record; anything left over is not in the alphabet)
+            if record.sequence.encode("latin-1", "replace").translate(None, _valid_bytes(self._type == SequenceType.Rna, self._mask)):
                 raise ValueError("invalid sequence: unexpected sequence character")
         self._records.append(record)
 
@@ -196,3 +194,15 @@ class Encoder:
 
 _VALID_DNA = set(b"ACGTRYSWKMBDHVN-")
 _VALID_RNA = set(b"ACGURYSWKMBDHVN-")
+_VALID_BYTES = {}
+
+
+def _valid_bytes(rna: bool, mask: bool) -> bytes:
+    """The alphabet SequenceWriter::encode accepts (encoder/writer.rs:31-90), lower case too when the mask is recorded."""
+    key = (rna, mask)
+    if key not in _VALID_BYTES:
+        ok = _VALID_RNA if rna else _VALID_DNA
+        if mask:
+            ok = ok | {c + 32 for c in ok if 65 <= c <= 90}
+        _VALID_BYTES[key] = bytes(sorted(ok))
+    return _VALID_BYTES[key]
