@@ -16,6 +16,10 @@ class _Buf(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
 
 
+class _InBuf(C.Structure):             # ZSTD_inBuffer over a bytes object: no copy, no cast (the per-record calls are the cost)
+    _fields_ = [("ptr", C.c_char_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
 _lib = None
 
 
@@ -28,7 +32,7 @@ def _zstd():
         L.ZSTD_CCtx_setParameter.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ZSTD_CCtx_setParameter.restype = C.c_size_t
         for f in ("ZSTD_compressStream",):
-            getattr(L, f).argtypes = [C.c_void_p, C.POINTER(_Buf), C.POINTER(_Buf)]
+            getattr(L, f).argtypes = [C.c_void_p, C.POINTER(_Buf), C.c_void_p]        # (input: byref of _Buf or _InBuf)
             getattr(L, f).restype = C.c_size_t
         for f in ("ZSTD_flushStream", "ZSTD_endStream"):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(_Buf)]
@@ -52,6 +56,8 @@ class StreamEncoder:
         self._z.ZSTD_CCtx_setParameter(self._c, _ZSTD_c_format, _ZSTD_f_zstd1_magicless)
         self._out = bytearray()
         self._scratch = (C.c_uint8 * (1 << 17))()
+        self._o = _Buf(C.addressof(self._scratch), len(self._scratch), 0)     # reused for every call
+        self._o_ref = C.byref(self._o)
         self.written = 0                      # WriteCounter (encoder/counter.rs:25-34): bytes accepted
 
     def _check(self, r):
@@ -59,35 +65,37 @@ class StreamEncoder:
             raise OSError("zstd: " + self._z.ZSTD_getErrorName(r).decode())
         return r
 
-    def _drain(self, o):
-        if o.pos:
-            self._out += bytes(self._scratch[:o.pos]) if o.pos < 4096 else C.string_at(self._scratch, o.pos)
+    def _drain(self):
+        n = self._o.pos
+        if n:
+            self._out += C.string_at(self._scratch, n)
+            self._o.pos = 0
 
     def write(self, data) -> None:
         n = len(data)
         if n == 0:
             return
-        src = (C.c_uint8 * n).from_buffer_copy(data) if not isinstance(data, C.Array) else data
-        i = _Buf(C.cast(src, C.c_void_p), n, 0)
-        while i.pos < i.size:
-            o = _Buf(C.cast(self._scratch, C.c_void_p), len(self._scratch), 0)
-            self._check(self._z.ZSTD_compressStream(self._c, C.byref(o), C.byref(i)))
-            self._drain(o)
+        if isinstance(data, C.Array):
+            i = _Buf(C.addressof(data), n, 0)
+        else:
+            i = _InBuf(data if isinstance(data, bytes) else bytes(data), n, 0)
+        i_ref = C.byref(i)
+        while i.pos < n:
+            self._check(self._z.ZSTD_compressStream(self._c, self._o_ref, i_ref))
+            self._drain()
         self.written += n
 
     def flush(self) -> None:
         r = 1
         while r:
-            o = _Buf(C.cast(self._scratch, C.c_void_p), len(self._scratch), 0)
-            r = self._check(self._z.ZSTD_flushStream(self._c, C.byref(o)))
-            self._drain(o)
+            r = self._check(self._z.ZSTD_flushStream(self._c, self._o_ref))
+            self._drain()
 
     def finish(self) -> bytes:
         r = 1
         while r:
-            o = _Buf(C.cast(self._scratch, C.c_void_p), len(self._scratch), 0)
-            r = self._check(self._z.ZSTD_endStream(self._c, C.byref(o)))
-            self._drain(o)
+            r = self._check(self._z.ZSTD_endStream(self._c, self._o_ref))
+            self._drain()
         self._z.ZSTD_freeCCtx(self._c)
         self._c = None
         return bytes(self._out)
