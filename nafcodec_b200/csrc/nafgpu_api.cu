@@ -304,7 +304,7 @@ static int d2h_results(nafgpu_ctx* c) {
 struct Copy { const uint8_t* src; uint64_t dst, size; };
 
 // Device allocation + H2D of descriptors and compressed frames for the plan in c->plan / c->arch.
-int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp_off, uint32_t n) {
+int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp_off, uint32_t n, bool copies_enqueued = false) {
     PrepClock clk;
     // lay the tasks' plans end to end: frames and Huffman items into the job plan (few), block descriptors later, straight
     // into the staging buffer
@@ -445,7 +445,7 @@ int finish_prepare(nafgpu_ctx* c, const std::vector<Copy>& copies, uint64_t comp
     if (stage_bytes) CUDA_TRY(c, cudaMemcpyAsync(c->desc.p, sp, stage_bytes, cudaMemcpyHostToDevice, c->st));
     uint64_t h2d = stage_bytes;
     for (const Copy& cp : copies) {
-        CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->comp.p + cp.dst, cp.src, cp.size, cudaMemcpyHostToDevice, c->st));
+        if (!copies_enqueued) CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->comp.p + cp.dst, cp.src, cp.size, cudaMemcpyHostToDevice, c->st));
         h2d += cp.size;
     }
 
@@ -758,6 +758,19 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
         }
     }
     PrepClock clk;
+    // The compressed sections do not wait for the header walk: their copies go first, so that they cross PCIe while the host walks
+    // (512 archives: 520 MB, 9.5 ms of copies beside 4.5 ms of walk).  The stream was synchronised above: nothing reads `comp`.
+    bool copies_enqueued = false;
+    {
+        const uint64_t comp_total = copies.empty() ? comp_off : align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
+        if (c->comp.ensure(comp_total + 64)) {
+            for (const Copy& cp : copies) CUDA_TRY(c, cudaMemcpyAsync((uint8_t*)c->comp.p + cp.dst, cp.src, cp.size, cudaMemcpyHostToDevice, c->st));
+            copies_enqueued = true;
+        }                                                          // (else: finish_prepare reports the failed allocation)
+    }
+    // (a failed prepare must not leave copies from the caller's buffers in flight: every error return below waits for them)
+    struct CopyGuard { cudaStream_t st; bool armed; ~CopyGuard() { if (armed) cudaStreamSynchronize(st); } } copy_guard{c->st, copies_enqueued};
+    clk.lap("compressed sections enqueued");
     // ---- pass 1 over the long sections: the chain of block headers alone, a cut every `every` blocks ---------------------------
     uint32_t split_min = 200000, every = 16384;                  // (sections of fewer blocks are walked in one piece)
     uint64_t long_bytes = 4u << 20;
@@ -888,7 +901,9 @@ int nafgpu_job_prepare(nafgpu_ctx* c, const nafgpu_archive* archives, uint32_t n
     }
     c->stats.algorithmic_bytes += c->stats.compressed_bytes;
     if (!copies.empty()) comp_off = align_up(copies.back().dst + copies.back().size + zf::COMP_PAD, 16);
-    return finish_prepare(c, copies, comp_off, n);
+    const int rc_finish = finish_prepare(c, copies, comp_off, n, copies_enqueued);
+    if (rc_finish == NAFGPU_OK) copy_guard.armed = false;
+    return rc_finish;
 }
 
 // One magicless zstd frame -> regen_size bytes at dst (host).  The pure-zstd boundary of the reference
